@@ -1,0 +1,179 @@
+/*
+ * sisgpu.h -- C ABI of the B200-native SIS hot path (libsisgpu.so).
+ *
+ * The reference (Hori-Lab/SIS, Fortran 2008) has no plugin/FFI boundary: the
+ * seam is a set of external subroutines that talk through module globals
+ * (SURVEY.md section 8b).  This header is the boundary the Fortran driver binds
+ * through ISO_C_BINDING (sis_b200/fortran/sisgpu_mod.F90).
+ * Each entry point names the reference routine / call site it replaces
+ * (file:line relative to the reference tree).
+ *
+ * Conventions
+ *  - plain C types only; every function returns 0 on success, non-zero on
+ *    error (message via sisgpu_last_error()); the Fortran shim turns non-zero
+ *    into `call sis_abort()` (src/sis_abort.F90:12-19).
+ *  - arrays are the Fortran module arrays passed by reference: column-major,
+ *    so xyz(3,nmp) arrives as [nmp][3] doubles.  Bead / pair indices crossing
+ *    the boundary are 1-based exactly as in the reference.
+ *  - `irep` is the 1-based in-process replica index of the reference.
+ *  - the library owns all device memory; the caller owns every host array.
+ *  - callers are single-threaded per handle (as the reference's drivers are).
+ *  - all arithmetic is fp64 (PREC = REAL64, src/const.F90:10).
+ */
+#ifndef SISGPU_H
+#define SISGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sisgpu sisgpu_t;
+
+#define SISGPU_ENE_N 11          /* energies(0:10), src/const_idx.F90:7-21 */
+#define SISGPU_NCCL_ID_BYTES 128
+
+const char *sisgpu_last_error(void);
+int sisgpu_version(void);
+
+/* ---- life cycle ------------------------------------------------------------ */
+/* replaces nothing in the reference; rank -> GPU mapping is new (myrank mod ngpu) */
+int sisgpu_create(sisgpu_t **out, int device);
+int sisgpu_destroy(sisgpu_t *h);
+
+/* ---- set-up: the outputs of the reference's init_* routines ------------------ */
+/* var_top (src/var_top.F90:9-28) after init_sequence/read_fasta; seq codes A0 U1 G2 C3 D4
+ * (src/const_idx.F90:31-40) per bead in bead order; moltypes RNA 1 / circRNA 2;
+ * has_charge from init_ele (src/init_ele.F90:45-62); is_frozen from init_freeze;
+ * mass from src/job_md.F90:116-133 (NULL = use those hard-coded masses) */
+int sisgpu_set_topology(sisgpu_t *h, int nmp, int nchains, const int *nmp_chain,
+                        const int *moltypes, const int *seq, const int *has_charge,
+                        const int *is_frozen, const double *mass);
+/* nrep_proc of src/init_replica.F90:56-65 */
+int sisgpu_set_replicas(sisgpu_t *h, int nrep_proc);
+/* var_potential bonded scalars read by src/read_force_field.F90:68-131.
+ * angl_type 0 = [potential.angle], 1 = [potential.angle_ReB];
+ * dih_flags bit0 = [potential.dihedral] (cos), bit1 = [potential.dihedral_exp] */
+int sisgpu_set_ff_bonded(sisgpu_t *h, double bond_k, double bond_r0, int angl_type,
+                         double angl_k, double angl_t0, int dih_flags, double dih_k,
+                         double dih_w, double dih_p0);
+int sisgpu_set_ff_wca(sisgpu_t *h, double sigma, double eps);
+/* [potential.basepair] + [Basepair]: bp_paras[3][15] for GC, AU, GU in .ff order
+ * (U0 bond_k bond_r angl_k1..4 angl_theta1..4 dihd_k1..2 dihd_phi1..2); the CG/UA/UG
+ * sets are derived as in src/read_force_field.F90:203-207 */
+int sisgpu_set_ff_bp(sisgpu_t *h, int model, int min_loop, int max_bp_per_nt, int nstep_MC,
+                     double cutoff_energy, const double *bp_paras);
+/* [NN] tables (21 stacks in NNT order, src/const_idx.F90:96-121) from which the 468-entry
+ * bp3 table of src/init_bp.F90:39-172 is rebuilt; replaces the N x N bp_map / bp3_map */
+int sisgpu_set_ff_nn(sisgpu_t *h, const double *NN_dH, const double *NN_dS, double dH0,
+                     double dS0, int flg_NNend, const double *NNend_dH,
+                     const double *NNend_dS, double dHend0, double dSend0);
+/* [Electrostatic] (src/read_input.F90:690-770) */
+int sisgpu_set_ele(sisgpu_t *h, int flg_ele, int cutoff_type, double cutoff_inp,
+                   int excl_bond, int excl_angle, double length_per_charge,
+                   int temp_independent, double tempK_ref);
+/* src/pbc.F90:5-9; also the target of pbc_resize (src/job_md.F90:576-594) */
+int sisgpu_set_pbc(sisgpu_t *h, int flg_pbc, const double *box);
+/* [MD]: integrator 1 = GJF-2GJ, 2 = Ermak-McCammon (src/const_idx.F90:51-57) */
+int sisgpu_set_md(sisgpu_t *h, int integrator, double dt, double viscosity_Pas,
+                  double nl_margin, uint64_t seed);
+int sisgpu_set_bias_ss(sisgpu_t *h, int flg, double force);
+int sisgpu_set_stage(sisgpu_t *h, int flg, double sigma, double eps);
+int sisgpu_set_tweezers_dcf(sisgpu_t *h, int n, const int *pairs, const double *direction);
+int sisgpu_set_tweezers_fr(sisgpu_t *h, int n, const int *pairs, const double *k,
+                           const double *init, const double *velo);
+int sisgpu_set_bias_rg(sisgpu_t *h, int flg, int pott, double k);
+int sisgpu_set_restraints(sisgpu_t *h, int n, const int *id, const double *rcut,
+                          const double *para);
+/* per-replica parameters (0-based irep here mirrors the oracle; the Fortran shim
+ * subtracts 1): temperature, ionic strength, DCF force magnitude, Rg0.  Performs
+ * set_ele (src/set_ele.F90:47-102) and set_md_coef (src/job_md.F90:700-767). */
+int sisgpu_set_replica_params(sisgpu_t *h, int irep, double tempK, double ionic_strength,
+                              double twz_force, double rg0);
+/* list_local (src/list_local.F90), init_bp tables (src/init_bp.F90), device allocation */
+int sisgpu_finalize_setup(sisgpu_t *h);
+
+/* ---- state ------------------------------------------------------------------ */
+/* xyz / velos / accels (3,nmp,irep) of src/var_state.F90:26-28; NULL = skip */
+int sisgpu_set_state(sisgpu_t *h, int irep, const double *xyz, const double *velos,
+                     const double *accels);
+int sisgpu_get_state(sisgpu_t *h, int irep, double *xyz, double *velos, double *accels);
+int sisgpu_set_step(sisgpu_t *h, int64_t istep);
+int sisgpu_get_step(sisgpu_t *h, int64_t *istep);
+
+/* ---- lists ------------------------------------------------------------------ */
+/* call neighbor_list(irep): src/job_md.F90:197,389,584 -> src/neighbor_list.F90 */
+int sisgpu_neighbor_list(sisgpu_t *h, int irep);
+/* call list_bp / list_exv / list_ele: src/main.F90:150-152 */
+int sisgpu_full_lists(sisgpu_t *h);
+int sisgpu_get_list_sizes(sisgpu_t *h, int irep, int *nwca, int *nele, int *nbp);
+/* wca_mp(2,nwca) ele_mp(2,nele) bp_mp(7,nbp) bp_coef(2,nbp) of src/var_potential.F90:85-112,
+ * 1-based, in the reference's (i, j) loop order */
+int sisgpu_get_lists(sisgpu_t *h, int irep, int *wca_mp, int *ele_mp, int *bp_mp,
+                     double *bp_coef);
+int sisgpu_get_local_lists(sisgpu_t *h, int *nbond, int *nangl, int *ndih, int *bond_mp,
+                           int *angl_mp, int *dih_mp);
+int sisgpu_bp3_table(sisgpu_t *h, int *n, int *hash4096, double *dH, double *dS);
+
+/* ---- hot path ----------------------------------------------------------------*/
+/* flg_bp_MC of src/job_md.F90:365-368 for the next force / energy call */
+int sisgpu_set_bp_mc(sisgpu_t *h, int flg_bp_MC);
+/* call force(irep, forces): src/job_md.F90:397, src/job_check_force.F90:53 */
+int sisgpu_force(sisgpu_t *h, int irep, double *forces);
+/* per-term force (the reference's DUMPFORCE probe); mask bit k = energies index k */
+int sisgpu_force_terms(sisgpu_t *h, int irep, unsigned mask, double *forces);
+/* call energy_sumup(irep, tempK, energies): src/job_md.F90:290, src/energy_replica.F90:54,121,
+ * src/job_check_force.F90:62,66.  recompute_bp != 0 <=> flg_bp_energy = .False. */
+int sisgpu_energy_sumup(sisgpu_t *h, int irep, double tempK, int recompute_bp,
+                        double *energies);
+/* call energy_kinetic: src/job_md.F90:291,501 */
+int sisgpu_energy_kinetic(sisgpu_t *h, int irep, double *ekin);
+/* bp_status / ene_bp for write_bp (src/write_bp.F90:36-49) */
+int sisgpu_get_bp_state(sisgpu_t *h, int irep, int *status, double *ene);
+int sisgpu_get_rg(sisgpu_t *h, int irep, double *rg);
+/* initial velocities / beta(0): src/job_md.F90:157-176 (counter-based generator) */
+int sisgpu_init_velocities(sisgpu_t *h, int irep);
+/* the loop body src/job_md.F90:360-460 for all local replicas, nsteps times, resident on
+ * the device; with REMD configured it also runs energy_replica + the allgather +
+ * replica_exchange + parameter refresh (src/job_md.F90:474-481,514-570) every
+ * nstep_exchange steps.  nrebuild (may be NULL) returns the neighbour-list rebuild count */
+int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild);
+/* job_check_force (src/job_check_force.F90:53-80): forces + central finite difference of
+ * energy_sumup for every coordinate, evaluated on the device */
+int sisgpu_check_force(sisgpu_t *h, double tempK, double *f_energy, double *f_force,
+                       double *maxdiff);
+/* launch statistics: kernels launched by this handle since creation */
+int sisgpu_launch_count(sisgpu_t *h, int64_t *n);
+/* options: name = "launch_mode" (0 stream, 1 graph), "threads_per_bead", "timing" */
+int sisgpu_set_option(sisgpu_t *h, const char *name, double value);
+/* CUDA-event time (ms) accumulated per kernel family since the last reset:
+ * out[0] step kernels, out[1] neighbour list, out[2] energy, out[3] exchange */
+int sisgpu_get_timers(sisgpu_t *h, double *out, int reset);
+
+/* ---- REMD ------------------------------------------------------------------- */
+/* init_replica (src/init_replica.F90) + make_replica_exchange_pair_tb
+ * (src/var_replica.F90:162-259).  nrep[4] / values[4][256] in REPT order
+ * TEMP, TWZDCF, ION, RG (src/const_idx.F90:87-94).  rank / nranks give the block
+ * distribution grep = rank*nrep_proc + irep (src/init_replica.F90:117-119). */
+int sisgpu_remd_setup(sisgpu_t *h, const int nrep[4], const double *values,
+                      int nstep_exchange, int rank, int nranks);
+/* NCCL plumbing for the one hot-loop collective, MPI_ALLREDUCE at src/job_md.F90:531-533:
+ * rank 0 calls sisgpu_nccl_unique_id and broadcasts the bytes (MPI_BCAST / torch.distributed) */
+int sisgpu_nccl_unique_id(unsigned char *id /*[SISGPU_NCCL_ID_BYTES]*/);
+int sisgpu_comm_init(sisgpu_t *h, int nranks, int rank, const unsigned char *id);
+int sisgpu_remd_pair_table(sisgpu_t *h, int *tb);
+int sisgpu_remd_state(sisgpu_t *h, int *rep2lab, int *lab2rep, double *lab2val);
+int sisgpu_remd_stats(sisgpu_t *h, int64_t *n_attempt, int64_t *n_accept);
+/* call energy_replica(...) on an exchange step: src/energy_replica.F90:45-163;
+ * energies [nrep_proc][11], replica_energies [nrep_all][2] after the allgather */
+int sisgpu_energy_replica(sisgpu_t *h, double *energies, double *replica_energies);
+/* call replica_exchange(velos, replica_energies, tempk): src/replica_exchange.F90:44-154,
+ * with caller-supplied uniforms (NULL = the library's counter-based stream) */
+int sisgpu_replica_exchange(sisgpu_t *h, const double *replica_energies,
+                            const double *uniforms, int *n_attempt, int *n_accept);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
