@@ -877,7 +877,13 @@ int oracle_neighbor_list(sis_oracle *o, int irep)
                             b[2] = (i == 1) ? imp + ni - 1 : imp - 1;
                             b[3] = (j == 1) ? jmp + nj - 1 : jmp - 1;
                             b[4] = (i == ni) ? imp + 1 - ni : imp + 1;
-                            b[5] = (j == ni) ? jmp + 1 - nj : jmp + 1; /* :212 tests nmp_chain(ichain) */
+                            /* :212 tests `j == nmp_chain(ichain)`; for chains of unequal length that
+                             * indexes a bead outside chain j (out of bounds in the worst case).
+                             * Identical to the intended nmp_chain(jchain) whenever the chain
+                             * lengths agree or the chains are linear of equal length (every
+                             * check/ input and C1-C5).  Oracle and GPU use the intended form;
+                             * DESIGN.md lists this as the one deliberate deviation. */
+                            b[5] = (j == nj) ? jmp + 1 - nj : jmp + 1;
                             b[6] = bptype;
                             if (o->bp_model == 5) {
                                 r->bp_coef[2 * ibp] = o->bp3_dH[bp3];

@@ -1,0 +1,1004 @@
+// sis_kernels.cuh -- sm_100a kernels of the SIS hot path.
+//
+// Layout (DESIGN.md "HBM layout"): positions are double4 AoS (one 32-byte sector per gather),
+// double-buffered so that one launch computes forces from buffer `cur` and writes the
+// integrated positions to buffer `cur^1`; velocities / beta / displacement are [bead][3]
+// doubles; neighbour rows are fixed-capacity (ELL) uint32 rows per bead holding the FULL
+// (both directions) list with two flag bits (WCA-listed, DH-listed), so a group of G lanes
+// owns one bead, streams its row coalesced and reduces with shuffles -- no atomics.
+#pragma once
+
+#include "sis_device.cuh"
+
+struct DevCtl {
+    unsigned long long step;   // istep of the NEXT step to execute minus 1 (job_md istep)
+    int cur;                   // which position buffer holds the current coordinates
+    int nl_overflow;           // max row length seen by the last list build
+    int bp_overflow;
+    unsigned long long steps_done;
+    // 0 = none; else the istep whose position update pushed some replica past the list margin.
+    // Kernels queued behind it see abort_word <= step and return without touching the state;
+    // blocks of the launch that raised it see abort_word > step and finish normally.
+    unsigned long long abort_word;
+    int max_force_flag;        // src/job_md.F90:403-407 (forces > 100 warning)
+    int pad;
+};
+SIS_D bool ctl_aborted(const DevCtl &c) { return c.abort_word != 0ull && c.abort_word <= c.step; }
+
+struct GridInfo {
+    double origin[3], inv_cell[3];
+    int n[3], ncell, pbc;
+};
+
+struct DevSys {
+    int nmp, nrep, K, KB, nblk;   // nblk = step-kernel blocks per replica
+    // topology
+    const int4 *meta;
+    const int *seq;
+    const double4 *coef;          // a, sqrt(b)h/m, sqrt(b)h (0 if frozen), noise0
+    const double *mass;
+    const int *hash;              // bp3 hash (4096), 1-based values, 0 = none
+    const double *bp3_dH, *bp3_dS;  // 1-based (index 0 unused)
+    // state [rep][nmp]
+    double4 *pos[2];
+    double *vel, *acc, *move;     // [rep][nmp][3]
+    double *force;                // [rep][nmp][3]
+    // lists
+    uint32_t *nbr;                // [rep][nmp][K]
+    int *nnbr;                    // [rep][nmp]
+    int2 *bprow;                  // [rep][nmp][KB]  {partner, ibp}
+    int *nbp_row;                 // [rep][nmp]
+    signed char *bp_type;         // [rep][nmp*KB] by ibp = owner*KB + slot
+    double2 *bp_coef;             // dH, dS*1e-3
+    int *bp_status, *bp_status_MC;
+    double *ene_bp;
+    int *nt_excess;               // [rep][nmp]
+    unsigned long long *mc_counter;  // [rep]
+    // cell grid [rep][...]
+    int *cell_of, *cell_count, *cell_start, *cell_cursor, *cell_beads;
+    int ncell_cap;
+    // parameters
+    RepParams *rp;
+    DevCtl *ctl;
+    int *need_rebuild;            // [rep]
+    double *blk_top2;             // [rep][nblk][2]
+    unsigned int *blk_counter;    // [rep]
+    double *ene_partial;          // [rep][nblk][ENE_N]
+    unsigned int *ene_counter;    // [rep]
+    double *ene_out;              // [rep][ENE_N]
+    // biases
+    const int *twz_pairs;         // [ntwz][2] 0-based
+    const double *twz_dir;        // [ntwz][3]
+    const int *twzfr_pairs;
+    const double *twzfr_k, *twzfr_init, *twzfr_velo;
+    const int *rest_id;           // [nrest][3] 0-based i, j, type
+    const double *rest_rcut, *rest_para;
+};
+
+struct StepArgs {
+    unsigned long long seed;
+    double nl_margin;
+    unsigned term_mask;   // bit k = energies index k
+    int use_mask;         // 0 all pairs; 1 only bp_status_MC (nstep_bp_MC > 0); 2 only bp_status
+    int only_rep;         // >= 0: single replica (per-irep API); -1: all (grid.y)
+};
+
+// sum over the G lanes that own one bead.  Host builds (tests/csrc/hostcheck.cu) run the same
+// force code with G = 1, where the group is a single "lane".
+template <int G>
+SIS_HD double group_sum(double v)
+{
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
+#else
+    static_assert(G >= 1, "group size");
+#endif
+    return v;
+}
+
+// ---- shared force evaluation: complete force on bead k, lane-partial -----------------------
+template <int G>
+SIS_HD Vec3 bead_force(const DevSys &S, const FFParams &P, const RepParams &R, const double4 *__restrict__ pos,
+                      int rep, int k, int lane, unsigned term_mask, int use_mask, unsigned long long istep,
+                      int write_bp)
+{
+    const int nmp = S.nmp;
+    const int4 mk4 = S.meta[k];
+    const Vec3 xk = v3(pos[k]);
+    Vec3 F = mk(0.0, 0.0, 0.0);
+
+    // -- pair loop: src/force_wca.F90:34-66, src/force_ele_DH.F90:39-81 ----------------------
+    if (term_mask & ((1u << ENE_EXV) | (1u << ENE_ELE))) {
+        const uint32_t *row = S.nbr + ((size_t)rep * nmp + k) * S.K;
+        const int nn = S.nnbr[(size_t)rep * nmp + k];
+        const double cut2 = R.ele_cutoff * R.ele_cutoff;
+        const bool do_wca = term_mask & (1u << ENE_EXV);
+        const bool do_ele = (term_mask & (1u << ENE_ELE)) && P.flg_ele;
+        for (int e = lane; e < nn; e += G) {
+            uint32_t ent = row[e];
+            Vec3 v = pbc_vec_d(P, xk, v3(pos[ent & NB_IDX]));
+            double d2 = dot(v, v), s = 0.0;
+            if (do_wca && (ent & NB_WCA) && d2 < P.wca_sigma2) s += wca_scalar(P, d2);
+            if (do_ele && (ent & NB_ELE) && d2 <= cut2) s += dh_scalar(R.ele_coef, R.inv_lambdaD, d2);
+            F += s * v;
+        }
+    }
+
+    // -- bonded terms, one instance per lane: 2 bonds, 3 angles, 4 dihedrals -------------------
+    for (int inst = lane; inst < 9; inst += G) {
+        int kind, p;   // kind 0 bond, 1 angle, 2 dihedral; p = position of k in the term
+        if (inst < 2) { kind = 0; p = inst; }
+        else if (inst < 5) { kind = 1; p = inst - 2; }
+        else { kind = 2; p = inst - 5; }
+        const int span = kind + 1;   // term covers beads a .. a+span
+        const bool on = (kind == 0) ? (term_mask & (1u << ENE_BOND))
+                        : (kind == 1) ? (term_mask & (1u << ENE_ANGL))
+                                      : ((term_mask & (1u << ENE_DIHE)) && (P.flg_dih_cos || P.flg_dih_exp));
+        // first bead a = k - p; term exists iff a and a+span exist (circRNA: always, n > span)
+        bool exists;
+        if (mk4.w & MF_CIRC) exists = mk4.y > span;
+        else exists = (mk4.z - p >= 0) && (mk4.z - p + span < mk4.y);
+        if (on && exists) {
+            Vec3 x[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (q <= span) x[q] = (q == p) ? xk : v3(pos[chain_nb(mk4, q - p)]);
+            Vec3 f;
+            if (kind == 0) f = bond_force(P, x[0], x[1], p);
+            else if (kind == 1) f = P.flg_angl_ReB ? angl_ReB_force(P, x[0], x[1], x[2], p)
+                                                  : angl_force(P, x[0], x[1], x[2], p);
+            else f = dih_force(P, x[0], x[1], x[2], x[3], p);
+            F += f;
+        }
+    }
+
+    // -- base pairs: rows of k (roles i/j), k+1 (k is the i-1/j-1 bead), k-1 (i+1/j+1) ---------
+    if (term_mask & (1u << ENE_BP)) {
+        const size_t rbase = (size_t)rep * nmp;
+        const size_t pbase = rbase * S.KB;
+        for (int cc = 0; cc < 3; cc++) {
+            const int c = (cc == 0) ? k : chain_nb(mk4, cc == 1 ? 1 : -1);
+            if (c < 0) continue;
+            const int nrow = S.nbp_row[rbase + c];
+            for (int e0 = 0; e0 < nrow; e0 += G) {
+                const int e = e0 + lane;
+                bool pass = false;
+                int j = 0, ibp = 0, role = 0, bi = 0, bj = 0, type = 1;
+                double dG = 1.0, a12 = 1.0;
+                Vec3 xs[6], v12 = mk(0, 0, 0);
+                if (e < nrow) {
+                    int2 ent = S.bprow[(rbase + c) * S.KB + e];
+                    j = ent.x; ibp = ent.y;
+                    bi = min(c, j); bj = max(c, j);
+                    if (cc == 0) role = (k == bi) ? 0 : 1;
+                    else if (cc == 1) role = (c == bi) ? 2 : 3;
+                    else role = (c == bi) ? 4 : 5;
+                    bool active = true;
+                    if (use_mask == 1) active = S.bp_status_MC[pbase + ibp] != 0;
+                    else if (use_mask == 2) active = S.bp_status[pbase + ibp] != 0;
+                    type = S.bp_type[pbase + ibp];
+                    if (P.bp_triplet) {
+                        double2 cf = S.bp_coef[pbase + ibp];
+                        dG = cf.x - R.tempK * cf.y;     // src/force_bp_triplet.F90:77
+                        if (dG >= 0.0) active = false;
+                    }
+                    if (active) {
+                        xs[0] = v3(pos[bi]); xs[1] = v3(pos[bj]);
+                        v12 = pbc_vec_d(P, xs[0], xs[1]);
+                        a12 = sqrt(dot(v12, v12));
+                        pass = fabs(a12 - P.bp[type].bond_r) <= P.bp[type].cutoff_ddist;
+                        if (!pass && P.bp_triplet && P.flg_bias_ss && role < 2) {
+                            Vec3 t = (P.bias_ss_force / a12) * v12;   // force_bp_triplet.F90:85-93
+                            if (role == 0) F -= t; else F += t;
+                        }
+                    }
+                    if (!pass && write_bp && cc == 0 && role == 0) {
+                        S.bp_status[pbase + ibp] = 0;
+                        S.ene_bp[pbase + ibp] = 0.0;
+                    }
+                }
+                // lanes that passed the gate evaluate the 6-body term
+                if (pass) {
+                    const int4 mi = S.meta[bi], mj = S.meta[bj];
+                    xs[2] = v3(pos[chain_nb(mi, -1)]); xs[3] = v3(pos[chain_nb(mj, -1)]);
+                    xs[4] = v3(pos[chain_nb(mi, +1)]); xs[5] = v3(pos[chain_nb(mj, +1)]);
+                    double u; Vec3 fr;
+                    bp_force_role(P, P.bp[type], xs, role, &u, &fr, &a12, &v12);
+                    double ene = P.bp_triplet ? P.bp[type].U0 * dG * exp(-u) : P.bp[type].U0 * exp(-u);
+                    bool ok = ene <= P.bp_cutoff_energy;
+                    if (ok) F += ene * fr;
+                    if (write_bp && cc == 0 && role == 0) {
+                        S.bp_status[pbase + ibp] = ok ? 1 : 0;
+                        S.ene_bp[pbase + ibp] = ok ? ene : 0.0;
+                    }
+                }
+            }
+        }
+    }
+
+    // -- per-bead biases (lane 0) --------------------------------------------------------------
+    if (lane == 0) {
+        if ((term_mask & (1u << ENE_STAGE)) && P.flg_stage) {   // src/force_stage.F90:17-37
+            double z = xk.z;
+            if (z < SIS_SMALL_VALUE) z = SIS_SMALL_VALUE;
+            z = P.stage_sigma / z;
+            F.z += (24.0 * P.stage_eps / P.stage_sigma) * (2 * powi(z, 13) - powi(z, 7));
+        }
+        if (term_mask & (1u << ENE_TWZ)) {                      // src/force_tweezers.F90:27-61
+            for (int t = 0; t < P.ntwz_DCF; t++) {
+                Vec3 f = R.twz_force * mk(S.twz_dir[3 * t], S.twz_dir[3 * t + 1], S.twz_dir[3 * t + 2]);
+                if (S.twz_pairs[2 * t] == k) F += f;
+                if (S.twz_pairs[2 * t + 1] == k) F -= f;
+            }
+            for (int t = 0; t < P.ntwz_FR; t++)
+                for (int s = 0; s < 2; s++)
+                    if (S.twzfr_pairs[2 * t + s] == k) {
+                        const double *ini = S.twzfr_init + 6 * t + 3 * s, *vel = S.twzfr_velo + 6 * t + 3 * s;
+                        double st = (double)istep;
+                        Vec3 p = mk(ini[0] + vel[0] * st, ini[1] + vel[1] * st, ini[2] + vel[2] * st);
+                        F += S.twzfr_k[2 * t + s] * pbc_vec_d(P, p, xk);
+                    }
+        }
+        if ((term_mask & (1u << ENE_RG)) && P.flg_bias_rg) {    // src/force_rg.F90:18-39
+            double rg = R.rg_val;
+            if (!(P.bias_rg_pott == 2 && rg <= R.bias_rg_0)) {
+                double factor = -P.bias_rg_k * (rg - R.bias_rg_0) / (rg * nmp);
+                F += factor * (xk - mk(R.rg_cm[0], R.rg_cm[1], R.rg_cm[2]));
+            }
+        }
+        if (term_mask & (1u << ENE_REST)) {                     // src/force_restraint.F90:19-41
+            for (int t = 0; t < P.nrest; t++) {
+                int ia = S.rest_id[3 * t], ib = S.rest_id[3 * t + 1], ty = S.rest_id[3 * t + 2];
+                if (ia != k && ib != k) continue;
+                Vec3 v = pbc_vec_d(P, v3(pos[ia]), v3(pos[ib]));
+                double r = sqrt(dot(v, v));
+                if (r >= S.rest_rcut[t]) continue;
+                double eps = S.rest_para[3 * t], d = S.rest_para[3 * t + 1], s = S.rest_para[3 * t + 2];
+                double th = tanh((r - d) / s);
+                double coef = 0.5 * eps / s * (1.0 - th * th) / r;
+                if (ia == k) F -= coef * v;
+                else if (ty == 1) F += coef * v;
+            }
+        }
+    }
+    F.x = group_sum<G>(F.x);
+    F.y = group_sum<G>(F.y);
+    F.z = group_sum<G>(F.z);
+    return F;
+}
+
+// merge two (max, second max) pairs
+SIS_D void top2_merge(double &a1, double &a2, double b1, double b2)
+{
+    double m1 = fmax(a1, b1);
+    double m2 = fmax(fmin(a1, b1), fmax(a2, b2));
+    a1 = m1; a2 = m2;
+}
+
+// ---- the MD step: force + integrate in one launch (src/job_md.F90:376-460) -------------------
+// MODE 0: integrate (writes buffer cur^1);  MODE 1: forces only (writes S.force, per-irep API)
+template <int G, int MODE>
+__global__ void __launch_bounds__(256) k_step(DevSys S, FFParams P, StepArgs A)
+{
+    constexpr int BPB = 256 / G;   // beads per block
+    const DevCtl ctl = *S.ctl;
+    if (MODE == 0 && ctl_aborted(ctl)) return;
+    const int rep = (A.only_rep >= 0) ? A.only_rep : blockIdx.y;
+    const int lane = threadIdx.x % G;
+    const int kraw = blockIdx.x * BPB + threadIdx.x / G;
+    const int nmp = S.nmp;
+    const bool valid = kraw < nmp;
+    const int k = valid ? kraw : nmp - 1;   // tail groups shadow the last bead (no writes)
+    const double4 *pos = S.pos[ctl.cur] + (size_t)rep * nmp;
+    const RepParams R = S.rp[rep];
+    const unsigned long long istep = ctl.step + (MODE == 0 ? 1ull : 0ull);
+
+    const Vec3 F = bead_force<G>(S, P, R, pos, rep, k, lane, A.term_mask, A.use_mask, istep,
+                                 valid && A.use_mask != 2);
+
+    if (MODE == 1) {
+        if (valid && lane < 3) S.force[((size_t)rep * nmp + k) * 3 + lane] = lane == 0 ? F.x : lane == 1 ? F.y : F.z;
+        return;
+    }
+
+    // integrate: lanes 0..2 own x, y, z (src/job_md.F90:415-456)
+    double xnew = 0.0, mv = 0.0;
+    if (valid && lane < 3) {
+        const double4 xo = pos[k];
+        const size_t o = ((size_t)rep * nmp + k) * 3 + lane;
+        const double4 c = S.coef[k];
+        const double f = lane == 0 ? F.x : lane == 1 ? F.y : F.z;
+        const double x = lane == 0 ? xo.x : lane == 1 ? xo.y : xo.z;
+        const double g = gauss_component(A.seed, (uint32_t)R.stream, istep, (uint32_t)k, lane);
+        double dx;
+        if (P.integrator == 1) {   // GJF-2GJ
+            const double accels_pre = (c.w * R.sqrt_tempK) * g;
+            const double v = c.x * S.vel[o] + c.y * f + (S.acc[o] + accels_pre);
+            S.vel[o] = v;
+            S.acc[o] = accels_pre;
+            dx = c.z * v;
+        } else {                   // Ermak-McCammon
+            dx = c.x * f + (c.w * R.sqrt_tempK) * g;
+        }
+        xnew = x + dx;
+        mv = S.move[o] + dx;
+        S.move[o] = mv;
+        if (f > 100.0) S.ctl->max_force_flag = 1;
+    }
+    const double nx = __shfl_sync(0xffffffffu, xnew, 0, G);
+    const double ny = __shfl_sync(0xffffffffu, xnew, 1, G);
+    const double nz = __shfl_sync(0xffffffffu, xnew, 2, G);
+    const double s0 = __shfl_sync(0xffffffffu, mv, 0, G);
+    const double s1 = __shfl_sync(0xffffffffu, mv, 1, G);
+    const double s2 = __shfl_sync(0xffffffffu, mv, 2, G);
+    const double d2 = s0 * s0 + s1 * s1 + s2 * s2;
+    if (valid && lane == 0) S.pos[ctl.cur ^ 1][(size_t)rep * nmp + k] = make_double4(nx, ny, nz, 0.0);
+
+    // displacement top-2 (src/job_md.F90:376-388) -> rebuild request for the NEXT step
+    __shared__ double s_t1[8], s_t2[8];
+    __shared__ bool s_last;
+    double t1 = (valid && lane == 0) ? d2 : 0.0, t2 = 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double b1 = __shfl_xor_sync(0xffffffffu, t1, o), b2 = __shfl_xor_sync(0xffffffffu, t2, o);
+        top2_merge(t1, t2, b1, b2);
+    }
+    const int warp = threadIdx.x / 32;
+    if (threadIdx.x % 32 == 0) { s_t1[warp] = t1; s_t2[warp] = t2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) top2_merge(t1, t2, s_t1[w], s_t2[w]);
+        double *bt = S.blk_top2 + ((size_t)rep * S.nblk + blockIdx.x) * 2;
+        bt[0] = t1; bt[1] = t2;
+        __threadfence();
+        unsigned int done = atomicAdd(&S.blk_counter[rep], 1u);
+        s_last = (done == (unsigned)S.nblk - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        t1 = 0.0; t2 = 0.0;
+        const volatile double *bt = S.blk_top2 + (size_t)rep * S.nblk * 2;
+        for (int b = threadIdx.x; b < S.nblk; b += blockDim.x) top2_merge(t1, t2, bt[2 * b], bt[2 * b + 1]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double b1 = __shfl_xor_sync(0xffffffffu, t1, o), b2 = __shfl_xor_sync(0xffffffffu, t2, o);
+            top2_merge(t1, t2, b1, b2);
+        }
+        __syncthreads();
+        if (threadIdx.x % 32 == 0) { s_t1[warp] = t1; s_t2[warp] = t2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; w++) top2_merge(t1, t2, s_t1[w], s_t2[w]);
+            S.blk_counter[rep] = 0;
+            if (sqrt(t1) + sqrt(t2) > A.nl_margin) {
+                S.need_rebuild[rep] = 1;
+                atomicExch(&S.ctl->abort_word, ctl.step + 1);
+            }
+            // the last replica to finish advances the step counter and flips the buffers
+            __threadfence();
+            unsigned int r = atomicAdd(&S.blk_counter[S.nrep], 1u);
+            const unsigned int nr = (A.only_rep >= 0) ? 1u : (unsigned)S.nrep;
+            if (r == nr - 1) {
+                S.blk_counter[S.nrep] = 0;
+                S.ctl->step = ctl.step + 1;
+                S.ctl->cur = ctl.cur ^ 1;
+                S.ctl->steps_done = ctl.steps_done + 1;
+                __threadfence();
+            }
+        }
+    }
+}
+
+// ---- base-pair evaluation pass (owner entries only) ------------------------------------------
+// SIDE 0: force-side formulas (pass 1 of src/force_bp_limit_triplet.F90:85-257)
+// SIDE 1: energy-side formulas (src/energy_bp*.F90), used when flg_bp_energy = .False.
+// count_excess: nt_bp_excess accumulation for the MC pruning
+template <int SIDE>
+__global__ void __launch_bounds__(256) k_bp_eval(DevSys S, FFParams P, int only_rep, double tK_override,
+                                                 int use_override, int use_mask, int count_excess)
+{
+    if (ctl_aborted(*S.ctl)) return;
+    const int rep = (only_rep >= 0) ? only_rep : blockIdx.y;
+    const int nmp = S.nmp;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over nmp*KB slots
+    if (idx >= nmp * S.KB) return;
+    const int k = idx / S.KB, e = idx % S.KB;
+    const size_t rbase = (size_t)rep * nmp, pbase = rbase * S.KB;
+    if (e >= S.nbp_row[rbase + k]) return;
+    const int2 ent = S.bprow[(rbase + k) * S.KB + e];
+    const int j = ent.x, ibp = ent.y;
+    if (j < k) return;   // owner = lower bead
+    const double4 *pos = S.pos[S.ctl->cur] + rbase;
+    const RepParams R = S.rp[rep];
+    int st = 0;
+    double en = 0.0;
+    bool active = !(use_mask && !S.bp_status_MC[pbase + ibp]);
+    const int type = S.bp_type[pbase + ibp];
+    double dG = 1.0;
+    if (P.bp_triplet) {
+        double tK = use_override ? tK_override : R.tempK;
+        if (SIDE == 1 && P.temp_independent) tK = 0.0;   // src/energy_bp_triplet.F90:27-31
+        double2 cf = S.bp_coef[pbase + ibp];
+        dG = cf.x - tK * cf.y;
+        if (dG >= 0.0) active = false;
+    }
+    if (active) {
+        const int4 mi = S.meta[k], mj = S.meta[j];
+        Vec3 xs[6];
+        xs[0] = v3(pos[k]); xs[1] = v3(pos[j]);
+        xs[2] = v3(pos[chain_nb(mi, -1)]); xs[3] = v3(pos[chain_nb(mj, -1)]);
+        xs[4] = v3(pos[chain_nb(mi, +1)]); xs[5] = v3(pos[chain_nb(mj, +1)]);
+        double u, a12; Vec3 fr, v12;
+        bool pass = (SIDE == 0) ? bp_force_role(P, P.bp[type], xs, 0, &u, &fr, &a12, &v12)
+                                : bp_energy_u(P, P.bp[type], xs, &u);
+        if (pass) {
+            double ene = P.bp_triplet ? P.bp[type].U0 * dG * exp(-u) : P.bp[type].U0 * exp(-u);
+            if (ene <= P.bp_cutoff_energy) { st = 1; en = ene; }
+        }
+    }
+    S.bp_status[pbase + ibp] = st;
+    S.ene_bp[pbase + ibp] = en;
+    if (count_excess && st) {
+        atomicAdd(&S.nt_excess[rbase + k], 1);
+        atomicAdd(&S.nt_excess[rbase + j], 1);
+    }
+}
+
+__global__ void k_excess_init(DevSys S, int only_rep, int max_bp_per_nt)
+{
+    if (ctl_aborted(*S.ctl)) return;
+    const int rep = (only_rep >= 0) ? only_rep : blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S.nmp) S.nt_excess[(size_t)rep * S.nmp + i] = -max_bp_per_nt;
+}
+
+// pass 2 of src/force_bp_limit_triplet.F90:260-328: one warp per replica runs the reference's
+// sequential delete loop; uniforms come from the counter-based stream 0x40000000 + grep.
+// deterministic != 0: temp_independent branch of src/energy_bp_limit_triplet.F90:167-176.
+__global__ void __launch_bounds__(32) k_bp_prune(DevSys S, FFParams P, unsigned long long seed, int only_rep,
+                                                  double tK_override, int use_override, int deterministic,
+                                                  int copy_to_mc)
+{
+    if (ctl_aborted(*S.ctl)) return;
+    const int rep = (only_rep >= 0) ? only_rep : blockIdx.x;
+    const int lane = threadIdx.x;
+    const int nmp = S.nmp, KB = S.KB;
+    const size_t rbase = (size_t)rep * nmp, pbase = rbase * KB;
+    const RepParams R = S.rp[rep];
+    const double beta = 1.0 / (SIS_BOLTZ_KCAL_MOL * (use_override ? tK_override : R.tempK));
+    int *excess = S.nt_excess + rbase;
+    unsigned long long ctr = S.mc_counter[rep];
+    const uint32_t stream = 0x40000000u + (uint32_t)R.stream;
+    for (;;) {
+        int nnt = 0;
+        for (int i = lane; i < nmp; i += 32) nnt += excess[i] > 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nnt += __shfl_xor_sync(0xffffffffu, nnt, o);
+        if (nnt == 0) break;
+        double rnd = uniform_counter(seed, stream, ctr++);
+        int pick = max(1, min((int)ceil(rnd * nnt), nnt));
+        // the pick-th bead with excess > 0 in ascending bead order (uniform across the warp)
+        int nt_delete = -1, seen = 0;
+        for (int base = 0; base < nmp && nt_delete < 0; base += 32) {
+            const int i = base + lane;
+            const unsigned m = __ballot_sync(0xffffffffu, i < nmp && excess[i] > 0);
+            const int c = __popc(m);
+            if (seen + c >= pick) {
+                int want = pick - seen;
+                for (int b = 0; b < 32; b++)
+                    if ((m >> b) & 1u)
+                        if (--want == 0) { nt_delete = base + b; break; }
+            }
+            seen += c;
+        }
+        unsigned long long used = 0;
+        if (lane == 0) {
+            const int nrow = S.nbp_row[rbase + nt_delete];
+            const int2 *row = S.bprow + (rbase + nt_delete) * KB;
+            int seq[64], nseq = 0;
+            for (int e = 0; e < nrow && nseq < 64; e++)
+                if (S.bp_status[pbase + row[e].y]) seq[nseq++] = row[e].y;
+            int ibp_delete = seq[0];
+            if (!deterministic) {
+                for (int i = 0; i < nseq; i++) {   // the reference's shuffle, :295-302
+                    rnd = uniform_counter(seed, stream, ctr + used++);
+                    const int sw = max(1, min((int)ceil(rnd * nseq), nseq));
+                    const int t = seq[i]; seq[i] = seq[sw - 1]; seq[sw - 1] = t;
+                }
+                ibp_delete = seq[0];
+                for (int i = 1; i < nseq; i++) {   // Metropolis sweep, :305-316
+                    const double ratio = exp((S.ene_bp[pbase + seq[i]] - S.ene_bp[pbase + ibp_delete]) * beta);
+                    rnd = uniform_counter(seed, stream, ctr + used++);
+                    if (rnd < ratio) ibp_delete = seq[i];
+                }
+            } else {
+                for (int i = 1; i < nseq; i++)
+                    if (S.ene_bp[pbase + seq[i]] > S.ene_bp[pbase + ibp_delete]) ibp_delete = seq[i];
+            }
+            S.bp_status[pbase + ibp_delete] = 0;
+            const int owner = ibp_delete / KB;
+            const int partner = S.bprow[(rbase + owner) * KB + ibp_delete % KB].x;
+            excess[owner] -= 1;
+            excess[partner] -= 1;
+        }
+        ctr += __shfl_sync(0xffffffffu, used, 0);
+        __syncwarp();
+    }
+    if (lane == 0) S.mc_counter[rep] = ctr;
+    __syncwarp();
+    if (copy_to_mc)   // src/job_md.F90:399-401
+        for (int i = lane; i < nmp * KB; i += 32) S.bp_status_MC[pbase + i] = S.bp_status[pbase + i];
+}
+
+__global__ void k_copy_status_mc(DevSys S, int only_rep)
+{
+    const int rep = (only_rep >= 0) ? only_rep : blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t pbase = (size_t)rep * S.nmp * S.KB;
+    if (i < S.nmp * S.KB) S.bp_status_MC[pbase + i] = S.bp_status[pbase + i];
+}
+
+// ---- Rg pre-pass (src/force_rg.F90:22-30, src/energy_rg.F90:22-28): one block per replica ----
+__global__ void __launch_bounds__(256) k_rg(DevSys S, int only_rep)
+{
+    const int rep = (only_rep >= 0) ? only_rep : blockIdx.x;
+    const int nmp = S.nmp;
+    const double4 *pos = S.pos[S.ctl->cur] + (size_t)rep * nmp;
+    __shared__ double sh[4][8];
+    __shared__ double cm[3];
+    double sx = 0, sy = 0, sz = 0;
+    for (int i = threadIdx.x; i < nmp; i += blockDim.x) { double4 p = pos[i]; sx += p.x; sy += p.y; sz += p.z; }
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    if (threadIdx.x % 32 == 0) { sh[0][threadIdx.x / 32] = sx; sh[1][threadIdx.x / 32] = sy; sh[2][threadIdx.x / 32] = sz; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0, c = 0;
+        for (int w = 0; w < 8; w++) { a += sh[0][w]; b += sh[1][w]; c += sh[2][w]; }
+        cm[0] = a / nmp; cm[1] = b / nmp; cm[2] = c / nmp;
+    }
+    __syncthreads();
+    double s2 = 0;
+    for (int i = threadIdx.x; i < nmp; i += blockDim.x) {
+        double4 p = pos[i];
+        double dx = p.x - cm[0], dy = p.y - cm[1], dz = p.z - cm[2];
+        s2 += dx * dx + dy * dy + dz * dz;
+    }
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    if (threadIdx.x % 32 == 0) sh[3][threadIdx.x / 32] = s2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < 8; w++) t += sh[3][w];
+        RepParams *R = S.rp + rep;
+        R->rg_cm[0] = cm[0]; R->rg_cm[1] = cm[1]; R->rg_cm[2] = cm[2];
+        R->rg_val = sqrt(t / nmp);
+    }
+}
+
+// ---- energies (src/energy_sumup.F90:15-54) ------------------------------------------------
+// pair and bonded terms are counted once (by the lower bead / the first bead of the term);
+// bp energies are the cached ene_bp written by k_step / k_bp_eval, masked by bp_status.
+// rp_alt != nullptr evaluates with another parameter block (REMD cross energies).
+template <int G>
+__global__ void __launch_bounds__(256) k_energy(DevSys S, FFParams P, const RepParams *rp_alt, int only_rep)
+{
+    constexpr int BPB = 256 / G;
+    const int rep = (only_rep >= 0) ? only_rep : blockIdx.y;
+    const int lane = threadIdx.x % G;
+    const int k = blockIdx.x * BPB + threadIdx.x / G;
+    const int nmp = S.nmp;
+    const double4 *pos = S.pos[S.ctl->cur] + (size_t)rep * nmp;
+    const RepParams R = rp_alt ? rp_alt[rep] : S.rp[rep];
+    double e[ENE_N];
+#pragma unroll
+    for (int t = 0; t < ENE_N; t++) e[t] = 0.0;
+    if (k < nmp) {
+        const int4 mk4 = S.meta[k];
+        const Vec3 xk = v3(pos[k]);
+        const uint32_t *row = S.nbr + ((size_t)rep * nmp + k) * S.K;
+        const int nn = S.nnbr[(size_t)rep * nmp + k];
+        for (int q = lane; q < nn; q += G) {
+            uint32_t ent = row[q];
+            int j = ent & NB_IDX;
+            if (j < k) continue;
+            Vec3 v = pbc_vec_d(P, xk, v3(pos[j]));
+            double d2 = dot(v, v);
+            if (ent & NB_WCA) e[ENE_EXV] += wca_energy(P, d2);
+            if ((ent & NB_ELE) && P.flg_ele) e[ENE_ELE] += dh_energy(P, R, d2);
+        }
+        if (lane < 3) {
+            const int span = lane + 1;
+            bool exists = (mk4.w & MF_CIRC) ? (mk4.y > span) : (mk4.z + span < mk4.y);
+            if (exists) {
+                Vec3 x1 = v3(pos[chain_nb(mk4, 1)]);
+                if (lane == 0) e[ENE_BOND] += bond_energy(P, xk, x1);
+                else if (lane == 1) e[ENE_ANGL] += angl_energy(P, xk, x1, v3(pos[chain_nb(mk4, 2)]));
+                else if (P.flg_dih_cos || P.flg_dih_exp)
+                    e[ENE_DIHE] += dih_energy(P, xk, x1, v3(pos[chain_nb(mk4, 2)]), v3(pos[chain_nb(mk4, 3)]));
+            }
+        }
+        {
+            const size_t rbase = (size_t)rep * nmp, pbase = rbase * S.KB;
+            const int nrow = S.nbp_row[rbase + k];
+            for (int q = lane; q < nrow; q += G) {
+                int2 ent = S.bprow[(rbase + k) * S.KB + q];
+                if (ent.x > k && S.bp_status[pbase + ent.y]) e[ENE_BP] += S.ene_bp[pbase + ent.y];
+            }
+        }
+        if (lane == 0 && P.flg_stage) {   // src/energy_stage.F90:28-36
+            double z = P.stage_sigma / xk.z;
+            e[ENE_STAGE] += 4 * P.stage_eps * (powi(z, 12) - powi(z, 6));
+            if (xk.z < 0.85 * P.stage_sigma) S.ctl->max_force_flag |= 2;   // reference aborts here
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int t = 0; t < P.ntwz_DCF; t++) {   // src/energy_tweezers.F90:21-31
+            Vec3 v = pbc_vec_d(P, v3(pos[S.twz_pairs[2 * t]]), v3(pos[S.twz_pairs[2 * t + 1]]));
+            e[ENE_TWZ] -= R.twz_force * (v.x * S.twz_dir[3 * t] + v.y * S.twz_dir[3 * t + 1] + v.z * S.twz_dir[3 * t + 2]);
+        }
+        for (int t = 0; t < P.nrest; t++) {      // src/energy_restraint.F90:19-33
+            Vec3 v = pbc_vec_d(P, v3(pos[S.rest_id[3 * t]]), v3(pos[S.rest_id[3 * t + 1]]));
+            double r = sqrt(dot(v, v));
+            if (r >= S.rest_rcut[t]) continue;
+            e[ENE_REST] -= 0.5 * S.rest_para[3 * t] * (1.0 - tanh((r - S.rest_para[3 * t + 1]) / S.rest_para[3 * t + 2]));
+        }
+        if (P.flg_bias_rg) {                     // src/energy_rg.F90:30-35 (rg from k_rg)
+            double rg = R.rg_val;
+            if (!(P.bias_rg_pott == 2 && rg <= R.bias_rg_0))
+                e[ENE_RG] += 0.5 * P.bias_rg_k * (rg - R.bias_rg_0) * (rg - R.bias_rg_0);
+        }
+    }
+    // block reduction (fixed order -> deterministic sums)
+    __shared__ double sh[8][ENE_N];
+    __shared__ bool s_last;
+#pragma unroll
+    for (int t = 1; t < ENE_N; t++) {
+        double v = e[t];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x % 32 == 0) sh[threadIdx.x / 32][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < ENE_N && threadIdx.x > 0) {
+        double v = 0;
+        for (int w = 0; w < 8; w++) v += sh[w][threadIdx.x];
+        S.ene_partial[((size_t)rep * S.nblk + blockIdx.x) * ENE_N + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int done = atomicAdd(&S.ene_counter[rep], 1u);
+        s_last = (done == (unsigned)S.nblk - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (threadIdx.x < ENE_N && threadIdx.x > 0) {
+            const volatile double *part = S.ene_partial + (size_t)rep * S.nblk * ENE_N;
+            double v = 0;
+            for (int b = 0; b < S.nblk; b++) v += part[(size_t)b * ENE_N + threadIdx.x];
+            S.ene_out[(size_t)rep * ENE_N + threadIdx.x] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0;
+            for (int t = 1; t < ENE_N; t++) tot += ((volatile double *)S.ene_out)[(size_t)rep * ENE_N + t];
+            S.ene_out[(size_t)rep * ENE_N] = tot;
+            S.ene_counter[rep] = 0;
+        }
+    }
+}
+
+// src/energy_kinetic.F90:17-29 (one block per replica; zeroes frozen velocities first)
+__global__ void __launch_bounds__(256) k_kinetic(DevSys S, double *out, int only_rep)
+{
+    const int rep = (only_rep >= 0) ? only_rep : blockIdx.x;
+    const int nmp = S.nmp;
+    double *vel = S.vel + (size_t)rep * nmp * 3;
+    double s = 0;
+    for (int i = threadIdx.x; i < nmp; i += blockDim.x) {
+        if (S.meta[i].w & MF_FROZEN) vel[3 * i] = vel[3 * i + 1] = vel[3 * i + 2] = 0.0;
+        s += S.mass[i] * (vel[3 * i] * vel[3 * i] + vel[3 * i + 1] * vel[3 * i + 1] + vel[3 * i + 2] * vel[3 * i + 2]);
+    }
+    __shared__ double sh[8];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x % 32 == 0) sh[threadIdx.x / 32] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < 8; w++) t += sh[w];
+        out[rep] = 0.5 * t;
+    }
+}
+
+// src/job_md.F90:157-176 initial velocities and beta(0) from the counter-based generator
+__global__ void k_init_velocities(DevSys S, unsigned long long seed, int rep)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.nmp * 3) return;
+    const int k = i / 3, c = i % 3;
+    const RepParams R = S.rp[rep];
+    const size_t o = ((size_t)rep * S.nmp + k) * 3 + c;
+    const double c1 = sqrt(R.tempK * SIS_BOLTZ_KCAL_MOL / S.mass[k]);
+    S.vel[o] = c1 * gauss_component(seed, (uint32_t)R.stream, 0x8000000000000000ull, (uint32_t)k, c);
+    S.acc[o] = (S.coef[k].w * R.sqrt_tempK) * gauss_component(seed, (uint32_t)R.stream, 0x8000000000000001ull, (uint32_t)k, c);
+}
+
+// T-REMD velocity rescale (src/replica_exchange.F90:175-213)
+__global__ void k_scale_velocities(DevSys S, int rep, double factor)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S.nmp * 3) S.vel[(size_t)rep * S.nmp * 3 + i] *= factor;
+}
+
+// ---- neighbour list on a cell grid (replaces the O(N^2) sweep of src/neighbor_list.F90) ------
+// 1. wrap (src/pbc.F90:196-226) + cell id + per-cell count
+__global__ void k_nl_wrap_count(DevSys S, FFParams P, GridInfo Gd, const int *rep_active)
+{
+    const int rep = blockIdx.y;
+    if (!rep_active[rep]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.nmp) return;
+    double4 *pos = S.pos[S.ctl->cur] + (size_t)rep * S.nmp;
+    double4 p = pos[i];
+    if (P.flg_pbc) {
+        p.x = wrap1(p.x, P.box[0]); p.y = wrap1(p.y, P.box[1]); p.z = wrap1(p.z, P.box[2]);
+        pos[i] = p;
+    }
+    int cx = min(max((int)((p.x - Gd.origin[0]) * Gd.inv_cell[0]), 0), Gd.n[0] - 1);
+    int cy = min(max((int)((p.y - Gd.origin[1]) * Gd.inv_cell[1]), 0), Gd.n[1] - 1);
+    int cz = min(max((int)((p.z - Gd.origin[2]) * Gd.inv_cell[2]), 0), Gd.n[2] - 1);
+    int c = (cz * Gd.n[1] + cy) * Gd.n[0] + cx;
+    S.cell_of[(size_t)rep * S.nmp + i] = c;
+    atomicAdd(&S.cell_count[(size_t)rep * S.ncell_cap + c], 1);
+}
+// 2. exclusive scan of the cell counts (one block per replica)
+__global__ void __launch_bounds__(1024) k_nl_scan(DevSys S, GridInfo Gd, const int *rep_active)
+{
+    const int rep = blockIdx.x;
+    if (!rep_active[rep]) return;
+    int *cnt = S.cell_count + (size_t)rep * S.ncell_cap;
+    int *start = S.cell_start + (size_t)rep * (S.ncell_cap + 1);
+    int *cur = S.cell_cursor + (size_t)rep * S.ncell_cap;
+    __shared__ int sh[1024];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < Gd.ncell; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = i < Gd.ncell ? cnt[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < Gd.ncell) { start[i] = carry + sh[threadIdx.x] - v; cur[i] = 0; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) start[Gd.ncell] = carry;
+}
+// 3. scatter beads into their cells
+__global__ void k_nl_fill(DevSys S, const int *rep_active)
+{
+    const int rep = blockIdx.y;
+    if (!rep_active[rep]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.nmp) return;
+    int c = S.cell_of[(size_t)rep * S.nmp + i];
+    int slot = S.cell_start[(size_t)rep * (S.ncell_cap + 1) + c] + atomicAdd(&S.cell_cursor[(size_t)rep * S.ncell_cap + c], 1);
+    S.cell_beads[(size_t)rep * S.nmp + slot] = i;
+}
+// 4. sort each cell by bead id (deterministic rows); also clears the counts for the next build
+__global__ void k_nl_sort(DevSys S, GridInfo Gd, const int *rep_active)
+{
+    const int rep = blockIdx.y;
+    if (!rep_active[rep]) return;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Gd.ncell) return;
+    const int *start = S.cell_start + (size_t)rep * (S.ncell_cap + 1);
+    int *b = S.cell_beads + (size_t)rep * S.nmp;
+    for (int i = start[c] + 1; i < start[c + 1]; i++) {
+        int v = b[i], j = i - 1;
+        while (j >= start[c] && b[j] > v) { b[j + 1] = b[j]; j--; }
+        b[j + 1] = v;
+    }
+    S.cell_count[(size_t)rep * S.ncell_cap + c] = 0;
+}
+
+SIS_D int uniq_cells(int c, int n, int pbc, int out[3])
+{
+    int cnt = 0;
+    for (int d = -1; d <= 1; d++) {
+        int q = c + d;
+        if (pbc) q = (q + n) % n;
+        else if (q < 0 || q >= n) continue;
+        bool dup = false;
+        for (int t = 0; t < cnt; t++) dup |= (out[t] == q);
+        if (!dup) out[cnt++] = q;
+    }
+    return cnt;
+}
+
+// 5. rows: the three lists of src/neighbor_list.F90:99-229 for bead i against every bead of the
+//    27 surrounding cells, same predicates (d2 <= cut^2 on wrapped coordinates, min image),
+//    same exclusion rules; FULL rows (j on both sides of i).  One warp per bead, ballot-compacted
+//    appends keep the row order deterministic (cell order, then bead id).
+struct NlArgs {
+    double wca_nl_cut2, bp_nl_cut2, nl_margin;
+    int excl_bond, excl_angle, bp_model, bp_min_loop;
+    int all_pairs;   // 0 cell grid; 1 list_exv/ele/bp (no cutoffs); 2 all-pairs sweep with cutoffs
+};
+// the list predicates of src/neighbor_list.F90:122-180 (and of src/list_exv.F90:36-52,
+// src/list_ele.F90:36-56 when A.all_pairs == 1) for the unordered bead pair {i, j}
+SIS_HD uint32_t nl_pair_flags(const NlArgs &A, const FFParams &P, int4 mi, int4 mj, int i, int j, double d2,
+                              double ele_nl_cut2)
+{
+    const bool full = A.all_pairs == 1;
+    uint32_t ent = 0;
+    const bool same = mi.x == mj.x;
+    // (lo, hi) = the reference's local (i, j) with i < j inside a chain
+    const int lo = min(mi.z, mj.z) + 1, hi = max(mi.z, mj.z) + 1, len = mi.y;
+    const bool circ = mi.w & MF_CIRC;
+    if ((mi.w & MF_SEQ_MASK) != SEQ_D && (mj.w & MF_SEQ_MASK) != SEQ_D && (full || d2 <= A.wca_nl_cut2)) {
+        bool add = true;
+        if (same) {
+            if (lo + 2 >= hi) add = false;
+            else if (circ && !full && hi + 2 >= lo + len) add = false;
+        }
+        if (add) ent |= NB_WCA;
+    }
+    if (P.flg_ele && (full || d2 <= ele_nl_cut2) && (mi.w & MF_CHARGE) && (mj.w & MF_CHARGE)) {
+        bool add = true;
+        if (full) {
+            // list_ele tests j == i+1 / i+2 on LOCAL indices for every chain pair
+            const int li = (i < j ? mi.z : mj.z) + 1, lj = (i < j ? mj.z : mi.z) + 1;
+            if (lj == li + 1 && A.excl_bond) add = false;
+            if (lj == li + 2 && A.excl_angle) add = false;
+        } else if (same) {
+            if (hi == lo + 1 && A.excl_bond) add = false;
+            if (hi == lo + 2 && A.excl_angle) add = false;
+            if (circ) {
+                if (lo == 1) {
+                    if (hi == len && A.excl_bond) add = false;
+                    if (hi == len - 1 && A.excl_angle) add = false;
+                } else if (lo == 2) {
+                    if (hi == len && A.excl_angle) add = false;
+                }
+            }
+        }
+        if (add) ent |= NB_ELE;
+    }
+    return ent;
+}
+// distance / index gate of the bp list: src/neighbor_list.F90:183, src/list_bp.F90:57
+SIS_HD bool nl_bp_geometry(const NlArgs &A, int i, int j, double d2)
+{
+    return A.all_pairs == 1 ? (abs(i - j) >= A.bp_min_loop + 1) : (d2 <= A.bp_nl_cut2);
+}
+__global__ void __launch_bounds__(256) k_nl_rows(DevSys S, FFParams P, GridInfo Gd, NlArgs A, const int *rep_active)
+{
+    const int rep = blockIdx.y;
+    if (!rep_active[rep]) return;
+    const int lane = threadIdx.x % 32;
+    const int i = blockIdx.x * 8 + threadIdx.x / 32;
+    const int nmp = S.nmp;
+    if (i >= nmp) return;
+    const size_t rbase = (size_t)rep * nmp;
+    const double4 *pos = S.pos[S.ctl->cur] + rbase;
+    const RepParams R = S.rp[rep];
+    const int4 mi = S.meta[i];
+    const Vec3 xi = v3(pos[i]);
+    const double ele_cut = R.ele_cutoff + A.nl_margin;
+    const double ele_nl_cut2 = ele_cut * ele_cut;
+    uint32_t *row = S.nbr + (rbase + i) * S.K;
+    int2 *brow = S.bprow + (rbase + i) * S.KB;
+    int nn = 0, nb = 0;
+    const int *cstart = S.cell_start + (size_t)rep * (S.ncell_cap + 1);
+    const int *cbeads = S.cell_beads + rbase;
+
+    const bool sweep_all = A.all_pairs != 0;   // iterate every bead instead of the 27 cells
+    const bool full = A.all_pairs == 1;        // the cutoff-free lists of list_exv/ele/bp
+    int lx[3], ly[3], lz[3], nx, ny, nz;
+    if (sweep_all) { nx = ny = nz = 1; lx[0] = ly[0] = lz[0] = 0; }
+    else {
+        int c = S.cell_of[rbase + i];
+        int cx = c % Gd.n[0], cy = (c / Gd.n[0]) % Gd.n[1], cz = c / (Gd.n[0] * Gd.n[1]);
+        nx = uniq_cells(cx, Gd.n[0], Gd.pbc, lx);
+        ny = uniq_cells(cy, Gd.n[1], Gd.pbc, ly);
+        nz = uniq_cells(cz, Gd.n[2], Gd.pbc, lz);
+    }
+    for (int a = 0; a < nz; a++)
+        for (int b = 0; b < ny; b++)
+            for (int cidx = 0; cidx < nx; cidx++) {
+                int beg, end;
+                if (sweep_all) { beg = 0; end = nmp; }
+                else {
+                    int cell = (lz[a] * Gd.n[1] + ly[b]) * Gd.n[0] + lx[cidx];
+                    beg = cstart[cell]; end = cstart[cell + 1];
+                }
+                for (int q0 = beg; q0 < end; q0 += 32) {
+                    const int q = q0 + lane;
+                    uint32_t ent = 0;
+                    int bp3 = 0, bptype = 0, j = -1;
+                    if (q < end) {
+                        j = sweep_all ? q : cbeads[q];
+                        if (j != i) {
+                            const int4 mj = S.meta[j];
+                            Vec3 v = pbc_vec_d(P, xi, v3(pos[j]));
+                            ent = nl_pair_flags(A, P, mi, mj, i, j, dot(v, v), ele_nl_cut2);
+                            if (nl_bp_geometry(A, i, j, dot(v, v))) {
+                                if (i < j) bp3 = bp_lookup(A.bp_model, A.bp_min_loop, S.hash, S.seq, i, mi, j, mj, &bptype);
+                                else bp3 = bp_lookup(A.bp_model, A.bp_min_loop, S.hash, S.seq, j, mj, i, mi, &bptype);
+                            }
+                        }
+                    }
+                    // compacted appends
+                    unsigned m = __ballot_sync(0xffffffffu, ent != 0);
+                    if (ent) {
+                        int p = nn + __popc(m & ((1u << lane) - 1));
+                        if (p < S.K) row[p] = ent | (uint32_t)j;
+                    }
+                    nn += __popc(m);
+                    unsigned mb = __ballot_sync(0xffffffffu, bp3 > 0);
+                    if (bp3 > 0) {
+                        int p = nb + __popc(mb & ((1u << lane) - 1));
+                        if (p < S.KB) {
+                            brow[p] = make_int2(j, -1);
+                            if (i < j) {   // owner stores the pair data at ibp = i*KB + p
+                                const size_t ibp = rbase * S.KB + (size_t)i * S.KB + p;
+                                S.bp_type[ibp] = (signed char)bptype;
+                                S.bp_coef[ibp] = (A.bp_model == 5) ? make_double2(S.bp3_dH[bp3], S.bp3_dS[bp3])
+                                                                   : make_double2(0.0, 0.0);
+                                S.bp_status[ibp] = 0;
+                                S.bp_status_MC[ibp] = 0;
+                                S.ene_bp[ibp] = 0.0;
+                            }
+                        }
+                    }
+                    nb += __popc(mb);
+                }
+            }
+    if (lane == 0) {
+        S.nnbr[rbase + i] = min(nn, S.K);
+        S.nbp_row[rbase + i] = min(nb, S.KB);
+        if (nn > S.K) atomicMax(&S.ctl->nl_overflow, nn);
+        if (nb > S.KB) atomicMax(&S.ctl->bp_overflow, nb);
+        S.move[(rbase + i) * 3] = 0.0; S.move[(rbase + i) * 3 + 1] = 0.0; S.move[(rbase + i) * 3 + 2] = 0.0;
+    }
+}
+// 6. pair ids: ibp = owner*KB + slot-in-owner-row, resolved for both directions
+__global__ void k_nl_bp_slots(DevSys S, const int *rep_active)
+{
+    const int rep = blockIdx.y;
+    if (!rep_active[rep]) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nmp = S.nmp, KB = S.KB;
+    if (idx >= nmp * KB) return;
+    const int k = idx / KB, e = idx % KB;
+    const size_t rbase = (size_t)rep * nmp;
+    if (e >= S.nbp_row[rbase + k]) return;
+    int2 *ent = S.bprow + (rbase + k) * KB + e;
+    const int j = ent->x;
+    if (j > k) { ent->y = k * KB + e; return; }
+    const int2 *jr = S.bprow + (rbase + j) * KB;
+    const int nj = S.nbp_row[rbase + j];
+    int found = -1;
+    for (int q = 0; q < nj; q++)
+        if (jr[q].x == k) { found = q; break; }
+    ent->y = j * KB + max(found, 0);
+}
+__global__ void k_nl_finish(DevSys S, const int *rep_active)
+{
+    const int rep = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rep < S.nrep && rep_active[rep]) S.need_rebuild[rep] = 0;
+    if (rep == 0) S.ctl->abort_word = 0ull;
+}

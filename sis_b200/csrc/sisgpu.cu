@@ -1,0 +1,1551 @@
+// sisgpu.cu -- host side of libsisgpu.so: the C ABI of include/sisgpu.h.
+//
+// Mirrors the call structure of the reference's drivers (src/job_md.F90, src/force.F90,
+// src/neighbor_list.F90, src/energy_sumup.F90, src/energy_replica.F90,
+// src/replica_exchange.F90) but keeps all state resident on the device and batches every
+// local replica into one launch (grid.y = replica).  No CPU fallback exists: every entry point
+// that computes runs CUDA kernels or fails.
+#include "../../include/sisgpu.h"
+#include "sis_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+static thread_local char g_err[1024] = "";
+static int set_err(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return 1;
+}
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) return set_err("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define TRY(call)                 \
+    do {                          \
+        int rc_ = (call);         \
+        if (rc_) return rc_;      \
+    } while (0)
+
+// ---- minimal NCCL binding (dlopen: the library must load on boxes without NCCL) ------------
+struct NcclId { char internal[SISGPU_NCCL_ID_BYTES]; };   // ncclUniqueId (passed by value)
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load()
+{
+    if (g_nccl.lib) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return set_err("cannot dlopen libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(void *))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void **, int, NcclId, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(g_nccl.lib, "ncclAllGather");
+    g_nccl.CommDestroy = (int (*)(void *))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather) return set_err("NCCL symbols missing");
+    return 0;
+}
+constexpr int NCCL_FLOAT64 = 8;   // ncclDouble in nccl.h
+
+// ---- host-side mirror of the reference's module state ----------------------------------------
+enum { REPT_TEMP = 0, REPT_TWZDCF = 1, REPT_ION = 2, REPT_RG = 3, REPT_MAX = 4 };
+constexpr int MAX_REP_PER_DIM = 256, MAX_REP_DIM = 3;
+
+struct HostRep {
+    double tempK = 300.0, ionic = 0.15, twz_force = 0.0, rg0 = 0.0;
+    double ele_coef = 0, lambdaD = 1, ele_cutoff = 0, diele = 0, diele_dTcoef = 0;
+};
+
+template <class T>
+struct DBuf {   // device buffer
+    T *p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count)
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = count;
+        if (count == 0) count = 1;
+        CK(cudaMalloc(&p, count * sizeof(T)));
+        CK(cudaMemset(p, 0, count * sizeof(T)));
+        return 0;
+    }
+    int upload(const std::vector<T> &v)
+    {
+        TRY(alloc(v.size()));
+        if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct sisgpu {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool finalized = false;
+    // topology
+    int nmp = 0, nchains = 0;
+    std::vector<int> nmp_chain, moltypes, chain_start, seq, ichain, lmp, has_charge, is_frozen;
+    std::vector<double> mass;
+    // force field
+    FFParams P{};
+    double bp_cutoff_dist = 0;
+    int bp_model = 5, bp_min_loop = 3, max_bp_per_nt = 1, nstep_bp_MC = 0;
+    double NN_dH[22]{}, NN_dS[22]{}, dH0 = 0, dS0 = 0, NNend_dH[7]{}, NNend_dS[7]{}, dHend0 = 0, dSend0 = 0;
+    int flg_NNend = 0, have_nn = 0;
+    std::vector<int> bp3_hash;          // 4096
+    std::vector<double> bp3_dH, bp3_dS; // 469 (1-based)
+    int bp3_n = 0;
+    // ele
+    int ele_cutoff_type = 1, excl_bond = 1, excl_angle = 1;
+    double ele_cutoff_inp = 0, length_per_charge = 0, tempK_ref = 0;
+    // md
+    double dt = 0.05, viscosity_Pas = 1e-5, nl_margin = 10.0;
+    unsigned long long seed = 0;
+    int flg_bp_MC = 0;
+    bool lists_full = false;   // list_exv/ele/bp mode (no rebuild trigger)
+    bool lists_built = false;
+    // biases (host copies)
+    std::vector<int> twz_pairs, twzfr_pairs, rest_id;
+    std::vector<double> twz_dir, twzfr_k, twzfr_init, twzfr_velo, rest_rcut, rest_para;
+    // replicas
+    int nrep = 1;
+    std::vector<HostRep> rep;
+    std::vector<RepParams> rp_host;
+    // REMD
+    bool flg_replica = false;
+    int nrep_all = 1, ndim_replica = 0, nrep_dim[REPT_MAX]{1, 1, 1, 1}, rank = 0, nranks = 1;
+    bool flg_repvar[REPT_MAX]{};
+    int type_array[MAX_REP_DIM]{};
+    std::vector<int> pair_tb, rep2lab, lab2rep;   // pair_tb [2*ndim][nrep_all]
+    std::vector<double> lab2val;                  // [REPT_MAX][nrep_all]
+    double replica_values[REPT_MAX][MAX_REP_PER_DIM]{};
+    int idx_pair = 1, nstep_exchange = 0;
+    unsigned long long exchange_counter = 0;
+    long long n_attempt = 0, n_accept = 0;
+    void *nccl_comm = nullptr;
+    // device
+    DevSys S{};
+    DBuf<int4> d_meta;
+    DBuf<int> d_seq, d_hash, d_nnbr, d_nbp_row, d_bp_status, d_bp_status_MC, d_nt_excess, d_cell_of,
+        d_cell_count, d_cell_start, d_cell_cursor, d_cell_beads, d_need_rebuild, d_rep_active, d_twz_pairs,
+        d_twzfr_pairs, d_rest_id;
+    DBuf<double4> d_coef, d_pos0, d_pos1;
+    DBuf<double> d_mass, d_bp3_dH, d_bp3_dS, d_vel, d_acc, d_move, d_force, d_ene_bp, d_blk_top2,
+        d_ene_partial, d_ene_out, d_kin, d_twz_dir, d_twzfr_k, d_twzfr_init, d_twzfr_velo, d_rest_rcut,
+        d_rest_para, d_gather_send, d_gather_recv;
+    DBuf<uint32_t> d_nbr;
+    DBuf<int2> d_bprow;
+    DBuf<signed char> d_bp_type;
+    DBuf<double2> d_bp_coef;
+    DBuf<unsigned long long> d_mc_counter;
+    DBuf<unsigned int> d_blk_counter, d_ene_counter;
+    DBuf<RepParams> d_rp, d_rp_alt;
+    DBuf<DevCtl> d_ctl;
+    DevCtl *h_ctl = nullptr;   // pinned
+    int *h_need = nullptr;     // pinned [nrep]
+    int K = 0, KB = 0, G = 32;
+    // stats / options
+    long long launches = 0, nrebuild = 0;
+    int launch_mode = 0, chunk = 32, timing = 0;
+    double t_step = 0, t_nl = 0, t_ene = 0, t_rex = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    long long istep_host = 0;
+};
+
+static inline dim3 grid1(int n, int b) { return dim3((unsigned)((n + b - 1) / b)); }
+
+const char *sisgpu_last_error(void) { return g_err; }
+int sisgpu_version(void) { return 100; }
+
+int sisgpu_create(sisgpu_t **out, int device)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err("no CUDA device available (%s); libsisgpu has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return set_err("device %d out of range (%d devices)", device, ndev);
+    CK(cudaSetDevice(device));
+    sisgpu *h = new sisgpu();
+    h->device = device;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+    h->P.integrator = 1;
+    h->P.bp_cutoff_energy = 0.001;
+    *out = h;
+    return 0;
+}
+
+int sisgpu_destroy(sisgpu_t *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
+    if (h->h_ctl) cudaFreeHost(h->h_ctl);
+    if (h->h_need) cudaFreeHost(h->h_need);
+    // DBuf members are released explicitly (no destructors touching CUDA at exit)
+    h->d_meta.release(); h->d_seq.release(); h->d_hash.release(); h->d_nnbr.release(); h->d_nbp_row.release();
+    h->d_bp_status.release(); h->d_bp_status_MC.release(); h->d_nt_excess.release(); h->d_cell_of.release();
+    h->d_cell_count.release(); h->d_cell_start.release(); h->d_cell_cursor.release(); h->d_cell_beads.release();
+    h->d_need_rebuild.release(); h->d_rep_active.release(); h->d_twz_pairs.release(); h->d_twzfr_pairs.release();
+    h->d_rest_id.release(); h->d_coef.release(); h->d_pos0.release(); h->d_pos1.release(); h->d_mass.release();
+    h->d_bp3_dH.release(); h->d_bp3_dS.release(); h->d_vel.release(); h->d_acc.release(); h->d_move.release();
+    h->d_force.release(); h->d_ene_bp.release(); h->d_blk_top2.release(); h->d_ene_partial.release();
+    h->d_ene_out.release(); h->d_kin.release(); h->d_twz_dir.release(); h->d_twzfr_k.release();
+    h->d_twzfr_init.release(); h->d_twzfr_velo.release(); h->d_rest_rcut.release(); h->d_rest_para.release();
+    h->d_gather_send.release(); h->d_gather_recv.release(); h->d_nbr.release(); h->d_bprow.release();
+    h->d_bp_type.release(); h->d_bp_coef.release(); h->d_mc_counter.release(); h->d_blk_counter.release();
+    h->d_ene_counter.release(); h->d_rp.release(); h->d_rp_alt.release(); h->d_ctl.release();
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+// ---- set-up -------------------------------------------------------------------------------
+int sisgpu_set_topology(sisgpu_t *h, int nmp, int nchains, const int *nmp_chain, const int *moltypes,
+                        const int *seq, const int *has_charge, const int *is_frozen, const double *mass)
+{
+    if (nmp <= 0 || nchains <= 0) return set_err("empty system");
+    if (nmp >= (1 << 30)) return set_err("nmp too large for 30-bit row entries");
+    int tot = 0;
+    for (int c = 0; c < nchains; c++) tot += nmp_chain[c];
+    if (tot != nmp) return set_err("sum(nmp_chain)=%d != nmp=%d", tot, nmp);
+    h->nmp = nmp; h->nchains = nchains;
+    h->nmp_chain.assign(nmp_chain, nmp_chain + nchains);
+    h->moltypes.assign(moltypes, moltypes + nchains);
+    h->seq.assign(seq, seq + nmp);
+    h->has_charge.assign(nmp, 1);
+    if (has_charge) h->has_charge.assign(has_charge, has_charge + nmp);
+    h->is_frozen.assign(nmp, 0);
+    if (is_frozen) h->is_frozen.assign(is_frozen, is_frozen + nmp);
+    h->chain_start.resize(nchains); h->ichain.resize(nmp); h->lmp.resize(nmp);
+    int imp = 0;
+    for (int c = 0; c < nchains; c++) {
+        h->chain_start[c] = imp;
+        for (int i = 0; i < nmp_chain[c]; i++, imp++) { h->ichain[imp] = c; h->lmp[imp] = i; }
+    }
+    h->mass.resize(nmp);
+    static const double m5[5] = {328.212, 305.164, 344.212, 304.182, 320.443};   // src/job_md.F90:116-133
+    for (int i = 0; i < nmp; i++) {
+        if (seq[i] < 0 || seq[i] > 4) return set_err("Unknown seq type %d at imp=%d", seq[i], i + 1);
+        h->mass[i] = mass ? mass[i] : m5[seq[i]];
+    }
+    return 0;
+}
+
+int sisgpu_set_replicas(sisgpu_t *h, int nrep_proc)
+{
+    if (nrep_proc < 1) return set_err("nrep_proc must be >= 1");
+    h->nrep = nrep_proc;
+    h->rep.assign(nrep_proc, HostRep());
+    return 0;
+}
+
+int sisgpu_set_ff_bonded(sisgpu_t *h, double bond_k, double bond_r0, int angl_type, double angl_k,
+                         double angl_t0, int dih_flags, double dih_k, double dih_w, double dih_p0)
+{
+    FFParams &P = h->P;
+    P.bond_k = bond_k; P.bond_r0 = bond_r0;
+    P.flg_angl_ReB = angl_type == 1;
+    P.angl_k = angl_k; P.angl_t0 = angl_t0; P.angl_co0 = cos(angl_t0);
+    P.flg_dih_cos = dih_flags & 1; P.flg_dih_exp = (dih_flags >> 1) & 1;
+    P.dih_k = dih_k; P.dih_w = dih_w; P.dih_p0 = dih_p0;
+    return 0;
+}
+
+int sisgpu_set_ff_wca(sisgpu_t *h, double sigma, double eps)
+{
+    FFParams &P = h->P;
+    P.wca_sigma = sigma; P.wca_eps = eps;
+    P.wca_sigma2 = sigma * sigma;
+    P.wca_coef = 12.0 * eps / P.wca_sigma2;   // src/force_wca.F90:40-41
+    return 0;
+}
+
+int sisgpu_set_ff_bp(sisgpu_t *h, int model, int min_loop, int max_bp_per_nt, int nstep_MC,
+                     double cutoff_energy, const double *q)
+{
+    if (model != 1 && model != 3 && model != 4 && model != 5) return set_err("invalid bp model %d", model);
+    h->bp_model = model; h->bp_min_loop = min_loop; h->max_bp_per_nt = max_bp_per_nt; h->nstep_bp_MC = nstep_MC;
+    FFParams &P = h->P;
+    P.bp_cutoff_energy = cutoff_energy;
+    P.bp_triplet = (model == 4 || model == 5);
+    P.nstep_bp_MC = nstep_MC;
+    for (int t = 0; t < 3; t++) {
+        BpPara b{};
+        const double *v = q + 15 * t;
+        b.U0 = v[0]; b.bond_k = v[1]; b.bond_r = v[2];
+        b.angl_k1 = v[3]; b.angl_k2 = v[4]; b.angl_k3 = v[5]; b.angl_k4 = v[6];
+        b.angl_theta1 = v[7]; b.angl_theta2 = v[8]; b.angl_theta3 = v[9]; b.angl_theta4 = v[10];
+        b.dihd_k1 = v[11]; b.dihd_k2 = v[12]; b.dihd_phi1 = v[13]; b.dihd_phi2 = v[14];
+        P.bp[1 + t] = b;
+        BpPara s = b;   // CG / UA / UG: src/read_force_field.F90:203-207
+        std::swap(s.angl_k1, s.angl_k2);
+        std::swap(s.angl_k3, s.angl_k4);
+        P.bp[4 + t] = s;
+    }
+    return 0;
+}
+
+int sisgpu_set_ff_nn(sisgpu_t *h, const double *NN_dH, const double *NN_dS, double dH0, double dS0,
+                     int flg_NNend, const double *NNend_dH, const double *NNend_dS, double dHend0, double dSend0)
+{
+    for (int i = 0; i < 21; i++) { h->NN_dH[i + 1] = NN_dH[i]; h->NN_dS[i + 1] = NN_dS[i]; }
+    h->dH0 = dH0; h->dS0 = dS0; h->flg_NNend = flg_NNend;
+    for (int i = 0; i < 6; i++) {
+        h->NNend_dH[i + 1] = NNend_dH ? NNend_dH[i] : 0.0;
+        h->NNend_dS[i + 1] = NNend_dS ? NNend_dS[i] : 0.0;
+    }
+    h->dHend0 = dHend0; h->dSend0 = dSend0; h->have_nn = 1;
+    return 0;
+}
+
+int sisgpu_set_ele(sisgpu_t *h, int flg_ele, int cutoff_type, double cutoff_inp, int excl_bond, int excl_angle,
+                   double length_per_charge, int temp_independent, double tempK_ref)
+{
+    if (flg_ele && cutoff_type != 1 && cutoff_type != 2) return set_err("Invalid ele_cutoff_type value in set_ele.");
+    h->P.flg_ele = flg_ele; h->ele_cutoff_type = cutoff_type; h->ele_cutoff_inp = cutoff_inp;
+    h->excl_bond = excl_bond; h->excl_angle = excl_angle; h->length_per_charge = length_per_charge;
+    h->P.temp_independent = temp_independent; h->tempK_ref = tempK_ref;
+    return 0;
+}
+
+int sisgpu_set_pbc(sisgpu_t *h, int flg_pbc, const double *box)
+{
+    h->P.flg_pbc = flg_pbc;
+    for (int i = 0; i < 3; i++) {
+        h->P.box[i] = box ? box[i] : 0.0;
+        h->P.box_half[i] = 0.5 * h->P.box[i];
+    }
+    if (flg_pbc && (h->P.box[0] <= 0 || h->P.box[1] <= 0 || h->P.box[2] <= 0)) return set_err("invalid PBC box");
+    return 0;
+}
+
+int sisgpu_set_md(sisgpu_t *h, int integrator, double dt, double viscosity_Pas, double nl_margin, uint64_t seed)
+{
+    if (integrator != 1 && integrator != 2) return set_err("unknown integrator %d", integrator);
+    h->P.integrator = integrator; h->dt = dt; h->viscosity_Pas = viscosity_Pas; h->nl_margin = nl_margin;
+    h->seed = seed;
+    return 0;
+}
+
+int sisgpu_set_bias_ss(sisgpu_t *h, int flg, double force) { h->P.flg_bias_ss = flg; h->P.bias_ss_force = force; return 0; }
+int sisgpu_set_stage(sisgpu_t *h, int flg, double sigma, double eps)
+{
+    h->P.flg_stage = flg; h->P.stage_sigma = sigma; h->P.stage_eps = eps;
+    return 0;
+}
+int sisgpu_set_tweezers_dcf(sisgpu_t *h, int n, const int *pairs, const double *direction)
+{
+    h->P.ntwz_DCF = n;
+    h->twz_pairs.resize(2 * n);
+    for (int i = 0; i < 2 * n; i++) h->twz_pairs[i] = pairs[i] - 1;
+    h->twz_dir.assign(direction, direction + 3 * n);
+    return 0;
+}
+int sisgpu_set_tweezers_fr(sisgpu_t *h, int n, const int *pairs, const double *k, const double *init, const double *velo)
+{
+    h->P.ntwz_FR = n;
+    h->twzfr_pairs.resize(2 * n);
+    for (int i = 0; i < 2 * n; i++) h->twzfr_pairs[i] = pairs[i] - 1;
+    h->twzfr_k.assign(k, k + 2 * n);
+    h->twzfr_init.assign(init, init + 6 * n);
+    h->twzfr_velo.assign(velo, velo + 6 * n);
+    return 0;
+}
+int sisgpu_set_bias_rg(sisgpu_t *h, int flg, int pott, double k)
+{
+    h->P.flg_bias_rg = flg; h->P.bias_rg_pott = pott; h->P.bias_rg_k = k;
+    return 0;
+}
+int sisgpu_set_restraints(sisgpu_t *h, int n, const int *id, const double *rcut, const double *para)
+{
+    h->P.nrest = n;
+    h->rest_id.resize(3 * n);
+    for (int i = 0; i < n; i++) {
+        h->rest_id[3 * i] = id[3 * i] - 1; h->rest_id[3 * i + 1] = id[3 * i + 1] - 1; h->rest_id[3 * i + 2] = id[3 * i + 2];
+    }
+    h->rest_rcut.assign(rcut, rcut + n);
+    h->rest_para.assign(para, para + 3 * n);
+    return 0;
+}
+
+// set_ele: src/set_ele.F90:47-102 (the non-_HTN_CONSISTENT branch the reference builds by default)
+static void host_set_ele(const sisgpu *h, HostRep &r, double tempk, double ionstr)
+{
+    const double MM_A = 87.740, MM_B = -0.40008, MM_C = 9.398e-4, MM_D = -1.410e-6;
+    const double PI = 4.0 * atan(1.0);
+    if (h->P.temp_independent == 0) {
+        double Tc = tempk - 273.15;
+        r.diele = MM_A + MM_B * Tc + MM_C * Tc * Tc + MM_D * Tc * Tc * Tc;
+    } else {
+        double Tc = h->tempK_ref - 273.15;
+        r.diele = MM_A + MM_B * Tc + MM_C * Tc * Tc + MM_D * Tc * Tc * Tc;
+        r.diele_dTcoef = 1.0 + h->tempK_ref / r.diele * (MM_B + 2.0 * MM_C * Tc + 3.0 * MM_D * Tc * Tc);
+    }
+    double lb = SIS_ELE * SIS_ELE / (4.0 * PI * SIS_EPS0 * r.diele * SIS_BOLTZ_J * tempk) * 1.0e10;
+    double Zp = h->length_per_charge / lb;
+    r.ele_coef = SIS_JOUL2KCAL_MOL * 1.0e10 * SIS_ELE * SIS_ELE / (4.0 * PI * SIS_EPS0 * r.diele);
+    r.ele_coef = r.ele_coef * Zp * Zp;
+    r.lambdaD = 1.0e10 * sqrt((1.0e-3 * SIS_EPS0 * r.diele * SIS_BOLTZ_J) / (2.0 * SIS_N_AVO * SIS_ELE * SIS_ELE)) *
+                sqrt(tempk / ionstr);
+}
+
+static void fill_rp(const sisgpu *h, int irep, RepParams &R)
+{
+    const HostRep &r = h->rep[irep];
+    memset(&R, 0, sizeof R);
+    R.tempK = r.tempK;
+    R.ele_coef = r.ele_coef;
+    R.inv_lambdaD = r.lambdaD != 0.0 ? 1.0 / r.lambdaD : 0.0;
+    R.ele_cutoff = r.ele_cutoff;
+    R.diele_dTcoef = r.diele_dTcoef;
+    R.sqrt_tempK = sqrt(r.tempK);
+    R.bias_rg_0 = r.rg0;
+    R.twz_force = r.twz_force;
+    R.stream = h->rank * h->nrep + irep;
+}
+
+static int push_rp(sisgpu *h)
+{
+    if (!h->finalized) return 0;
+    h->rp_host.resize(h->nrep);
+    for (int i = 0; i < h->nrep; i++) fill_rp(h, i, h->rp_host[i]);
+    CK(cudaMemcpyAsync(h->d_rp.p, h->rp_host.data(), h->nrep * sizeof(RepParams), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int sisgpu_set_replica_params(sisgpu_t *h, int irep, double tempK, double ionic_strength, double twz_force, double rg0)
+{
+    if ((int)h->rep.size() != h->nrep) h->rep.assign(h->nrep, HostRep());
+    if (irep < 0 || irep >= h->nrep) return set_err("irep %d out of range", irep);
+    HostRep &r = h->rep[irep];
+    r.tempK = tempK; r.ionic = ionic_strength; r.twz_force = twz_force; r.rg0 = rg0;
+    if (h->P.flg_ele) {
+        host_set_ele(h, r, tempK, ionic_strength);
+        if (h->ele_cutoff_type == 1) r.ele_cutoff = h->ele_cutoff_inp;
+        else if (r.ele_cutoff == 0.0) r.ele_cutoff = h->ele_cutoff_inp * r.lambdaD;   // src/init_ele.F90:88-90
+    }
+    return push_rp(h);
+}
+
+// 21 nearest-neighbour stacks in NNT order (src/const_idx.F90:96-121); "XY_WZ" = 5'-XY-3' / 3'-WZ-5'
+static int nn_index(int x, int y, int w, int z)
+{
+    static const char *names[21] = {"GC_CG", "CC_GG", "GA_CU", "CG_GC", "AC_UG", "CA_GU", "AG_UC", "UA_AU", "AU_UA",
+                                    "AA_UU", "GC_UG", "CU_GG", "GG_CU", "CG_GU", "AU_UG", "GA_UU", "UG_GU", "UA_GU",
+                                    "GG_UU", "GU_UG", "AG_UU"};
+    static const char S[4] = {'A', 'U', 'G', 'C'};
+    const char a[6] = {S[x], S[y], '_', S[w], S[z], 0};
+    const char b[6] = {S[z], S[w], '_', S[y], S[x], 0};   // the same stack read from the other strand
+    for (int n = 0; n < 21; n++)
+        if (!strcmp(a, names[n]) || !strcmp(b, names[n])) return n + 1;
+    return 0;
+}
+
+// the 468-entry triplet table of src/init_bp.F90:39-172, enumerated in the same order so that the
+// bp3 indices (and with them bp_coef) agree with the reference's
+static int build_bp3_table(sisgpu *h)
+{
+    h->bp3_hash.assign(4096, 0);
+    h->bp3_dH.assign(469, 0.0);
+    h->bp3_dS.assign(469, 0.0);
+    auto end_type = [](int x, int y, int w, int z) -> int {   // NNENDT, src/const_idx.F90:123-132
+        auto is = [](int a, int b, int p, int q) { return (a == p && b == q) || (a == q && b == p); };
+        bool au = is(x, y, SEQ_A, SEQ_U), gu = is(x, y, SEQ_G, SEQ_U);
+        int on = is(w, z, SEQ_A, SEQ_U) ? 0 : is(w, z, SEQ_G, SEQ_C) ? 1 : is(w, z, SEQ_G, SEQ_U) ? 2 : -1;
+        if (on < 0) return 0;
+        if (au) return on == 0 ? 1 : on == 1 ? 2 : 3;   // AUonAU, AUonCG, AUonGU
+        if (gu) return on == 1 ? 4 : on == 0 ? 5 : 6;   // GUonCG, GUonAU, GUonGU
+        return 0;
+    };
+    int n = 0;
+    for (int x = 0; x <= 2; x++)
+        for (int y = x + 1; y <= 3; y++) {
+            if (!is_complement(x, y)) continue;
+            for (int w = 0; w <= 3; w++)
+                for (int z = 0; z <= 3; z++) {
+                    const bool up = is_complement(w, z);
+                    const double upH = up ? 0.5 * (h->NN_dH[nn_index(w, x, z, y)] - h->dH0) : 0.0;
+                    const double upS = up ? 0.5 * (h->NN_dS[nn_index(w, x, z, y)] - h->dS0) : 0.0;
+                    for (int u = 0; u <= 3; u++)
+                        for (int v = 0; v <= 3; v++) {
+                            const bool lo = is_complement(u, v);
+                            if (!up && !lo) continue;
+                            ++n;
+                            h->bp3_hash[bp3_hash_key(w, x, u, z, y, v)] = n;
+                            double dH = upH, dS = upS;
+                            if (lo) {
+                                dH = upH + 0.5 * (h->NN_dH[nn_index(x, u, y, v)] - h->dH0);
+                                dS = upS + 0.5 * (h->NN_dS[nn_index(x, u, y, v)] - h->dS0);
+                            }
+                            dS *= 1.0e-3;
+                            if (h->flg_NNend && up != lo) {
+                                int t = up ? end_type(x, y, w, z) : end_type(x, y, u, v);
+                                if (t) {
+                                    dH += h->NNend_dH[t] - h->dHend0;
+                                    dS += (h->NNend_dS[t] - h->dSend0) * 1.0e-3;
+                                }
+                            }
+                            h->bp3_dH[n] = dH;
+                            h->bp3_dS[n] = dS;
+                        }
+                }
+        }
+    h->bp3_n = n;
+    if (n != 468) return set_err("bp3 table has %d entries, expected 468", n);
+    return 0;
+}
+
+static int alloc_lists(sisgpu *h, int K, int KB)
+{
+    const size_t R = h->nrep, N = h->nmp;
+    if (K != h->K) {
+        h->K = K;
+        TRY(h->d_nbr.alloc(R * N * K));
+    }
+    if (KB != h->KB) {
+        h->KB = KB;
+        TRY(h->d_bprow.alloc(R * N * KB));
+        TRY(h->d_bp_type.alloc(R * N * KB));
+        TRY(h->d_bp_coef.alloc(R * N * KB));
+        TRY(h->d_bp_status.alloc(R * N * KB));
+        TRY(h->d_bp_status_MC.alloc(R * N * KB));
+        TRY(h->d_ene_bp.alloc(R * N * KB));
+    }
+    DevSys &S = h->S;
+    S.K = h->K; S.KB = h->KB;
+    S.nbr = h->d_nbr.p; S.bprow = h->d_bprow.p; S.bp_type = h->d_bp_type.p; S.bp_coef = h->d_bp_coef.p;
+    S.bp_status = h->d_bp_status.p; S.bp_status_MC = h->d_bp_status_MC.p; S.ene_bp = h->d_ene_bp.p;
+    return 0;
+}
+
+static int alloc_cells(sisgpu *h, int ncell)
+{
+    if (ncell <= h->S.ncell_cap) return 0;
+    const size_t R = h->nrep;
+    int cap = std::max(ncell, 64);
+    TRY(h->d_cell_count.alloc(R * cap));
+    TRY(h->d_cell_start.alloc(R * (cap + 1)));
+    TRY(h->d_cell_cursor.alloc(R * cap));
+    h->S.ncell_cap = cap;
+    h->S.cell_count = h->d_cell_count.p; h->S.cell_start = h->d_cell_start.p; h->S.cell_cursor = h->d_cell_cursor.p;
+    return 0;
+}
+
+// md_coef / md_coef_rep of src/job_md.F90:94-108,700-767; noise0 * sqrt(T) = md_coef_rep(1)
+static void build_coef(const sisgpu *h, std::vector<double4> &coef)
+{
+    const double PI = 4.0 * atan(1.0), radius = 10.0;
+    coef.resize(h->nmp);
+    for (int i = 0; i < h->nmp; i++) {
+        double4 c;
+        if (h->P.integrator == 1) {
+            double v = h->viscosity_Pas * sqrt(1.0e3 / SIS_KCAL2JOUL) * SIS_N_AVO * 1.0e-20;
+            double fric = 6.0 * PI * v * radius;
+            double c1 = 0.5 * h->dt * fric / h->mass[i];
+            double c2 = sqrt(1.0 / (1.0 + c1));
+            c.x = (1.0 - c1) / (1.0 + c1);
+            c.y = c2 * h->dt / h->mass[i];
+            c.z = h->is_frozen[i] ? 0.0 : c2 * h->dt;
+            c.w = 0.5 * c2 / h->mass[i] * sqrt(2.0 * fric * SIS_BOLTZ_KCAL_MOL * h->dt);
+        } else {
+            double v = (SIS_JOUL2KCAL_MOL * 1.0e-18) * h->viscosity_Pas;
+            double fric = 6.0 * PI * v * radius;
+            c.x = h->is_frozen[i] ? 0.0 : h->dt / fric;
+            c.y = c.z = 0.0;
+            c.w = h->is_frozen[i] ? 0.0 : sqrt(2.0 * SIS_BOLTZ_KCAL_MOL * h->dt / fric);
+        }
+        coef[i] = c;
+    }
+}
+
+// host half of finalize_setup: everything init_bp / list_local / set_md_coef leave behind
+// (src/init_bp.F90:39-172,319-346; src/job_md.F90:700-767), no device work
+static int host_prepare(sisgpu *h, std::vector<int4> &meta, std::vector<double4> &coef)
+{
+    if (!h->nmp) return set_err("topology not set");
+    if ((int)h->rep.size() != h->nrep) h->rep.assign(h->nrep, HostRep());
+    const int N = h->nmp;
+    FFParams &P = h->P;
+    if (h->bp_model == 5) {
+        if (!h->have_nn) return set_err("[NN] required in FF file (bp model 5)");
+        TRY(build_bp3_table(h));
+    } else {
+        h->bp3_hash.assign(4096, 0); h->bp3_dH.assign(469, 0.0); h->bp3_dS.assign(469, 0.0);
+    }
+    // bp cutoffs: src/init_bp.F90:319-346
+    if (fabs(P.bp_cutoff_energy) <= SIS_SMALL_VALUE) {
+        h->bp_cutoff_dist = 18.0;
+        for (int t = 1; t <= 6; t++) P.bp[t].cutoff_ddist = h->bp_cutoff_dist - 13.8;
+    } else {
+        h->bp_cutoff_dist = 0.0;
+        for (int t = 1; t <= 6; t++) {
+            P.bp[t].cutoff_ddist = sqrt(log(fabs(10.0 / P.bp_cutoff_energy)) / P.bp[t].bond_k);
+            h->bp_cutoff_dist = std::max(h->bp_cutoff_dist, P.bp[t].bond_r + P.bp[t].cutoff_ddist);
+        }
+    }
+    P.bp[0] = P.bp[1];
+    meta.resize(N);
+    for (int i = 0; i < N; i++) {
+        int c = h->ichain[i];
+        int fl = h->seq[i] & MF_SEQ_MASK;
+        if (h->has_charge[i]) fl |= MF_CHARGE;
+        if (h->moltypes[c] == MOLT_CIRC) fl |= MF_CIRC;
+        if (h->is_frozen[i]) fl |= MF_FROZEN;
+        meta[i] = make_int4(h->chain_start[c], h->nmp_chain[c], h->lmp[i], fl);
+    }
+    build_coef(h, coef);
+    return 0;
+}
+
+int sisgpu_finalize_setup(sisgpu_t *h)
+{
+    std::vector<int4> meta;
+    std::vector<double4> coef;
+    TRY(host_prepare(h, meta, coef));
+    CK(cudaSetDevice(h->device));
+    const int N = h->nmp, R = h->nrep;
+    TRY(h->d_meta.upload(meta));
+    TRY(h->d_seq.upload(h->seq));
+    TRY(h->d_coef.upload(coef));
+    TRY(h->d_mass.upload(h->mass));
+    TRY(h->d_hash.upload(h->bp3_hash));
+    TRY(h->d_bp3_dH.upload(h->bp3_dH));
+    TRY(h->d_bp3_dS.upload(h->bp3_dS));
+    TRY(h->d_twz_pairs.upload(h->twz_pairs)); TRY(h->d_twz_dir.upload(h->twz_dir));
+    TRY(h->d_twzfr_pairs.upload(h->twzfr_pairs)); TRY(h->d_twzfr_k.upload(h->twzfr_k));
+    TRY(h->d_twzfr_init.upload(h->twzfr_init)); TRY(h->d_twzfr_velo.upload(h->twzfr_velo));
+    TRY(h->d_rest_id.upload(h->rest_id)); TRY(h->d_rest_rcut.upload(h->rest_rcut)); TRY(h->d_rest_para.upload(h->rest_para));
+    // state
+    const size_t RN = (size_t)R * N;
+    TRY(h->d_pos0.alloc(RN)); TRY(h->d_pos1.alloc(RN));
+    TRY(h->d_vel.alloc(RN * 3)); TRY(h->d_acc.alloc(RN * 3)); TRY(h->d_move.alloc(RN * 3)); TRY(h->d_force.alloc(RN * 3));
+    TRY(h->d_nnbr.alloc(RN)); TRY(h->d_nbp_row.alloc(RN)); TRY(h->d_nt_excess.alloc(RN));
+    TRY(h->d_cell_of.alloc(RN)); TRY(h->d_cell_beads.alloc(RN));
+    TRY(h->d_mc_counter.alloc(R)); TRY(h->d_need_rebuild.alloc(R)); TRY(h->d_rep_active.alloc(R));
+    TRY(h->d_rp.alloc(R)); TRY(h->d_rp_alt.alloc(R)); TRY(h->d_ctl.alloc(1));
+    TRY(h->d_kin.alloc(R));
+    const int BPB = 256 / h->G;
+    const int nblk = (N + BPB - 1) / BPB;
+    TRY(h->d_blk_top2.alloc((size_t)R * nblk * 2)); TRY(h->d_blk_counter.alloc(R + 1));
+    TRY(h->d_ene_partial.alloc((size_t)R * nblk * ENE_N)); TRY(h->d_ene_counter.alloc(R)); TRY(h->d_ene_out.alloc((size_t)R * ENE_N));
+    TRY(h->d_gather_send.alloc(2 * (size_t)R)); TRY(h->d_gather_recv.alloc(2 * (size_t)std::max(h->nrep_all, R)));
+    if (!h->h_ctl) CK(cudaMallocHost(&h->h_ctl, sizeof(DevCtl)));
+    if (!h->h_need) CK(cudaMallocHost(&h->h_need, sizeof(int) * R));
+    DevSys &S = h->S;
+    S.nmp = N; S.nrep = R; S.nblk = nblk;
+    S.meta = h->d_meta.p; S.seq = h->d_seq.p; S.coef = h->d_coef.p; S.mass = h->d_mass.p; S.hash = h->d_hash.p;
+    S.bp3_dH = h->d_bp3_dH.p; S.bp3_dS = h->d_bp3_dS.p;
+    S.pos[0] = h->d_pos0.p; S.pos[1] = h->d_pos1.p; S.vel = h->d_vel.p; S.acc = h->d_acc.p; S.move = h->d_move.p;
+    S.force = h->d_force.p; S.nnbr = h->d_nnbr.p; S.nbp_row = h->d_nbp_row.p; S.nt_excess = h->d_nt_excess.p;
+    S.mc_counter = h->d_mc_counter.p; S.cell_of = h->d_cell_of.p; S.cell_beads = h->d_cell_beads.p;
+    S.rp = h->d_rp.p; S.ctl = h->d_ctl.p; S.need_rebuild = h->d_need_rebuild.p; S.blk_top2 = h->d_blk_top2.p;
+    S.blk_counter = h->d_blk_counter.p; S.ene_partial = h->d_ene_partial.p; S.ene_counter = h->d_ene_counter.p;
+    S.ene_out = h->d_ene_out.p;
+    S.twz_pairs = h->d_twz_pairs.p; S.twz_dir = h->d_twz_dir.p; S.twzfr_pairs = h->d_twzfr_pairs.p;
+    S.twzfr_k = h->d_twzfr_k.p; S.twzfr_init = h->d_twzfr_init.p; S.twzfr_velo = h->d_twzfr_velo.p;
+    S.rest_id = h->d_rest_id.p; S.rest_rcut = h->d_rest_rcut.p; S.rest_para = h->d_rest_para.p;
+    S.ncell_cap = 0;
+    h->K = h->KB = 0;
+    TRY(alloc_lists(h, 128, 16));
+    TRY(alloc_cells(h, 64));
+    h->finalized = true;
+    TRY(push_rp(h));
+    return 0;
+}
+
+// ---- state --------------------------------------------------------------------------------
+static int sync_ctl(sisgpu *h)
+{
+    CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl.p, sizeof(DevCtl), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_need, h->d_need_rebuild.p, sizeof(int) * h->nrep, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int sisgpu_set_state(sisgpu_t *h, int irep, const double *xyz, const double *velos, const double *accels)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    if (irep < 0 || irep >= h->nrep) return set_err("irep out of range");
+    CK(cudaSetDevice(h->device));
+    TRY(sync_ctl(h));
+    const int N = h->nmp;
+    if (xyz) {
+        std::vector<double4> p(N);
+        for (int i = 0; i < N; i++) p[i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0);
+        CK(cudaMemcpy(h->S.pos[h->h_ctl->cur] + (size_t)irep * N, p.data(), N * sizeof(double4), cudaMemcpyHostToDevice));
+    }
+    if (velos) CK(cudaMemcpy(h->S.vel + (size_t)irep * N * 3, velos, 3 * N * sizeof(double), cudaMemcpyHostToDevice));
+    if (accels) CK(cudaMemcpy(h->S.acc + (size_t)irep * N * 3, accels, 3 * N * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int sisgpu_get_state(sisgpu_t *h, int irep, double *xyz, double *velos, double *accels)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    if (irep < 0 || irep >= h->nrep) return set_err("irep out of range");
+    CK(cudaSetDevice(h->device));
+    TRY(sync_ctl(h));
+    const int N = h->nmp;
+    if (xyz) {
+        std::vector<double4> p(N);
+        CK(cudaMemcpy(p.data(), h->S.pos[h->h_ctl->cur] + (size_t)irep * N, N * sizeof(double4), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < N; i++) { xyz[3 * i] = p[i].x; xyz[3 * i + 1] = p[i].y; xyz[3 * i + 2] = p[i].z; }
+    }
+    if (velos) CK(cudaMemcpy(velos, h->S.vel + (size_t)irep * N * 3, 3 * N * sizeof(double), cudaMemcpyDeviceToHost));
+    if (accels) CK(cudaMemcpy(accels, h->S.acc + (size_t)irep * N * 3, 3 * N * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int sisgpu_set_step(sisgpu_t *h, int64_t istep)
+{
+    TRY(sync_ctl(h));
+    h->h_ctl->step = (unsigned long long)istep;
+    CK(cudaMemcpy(h->d_ctl.p, h->h_ctl, sizeof(DevCtl), cudaMemcpyHostToDevice));
+    h->istep_host = istep;
+    return 0;
+}
+int sisgpu_get_step(sisgpu_t *h, int64_t *istep)
+{
+    TRY(sync_ctl(h));
+    *istep = (int64_t)h->h_ctl->step;
+    return 0;
+}
+
+// ---- neighbour lists ----------------------------------------------------------------------
+static void timer_begin(sisgpu *h) { if (h->timing) cudaEventRecord(h->ev0, h->stream); }
+static void timer_end(sisgpu *h, double &acc)
+{
+    if (!h->timing) return;
+    cudaEventRecord(h->ev1, h->stream);
+    cudaEventSynchronize(h->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    acc += ms;
+}
+
+static NlArgs nl_args(const sisgpu *h, bool all_pairs)
+{
+    NlArgs A{};
+    A.nl_margin = h->nl_margin;
+    A.wca_nl_cut2 = (h->P.wca_sigma + h->nl_margin) * (h->P.wca_sigma + h->nl_margin);
+    A.bp_nl_cut2 = h->P.flg_bias_ss ? 9999999999.9 : (h->bp_cutoff_dist + h->nl_margin) * (h->bp_cutoff_dist + h->nl_margin);
+    A.excl_bond = h->excl_bond; A.excl_angle = h->excl_angle;
+    A.bp_model = h->bp_model; A.bp_min_loop = h->bp_min_loop;
+    A.all_pairs = all_pairs;
+    return A;
+}
+
+// builds the rows of the replicas flagged in `active`; all_pairs = list_exv/list_ele/list_bp mode
+static int build_lists(sisgpu *h, const std::vector<int> &active, bool all_pairs)
+{
+    CK(cudaSetDevice(h->device));
+    const int N = h->nmp, R = h->nrep;
+    DevSys &S = h->S;
+    timer_begin(h);
+    // src/neighbor_list.F90:80-82: ele_cutoff refreshed here for cutoff_type 2
+    double rc = std::max(h->P.wca_sigma, h->P.flg_bias_ss ? 0.0 : h->bp_cutoff_dist);
+    bool rp_dirty = false;
+    for (int r = 0; r < R; r++) {
+        if (!active[r]) continue;
+        if (h->P.flg_ele) {
+            if (h->ele_cutoff_type == 2) {
+                double c = h->ele_cutoff_inp * h->rep[r].lambdaD;
+                if (c != h->rep[r].ele_cutoff) { h->rep[r].ele_cutoff = c; rp_dirty = true; }
+            }
+            rc = std::max(rc, h->rep[r].ele_cutoff);
+        }
+    }
+    if (rp_dirty) TRY(push_rp(h));
+    rc += h->nl_margin;
+    TRY(sync_ctl(h));
+    const int cur = h->h_ctl->cur;
+    GridInfo Gd{};
+    Gd.pbc = h->P.flg_pbc;
+    const bool brute = all_pairs || h->P.flg_bias_ss;   // Bias_SS: bp cutoff is infinite
+    if (!brute) {
+        double lo[3], hi[3];
+        if (h->P.flg_pbc) {
+            for (int d = 0; d < 3; d++) { lo[d] = 0.0; hi[d] = h->P.box[d]; }
+        } else {
+            // bounding box of the active replicas (host reduction; rebuilds are rare)
+            std::vector<double4> p(N);
+            for (int d = 0; d < 3; d++) { lo[d] = 1e300; hi[d] = -1e300; }
+            for (int r = 0; r < R; r++) {
+                if (!active[r]) continue;
+                CK(cudaMemcpy(p.data(), S.pos[cur] + (size_t)r * N, N * sizeof(double4), cudaMemcpyDeviceToHost));
+                for (int i = 0; i < N; i++) {
+                    lo[0] = std::min(lo[0], p[i].x); hi[0] = std::max(hi[0], p[i].x);
+                    lo[1] = std::min(lo[1], p[i].y); hi[1] = std::max(hi[1], p[i].y);
+                    lo[2] = std::min(lo[2], p[i].z); hi[2] = std::max(hi[2], p[i].z);
+                }
+            }
+        }
+        long long ncell = 1;
+        for (int d = 0; d < 3; d++) {
+            double ext = std::max(hi[d] - lo[d], 1e-9);
+            int n = (int)floor(ext / (rc * 1.000001));
+            n = std::max(1, std::min(n, 128));
+            Gd.n[d] = n;
+            Gd.origin[d] = lo[d];
+            Gd.inv_cell[d] = n / ext;
+            ncell *= n;
+        }
+        Gd.ncell = (int)ncell;
+        TRY(alloc_cells(h, Gd.ncell));
+    } else {
+        Gd.n[0] = Gd.n[1] = Gd.n[2] = 1; Gd.ncell = 1;
+    }
+    CK(cudaMemcpyAsync(h->d_rep_active.p, active.data(), R * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    NlArgs A = nl_args(h, brute);
+    A.all_pairs = all_pairs ? 1 : (brute ? 2 : 0);
+    for (int attempt = 0; attempt < 8; attempt++) {
+        h->h_ctl->nl_overflow = 0; h->h_ctl->bp_overflow = 0;
+        CK(cudaMemcpyAsync(&h->d_ctl.p->nl_overflow, &h->h_ctl->nl_overflow, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        if (!brute) {
+            if (attempt == 0) {
+                CK(cudaMemsetAsync(S.cell_count, 0, (size_t)R * S.ncell_cap * sizeof(int), h->stream));
+                k_nl_wrap_count<<<dim3((N + 255) / 256, R), 256, 0, h->stream>>>(S, h->P, Gd, h->d_rep_active.p);
+                k_nl_scan<<<R, 1024, 0, h->stream>>>(S, Gd, h->d_rep_active.p);
+                k_nl_fill<<<dim3((N + 255) / 256, R), 256, 0, h->stream>>>(S, h->d_rep_active.p);
+                k_nl_sort<<<dim3((Gd.ncell + 255) / 256, R), 256, 0, h->stream>>>(S, Gd, h->d_rep_active.p);
+                h->launches += 4;
+            }
+        } else if (h->P.flg_pbc && !all_pairs && attempt == 0) {
+            // Bias_SS with PBC still wraps first (src/neighbor_list.F90:28-30); reuse the wrap kernel on a 1-cell grid
+            TRY(alloc_cells(h, 1));
+            CK(cudaMemsetAsync(S.cell_count, 0, (size_t)R * S.ncell_cap * sizeof(int), h->stream));
+            k_nl_wrap_count<<<dim3((N + 255) / 256, R), 256, 0, h->stream>>>(S, h->P, Gd, h->d_rep_active.p);
+            h->launches += 1;
+        }
+        k_nl_rows<<<dim3((N + 7) / 8, R), 256, 0, h->stream>>>(S, h->P, Gd, A, h->d_rep_active.p);
+        h->launches += 1;
+        TRY(sync_ctl(h));
+        CK(cudaGetLastError());
+        if (h->h_ctl->nl_overflow > h->K || h->h_ctl->bp_overflow > h->KB) {
+            int K = h->K, KB = h->KB;
+            if (h->h_ctl->nl_overflow > K) K = ((int)(h->h_ctl->nl_overflow * 1.2) + 31) / 32 * 32;   // growth as the reference's x1.2
+            if (h->h_ctl->bp_overflow > KB) KB = ((int)(h->h_ctl->bp_overflow * 1.2) + 7) / 8 * 8;
+            // a capacity change relocates every replica's rows: rebuild all of them
+            std::vector<int> all(R, 1);
+            bool was_all = true;
+            for (int r = 0; r < R; r++) was_all &= (active[r] != 0);
+            TRY(alloc_lists(h, K, KB));
+            if (!was_all) return build_lists(h, all, all_pairs);
+            continue;
+        }
+        k_nl_bp_slots<<<dim3((N * h->KB + 255) / 256, R), 256, 0, h->stream>>>(S, h->d_rep_active.p);
+        k_nl_finish<<<(R + 63) / 64, 64, 0, h->stream>>>(S, h->d_rep_active.p);
+        h->launches += 2;
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaGetLastError());
+        timer_end(h, h->t_nl);
+        h->lists_full = all_pairs;
+        h->lists_built = true;
+        return 0;
+    }
+    return set_err("neighbour list capacity did not converge");
+}
+
+int sisgpu_neighbor_list(sisgpu_t *h, int irep)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    if (irep < 0 || irep >= h->nrep) return set_err("irep out of range");
+    std::vector<int> act(h->nrep, 0);
+    act[irep] = 1;
+    h->nrebuild++;
+    return build_lists(h, act, false);
+}
+
+int sisgpu_full_lists(sisgpu_t *h)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    std::vector<int> act(h->nrep, 1);
+    // src/main.F90:150-152 path; ele_cutoff for cutoff_type 2 as set by init_ele
+    return build_lists(h, act, true);
+}
+
+// half lists in the reference's loop order (ichain, jchain, i, j): src/neighbor_list.F90:99-118
+struct HalfLists {
+    std::vector<std::pair<int, int>> wca, ele;
+    std::vector<int> bp_i, bp_j, bp_ibp;
+};
+static int fetch_half_lists(sisgpu *h, int irep, HalfLists &L)
+{
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    const int N = h->nmp, K = h->K, KB = h->KB;
+    std::vector<uint32_t> nbr((size_t)N * K);
+    std::vector<int> nn(N), nb(N);
+    std::vector<int2> bprow((size_t)N * KB);
+    CK(cudaMemcpy(nbr.data(), h->S.nbr + (size_t)irep * N * K, nbr.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(nn.data(), h->S.nnbr + (size_t)irep * N, N * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(nb.data(), h->S.nbp_row + (size_t)irep * N, N * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(bprow.data(), h->S.bprow + (size_t)irep * N * KB, bprow.size() * sizeof(int2), cudaMemcpyDeviceToHost));
+    auto key_less = [h](const std::pair<int, int> &a, const std::pair<int, int> &b) {
+        int ac = h->ichain[a.first], bc = h->ichain[b.first];
+        if (ac != bc) return ac < bc;
+        int ajc = h->ichain[a.second], bjc = h->ichain[b.second];
+        if (ajc != bjc) return ajc < bjc;
+        if (a.first != b.first) return a.first < b.first;
+        return a.second < b.second;
+    };
+    for (int i = 0; i < N; i++)
+        for (int e = 0; e < nn[i]; e++) {
+            uint32_t ent = nbr[(size_t)i * K + e];
+            int j = ent & NB_IDX;
+            if (j <= i) continue;
+            if (ent & NB_WCA) L.wca.emplace_back(i, j);
+            if (ent & NB_ELE) L.ele.emplace_back(i, j);
+        }
+    std::sort(L.wca.begin(), L.wca.end(), key_less);
+    std::sort(L.ele.begin(), L.ele.end(), key_less);
+    std::vector<std::pair<std::pair<int, int>, int>> bp;
+    for (int i = 0; i < N; i++)
+        for (int e = 0; e < nb[i]; e++) {
+            int2 ent = bprow[(size_t)i * KB + e];
+            if (ent.x > i) bp.push_back({{i, ent.x}, ent.y});
+        }
+    std::sort(bp.begin(), bp.end(), [&](const std::pair<std::pair<int, int>, int> &a, const std::pair<std::pair<int, int>, int> &b) {
+        return key_less(a.first, b.first);
+    });
+    for (auto &b : bp) { L.bp_i.push_back(b.first.first); L.bp_j.push_back(b.first.second); L.bp_ibp.push_back(b.second); }
+    return 0;
+}
+
+int sisgpu_get_list_sizes(sisgpu_t *h, int irep, int *nwca, int *nele, int *nbp)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    HalfLists L;
+    TRY(fetch_half_lists(h, irep, L));
+    *nwca = (int)L.wca.size(); *nele = (int)L.ele.size(); *nbp = (int)L.bp_i.size();
+    return 0;
+}
+
+static int host_chain_nb(const sisgpu *h, int imp, int off)
+{
+    int c = h->ichain[imp], l = h->lmp[imp] + off, n = h->nmp_chain[c];
+    if (h->moltypes[c] == MOLT_CIRC) { l %= n; if (l < 0) l += n; return h->chain_start[c] + l; }
+    // linear chain ends never enter the bp list; mirror the reference's index arithmetic anyway
+    return imp + off;
+}
+
+int sisgpu_get_lists(sisgpu_t *h, int irep, int *wca_mp, int *ele_mp, int *bp_mp, double *bp_coef)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    HalfLists L;
+    TRY(fetch_half_lists(h, irep, L));
+    if (wca_mp) for (size_t k = 0; k < L.wca.size(); k++) { wca_mp[2 * k] = L.wca[k].first + 1; wca_mp[2 * k + 1] = L.wca[k].second + 1; }
+    if (ele_mp) for (size_t k = 0; k < L.ele.size(); k++) { ele_mp[2 * k] = L.ele[k].first + 1; ele_mp[2 * k + 1] = L.ele[k].second + 1; }
+    const size_t nb = L.bp_i.size();
+    if (nb && (bp_mp || bp_coef)) {
+        const size_t NKB = (size_t)h->nmp * h->KB;
+        std::vector<signed char> type(NKB);
+        std::vector<double2> coef(NKB);
+        CK(cudaMemcpy(type.data(), h->S.bp_type + irep * NKB, NKB, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(coef.data(), h->S.bp_coef + irep * NKB, NKB * sizeof(double2), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < nb; k++) {
+            int i = L.bp_i[k], j = L.bp_j[k], ibp = L.bp_ibp[k];
+            if (bp_mp) {
+                int *b = bp_mp + 7 * k;
+                b[0] = i + 1; b[1] = j + 1;
+                b[2] = host_chain_nb(h, i, -1) + 1; b[3] = host_chain_nb(h, j, -1) + 1;
+                b[4] = host_chain_nb(h, i, +1) + 1; b[5] = host_chain_nb(h, j, +1) + 1;
+                b[6] = type[ibp];
+            }
+            if (bp_coef) { bp_coef[2 * k] = coef[ibp].x; bp_coef[2 * k + 1] = coef[ibp].y; }
+        }
+    }
+    return 0;
+}
+
+// list_local (src/list_local.F90:16-119) is implicit on the device (consecutive beads per chain
+// + circRNA closures); this getter materialises it for parity checks and the Fortran shim
+int sisgpu_get_local_lists(sisgpu_t *h, int *nbond, int *nangl, int *ndih, int *bond_mp, int *angl_mp, int *dih_mp)
+{
+    std::vector<int> bd, an, di;
+    const bool has_dih = h->P.flg_dih_cos || h->P.flg_dih_exp;
+    for (int c = 0; c < h->nchains; c++) {
+        const int n = h->nmp_chain[c], s = h->chain_start[c];
+        const bool circ = h->moltypes[c] == MOLT_CIRC;
+        auto at = [&](int l) { return s + ((l % n) + n) % n + 1; };
+        for (int i = 0; i + 1 < n; i++) { bd.push_back(at(i)); bd.push_back(at(i + 1)); }
+        for (int i = 0; i + 2 < n; i++) for (int q = 0; q < 3; q++) an.push_back(at(i + q));
+        if (has_dih) for (int i = 0; i + 3 < n; i++) for (int q = 0; q < 4; q++) di.push_back(at(i + q));
+        if (circ) {
+            bd.push_back(at(n - 1)); bd.push_back(at(n));
+            for (int a = n - 2; a <= n - 1; a++) for (int q = 0; q < 3; q++) an.push_back(at(a + q));
+            if (has_dih) for (int a = n - 3; a <= n - 1; a++) for (int q = 0; q < 4; q++) di.push_back(at(a + q));
+        }
+    }
+    *nbond = (int)bd.size() / 2; *nangl = (int)an.size() / 3; *ndih = (int)di.size() / 4;
+    if (bond_mp) std::copy(bd.begin(), bd.end(), bond_mp);
+    if (angl_mp) std::copy(an.begin(), an.end(), angl_mp);
+    if (dih_mp) std::copy(di.begin(), di.end(), dih_mp);
+    return 0;
+}
+
+int sisgpu_bp3_table(sisgpu_t *h, int *n, int *hash4096, double *dH, double *dS)
+{
+    if (h->bp3_hash.empty()) return set_err("finalize_setup not called");
+    *n = h->bp3_n;
+    if (hash4096) std::copy(h->bp3_hash.begin(), h->bp3_hash.end(), hash4096);
+    if (dH) std::copy(h->bp3_dH.begin() + 1, h->bp3_dH.end(), dH);
+    if (dS) std::copy(h->bp3_dS.begin() + 1, h->bp3_dS.end(), dS);
+    return 0;
+}
+
+// ---- hot path -----------------------------------------------------------------------------
+int sisgpu_set_bp_mc(sisgpu_t *h, int flg) { h->flg_bp_MC = flg; return 0; }
+
+static StepArgs step_args(const sisgpu *h, unsigned mask, int use_mask, int only_rep)
+{
+    StepArgs A{};
+    A.seed = h->seed; A.nl_margin = h->lists_full ? 1e300 : h->nl_margin;
+    A.term_mask = mask; A.use_mask = use_mask; A.only_rep = only_rep;
+    return A;
+}
+
+template <int MODE>
+static void launch_step(sisgpu *h, const StepArgs &A)
+{
+    const int BPB = 256 / h->G;
+    dim3 grid((h->nmp + BPB - 1) / BPB, A.only_rep >= 0 ? 1 : h->nrep);
+    switch (h->G) {
+    case 8: k_step<8, MODE><<<grid, 256, 0, h->stream>>>(h->S, h->P, A); break;
+    case 16: k_step<16, MODE><<<grid, 256, 0, h->stream>>>(h->S, h->P, A); break;
+    default: k_step<32, MODE><<<grid, 256, 0, h->stream>>>(h->S, h->P, A); break;
+    }
+    h->launches++;
+}
+
+// evaluation + MC pruning passes of force_bp_limit_triplet / energy_bp_limit_triplet
+template <int SIDE>
+static void launch_bp_eval(sisgpu *h, int only_rep, bool with_prune, double tK, int use_override, int use_mask,
+                           int copy_to_mc, int deterministic)
+{
+    const int R = only_rep >= 0 ? 1 : h->nrep;
+    if (with_prune) {
+        k_excess_init<<<dim3((h->nmp + 255) / 256, R), 256, 0, h->stream>>>(h->S, only_rep, h->max_bp_per_nt);
+        h->launches++;
+    }
+    k_bp_eval<SIDE><<<dim3((h->nmp * h->KB + 255) / 256, R), 256, 0, h->stream>>>(h->S, h->P, only_rep, tK, use_override,
+                                                                                use_mask, with_prune ? 1 : 0);
+    h->launches++;
+    if (with_prune) {
+        k_bp_prune<<<R, 32, 0, h->stream>>>(h->S, h->P, h->seed, only_rep, tK, use_override, deterministic, copy_to_mc);
+        h->launches++;
+    }
+}
+
+static void launch_rg(sisgpu *h, int only_rep)
+{
+    if (!h->P.flg_bias_rg) return;
+    k_rg<<<only_rep >= 0 ? 1 : h->nrep, 256, 0, h->stream>>>(h->S, only_rep);
+    h->launches++;
+}
+
+int sisgpu_force_terms(sisgpu_t *h, int irep, unsigned mask, double *forces)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    if (irep < 0 || irep >= h->nrep) return set_err("irep out of range");
+    CK(cudaSetDevice(h->device));
+    int use_mask = h->nstep_bp_MC > 0 ? 1 : 0;
+    if ((mask & (1u << ENE_BP)) && h->flg_bp_MC) {
+        // src/force.F90:44-49 -> force_bp_limit_triplet: evaluate all, prune, scatter survivors
+        launch_bp_eval<0>(h, irep, true, 0.0, 0, 0, 0, 0);
+        use_mask = 2;
+    }
+    if (mask & (1u << ENE_RG)) launch_rg(h, irep);
+    launch_step<1>(h, step_args(h, mask, use_mask, irep));
+    CK(cudaMemcpyAsync(forces, h->S.force + (size_t)irep * h->nmp * 3, 3 * h->nmp * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+int sisgpu_force(sisgpu_t *h, int irep, double *forces) { return sisgpu_force_terms(h, irep, 0x7FEu, forces); }
+
+static int energy_launch(sisgpu *h, int only_rep, const RepParams *rp_alt)
+{
+    const int BPB = 256 / h->G;
+    dim3 grid((h->nmp + BPB - 1) / BPB, only_rep >= 0 ? 1 : h->nrep);
+    switch (h->G) {
+    case 8: k_energy<8><<<grid, 256, 0, h->stream>>>(h->S, h->P, rp_alt, only_rep); break;
+    case 16: k_energy<16><<<grid, 256, 0, h->stream>>>(h->S, h->P, rp_alt, only_rep); break;
+    default: k_energy<32><<<grid, 256, 0, h->stream>>>(h->S, h->P, rp_alt, only_rep); break;
+    }
+    h->launches++;
+    return 0;
+}
+
+int sisgpu_energy_sumup(sisgpu_t *h, int irep, double tempK, int recompute_bp, double *energies)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    if (irep < 0 || irep >= h->nrep) return set_err("irep out of range");
+    CK(cudaSetDevice(h->device));
+    timer_begin(h);
+    if (recompute_bp) {
+        // energy_bp / energy_bp_triplet / energy_bp_limit_triplet with flg_bp_energy = .False.
+        const bool limit = h->flg_bp_MC != 0;
+        launch_bp_eval<1>(h, irep, limit, tempK, 1, (!limit && h->nstep_bp_MC > 0) ? 1 : 0, 0, h->P.temp_independent);
+    }
+    launch_rg(h, irep);
+    TRY(energy_launch(h, irep, nullptr));
+    CK(cudaMemcpyAsync(energies, h->S.ene_out + (size_t)irep * ENE_N, ENE_N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    TRY(sync_ctl(h));
+    CK(cudaGetLastError());
+    timer_end(h, h->t_ene);
+    if (h->h_ctl->max_force_flag & 2) return set_err("Error: Z-coordinate < 0.85 * stage_sigma in energy_stage. Abort!");
+    return 0;
+}
+
+int sisgpu_energy_kinetic(sisgpu_t *h, int irep, double *ekin)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    CK(cudaSetDevice(h->device));
+    k_kinetic<<<1, 256, 0, h->stream>>>(h->S, h->d_kin.p, irep);
+    h->launches++;
+    CK(cudaMemcpyAsync(ekin, h->d_kin.p + irep, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int sisgpu_get_bp_state(sisgpu_t *h, int irep, int *status, double *ene)
+{
+    HalfLists L;
+    TRY(fetch_half_lists(h, irep, L));
+    const size_t NKB = (size_t)h->nmp * h->KB;
+    std::vector<int> st(NKB);
+    std::vector<double> en(NKB);
+    CK(cudaMemcpy(st.data(), h->S.bp_status + irep * NKB, NKB * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(en.data(), h->S.ene_bp + irep * NKB, NKB * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < L.bp_ibp.size(); k++) {
+        if (status) status[k] = st[L.bp_ibp[k]];
+        if (ene) ene[k] = en[L.bp_ibp[k]];
+    }
+    return 0;
+}
+
+int sisgpu_get_rg(sisgpu_t *h, int irep, double *rg)
+{
+    RepParams R;
+    CK(cudaMemcpy(&R, h->d_rp.p + irep, sizeof R, cudaMemcpyDeviceToHost));
+    *rg = R.rg_val;
+    return 0;
+}
+
+int sisgpu_init_velocities(sisgpu_t *h, int irep)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    CK(cudaSetDevice(h->device));
+    k_init_velocities<<<(h->nmp * 3 + 255) / 256, 256, 0, h->stream>>>(h->S, h->seed, irep);
+    h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- REMD (host mirror of var_replica / init_replica / replica_exchange) ---------------------
+static int get_pair(const sisgpu *h, int label) { return h->pair_tb[(size_t)(h->idx_pair - 1) * h->nrep_all + label - 1]; }
+
+static void label_params(const sisgpu *h, int label, const HostRep &cur, double &T, double &I, double &f, double &g0)
+{
+    const int n = h->nrep_all, l = label - 1;
+    T = h->flg_repvar[REPT_TEMP] ? h->lab2val[REPT_TEMP * n + l] : cur.tempK;
+    I = h->flg_repvar[REPT_ION] ? h->lab2val[REPT_ION * n + l] : cur.ionic;
+    f = h->flg_repvar[REPT_TWZDCF] ? h->lab2val[REPT_TWZDCF * n + l] : cur.twz_force;
+    g0 = h->flg_repvar[REPT_RG] ? h->lab2val[REPT_RG * n + l] : cur.rg0;
+}
+
+// parameter refresh of src/job_md.F90:538-567: set_md_coef (T), set_ele, twz forces, Rg0.
+// ele_cutoff is NOT refreshed here (reference quirk: only neighbor_list does, for cutoff_type 2).
+static void apply_label(sisgpu *h, int irep, int label)
+{
+    HostRep &r = h->rep[irep];
+    double T, I, f, g0;
+    label_params(h, label, r, T, I, f, g0);
+    r.tempK = T; r.ionic = I; r.twz_force = f; r.rg0 = g0;
+    if (h->P.flg_ele) host_set_ele(h, r, T, I);
+}
+
+int sisgpu_remd_setup(sisgpu_t *h, const int nrep[4], const double *values, int nstep_exchange, int rank, int nranks)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    h->flg_replica = true; h->ndim_replica = 0; h->nrep_all = 1;
+    for (int v = 0; v < REPT_MAX; v++) {
+        h->nrep_dim[v] = nrep[v];
+        h->flg_repvar[v] = nrep[v] > 1;
+        if (nrep[v] > MAX_REP_PER_DIM) return set_err("too many replicas in one dimension");
+        for (int k = 0; k < nrep[v]; k++) h->replica_values[v][k] = values[v * MAX_REP_PER_DIM + k];
+        if (h->flg_repvar[v]) { h->ndim_replica++; h->nrep_all *= nrep[v]; }
+    }
+    if (h->ndim_replica > MAX_REP_DIM) return set_err("too many replica dimensions");
+    if (nranks > h->nrep_all) return set_err("Error: the number of MPI processes should be equal to or smaller than the number of replicas.");
+    if (h->nrep_all % nranks) return set_err("Error: the number of replicas has to be a multiple of the number of MPI processes.");
+    if (h->nrep_all / nranks != h->nrep) return set_err("nrep_proc=%d but nrep_all/nranks=%d", h->nrep, h->nrep_all / nranks);
+    h->rank = rank; h->nranks = nranks; h->nstep_exchange = nstep_exchange;
+    const int n = h->nrep_all;
+    h->rep2lab.resize(n); h->lab2rep.resize(n);
+    h->lab2val.assign((size_t)REPT_MAX * n, 1.0e31);
+    // lab2val: src/init_replica.F90:70-92
+    int n_division = 1;
+    for (int v = 0; v < REPT_MAX; v++) {
+        if (!h->flg_repvar[v]) continue;
+        const int n_division_pre = n_division;
+        n_division *= h->nrep_dim[v];
+        const int n_continue = n / n_division, n_skip = n / n_division_pre;
+        for (int ir = 0; ir < h->nrep_dim[v]; ir++)
+            for (int ido = 0; ido < n_division_pre; ido++)
+                for (int is = 0; is < n_continue; is++)
+                    h->lab2val[(size_t)v * n + ir * n_continue + ido * n_skip + is] = h->replica_values[v][ir];
+    }
+    for (int g = 0; g < n; g++) { h->rep2lab[g] = g + 1; h->lab2rep[g] = g + 1; }
+    int idx = 0;
+    for (int v = 0; v < REPT_MAX; v++) if (h->flg_repvar[v]) h->type_array[idx++] = v;
+    // exchange_pair_tb: src/var_replica.F90:162-259 (odd/even neighbour pairs per dimension)
+    const int ncol = 2 * h->ndim_replica;
+    h->pair_tb.assign((size_t)ncol * n, 0);
+    int col = 0;
+    for (int parity = 1; parity <= 2; parity++) {
+        n_division = 1;
+        for (int d = 0; d < h->ndim_replica; d++, col++) {
+            int *tb = h->pair_tb.data() + (size_t)col * n;
+            const int nv = h->nrep_dim[h->type_array[d]];
+            const int n_division_pre = n_division;
+            n_division *= nv;
+            const int n_continue = n / n_division;
+            int iset = 0;
+            for (int cyc = 0; cyc < n_division_pre; cyc++) {
+                bool post_zero;
+                int start;
+                if (parity == 1) { post_zero = (nv % 2 == 1); start = 1; }
+                else { iset += n_continue; post_zero = (nv % 2 == 0); start = 2; }   // leading block unpaired
+                for (int ir = start; ir <= nv - 1; ir += 2)
+                    for (int ic = 1; ic <= 2 * n_continue; ic++) {
+                        iset++;
+                        tb[iset - 1] = ic <= n_continue ? iset + n_continue : iset - n_continue;
+                    }
+                if (post_zero) iset += n_continue;
+            }
+        }
+    }
+    h->idx_pair = 1;
+    h->d_gather_recv.alloc(2 * (size_t)n);
+    for (int irep = 0; irep < h->nrep; irep++) {
+        const int grep = rank * h->nrep + irep;
+        apply_label(h, irep, h->rep2lab[grep]);
+        HostRep &r = h->rep[irep];
+        if (h->P.flg_ele) {
+            if (h->ele_cutoff_type == 1) r.ele_cutoff = h->ele_cutoff_inp;
+            else r.ele_cutoff = h->ele_cutoff_inp * r.lambdaD;
+        }
+    }
+    return push_rp(h);
+}
+
+int sisgpu_nccl_unique_id(unsigned char *id)
+{
+    TRY(nccl_load());
+    NcclId nid;
+    int rc = g_nccl.GetUniqueId(&nid);
+    if (rc) return set_err("ncclGetUniqueId failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    memcpy(id, nid.internal, SISGPU_NCCL_ID_BYTES);
+    return 0;
+}
+
+int sisgpu_comm_init(sisgpu_t *h, int nranks, int rank, const unsigned char *id)
+{
+    TRY(nccl_load());
+    CK(cudaSetDevice(h->device));
+    NcclId nid;
+    memcpy(nid.internal, id, SISGPU_NCCL_ID_BYTES);
+    int rc = g_nccl.CommInitRank(&h->nccl_comm, nranks, nid, rank);
+    if (rc) return set_err("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    return 0;
+}
+
+int sisgpu_remd_pair_table(sisgpu_t *h, int *tb)
+{
+    std::copy(h->pair_tb.begin(), h->pair_tb.end(), tb);
+    return 0;
+}
+int sisgpu_remd_state(sisgpu_t *h, int *rep2lab, int *lab2rep, double *lab2val)
+{
+    if (rep2lab) std::copy(h->rep2lab.begin(), h->rep2lab.end(), rep2lab);
+    if (lab2rep) std::copy(h->lab2rep.begin(), h->lab2rep.end(), lab2rep);
+    if (lab2val) std::copy(h->lab2val.begin(), h->lab2val.end(), lab2val);
+    return 0;
+}
+int sisgpu_remd_stats(sisgpu_t *h, int64_t *n_attempt, int64_t *n_accept)
+{
+    *n_attempt = h->n_attempt; *n_accept = h->n_accept;
+    return 0;
+}
+
+// energy_replica on an exchange step (src/energy_replica.F90:45-163): own-parameter energies
+// (cached bp energies), then partner-parameter energies with the bp term recomputed, then the
+// allgather that replaces MPI_ALLREDUCE (src/job_md.F90:531-533)
+int sisgpu_energy_replica(sisgpu_t *h, double *energies, double *replica_energies)
+{
+    if (!h->flg_replica) return set_err("REMD not configured");
+    CK(cudaSetDevice(h->device));
+    timer_begin(h);
+    const int R = h->nrep, n = h->nrep_all;
+    std::vector<double> e_own((size_t)R * ENE_N), e_opp((size_t)R * ENE_N);
+    if (h->flg_bp_MC && h->nstep_bp_MC > 0)   // src/job_md.F90:476-479: flg_bp_energy = .False. with MC
+        launch_bp_eval<1>(h, -1, true, 0.0, 0, 0, 0, h->P.temp_independent);
+    launch_rg(h, -1);
+    TRY(energy_launch(h, -1, nullptr));
+    CK(cudaMemcpyAsync(e_own.data(), h->S.ene_out, e_own.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    // partner parameter blocks
+    std::vector<RepParams> alt(R);
+    std::vector<int> has_opp(R, 0);
+    for (int irep = 0; irep < R; irep++) {
+        const int grep = h->rank * R + irep;
+        const int label_own = h->rep2lab[grep], label_opp = get_pair(h, label_own);
+        fill_rp(h, irep, alt[irep]);
+        if (label_opp == 0 || label_opp > n) continue;
+        has_opp[irep] = 1;
+        HostRep saved = h->rep[irep];
+        apply_label(h, irep, label_opp);
+        fill_rp(h, irep, alt[irep]);
+        h->rep[irep] = saved;
+    }
+    CK(cudaMemcpyAsync(h->d_rp_alt.p, alt.data(), R * sizeof(RepParams), cudaMemcpyHostToDevice, h->stream));
+    // cross energies: bp term recomputed with the partner temperature (flg_bp_energy = .False., :72)
+    {
+        // swap in the alternative block for the bp evaluation (tempK per replica comes from rp)
+        CK(cudaStreamSynchronize(h->stream));
+        const bool limit = h->flg_bp_MC != 0;
+        RepParams *saved = h->S.rp;
+        h->S.rp = h->d_rp_alt.p;
+        launch_bp_eval<1>(h, -1, limit, 0.0, 0, (!limit && h->nstep_bp_MC > 0) ? 1 : 0, 0, h->P.temp_independent);
+        launch_rg(h, -1);
+        TRY(energy_launch(h, -1, nullptr));
+        h->S.rp = saved;
+    }
+    CK(cudaMemcpyAsync(e_opp.data(), h->S.ene_out, e_opp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    std::vector<double> send(2 * (size_t)R);
+    for (int irep = 0; irep < R; irep++) {
+        send[2 * irep] = e_own[(size_t)irep * ENE_N];
+        send[2 * irep + 1] = has_opp[irep] ? e_opp[(size_t)irep * ENE_N] : 0.0;
+    }
+    if (h->nranks > 1) {
+        if (!h->nccl_comm) return set_err("sisgpu_comm_init not called for a multi-rank REMD");
+        CK(cudaMemcpyAsync(h->d_gather_send.p, send.data(), send.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        int rc = g_nccl.AllGather(h->d_gather_send.p, h->d_gather_recv.p, 2 * (size_t)R, NCCL_FLOAT64, h->nccl_comm, h->stream);
+        if (rc) return set_err("ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+        CK(cudaMemcpyAsync(replica_energies, h->d_gather_recv.p, 2 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    } else {
+        std::copy(send.begin(), send.end(), replica_energies);
+    }
+    if (energies) std::copy(e_own.begin(), e_own.end(), energies);
+    timer_end(h, h->t_rex);
+    return 0;
+}
+
+// replica_exchange (src/replica_exchange.F90:44-154): identical decisions on every rank
+int sisgpu_replica_exchange(sisgpu_t *h, const double *E, const double *uniforms, int *n_attempt, int *n_accept)
+{
+    if (!h->flg_replica) return set_err("REMD not configured");
+    CK(cudaSetDevice(h->device));
+    const int n = h->nrep_all, R = h->nrep;
+    int nrand = 0, natt = 0, nacc = 0;
+    // the reference draws ceil(nrep_all/2) numbers up front from mts_rep (:44-48)
+    const int ndraw = (n + 1) / 2;
+    std::vector<double> u(ndraw);
+    for (int i = 0; i < ndraw; i++)
+        u[i] = uniforms ? uniforms[i] : uniform_counter(h->seed, 0x7fffffffu, h->exchange_counter + i);
+    if (!uniforms) h->exchange_counter += ndraw;
+    for (int l_i = 1; l_i <= n; l_i++) {
+        const int l_j = get_pair(h, l_i);
+        if (l_j < l_i) continue;
+        const double rnd = u[nrand++];
+        const int rep_i = h->lab2rep[l_i - 1], rep_j = h->lab2rep[l_j - 1];
+        double temp_m, temp_n;
+        if (h->flg_repvar[REPT_TEMP]) {
+            temp_m = h->lab2val[(size_t)REPT_TEMP * n + l_i - 1];
+            temp_n = h->lab2val[(size_t)REPT_TEMP * n + l_j - 1];
+        } else temp_m = temp_n = h->rep[0].tempK;
+        const double pot_i_m = E[2 * (rep_i - 1)], pot_i_n = E[2 * (rep_i - 1) + 1];
+        const double pot_j_n = E[2 * (rep_j - 1)], pot_j_m = E[2 * (rep_j - 1) + 1];
+        const double delta = ((pot_j_m - pot_i_m) / temp_m - (pot_j_n - pot_i_n) / temp_n) / SIS_BOLTZ_KCAL_MOL;
+        natt++;
+        if (delta < 0.0 || rnd <= exp(-delta)) {
+            nacc++;
+            h->rep2lab[rep_i - 1] = l_j; h->rep2lab[rep_j - 1] = l_i;
+            h->lab2rep[l_i - 1] = rep_j; h->lab2rep[l_j - 1] = rep_i;
+            if (h->flg_repvar[REPT_TEMP]) {   // scale_velo :175-213, only for locally held replicas
+                const double sf = sqrt(temp_n / temp_m);
+                const int li = rep_i - 1 - h->rank * R, lj = rep_j - 1 - h->rank * R;
+                if (li >= 0 && li < R) { k_scale_velocities<<<(3 * h->nmp + 255) / 256, 256, 0, h->stream>>>(h->S, li, sf); h->launches++; }
+                if (lj >= 0 && lj < R) { k_scale_velocities<<<(3 * h->nmp + 255) / 256, 256, 0, h->stream>>>(h->S, lj, 1.0 / sf); h->launches++; }
+            }
+        }
+    }
+    h->idx_pair = (h->idx_pair == 2 * h->ndim_replica) ? 1 : h->idx_pair + 1;   // set_forward
+    for (int irep = 0; irep < R; irep++) apply_label(h, irep, h->rep2lab[h->rank * R + irep]);
+    TRY(push_rp(h));
+    h->n_attempt += natt; h->n_accept += nacc;
+    if (n_attempt) *n_attempt = natt;
+    if (n_accept) *n_accept = nacc;
+    return 0;
+}
+
+// ---- the MD loop --------------------------------------------------------------------------
+int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    if (h->lists_full) return set_err("md_steps needs neighbour lists (call sisgpu_neighbor_list first)");
+    CK(cudaSetDevice(h->device));
+    if (!h->lists_built) {   // src/job_md.F90:196-198
+        std::vector<int> all(h->nrep, 1);
+        TRY(build_lists(h, all, false));
+    }
+    TRY(sync_ctl(h));
+    const long long start = (long long)h->h_ctl->step, target = start + nsteps;
+    long long nreb0 = h->nrebuild;
+    bool force_mc = false;
+    const int R = h->nrep;
+    const unsigned mask_all = 0x7FEu;
+    while ((long long)h->h_ctl->step < target) {
+        // rebuild requested by the previous position update (src/job_md.F90:388-395)
+        bool any = false;
+        std::vector<int> act(R, 0);
+        for (int r = 0; r < R; r++) if (h->h_need[r]) { act[r] = 1; any = true; h->nrebuild++; }
+        if (any) {
+            TRY(build_lists(h, act, false));
+            if (h->nstep_bp_MC > 0) force_mc = true;
+            TRY(sync_ctl(h));
+        } else if (h->h_ctl->abort_word) {
+            return set_err("internal: abort without rebuild request");
+        }
+        long long cur = (long long)h->h_ctl->step;
+        long long stop = target;
+        if (h->flg_replica && h->nstep_exchange > 0) {
+            long long next_ex = (cur / h->nstep_exchange + 1) * (long long)h->nstep_exchange;
+            stop = std::min(stop, next_ex);
+        }
+        int nchunk = (int)std::min<long long>(h->chunk, stop - cur);
+        timer_begin(h);
+        for (int s = 0; s < nchunk; s++) {
+            const long long istep = cur + s + 1;
+            bool mc = false;
+            if (h->nstep_bp_MC > 0) mc = (istep % h->nstep_bp_MC == 0) || (s == 0 && force_mc);
+            if (mc) launch_bp_eval<0>(h, -1, true, 0.0, 0, 0, 1, 0);
+            launch_rg(h, -1);
+            launch_step<0>(h, step_args(h, mask_all, h->nstep_bp_MC > 0 ? 1 : 0, -1));
+        }
+        force_mc = false;
+        TRY(sync_ctl(h));
+        CK(cudaGetLastError());
+        timer_end(h, h->t_step);
+        // exchange step (src/job_md.F90:474-481,514-570)
+        if (h->flg_replica && h->nstep_exchange > 0 && !h->h_ctl->abort_word &&
+            (long long)h->h_ctl->step % h->nstep_exchange == 0 && (long long)h->h_ctl->step > cur) {
+            std::vector<double> re(2 * (size_t)h->nrep_all);
+            const int mc_saved = h->flg_bp_MC;
+            if (h->nstep_bp_MC > 0) h->flg_bp_MC = 1;   // src/job_md.F90:476-479
+            TRY(sisgpu_energy_replica(h, nullptr, re.data()));
+            h->flg_bp_MC = mc_saved;
+            timer_begin(h);
+            TRY(sisgpu_replica_exchange(h, re.data(), nullptr, nullptr, nullptr));
+            timer_end(h, h->t_rex);
+        }
+    }
+    if (h->h_ctl->max_force_flag & 1) {
+        fprintf(stderr, "Warning: maxval(forces) > 100.0 during the last md_steps call (step %lld)\n", (long long)h->h_ctl->step);
+        h->h_ctl->max_force_flag = 0;
+        CK(cudaMemcpy(&h->d_ctl.p->max_force_flag, &h->h_ctl->max_force_flag, sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (nrebuild_out) *nrebuild_out = h->nrebuild - nreb0;
+    return 0;
+}
+
+// job_check_force: src/job_check_force.F90:53-80
+int sisgpu_check_force(sisgpu_t *h, double tempK, double *f_energy, double *f_force, double *maxdiff)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    if (h->nrep != 1) return set_err("check_force runs with one replica (IREP = 1)");
+    const float small_f = 0.001f;
+    const double small = small_f;   // `small = 0.001` is a default-real literal in the reference
+    const int N = h->nmp;
+    TRY(sisgpu_force(h, 0, f_force));
+    std::vector<double> x(3 * (size_t)N);
+    TRY(sisgpu_get_state(h, 0, x.data(), nullptr, nullptr));
+    double e[ENE_N], md = 0.0;
+    const int cur = h->h_ctl->cur;
+    for (int imp = 0; imp < N; imp++)
+        for (int k = 0; k < 3; k++) {
+            double4 p = make_double4(x[3 * imp], x[3 * imp + 1], x[3 * imp + 2], 0.0), q = p;
+            double *c = k == 0 ? &q.x : k == 1 ? &q.y : &q.z;
+            const double save = *c;
+            *c = save + small;
+            CK(cudaMemcpyAsync(h->S.pos[cur] + imp, &q, sizeof q, cudaMemcpyHostToDevice, h->stream));
+            TRY(sisgpu_energy_sumup(h, 0, tempK, 1, e));
+            const double e_save = e[0];
+            *c = save - small;
+            CK(cudaMemcpyAsync(h->S.pos[cur] + imp, &q, sizeof q, cudaMemcpyHostToDevice, h->stream));
+            TRY(sisgpu_energy_sumup(h, 0, tempK, 1, e));
+            f_energy[3 * imp + k] = -(e_save - e[0]) / (2.0 * small);
+            CK(cudaMemcpyAsync(h->S.pos[cur] + imp, &p, sizeof p, cudaMemcpyHostToDevice, h->stream));
+            md = std::max(md, fabs(f_energy[3 * imp + k] - f_force[3 * imp + k]));
+        }
+    CK(cudaStreamSynchronize(h->stream));
+    if (maxdiff) *maxdiff = md;
+    return 0;
+}
+
+int sisgpu_launch_count(sisgpu_t *h, int64_t *n) { *n = h->launches; return 0; }
+
+int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
+{
+    std::string s(name);
+    if (s == "launch_mode") h->launch_mode = (int)value;
+    else if (s == "chunk") h->chunk = std::max(1, (int)value);
+    else if (s == "timing") h->timing = (int)value;
+    else if (s == "threads_per_bead") {
+        int g = (int)value;
+        if (g != 8 && g != 16 && g != 32) return set_err("threads_per_bead must be 8, 16 or 32");
+        if (h->finalized) return set_err("threads_per_bead must be set before finalize_setup");
+        h->G = g;
+    } else return set_err("unknown option %s", name);
+    return 0;
+}
+
+int sisgpu_get_timers(sisgpu_t *h, double *out, int reset)
+{
+    out[0] = h->t_step; out[1] = h->t_nl; out[2] = h->t_ene; out[3] = h->t_rex;
+    if (reset) h->t_step = h->t_nl = h->t_ene = h->t_rex = 0;
+    return 0;
+}

@@ -1,0 +1,194 @@
+// hostcheck.cu -- TEST-ONLY host build of the product's force and list code.
+//
+// There is no GPU in the build container, so the kernels cannot run there.  This file compiles
+// the product sources (sis_b200/csrc/sisgpu.cu and the __host__ __device__ math / gather code in
+// sis_kernels.cuh) for the HOST and drives `bead_force<1>` and the list predicates serially, so
+// the CPU test-suite can compare the product's arithmetic, term roles and exclusion rules with
+// the oracle before any GPU time is spent.  It is not linked into libsisgpu.so and nothing in
+// sis_b200/ loads it.
+#include "../../sis_b200/csrc/sisgpu.cu"
+
+struct HostCheck {
+    sisgpu *h = nullptr;
+    std::vector<int4> meta;
+    std::vector<double4> coef, pos;
+    std::vector<uint32_t> nbr;
+    std::vector<int> nnbr, nbp_row, bp_status, bp_status_MC;
+    std::vector<int2> bprow;
+    std::vector<signed char> bp_type;
+    std::vector<double2> bp_coef;
+    std::vector<double> ene_bp;
+    RepParams rp{};
+    DevSys S{};
+    int K = 0, KB = 0;
+};
+
+extern "C" {
+
+int hc_create(HostCheck **out)
+{
+    HostCheck *c = new HostCheck();
+    c->h = new sisgpu();
+    c->h->P.integrator = 1;
+    c->h->P.bp_cutoff_energy = 0.001;
+    *out = c;
+    return 0;
+}
+sisgpu *hc_handle(HostCheck *c) { return c->h; }
+void hc_destroy(HostCheck *c) { delete c->h; delete c; }
+
+int hc_prepare(HostCheck *c)
+{
+    sisgpu *h = c->h;
+    TRY(host_prepare(h, c->meta, c->coef));
+    fill_rp(h, 0, c->rp);
+    DevSys &S = c->S;
+    S.nmp = h->nmp; S.nrep = 1;
+    S.meta = c->meta.data(); S.seq = h->seq.data(); S.coef = c->coef.data(); S.mass = h->mass.data();
+    S.hash = h->bp3_hash.data(); S.bp3_dH = h->bp3_dH.data(); S.bp3_dS = h->bp3_dS.data();
+    S.twz_pairs = h->twz_pairs.data(); S.twz_dir = h->twz_dir.data(); S.twzfr_pairs = h->twzfr_pairs.data();
+    S.twzfr_k = h->twzfr_k.data(); S.twzfr_init = h->twzfr_init.data(); S.twzfr_velo = h->twzfr_velo.data();
+    S.rest_id = h->rest_id.data(); S.rest_rcut = h->rest_rcut.data(); S.rest_para = h->rest_para.data();
+    return 0;
+}
+
+// rows from the product's predicates by an all-pairs sweep (what k_nl_rows evaluates per candidate)
+int hc_build_lists(HostCheck *c, double *xyz, int all_pairs)
+{
+    sisgpu *h = c->h;
+    const int N = h->nmp;
+    const FFParams &P = h->P;
+    if (h->P.flg_ele && h->ele_cutoff_type == 2) h->rep[0].ele_cutoff = h->ele_cutoff_inp * h->rep[0].lambdaD;
+    fill_rp(h, 0, c->rp);
+    c->pos.resize(N);
+    for (int i = 0; i < N; i++) {
+        double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        if (P.flg_pbc && !all_pairs) { x = wrap1(x, P.box[0]); y = wrap1(y, P.box[1]); z = wrap1(z, P.box[2]); }
+        xyz[3 * i] = x; xyz[3 * i + 1] = y; xyz[3 * i + 2] = z;
+        c->pos[i] = make_double4(x, y, z, 0.0);
+    }
+    NlArgs A = nl_args(h, all_pairs != 0);
+    A.all_pairs = all_pairs ? 1 : 0;
+    const double ec = c->rp.ele_cutoff + A.nl_margin, ele_nl_cut2 = ec * ec;
+    std::vector<std::vector<uint32_t>> rows(N);
+    std::vector<std::vector<int>> brows(N);
+    std::vector<std::vector<int>> btype(N), bidx(N);
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++) {
+            if (i == j) continue;
+            Vec3 v = pbc_vec_d(P, v3(c->pos[i]), v3(c->pos[j]));
+            const double d2 = dot(v, v);
+            uint32_t ent = nl_pair_flags(A, P, c->meta[i], c->meta[j], i, j, d2, ele_nl_cut2);
+            if (ent) rows[i].push_back(ent | (uint32_t)j);
+            if (nl_bp_geometry(A, i, j, d2)) {
+                int bptype = 0, bp3;
+                if (i < j) bp3 = bp_lookup(A.bp_model, A.bp_min_loop, h->bp3_hash.data(), h->seq.data(), i, c->meta[i], j, c->meta[j], &bptype);
+                else bp3 = bp_lookup(A.bp_model, A.bp_min_loop, h->bp3_hash.data(), h->seq.data(), j, c->meta[j], i, c->meta[i], &bptype);
+                if (bp3 > 0) { brows[i].push_back(j); btype[i].push_back(bptype); bidx[i].push_back(bp3); }
+            }
+        }
+    size_t K = 1, KB = 1;
+    for (int i = 0; i < N; i++) { K = std::max(K, rows[i].size()); KB = std::max(KB, brows[i].size()); }
+    c->K = (int)K; c->KB = (int)KB;
+    c->nbr.assign((size_t)N * K, 0); c->nnbr.assign(N, 0); c->nbp_row.assign(N, 0);
+    c->bprow.assign((size_t)N * KB, make_int2(0, 0));
+    c->bp_type.assign((size_t)N * KB, 0); c->bp_coef.assign((size_t)N * KB, make_double2(0, 0));
+    c->bp_status.assign((size_t)N * KB, 0); c->bp_status_MC.assign((size_t)N * KB, 1); c->ene_bp.assign((size_t)N * KB, 0.0);
+    for (int i = 0; i < N; i++) {
+        c->nnbr[i] = (int)rows[i].size();
+        std::copy(rows[i].begin(), rows[i].end(), c->nbr.begin() + (size_t)i * K);
+        c->nbp_row[i] = (int)brows[i].size();
+        for (size_t e = 0; e < brows[i].size(); e++) {
+            const int j = brows[i][e];
+            int ibp;
+            if (j > i) {
+                ibp = i * (int)KB + (int)e;
+                c->bp_type[ibp] = (signed char)btype[i][e];
+                if (h->bp_model == 5) c->bp_coef[ibp] = make_double2(h->bp3_dH[bidx[i][e]], h->bp3_dS[bidx[i][e]]);
+            } else {
+                size_t q = std::find(brows[j].begin(), brows[j].end(), i) - brows[j].begin();
+                ibp = j * (int)KB + (int)q;
+            }
+            c->bprow[(size_t)i * KB + e] = make_int2(j, ibp);
+        }
+    }
+    DevSys &S = c->S;
+    S.K = c->K; S.KB = c->KB;
+    S.nbr = c->nbr.data(); S.nnbr = c->nnbr.data(); S.bprow = c->bprow.data(); S.nbp_row = c->nbp_row.data();
+    S.bp_type = c->bp_type.data(); S.bp_coef = c->bp_coef.data(); S.bp_status = c->bp_status.data();
+    S.bp_status_MC = c->bp_status_MC.data(); S.ene_bp = c->ene_bp.data();
+    return 0;
+}
+
+int hc_list_sizes(HostCheck *c, int *nwca, int *nele, int *nbp)
+{
+    const int N = c->h->nmp;
+    int a = 0, b = 0, d = 0;
+    for (int i = 0; i < N; i++) {
+        for (int e = 0; e < c->nnbr[i]; e++) {
+            uint32_t ent = c->nbr[(size_t)i * c->K + e];
+            if ((int)(ent & NB_IDX) > i) { a += (ent & NB_WCA) != 0; b += (ent & NB_ELE) != 0; }
+        }
+        for (int e = 0; e < c->nbp_row[i]; e++) d += c->bprow[(size_t)i * c->KB + e].x > i;
+    }
+    *nwca = a; *nele = b; *nbp = d;
+    return 0;
+}
+
+// half lists, 1-based, sorted by (i, j); bp rows carry (i, j, type) and (dH, dS)
+int hc_get_lists(HostCheck *c, int *wca, int *ele, int *bp, double *coef)
+{
+    const int N = c->h->nmp;
+    size_t a = 0, b = 0, d = 0;
+    for (int i = 0; i < N; i++) {
+        for (int e = 0; e < c->nnbr[i]; e++) {
+            uint32_t ent = c->nbr[(size_t)i * c->K + e];
+            int j = ent & NB_IDX;
+            if (j <= i) continue;
+            if (ent & NB_WCA) { wca[2 * a] = i + 1; wca[2 * a + 1] = j + 1; a++; }
+            if (ent & NB_ELE) { ele[2 * b] = i + 1; ele[2 * b + 1] = j + 1; b++; }
+        }
+        for (int e = 0; e < c->nbp_row[i]; e++) {
+            int2 ent = c->bprow[(size_t)i * c->KB + e];
+            if (ent.x <= i) continue;
+            bp[3 * d] = i + 1; bp[3 * d + 1] = ent.x + 1; bp[3 * d + 2] = c->bp_type[ent.y];
+            coef[2 * d] = c->bp_coef[ent.y].x; coef[2 * d + 1] = c->bp_coef[ent.y].y;
+            d++;
+        }
+    }
+    return 0;
+}
+
+// the product's gather force code, one "lane" per bead
+int hc_force(HostCheck *c, const double *xyz, unsigned mask, double *forces)
+{
+    const int N = c->h->nmp;
+    c->pos.resize(N);
+    for (int i = 0; i < N; i++) c->pos[i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0);
+    for (int k = 0; k < N; k++) {
+        Vec3 F = bead_force<1>(c->S, c->h->P, c->rp, c->pos.data(), 0, k, 0, mask, 0, 0ull, 1);
+        forces[3 * k] = F.x; forces[3 * k + 1] = F.y; forces[3 * k + 2] = F.z;
+    }
+    return 0;
+}
+
+double hc_gauss(unsigned long long seed, unsigned stream, unsigned long long step, unsigned bead, int comp)
+{
+    return gauss_component(seed, stream, step, bead, comp);
+}
+double hc_uniform(unsigned long long seed, unsigned stream, unsigned long long counter)
+{
+    return uniform_counter(seed, stream, counter);
+}
+int hc_coef(HostCheck *c, int imp, double *out)
+{
+    double4 v = c->coef[imp];
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w * c->rp.sqrt_tempK;
+    return 0;
+}
+int hc_rep_params(HostCheck *c, double *out)
+{
+    out[0] = c->h->rep[0].ele_coef; out[1] = c->h->rep[0].lambdaD; out[2] = c->h->rep[0].ele_cutoff; out[3] = c->h->rep[0].diele;
+    return 0;
+}
+}

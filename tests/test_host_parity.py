@@ -1,0 +1,123 @@
+"""CPU-side parity of the PRODUCT's force / list code against the oracle.
+
+The product's term arithmetic, gather roles and list predicates are `__host__ __device__`
+code shared by the kernels; tests/csrc/hostcheck.cu compiles them for the host.  These tests
+run in the build container (no GPU) so that sign, role and exclusion-rule errors are caught
+before GPU time is spent; the GPU parity tests proper are tests/test_gpu_parity.py.
+"""
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from sis_b200 import fixtures as fx
+from sis_b200.system import SystemSpec
+from tests.hostcheck import HostCheck
+
+TERMS = {"bond": 1, "angl": 2, "dihe": 3, "bp": 4, "exv": 5, "ele": 6}
+
+
+def pairset(a):
+    return set(map(tuple, np.asarray(a)[:, :2].tolist()))
+
+
+def circ_spec():
+    """Two circular RNAs + one linear chain with a dummy bead: exercises the closure terms,
+    the circRNA exclusions of src/neighbor_list.F90:131-135,159-166 and SEQT%D handling."""
+    rng = np.random.default_rng(7)
+    seqs = ["GCGCAAUUGGCCAAGCUU", "AUGCGCAUAUGGCCAU", "GGDACUAGCUUAGCC"]
+    n = sum(map(len, seqs))
+    # compact random blob, ~6 A spacing along each chain
+    xyz = []
+    for s in seqs:
+        p = rng.normal(scale=15.0, size=3)
+        for _ in s:
+            step = rng.normal(size=3)
+            p = p + 5.8 * step / np.linalg.norm(step)
+            xyz.append(p.copy())
+    spec = SystemSpec(seqs=seqs, ff=fx.force_field("sis_dih_ReB_NN"), moltypes=[2, 2, 1], xyz=np.array(xyz),
+                      tempK=300.0, dt=0.05, bp_model=5, nstep_MC=0, flg_ele=True, ele_cutoff_type=2,
+                      ele_cutoff=10.0)
+    assert spec.nmp == n
+    return spec
+
+
+SPECS = {
+    "t2s2hp": lambda: fx.t2s2hp("T2S2HP_folded", nstep_MC=0),
+    "cag47_4_pbc": lambda: fx.cag47(4, pbc=True),
+    "circ": circ_spec,
+}
+
+
+def both(spec):
+    o, hcx = Oracle(), HostCheck()
+    spec.configure(o)
+    spec.configure(hcx)
+    return o, hcx
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+@pytest.mark.parametrize("full", [False, True])
+def test_lists_bit_exact(name, full):
+    spec = SPECS[name]()
+    o, hcx = both(spec)
+    if full:
+        o.full_lists()
+    else:
+        o.neighbor_list(0)
+    hcx.build_lists(all_pairs=full)
+    wo, eo, bo, co = o.get_lists(0)
+    wh, eh, bh, ch = hcx.lists()
+    assert pairset(wo) == pairset(wh)
+    assert pairset(eo) == pairset(eh)
+    assert pairset(bo) == pairset(bh)
+    # bp type and (dH, dS) per pair
+    do = {(r[0], r[1]): (r[6], tuple(c)) for r, c in zip(bo.tolist(), co.tolist())}
+    dh = {(r[0], r[1]): (r[2], tuple(c)) for r, c in zip(bh.tolist(), ch.tolist())}
+    assert do == dh
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+def test_forces_per_term(name):
+    spec = SPECS[name]()
+    o, hcx = both(spec)
+    o.neighbor_list(0)
+    hcx.build_lists(False)
+    x, _, _ = o.get_state(0)            # wrapped coordinates
+    assert np.allclose(x, hcx.xyz, rtol=0, atol=1e-12)
+    for term, bit in TERMS.items():
+        fo = o.force_terms(0, 1 << bit)
+        fh = hcx.force_terms(0, 1 << bit)
+        scale = max(np.abs(fo).max(), 1e-12)
+        assert np.abs(fo - fh).max() / scale < 1e-10, term
+    fo, fh = o.force(0), hcx.force_terms(0, 0x7FE)
+    assert np.abs(fo - fh).max() / np.abs(fo).max() < 1e-10
+
+
+def test_bp3_table_matches_oracle():
+    spec = fx.t2s2hp()
+    o, hcx = both(spec)
+    no, ho, dHo, dSo = o.bp3_table()
+    nh, hh, dHh, dSh = hcx.bp3_table()
+    assert no == nh == 468
+    assert (ho == hh).all()
+    assert np.array_equal(dHo, dHh) and np.array_equal(dSo, dSh)
+
+
+def test_rng_and_coefficients_match_oracle():
+    spec = fx.t2s2hp()
+    o, hcx = both(spec)
+    for stream, step, bead in [(0, 1, 0), (3, 12345678901, 26), (63, 2**40 + 5, 9023)]:
+        assert np.allclose(o.gauss(123, stream, step, bead), hcx.gauss(123, stream, step, bead), rtol=1e-13, atol=1e-15)
+        assert o.uniform(123, stream, step) == hcx.uniform(123, stream, step)
+    for imp in (0, 5, 26):
+        assert np.allclose(o.md_coef(0, imp), hcx.coef(imp), rtol=1e-14)
+    eo, eh = o.get_ele(0), hcx.rep_params()
+    for k in ("ele_coef", "lambdaD", "diele"):
+        assert eo[k] == pytest.approx(eh[k], rel=1e-15)
+
+
+def test_gauss_statistics():
+    hcx = HostCheck()
+    g = np.array([hcx.gauss(1, 0, s, b) for s in range(1, 60) for b in range(60)])
+    assert abs(g.mean()) < 0.03 and abs(g.std() - 1.0) < 0.03
+    assert abs(np.corrcoef(g[:, 0], g[:, 1])[0, 1]) < 0.03
