@@ -1,0 +1,100 @@
+"""Host-side mirror of the reference's hot-path interface on top of `libsisgpu.so`.
+
+`SisGpu` exposes the same calls the Fortran driver makes (`neighbor_list`, `force`,
+`energy_sumup`, `energy_replica`, `replica_exchange`, the `job_md` loop body as `md_steps`,
+`check_force`), with the reference's argument meaning, through the C ABI of
+`include/sisgpu.h`.  There is no CPU fallback: without the built library or without a CUDA
+device construction fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from ._capi import CApi, SisError, _d, _i, load_library
+
+LIB_PATH = Path(__file__).resolve().parent / "libsisgpu.so"
+_lib = None
+
+
+def library() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = load_library(LIB_PATH)
+    return _lib
+
+
+class SisGpu(CApi):
+    def __init__(self, device: int = 0, **options):
+        lib = library()
+        h = C.c_void_p()
+        lib.sisgpu_last_error.restype = C.c_char_p
+        if lib.sisgpu_create(C.byref(h), C.c_int(device)) != 0:
+            raise SisError("sisgpu_create: " + lib.sisgpu_last_error().decode())
+        super().__init__(lib, "sisgpu_", h)
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sisgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name: str, value: float):
+        self._call("set_option", C.c_char_p(name.encode()), C.c_double(value))
+
+    # ---- job_md loop body ----------------------------------------------------------
+    def md_steps(self, nsteps: int) -> int:
+        nreb = C.c_int64()
+        self._call("md_steps", C.c_int64(nsteps), C.byref(nreb))
+        return nreb.value
+
+    def get_step(self) -> int:
+        s = C.c_int64()
+        self._call("get_step", C.byref(s))
+        return s.value
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        self._call("launch_count", C.byref(n))
+        return n.value
+
+    def get_timers(self, reset=False) -> dict:
+        out = np.zeros(4)
+        self._call("get_timers", _d(out), C.c_int(int(reset)))
+        return dict(zip(["step_ms", "nl_ms", "energy_ms", "exchange_ms"], out.tolist()))
+
+    # ---- REMD ------------------------------------------------------------------------
+    def remd_setup(self, nrep, values, nstep_exchange, rank=0, nranks=1):
+        nr, vals = self._remd_args(nrep, values)
+        self._call("remd_setup", _i(nr), _d(vals), C.c_int(nstep_exchange), C.c_int(rank), C.c_int(nranks))
+
+    def remd_stats(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._call("remd_stats", C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def comm_init_torch(self):
+        """NCCL communicator for the exchange all-gather; the unique id travels over the
+        torch.distributed process group (the Fortran driver would MPI_BCAST it)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            if self.lib.sisgpu_nccl_unique_id(buf) != 0:
+                raise SisError(self._err().decode())
+        t = torch.tensor(list(buf), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, 0)
+        raw = bytes(t.cpu().tolist())
+        self._call("comm_init", C.c_int(world), C.c_int(rank), C.c_char_p(raw))

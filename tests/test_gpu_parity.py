@@ -1,0 +1,163 @@
+"""GPU parity tests proper: the CUDA path, through the C ABI, against the CPU oracle on the same
+seeded inputs (bit-exact lists, 1e-10 forces / energies), plus size-independent properties at
+the benchmark sizes."""
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from sis_b200 import fixtures as fx
+from sis_b200 import synth
+from tests.test_host_parity import SPECS, TERMS, pairset
+
+pytestmark = pytest.mark.gpu
+
+FORCE_TOL = 1e-10   # norm-relative, fp64 mode (north_star)
+
+
+def gpu():
+    from sis_b200.api import SisGpu
+    return SisGpu(0)
+
+
+def both(spec):
+    g, o = gpu(), Oracle()
+    spec.configure(g)
+    spec.configure(o)
+    return g, o
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+@pytest.mark.parametrize("full", [False, True])
+def test_lists_bit_exact(name, full):
+    spec = SPECS[name]()
+    g, o = both(spec)
+    if full:
+        g.full_lists(); o.full_lists()
+    else:
+        g.neighbor_list(0); o.neighbor_list(0)
+    wg, eg, bg, cg = g.get_lists(0)
+    wo, eo, bo, co = o.get_lists(0)
+    # identical index sets AND identical order (the reference's loop order)
+    assert np.array_equal(wg, wo)
+    assert np.array_equal(eg, eo)
+    assert np.array_equal(bg, bo)
+    assert np.array_equal(cg, co)
+    xg, _, _ = g.get_state(0)
+    xo, _, _ = o.get_state(0)
+    assert np.array_equal(xg, xo)   # pbc_wrap is bit-exact
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+def test_forces_and_energies(name):
+    spec = SPECS[name]()
+    g, o = both(spec)
+    g.neighbor_list(0); o.neighbor_list(0)
+    for term, bit in TERMS.items():
+        assert rel(g.force_terms(0, 1 << bit), o.force_terms(0, 1 << bit)) < FORCE_TOL, term
+    assert rel(g.force(0), o.force(0)) < FORCE_TOL
+    eg = g.energy_sumup(0, spec.tempK, True)
+    eo = o.energy_sumup(0, spec.tempK, True)
+    assert np.allclose(eg, eo, rtol=1e-10, atol=1e-9), (eg, eo)
+    # cached bp energies from the force pass (flg_bp_energy = .True.)
+    g.force(0); o.force(0)
+    assert np.allclose(g.energy_sumup(0, spec.tempK, False), o.energy_sumup(0, spec.tempK, False), rtol=1e-10, atol=1e-9)
+    sg, ng = g.get_bp_state(0)
+    so, no = o.get_bp_state(0)
+    assert np.array_equal(sg, so)
+    assert np.allclose(ng, no, rtol=1e-10, atol=1e-12)
+
+
+def test_c4_lists_forces_vs_oracle():
+    """64 x CAG47 in the 809.972 A box (BASELINE config 4): cell-grid lists == O(N^2) oracle."""
+    spec = synth.c4()
+    g, o = both(spec)
+    g.neighbor_list(0); o.neighbor_list(0)
+    assert g.get_list_sizes(0) == o.get_list_sizes(0)
+    wg, eg, bg, cg = g.get_lists(0)
+    wo, eo, bo, co = o.get_lists(0)
+    assert np.array_equal(wg, wo) and np.array_equal(eg, eo) and np.array_equal(bg, bo)
+    assert rel(g.force(0), o.force(0)) < FORCE_TOL
+    assert np.allclose(g.energy_sumup(0, spec.tempK, True), o.energy_sumup(0, spec.tempK, True), rtol=1e-10, atol=1e-8)
+
+
+@pytest.mark.parametrize("name", ["t2s2hp", "cag47_4_pbc"])
+def test_trajectory_matches_oracle_short(name):
+    """Same counter-based Gaussians on both sides: the GJF-2GJ update (src/job_md.F90:415-444) must
+    track the oracle over a short run (divergence grows chaotically, so the window is short)."""
+    spec = SPECS[name]()
+    g, o = both(spec)
+    g.init_velocities(0); o.init_velocities(0)
+    xg, vg, ag = g.get_state(0)
+    xo, vo, ao = o.get_state(0)
+    assert np.allclose(vg, vo, rtol=1e-12, atol=1e-14) and np.allclose(ag, ao, rtol=1e-12, atol=1e-16)
+    g.neighbor_list(0); o.neighbor_list(0)
+    g.md_steps(25)
+    o.md_run(25)
+    xg, vg, ag = g.get_state(0)
+    xo, vo, ao = o.get_state(0)
+    assert np.abs(xg - xo).max() < 1e-8
+    assert np.abs(vg - vo).max() < 1e-9
+    assert g.get_step() == 25
+
+
+def test_rebuild_trigger_matches_oracle():
+    """Displacement top-2 test (src/job_md.F90:376-395): same rebuild count as the oracle over a
+    run long enough to cross the margin several times (small margin to force rebuilds)."""
+    spec = fx.cag47(4, pbc=True)
+    spec.nl_margin = 1.0
+    g, o = both(spec)
+    g.init_velocities(0); o.init_velocities(0)
+    g.neighbor_list(0); o.neighbor_list(0)
+    nreb_g = g.md_steps(120)
+    nreb_o = o.md_run(120)
+    assert nreb_g == nreb_o and nreb_g >= 2
+    xg, _, _ = g.get_state(0)
+    xo, _, _ = o.get_state(0)
+    assert np.abs(xg - xo).max() < 1e-6
+
+
+def test_check_force_job():
+    """job_check_force through the C ABI: |f_energy - f_force| <= 1e-3 (src/job_check_force.F90:21,78)."""
+    spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=0)
+    rng = np.random.default_rng(5)
+    spec.xyz = spec.xyz + 0.001 * rng.random(spec.xyz.shape)
+    g, o = both(spec)
+    g.full_lists(); o.full_lists()
+    fe, ff, md = g.check_force(spec.tempK)
+    feo, ffo, mdo = o.check_force(spec.tempK)
+    assert md <= 1e-3
+    assert rel(ff, ffo) < FORCE_TOL
+    assert np.abs(fe - feo).max() < 1e-6
+
+
+def test_c4_properties_long_run():
+    """Benchmark-size properties: finite coordinates, momentum-free forces, bounded bonds, lists
+    stay supersets of the exact cutoff sets after rebuild-driven dynamics."""
+    spec = synth.c4()
+    g = gpu()
+    spec.configure(g)
+    g.init_velocities(0)
+    g.neighbor_list(0)
+    nreb = g.md_steps(600)
+    x, v, a = g.get_state(0)
+    assert np.isfinite(x).all() and np.isfinite(v).all()
+    f = g.force(0)
+    assert np.abs(f.sum(axis=0)).max() < 1e-7
+    d = np.linalg.norm(np.diff(x.reshape(64, 141, 3), axis=1), axis=2)
+    assert d.min() > 4.0 and d.max() < 8.0
+    # temperature from kinetic energy (GJF-2GJ half-step velocity): within 10 % of 310.15 K
+    ek = g.energy_kinetic(0)
+    T = 2.0 * ek / (3 * spec.nmp * 0.0019872042586408316)
+    assert abs(T / spec.tempK - 1.0) < 0.1, T
+    # after the run: rebuild on both sides and compare exactly
+    o = Oracle()
+    spec.configure(o)
+    o.set_state(0, x)
+    g.neighbor_list(0); o.neighbor_list(0)
+    assert g.get_list_sizes(0) == o.get_list_sizes(0)
+    assert rel(g.force(0), o.force(0)) < FORCE_TOL
+    assert nreb >= 1
