@@ -118,6 +118,10 @@ def main():
     ap.add_argument("--md-steps", type=int, default=1000, help="MD steps per contract step (chunk)")
     ap.add_argument("--ref-md-steps", type=int, default=20)
     ap.add_argument("--cpu-baseline-steps", type=int, default=200)
+    ap.add_argument("--launch-mode", type=int, default=None, help="0 stream launches, 1 CUDA-graph chunks")
+    ap.add_argument("--chunk", type=int, default=None)
+    ap.add_argument("--tpb", type=int, default=None, help="lanes per bead in the pair task")
+    ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -134,6 +138,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     spec, wl = build_system(args)
     g = SisGpu(local)
+    for name, val in (("launch_mode", args.launch_mode), ("chunk", args.chunk), ("threads_per_bead", args.tpb)):
+        if val is not None:
+            g.set_option(name, val)
     spec.configure(g)
     if world > 1:
         temps = [spec.tempK + 2.0 * k for k in range(world)]
@@ -224,6 +231,8 @@ def main():
         }
         # CPU baseline (oracle port, bounded sample) on this box's host cores
         try:
+            if args.no_cpu:
+                raise RuntimeError("skipped (--no-cpu)")
             from oracle.oracle import Oracle
             o = Oracle(omp=True)
             spec.configure(o)

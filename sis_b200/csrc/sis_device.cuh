@@ -252,10 +252,10 @@ SIS_HD double dh_energy(const FFParams &P, const RepParams &R, double d2)
 // Force side of src/force_bp.F90:50-204 / force_bp_triplet.F90:62-240 / pass 1 of
 // force_bp_limit_triplet.F90:85-257.  x[0..5] = beads i, j, i-1, j-1, i+1, j+1.
 // Returns false when the distance gate |r12 - r0| > cutoff_ddist fails.  On success *u_out is
-// the exponent and *frole the (unscaled) d(u)/dr contribution on bead `role` (0..5).
+// the exponent and f[0..5] the (unscaled) d(u)/dr contributions on the six beads.
 // acos arguments are NOT clamped here, exactly as in the reference's force routines.
-SIS_HD bool bp_force_role(const FFParams &P, const BpPara &p, const Vec3 *x, int role, double *u_out,
-                          Vec3 *frole, double *a12_out, Vec3 *v12_out)
+SIS_HD bool bp_force_all(const FFParams &P, const BpPara &p, const Vec3 *x, double *u_out, Vec3 *f,
+                         double *a12_out, Vec3 *v12_out)
 {
     Vec3 v12 = pbc_vec_d(P, x[0], x[1]);
     double d1212 = dot(v12, v12), a12 = sqrt(d1212);
@@ -264,7 +264,6 @@ SIS_HD bool bp_force_role(const FFParams &P, const BpPara &p, const Vec3 *x, int
     *v12_out = v12;
     if (fabs(d) > p.cutoff_ddist) return false;
     double u = p.bond_k * d * d;
-    Vec3 f[6];
 #pragma unroll
     for (int s = 0; s < 6; s++) f[s] = mk(0.0, 0.0, 0.0);
     Vec3 fi = (2.0 * p.bond_k * d / a12) * v12, fk, fl;
@@ -335,11 +334,6 @@ SIS_HD bool bp_force_role(const FFParams &P, const BpPara &p, const Vec3 *x, int
     f[0] += (-1.0 + r1215) * fl - r1262 * fi;
     f[4] += fl;
     *u_out = u;
-    Vec3 r = f[0];
-#pragma unroll
-    for (int s = 1; s < 6; s++)
-        if (role == s) r = f[s];
-    *frole = r;
     return true;
 }
 

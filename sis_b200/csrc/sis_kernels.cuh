@@ -31,7 +31,9 @@ struct GridInfo {
 };
 
 struct DevSys {
-    int nmp, nrep, K, KB, nblk;   // nblk = step-kernel blocks per replica
+    int nmp, nrep, K, KB;
+    int nblk;                     // integrate-kernel blocks per replica (64 beads each)
+    int nblk_ene;                 // energy-kernel blocks per replica
     // topology
     const int4 *meta;
     const int *seq;
@@ -43,6 +45,7 @@ struct DevSys {
     double4 *pos[2];
     double *vel, *acc, *move;     // [rep][nmp][3]
     double *force;                // [rep][nmp][3]
+    double *f_pair, *f_loc, *f_bp;  // partial forces of the three task families [rep][nmp][3]
     // lists
     uint32_t *nbr;                // [rep][nmp][K]
     int *nnbr;                    // [rep][nmp]
@@ -52,6 +55,9 @@ struct DevSys {
     double2 *bp_coef;             // dH, dS*1e-3
     int *bp_status, *bp_status_MC;
     double *ene_bp;
+    int *bp_half;                 // [rep][bp_half_cap] compact list of owner ibp
+    int *nbp_half;                // [rep]
+    int bp_half_cap;
     int *nt_excess;               // [rep][nmp]
     unsigned long long *mc_counter;  // [rep]
     // cell grid [rep][...]
@@ -81,6 +87,8 @@ struct StepArgs {
     unsigned term_mask;   // bit k = energies index k
     int use_mask;         // 0 all pairs; 1 only bp_status_MC (nstep_bp_MC > 0); 2 only bp_status
     int only_rep;         // >= 0: single replica (per-irep API); -1: all (grid.y)
+    int integrate;        // 1: MD step (job_md loop body); 0: force() only
+    int nblk_pair, nblk_loc;
 };
 
 // sum over the G lanes that own one bead.  Host builds (tests/csrc/hostcheck.cu) run the same
@@ -97,35 +105,51 @@ SIS_HD double group_sum(double v)
     return v;
 }
 
-// ---- shared force evaluation: complete force on bead k, lane-partial -----------------------
+// ---- force tasks --------------------------------------------------------------------------
+// The step is three concurrent task families (DESIGN.md "step graph"):
+//   pair   : GP lanes own bead k and stream its FULL neighbour row (WCA + DH), plain store
+//   local  : 8 lanes own bead k: the 9 bonded term instances k takes part in + per-bead biases
+//   bp     : one thread per base-pair candidate (half list), 6-bead scatter with fp64 atomics
+// followed by the integrate kernel that sums the three partial forces.
+
+// src/force_wca.F90:34-66, src/force_ele_DH.F90:39-81 in gather form (lane-partial sum)
 template <int G>
-SIS_HD Vec3 bead_force(const DevSys &S, const FFParams &P, const RepParams &R, const double4 *__restrict__ pos,
-                      int rep, int k, int lane, unsigned term_mask, int use_mask, unsigned long long istep,
-                      int write_bp)
+SIS_HD Vec3 pair_force(const DevSys &S, const FFParams &P, const RepParams &R, const double4 *__restrict__ pos,
+                       int rep, int k, int lane, unsigned term_mask)
 {
+    Vec3 F = mk(0.0, 0.0, 0.0);
+    if (!(term_mask & ((1u << ENE_EXV) | (1u << ENE_ELE)))) return F;
+    const int nmp = S.nmp;
+    const Vec3 xk = v3(pos[k]);
+    const uint32_t *row = S.nbr + ((size_t)rep * nmp + k) * S.K;
+    const int nn = S.nnbr[(size_t)rep * nmp + k];
+    const double cut2 = R.ele_cutoff * R.ele_cutoff;
+    const bool do_wca = term_mask & (1u << ENE_EXV);
+    const bool do_ele = (term_mask & (1u << ENE_ELE)) && P.flg_ele;
+    for (int e = lane; e < nn; e += G) {
+        const uint32_t ent = row[e];
+        const Vec3 v = pbc_vec_d(P, xk, v3(pos[ent & NB_IDX]));
+        const double d2 = dot(v, v);
+        double s = 0.0;
+        if (do_wca && (ent & NB_WCA) && d2 < P.wca_sigma2) s += wca_scalar(P, d2);
+        if (do_ele && (ent & NB_ELE) && d2 <= cut2) s += dh_scalar(R.ele_coef, R.inv_lambdaD, d2);
+        F += s * v;
+    }
+    return F;
+}
+
+// bonded terms (src/force_bond.F90, force_angl*.F90, force_dih_*.F90), one term instance per
+// lane: 2 bonds, 3 angles, 4 dihedrals; plus the per-bead biases on one lane
+// (src/force_stage.F90, force_tweezers.F90, force_rg.F90, force_restraint.F90)
+template <int G>
+SIS_HD Vec3 local_force(const DevSys &S, const FFParams &P, const RepParams &R, const double4 *__restrict__ pos,
+                        int rep, int k, int lane, unsigned term_mask, unsigned long long istep)
+{
+    (void)rep;
     const int nmp = S.nmp;
     const int4 mk4 = S.meta[k];
     const Vec3 xk = v3(pos[k]);
     Vec3 F = mk(0.0, 0.0, 0.0);
-
-    // -- pair loop: src/force_wca.F90:34-66, src/force_ele_DH.F90:39-81 ----------------------
-    if (term_mask & ((1u << ENE_EXV) | (1u << ENE_ELE))) {
-        const uint32_t *row = S.nbr + ((size_t)rep * nmp + k) * S.K;
-        const int nn = S.nnbr[(size_t)rep * nmp + k];
-        const double cut2 = R.ele_cutoff * R.ele_cutoff;
-        const bool do_wca = term_mask & (1u << ENE_EXV);
-        const bool do_ele = (term_mask & (1u << ENE_ELE)) && P.flg_ele;
-        for (int e = lane; e < nn; e += G) {
-            uint32_t ent = row[e];
-            Vec3 v = pbc_vec_d(P, xk, v3(pos[ent & NB_IDX]));
-            double d2 = dot(v, v), s = 0.0;
-            if (do_wca && (ent & NB_WCA) && d2 < P.wca_sigma2) s += wca_scalar(P, d2);
-            if (do_ele && (ent & NB_ELE) && d2 <= cut2) s += dh_scalar(R.ele_coef, R.inv_lambdaD, d2);
-            F += s * v;
-        }
-    }
-
-    // -- bonded terms, one instance per lane: 2 bonds, 3 angles, 4 dihedrals -------------------
     for (int inst = lane; inst < 9; inst += G) {
         int kind, p;   // kind 0 bond, 1 angle, 2 dihedral; p = position of k in the term
         if (inst < 2) { kind = 0; p = inst; }
@@ -135,7 +159,7 @@ SIS_HD Vec3 bead_force(const DevSys &S, const FFParams &P, const RepParams &R, c
         const bool on = (kind == 0) ? (term_mask & (1u << ENE_BOND))
                         : (kind == 1) ? (term_mask & (1u << ENE_ANGL))
                                       : ((term_mask & (1u << ENE_DIHE)) && (P.flg_dih_cos || P.flg_dih_exp));
-        // first bead a = k - p; term exists iff a and a+span exist (circRNA: always, n > span)
+        // first bead a = k - p; the term exists iff a and a+span exist (circRNA: always, n > span)
         bool exists;
         if (mk4.w & MF_CIRC) exists = mk4.y > span;
         else exists = (mk4.z - p >= 0) && (mk4.z - p + span < mk4.y);
@@ -152,73 +176,7 @@ SIS_HD Vec3 bead_force(const DevSys &S, const FFParams &P, const RepParams &R, c
             F += f;
         }
     }
-
-    // -- base pairs: rows of k (roles i/j), k+1 (k is the i-1/j-1 bead), k-1 (i+1/j+1) ---------
-    if (term_mask & (1u << ENE_BP)) {
-        const size_t rbase = (size_t)rep * nmp;
-        const size_t pbase = rbase * S.KB;
-        for (int cc = 0; cc < 3; cc++) {
-            const int c = (cc == 0) ? k : chain_nb(mk4, cc == 1 ? 1 : -1);
-            if (c < 0) continue;
-            const int nrow = S.nbp_row[rbase + c];
-            for (int e0 = 0; e0 < nrow; e0 += G) {
-                const int e = e0 + lane;
-                bool pass = false;
-                int j = 0, ibp = 0, role = 0, bi = 0, bj = 0, type = 1;
-                double dG = 1.0, a12 = 1.0;
-                Vec3 xs[6], v12 = mk(0, 0, 0);
-                if (e < nrow) {
-                    int2 ent = S.bprow[(rbase + c) * S.KB + e];
-                    j = ent.x; ibp = ent.y;
-                    bi = min(c, j); bj = max(c, j);
-                    if (cc == 0) role = (k == bi) ? 0 : 1;
-                    else if (cc == 1) role = (c == bi) ? 2 : 3;
-                    else role = (c == bi) ? 4 : 5;
-                    bool active = true;
-                    if (use_mask == 1) active = S.bp_status_MC[pbase + ibp] != 0;
-                    else if (use_mask == 2) active = S.bp_status[pbase + ibp] != 0;
-                    type = S.bp_type[pbase + ibp];
-                    if (P.bp_triplet) {
-                        double2 cf = S.bp_coef[pbase + ibp];
-                        dG = cf.x - R.tempK * cf.y;     // src/force_bp_triplet.F90:77
-                        if (dG >= 0.0) active = false;
-                    }
-                    if (active) {
-                        xs[0] = v3(pos[bi]); xs[1] = v3(pos[bj]);
-                        v12 = pbc_vec_d(P, xs[0], xs[1]);
-                        a12 = sqrt(dot(v12, v12));
-                        pass = fabs(a12 - P.bp[type].bond_r) <= P.bp[type].cutoff_ddist;
-                        if (!pass && P.bp_triplet && P.flg_bias_ss && role < 2) {
-                            Vec3 t = (P.bias_ss_force / a12) * v12;   // force_bp_triplet.F90:85-93
-                            if (role == 0) F -= t; else F += t;
-                        }
-                    }
-                    if (!pass && write_bp && cc == 0 && role == 0) {
-                        S.bp_status[pbase + ibp] = 0;
-                        S.ene_bp[pbase + ibp] = 0.0;
-                    }
-                }
-                // lanes that passed the gate evaluate the 6-body term
-                if (pass) {
-                    const int4 mi = S.meta[bi], mj = S.meta[bj];
-                    xs[2] = v3(pos[chain_nb(mi, -1)]); xs[3] = v3(pos[chain_nb(mj, -1)]);
-                    xs[4] = v3(pos[chain_nb(mi, +1)]); xs[5] = v3(pos[chain_nb(mj, +1)]);
-                    double u; Vec3 fr;
-                    bp_force_role(P, P.bp[type], xs, role, &u, &fr, &a12, &v12);
-                    double ene = P.bp_triplet ? P.bp[type].U0 * dG * exp(-u) : P.bp[type].U0 * exp(-u);
-                    bool ok = ene <= P.bp_cutoff_energy;
-                    if (ok) F += ene * fr;
-                    if (write_bp && cc == 0 && role == 0) {
-                        S.bp_status[pbase + ibp] = ok ? 1 : 0;
-                        S.ene_bp[pbase + ibp] = ok ? ene : 0.0;
-                    }
-                }
-            }
-        }
-    }
-
-    // -- per-bead biases (lane 0) --------------------------------------------------------------
-    if (lane == 0) {
+    if (lane == (G > 9 ? 9 : 0)) {
         if ((term_mask & (1u << ENE_STAGE)) && P.flg_stage) {   // src/force_stage.F90:17-37
             double z = xk.z;
             if (z < SIS_SMALL_VALUE) z = SIS_SMALL_VALUE;
@@ -262,10 +220,59 @@ SIS_HD Vec3 bead_force(const DevSys &S, const FFParams &P, const RepParams &R, c
             }
         }
     }
-    F.x = group_sum<G>(F.x);
-    F.y = group_sum<G>(F.y);
-    F.z = group_sum<G>(F.z);
     return F;
+}
+
+// one base-pair candidate (owner bead k, row slot e): src/force_bp.F90:50-204,
+// force_bp_triplet.F90:62-240.  Returns how many bead forces to scatter (0, 2 for the Bias_SS
+// branch, 6) into beads[] / f[]; writes bp_status / ene_bp when write_bp.
+// use_mask: 0 all pairs; 1 only bp_status_MC; 2 only bp_status (after the MC pruning)
+SIS_HD int bp_pair_force(const DevSys &S, const FFParams &P, const RepParams &R, const double4 *__restrict__ pos,
+                         int rep, int k, int e, int use_mask, int write_bp, int *beads, Vec3 *f)
+{
+    const int nmp = S.nmp;
+    const size_t rbase = (size_t)rep * nmp, pbase = rbase * S.KB;
+    const int2 ent = S.bprow[(rbase + k) * S.KB + e];
+    const int j = ent.x, ibp = ent.y;
+    bool active = true;
+    if (use_mask == 1) active = S.bp_status_MC[pbase + ibp] != 0;
+    else if (use_mask == 2) active = S.bp_status[pbase + ibp] != 0;
+    const int type = S.bp_type[pbase + ibp];
+    double dG = 1.0;
+    if (P.bp_triplet) {
+        const double2 cf = S.bp_coef[pbase + ibp];
+        dG = cf.x - R.tempK * cf.y;     // src/force_bp_triplet.F90:77
+        if (dG >= 0.0) active = false;
+    }
+    int nout = 0, st = 0;
+    double en = 0.0;
+    if (active) {
+        const int4 mi = S.meta[k], mj = S.meta[j];
+        beads[0] = k; beads[1] = j;
+        beads[2] = chain_nb(mi, -1); beads[3] = chain_nb(mj, -1);
+        beads[4] = chain_nb(mi, +1); beads[5] = chain_nb(mj, +1);
+        Vec3 xs[6];
+#pragma unroll
+        for (int s = 0; s < 6; s++) xs[s] = v3(pos[beads[s]]);
+        double u, a12;
+        Vec3 v12;
+        if (bp_force_all(P, P.bp[type], xs, &u, f, &a12, &v12)) {
+            const double ene = P.bp_triplet ? P.bp[type].U0 * dG * exp(-u) : P.bp[type].U0 * exp(-u);
+            if (ene <= P.bp_cutoff_energy) {
+                st = 1; en = ene; nout = 6;
+#pragma unroll
+                for (int s = 0; s < 6; s++) f[s] = ene * f[s];
+            }
+        } else if (P.bp_triplet && P.flg_bias_ss) {   // src/force_bp_triplet.F90:85-93
+            const Vec3 t = (P.bias_ss_force / a12) * v12;
+            f[0] = -t; f[1] = t; nout = 2;
+        }
+    }
+    if (write_bp) {
+        S.bp_status[pbase + ibp] = st;
+        S.ene_bp[pbase + ibp] = en;
+    }
+    return nout;
 }
 
 // merge two (max, second max) pairs
@@ -276,66 +283,116 @@ SIS_D void top2_merge(double &a1, double &a2, double b1, double b2)
     a1 = m1; a2 = m2;
 }
 
-// ---- the MD step: force + integrate in one launch (src/job_md.F90:376-460) -------------------
-// MODE 0: integrate (writes buffer cur^1);  MODE 1: forces only (writes S.force, per-irep API)
-template <int G, int MODE>
-__global__ void __launch_bounds__(256) k_step(DevSys S, FFParams P, StepArgs A)
+// pair + local task kernel: blocks [0, nblk_pair) run the pair role with GP lanes per bead,
+// blocks [nblk_pair, nblk_pair + nblk_loc) the local role with 8 lanes per bead
+template <int GP>
+__global__ void __launch_bounds__(256, 4) k_force_local(DevSys S, FFParams P, StepArgs A)
 {
-    constexpr int BPB = 256 / G;   // beads per block
     const DevCtl ctl = *S.ctl;
-    if (MODE == 0 && ctl_aborted(ctl)) return;
+    if (A.integrate && ctl_aborted(ctl)) return;
     const int rep = (A.only_rep >= 0) ? A.only_rep : blockIdx.y;
-    const int lane = threadIdx.x % G;
-    const int kraw = blockIdx.x * BPB + threadIdx.x / G;
     const int nmp = S.nmp;
-    const bool valid = kraw < nmp;
-    const int k = valid ? kraw : nmp - 1;   // tail groups shadow the last bead (no writes)
     const double4 *pos = S.pos[ctl.cur] + (size_t)rep * nmp;
     const RepParams R = S.rp[rep];
-    const unsigned long long istep = ctl.step + (MODE == 0 ? 1ull : 0ull);
-
-    const Vec3 F = bead_force<G>(S, P, R, pos, rep, k, lane, A.term_mask, A.use_mask, istep,
-                                 valid && A.use_mask != 2);
-
-    if (MODE == 1) {
-        if (valid && lane < 3) S.force[((size_t)rep * nmp + k) * 3 + lane] = lane == 0 ? F.x : lane == 1 ? F.y : F.z;
-        return;
+    const unsigned long long istep = ctl.step + (A.integrate ? 1ull : 0ull);
+    if ((int)blockIdx.x < A.nblk_pair) {
+        constexpr int BPB = 256 / GP;
+        const int lane = threadIdx.x % GP;
+        const int kraw = blockIdx.x * BPB + threadIdx.x / GP;
+        const bool valid = kraw < nmp;
+        const int k = valid ? kraw : nmp - 1;   // tail groups shadow the last bead (no writes)
+        Vec3 F = pair_force<GP>(S, P, R, pos, rep, k, lane, A.term_mask);
+        F.x = group_sum<GP>(F.x); F.y = group_sum<GP>(F.y); F.z = group_sum<GP>(F.z);
+        if (valid && lane < 3) S.f_pair[((size_t)rep * nmp + k) * 3 + lane] = lane == 0 ? F.x : lane == 1 ? F.y : F.z;
+    } else {
+        constexpr int GL = 8, BPB = 256 / GL;
+        const int lane = threadIdx.x % GL;
+        const int kraw = (blockIdx.x - A.nblk_pair) * BPB + threadIdx.x / GL;
+        const bool valid = kraw < nmp;
+        const int k = valid ? kraw : nmp - 1;
+        Vec3 F = local_force<GL>(S, P, R, pos, rep, k, lane, A.term_mask, istep);
+        F.x = group_sum<GL>(F.x); F.y = group_sum<GL>(F.y); F.z = group_sum<GL>(F.z);
+        if (valid && lane < 3) S.f_loc[((size_t)rep * nmp + k) * 3 + lane] = lane == 0 ? F.x : lane == 1 ? F.y : F.z;
     }
+}
 
-    // integrate: lanes 0..2 own x, y, z (src/job_md.F90:415-456)
+// bp task kernel: one thread per half-list candidate
+__global__ void __launch_bounds__(128) k_force_bp(DevSys S, FFParams P, StepArgs A)
+{
+    const DevCtl ctl = *S.ctl;
+    if (A.integrate && ctl_aborted(ctl)) return;
+    const int rep = (A.only_rep >= 0) ? A.only_rep : blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S.nbp_half[rep]) return;
+    const int nmp = S.nmp;
+    const int ibp = S.bp_half[(size_t)rep * S.bp_half_cap + t];
+    const double4 *pos = S.pos[ctl.cur] + (size_t)rep * nmp;
+    const RepParams R = S.rp[rep];
+    int beads[6];
+    Vec3 f[6];
+    const int n = bp_pair_force(S, P, R, pos, rep, ibp / S.KB, ibp % S.KB, A.use_mask, A.use_mask != 2, beads, f);
+    double *fb = S.f_bp + (size_t)rep * nmp * 3;
+    for (int s = 0; s < n; s++) {
+        atomicAdd(fb + 3 * beads[s], f[s].x);
+        atomicAdd(fb + 3 * beads[s] + 1, f[s].y);
+        atomicAdd(fb + 3 * beads[s] + 2, f[s].z);
+    }
+}
+
+// integrate (src/job_md.F90:409-456) + displacement top-2 (src/job_md.F90:376-388).
+// 4 lanes per bead, lanes 0..2 own x, y, z.  integrate == 0: only sums the partial forces into
+// S.force (the per-irep force() API).  Consumes and clears the bp scatter buffer.
+__global__ void __launch_bounds__(256) k_integrate(DevSys S, FFParams P, StepArgs A)
+{
+    const DevCtl ctl = *S.ctl;
+    if (A.integrate && ctl_aborted(ctl)) return;
+    const int rep = (A.only_rep >= 0) ? A.only_rep : blockIdx.y;
+    const int lane = threadIdx.x % 4;
+    const int k = blockIdx.x * 64 + threadIdx.x / 4;
+    const int nmp = S.nmp;
+    const bool valid = k < nmp;
+    const double4 *pos = S.pos[ctl.cur] + (size_t)rep * nmp;
+    const RepParams R = S.rp[rep];
+    const unsigned long long istep = ctl.step + 1ull;
     double xnew = 0.0, mv = 0.0;
     if (valid && lane < 3) {
-        const double4 xo = pos[k];
         const size_t o = ((size_t)rep * nmp + k) * 3 + lane;
-        const double4 c = S.coef[k];
-        const double f = lane == 0 ? F.x : lane == 1 ? F.y : F.z;
-        const double x = lane == 0 ? xo.x : lane == 1 ? xo.y : xo.z;
-        const double g = gauss_component(A.seed, (uint32_t)R.stream, istep, (uint32_t)k, lane);
-        double dx;
-        if (P.integrator == 1) {   // GJF-2GJ
-            const double accels_pre = (c.w * R.sqrt_tempK) * g;
-            const double v = c.x * S.vel[o] + c.y * f + (S.acc[o] + accels_pre);
-            S.vel[o] = v;
-            S.acc[o] = accels_pre;
-            dx = c.z * v;
-        } else {                   // Ermak-McCammon
-            dx = c.x * f + (c.w * R.sqrt_tempK) * g;
+        const double f = S.f_pair[o] + S.f_loc[o] + S.f_bp[o];
+        S.f_bp[o] = 0.0;
+        if (!A.integrate) {
+            S.force[o] = f;
+        } else {
+            const double4 xo = pos[k];
+            const double4 c = S.coef[k];
+            const double x = lane == 0 ? xo.x : lane == 1 ? xo.y : xo.z;
+            const double g = gauss_component(A.seed, (uint32_t)R.stream, istep, (uint32_t)k, lane);
+            double dx;
+            if (P.integrator == 1) {   // GJF-2GJ
+                const double accels_pre = (c.w * R.sqrt_tempK) * g;
+                const double v = c.x * S.vel[o] + c.y * f + (S.acc[o] + accels_pre);
+                S.vel[o] = v;
+                S.acc[o] = accels_pre;
+                dx = c.z * v;
+            } else {                   // Ermak-McCammon
+                dx = c.x * f + (c.w * R.sqrt_tempK) * g;
+            }
+            xnew = x + dx;
+            mv = S.move[o] + dx;
+            S.move[o] = mv;
+            if (f > 100.0) S.ctl->max_force_flag = 1;
         }
-        xnew = x + dx;
-        mv = S.move[o] + dx;
-        S.move[o] = mv;
-        if (f > 100.0) S.ctl->max_force_flag = 1;
     }
-    const double nx = __shfl_sync(0xffffffffu, xnew, 0, G);
-    const double ny = __shfl_sync(0xffffffffu, xnew, 1, G);
-    const double nz = __shfl_sync(0xffffffffu, xnew, 2, G);
-    const double s0 = __shfl_sync(0xffffffffu, mv, 0, G);
-    const double s1 = __shfl_sync(0xffffffffu, mv, 1, G);
-    const double s2 = __shfl_sync(0xffffffffu, mv, 2, G);
+    if (!A.integrate) return;
+    const double nx = __shfl_sync(0xffffffffu, xnew, 0, 4);
+    const double ny = __shfl_sync(0xffffffffu, xnew, 1, 4);
+    const double nz = __shfl_sync(0xffffffffu, xnew, 2, 4);
+    const double s0 = __shfl_sync(0xffffffffu, mv, 0, 4);
+    const double s1 = __shfl_sync(0xffffffffu, mv, 1, 4);
+    const double s2 = __shfl_sync(0xffffffffu, mv, 2, 4);
     const double d2 = s0 * s0 + s1 * s1 + s2 * s2;
     if (valid && lane == 0) S.pos[ctl.cur ^ 1][(size_t)rep * nmp + k] = make_double4(nx, ny, nz, 0.0);
 
-    // displacement top-2 (src/job_md.F90:376-388) -> rebuild request for the NEXT step
+    // displacement top-2 -> rebuild request for the NEXT step
     __shared__ double s_t1[8], s_t2[8];
     __shared__ bool s_last;
     double t1 = (valid && lane == 0) ? d2 : 0.0, t2 = 0.0;
@@ -430,8 +487,8 @@ __global__ void __launch_bounds__(256) k_bp_eval(DevSys S, FFParams P, int only_
         xs[0] = v3(pos[k]); xs[1] = v3(pos[j]);
         xs[2] = v3(pos[chain_nb(mi, -1)]); xs[3] = v3(pos[chain_nb(mj, -1)]);
         xs[4] = v3(pos[chain_nb(mi, +1)]); xs[5] = v3(pos[chain_nb(mj, +1)]);
-        double u, a12; Vec3 fr, v12;
-        bool pass = (SIDE == 0) ? bp_force_role(P, P.bp[type], xs, 0, &u, &fr, &a12, &v12)
+        double u, a12; Vec3 fr[6], v12;
+        bool pass = (SIDE == 0) ? bp_force_all(P, P.bp[type], xs, &u, fr, &a12, &v12)
                                 : bp_energy_u(P, P.bp[type], xs, &u);
         if (pass) {
             double ene = P.bp_triplet ? P.bp[type].U0 * dG * exp(-u) : P.bp[type].U0 * exp(-u);
@@ -666,21 +723,21 @@ __global__ void __launch_bounds__(256) k_energy(DevSys S, FFParams P, const RepP
     if (threadIdx.x < ENE_N && threadIdx.x > 0) {
         double v = 0;
         for (int w = 0; w < 8; w++) v += sh[w][threadIdx.x];
-        S.ene_partial[((size_t)rep * S.nblk + blockIdx.x) * ENE_N + threadIdx.x] = v;
+        S.ene_partial[((size_t)rep * S.nblk_ene + blockIdx.x) * ENE_N + threadIdx.x] = v;
     }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned int done = atomicAdd(&S.ene_counter[rep], 1u);
-        s_last = (done == (unsigned)S.nblk - 1);
+        s_last = (done == (unsigned)S.nblk_ene - 1);
     }
     __syncthreads();
     if (s_last) {
         __threadfence();
         if (threadIdx.x < ENE_N && threadIdx.x > 0) {
-            const volatile double *part = S.ene_partial + (size_t)rep * S.nblk * ENE_N;
+            const volatile double *part = S.ene_partial + (size_t)rep * S.nblk_ene * ENE_N;
             double v = 0;
-            for (int b = 0; b < S.nblk; b++) v += part[(size_t)b * ENE_N + threadIdx.x];
+            for (int b = 0; b < S.nblk_ene; b++) v += part[(size_t)b * ENE_N + threadIdx.x];
             S.ene_out[(size_t)rep * ENE_N + threadIdx.x] = v;
         }
         __syncthreads();
@@ -988,13 +1045,23 @@ __global__ void k_nl_bp_slots(DevSys S, const int *rep_active)
     if (e >= S.nbp_row[rbase + k]) return;
     int2 *ent = S.bprow + (rbase + k) * KB + e;
     const int j = ent->x;
-    if (j > k) { ent->y = k * KB + e; return; }
+    if (j > k) {
+        ent->y = k * KB + e;
+        const int t = atomicAdd(&S.nbp_half[rep], 1);
+        if (t < S.bp_half_cap) S.bp_half[(size_t)rep * S.bp_half_cap + t] = k * KB + e;
+        return;
+    }
     const int2 *jr = S.bprow + (rbase + j) * KB;
     const int nj = S.nbp_row[rbase + j];
     int found = -1;
     for (int q = 0; q < nj; q++)
         if (jr[q].x == k) { found = q; break; }
     ent->y = j * KB + max(found, 0);
+}
+__global__ void k_nl_begin_slots(DevSys S, const int *rep_active)
+{
+    const int rep = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rep < S.nrep && rep_active[rep]) S.nbp_half[rep] = 0;
 }
 __global__ void k_nl_finish(DevSys S, const int *rep_active)
 {

@@ -102,7 +102,10 @@ struct DBuf {   // device buffer
 
 struct sisgpu {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: the bp task branch of the step
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaGraphExec_t graph_chunk = nullptr;               // `chunk` MD steps as one graph launch
+    int graph_chunk_steps = 0;
     bool finalized = false;
     // topology
     int nmp = 0, nchains = 0;
@@ -126,6 +129,7 @@ struct sisgpu {
     int flg_bp_MC = 0;
     bool lists_full = false;   // list_exv/ele/bp mode (no rebuild trigger)
     bool lists_built = false;
+    int nbp_half_max = 0;      // max over replicas of the half-list bp candidate count
     // biases (host copies)
     std::vector<int> twz_pairs, twzfr_pairs, rest_id;
     std::vector<double> twz_dir, twzfr_k, twzfr_init, twzfr_velo, rest_rcut, rest_para;
@@ -152,6 +156,8 @@ struct sisgpu {
         d_cell_count, d_cell_start, d_cell_cursor, d_cell_beads, d_need_rebuild, d_rep_active, d_twz_pairs,
         d_twzfr_pairs, d_rest_id;
     DBuf<double4> d_coef, d_pos0, d_pos1;
+    DBuf<double> d_f_pair, d_f_loc, d_f_bp;
+    DBuf<int> d_bp_half, d_nbp_half;
     DBuf<double> d_mass, d_bp3_dH, d_bp3_dS, d_vel, d_acc, d_move, d_force, d_ene_bp, d_blk_top2,
         d_ene_partial, d_ene_out, d_kin, d_twz_dir, d_twzfr_k, d_twzfr_init, d_twzfr_velo, d_rest_rcut,
         d_rest_para, d_gather_send, d_gather_recv;
@@ -165,10 +171,10 @@ struct sisgpu {
     DBuf<DevCtl> d_ctl;
     DevCtl *h_ctl = nullptr;   // pinned
     int *h_need = nullptr;     // pinned [nrep]
-    int K = 0, KB = 0, G = 32;
+    int K = 0, KB = 0, G = 8;   // G = lanes per bead in the pair task
     // stats / options
-    long long launches = 0, nrebuild = 0;
-    int launch_mode = 0, chunk = 32, timing = 0;
+    long long launches = 0, nrebuild = 0, graph_launches_per_chunk = 0;
+    int launch_mode = 1, chunk = 16, timing = 0;   // launch_mode 1: CUDA-graph chunks
     double t_step = 0, t_nl = 0, t_ene = 0, t_rex = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long long istep_host = 0;
@@ -190,6 +196,9 @@ int sisgpu_create(sisgpu_t **out, int device)
     sisgpu *h = new sisgpu();
     h->device = device;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
     h->P.integrator = 1;
@@ -219,11 +228,23 @@ int sisgpu_destroy(sisgpu_t *h)
     h->d_gather_send.release(); h->d_gather_recv.release(); h->d_nbr.release(); h->d_bprow.release();
     h->d_bp_type.release(); h->d_bp_coef.release(); h->d_mc_counter.release(); h->d_blk_counter.release();
     h->d_ene_counter.release(); h->d_rp.release(); h->d_rp_alt.release(); h->d_ctl.release();
+    if (h->graph_chunk) cudaGraphExecDestroy(h->graph_chunk);
+    h->d_f_pair.release(); h->d_f_loc.release(); h->d_f_bp.release(); h->d_bp_half.release(); h->d_nbp_half.release();
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
+    cudaEventDestroy(h->ev_fork);
+    cudaEventDestroy(h->ev_join);
+    cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->stream);
     delete h;
     return 0;
+}
+
+// kernel arguments (DevSys, FFParams, StepArgs) are baked into the instantiated graph: anything
+// that changes them drops it
+static void invalidate_graphs(sisgpu *h)
+{
+    if (h->graph_chunk) { cudaGraphExecDestroy(h->graph_chunk); h->graph_chunk = nullptr; }
 }
 
 // ---- set-up -------------------------------------------------------------------------------
@@ -343,6 +364,7 @@ int sisgpu_set_pbc(sisgpu_t *h, int flg_pbc, const double *box)
         h->P.box_half[i] = 0.5 * h->P.box[i];
     }
     if (flg_pbc && (h->P.box[0] <= 0 || h->P.box[1] <= 0 || h->P.box[2] <= 0)) return set_err("invalid PBC box");
+    invalidate_graphs(h);
     return 0;
 }
 
@@ -351,6 +373,7 @@ int sisgpu_set_md(sisgpu_t *h, int integrator, double dt, double viscosity_Pas, 
     if (integrator != 1 && integrator != 2) return set_err("unknown integrator %d", integrator);
     h->P.integrator = integrator; h->dt = dt; h->viscosity_Pas = viscosity_Pas; h->nl_margin = nl_margin;
     h->seed = seed;
+    invalidate_graphs(h);
     return 0;
 }
 
@@ -538,9 +561,12 @@ static int alloc_lists(sisgpu *h, int K, int KB)
         TRY(h->d_bp_status.alloc(R * N * KB));
         TRY(h->d_bp_status_MC.alloc(R * N * KB));
         TRY(h->d_ene_bp.alloc(R * N * KB));
+        TRY(h->d_bp_half.alloc(R * N * KB));
     }
+    invalidate_graphs(h);
     DevSys &S = h->S;
     S.K = h->K; S.KB = h->KB;
+    S.bp_half = h->d_bp_half.p; S.bp_half_cap = (int)(N * h->KB);
     S.nbr = h->d_nbr.p; S.bprow = h->d_bprow.p; S.bp_type = h->d_bp_type.p; S.bp_coef = h->d_bp_coef.p;
     S.bp_status = h->d_bp_status.p; S.bp_status_MC = h->d_bp_status_MC.p; S.ene_bp = h->d_ene_bp.p;
     return 0;
@@ -652,15 +678,18 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     TRY(h->d_mc_counter.alloc(R)); TRY(h->d_need_rebuild.alloc(R)); TRY(h->d_rep_active.alloc(R));
     TRY(h->d_rp.alloc(R)); TRY(h->d_rp_alt.alloc(R)); TRY(h->d_ctl.alloc(1));
     TRY(h->d_kin.alloc(R));
-    const int BPB = 256 / h->G;
-    const int nblk = (N + BPB - 1) / BPB;
+    const int nblk = (N + 63) / 64;            // integrate kernel: 64 beads per block
+    const int nblk_ene = (N + 31) / 32;        // energy kernel: 8 lanes per bead
     TRY(h->d_blk_top2.alloc((size_t)R * nblk * 2)); TRY(h->d_blk_counter.alloc(R + 1));
-    TRY(h->d_ene_partial.alloc((size_t)R * nblk * ENE_N)); TRY(h->d_ene_counter.alloc(R)); TRY(h->d_ene_out.alloc((size_t)R * ENE_N));
+    TRY(h->d_ene_partial.alloc((size_t)R * nblk_ene * ENE_N)); TRY(h->d_ene_counter.alloc(R)); TRY(h->d_ene_out.alloc((size_t)R * ENE_N));
+    TRY(h->d_f_pair.alloc(RN * 3)); TRY(h->d_f_loc.alloc(RN * 3)); TRY(h->d_f_bp.alloc(RN * 3));
+    TRY(h->d_nbp_half.alloc(R));
     TRY(h->d_gather_send.alloc(2 * (size_t)R)); TRY(h->d_gather_recv.alloc(2 * (size_t)std::max(h->nrep_all, R)));
     if (!h->h_ctl) CK(cudaMallocHost(&h->h_ctl, sizeof(DevCtl)));
     if (!h->h_need) CK(cudaMallocHost(&h->h_need, sizeof(int) * R));
     DevSys &S = h->S;
-    S.nmp = N; S.nrep = R; S.nblk = nblk;
+    S.nmp = N; S.nrep = R; S.nblk = nblk; S.nblk_ene = nblk_ene;
+    S.f_pair = h->d_f_pair.p; S.f_loc = h->d_f_loc.p; S.f_bp = h->d_f_bp.p; S.nbp_half = h->d_nbp_half.p;
     S.meta = h->d_meta.p; S.seq = h->d_seq.p; S.coef = h->d_coef.p; S.mass = h->d_mass.p; S.hash = h->d_hash.p;
     S.bp3_dH = h->d_bp3_dH.p; S.bp3_dS = h->d_bp3_dS.p;
     S.pos[0] = h->d_pos0.p; S.pos[1] = h->d_pos1.p; S.vel = h->d_vel.p; S.acc = h->d_acc.p; S.move = h->d_move.p;
@@ -861,10 +890,19 @@ static int build_lists(sisgpu *h, const std::vector<int> &active, bool all_pairs
             if (!was_all) return build_lists(h, all, all_pairs);
             continue;
         }
+        k_nl_begin_slots<<<(R + 63) / 64, 64, 0, h->stream>>>(S, h->d_rep_active.p);
         k_nl_bp_slots<<<dim3((N * h->KB + 255) / 256, R), 256, 0, h->stream>>>(S, h->d_rep_active.p);
         k_nl_finish<<<(R + 63) / 64, 64, 0, h->stream>>>(S, h->d_rep_active.p);
-        h->launches += 2;
-        CK(cudaStreamSynchronize(h->stream));
+        h->launches += 3;
+        {
+            std::vector<int> nh(R);
+            CK(cudaMemcpyAsync(nh.data(), h->d_nbp_half.p, R * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            int mx = 0;
+            for (int r = 0; r < R; r++) mx = std::max(mx, nh[r]);
+            // the bp task grid is sized from this count; regrow (and re-capture) with slack
+            if (mx > h->nbp_half_max || mx < h->nbp_half_max / 4) { h->nbp_half_max = mx + mx / 4 + 128; invalidate_graphs(h); }
+        }
         CK(cudaGetLastError());
         timer_end(h, h->t_nl);
         h->lists_full = all_pairs;
@@ -933,8 +971,9 @@ static int fetch_half_lists(sisgpu *h, int irep, HalfLists &L)
             int2 ent = bprow[(size_t)i * KB + e];
             if (ent.x > i) bp.push_back({{i, ent.x}, ent.y});
         }
+    // src/list_bp.F90:55-57 walks (imp, jmp) in global order; neighbor_list walks chain pairs
     std::sort(bp.begin(), bp.end(), [&](const std::pair<std::pair<int, int>, int> &a, const std::pair<std::pair<int, int>, int> &b) {
-        return key_less(a.first, b.first);
+        return h->lists_full ? a.first < b.first : key_less(a.first, b.first);
     });
     for (auto &b : bp) { L.bp_i.push_back(b.first.first); L.bp_j.push_back(b.first.second); L.bp_ibp.push_back(b.second); }
     return 0;
@@ -1025,25 +1064,40 @@ int sisgpu_bp3_table(sisgpu_t *h, int *n, int *hash4096, double *dH, double *dS)
 // ---- hot path -----------------------------------------------------------------------------
 int sisgpu_set_bp_mc(sisgpu_t *h, int flg) { h->flg_bp_MC = flg; return 0; }
 
-static StepArgs step_args(const sisgpu *h, unsigned mask, int use_mask, int only_rep)
+static StepArgs step_args(const sisgpu *h, unsigned mask, int use_mask, int only_rep, int integrate)
 {
     StepArgs A{};
     A.seed = h->seed; A.nl_margin = h->lists_full ? 1e300 : h->nl_margin;
-    A.term_mask = mask; A.use_mask = use_mask; A.only_rep = only_rep;
+    A.term_mask = mask; A.use_mask = use_mask; A.only_rep = only_rep; A.integrate = integrate;
+    A.nblk_pair = (h->nmp + 256 / h->G - 1) / (256 / h->G);
+    A.nblk_loc = (h->nmp + 31) / 32;
     return A;
 }
 
-template <int MODE>
-static void launch_step(sisgpu *h, const StepArgs &A)
+// one force evaluation (+ integration): the pair/local task kernel on `stream`, the bp task
+// kernel concurrently on `stream2` (fork/join through events; inside a stream capture these
+// become the two parallel branches of the step graph), then the integrate kernel
+static void enqueue_step(sisgpu *h, const StepArgs &A)
 {
-    const int BPB = 256 / h->G;
-    dim3 grid((h->nmp + BPB - 1) / BPB, A.only_rep >= 0 ? 1 : h->nrep);
-    switch (h->G) {
-    case 8: k_step<8, MODE><<<grid, 256, 0, h->stream>>>(h->S, h->P, A); break;
-    case 16: k_step<16, MODE><<<grid, 256, 0, h->stream>>>(h->S, h->P, A); break;
-    default: k_step<32, MODE><<<grid, 256, 0, h->stream>>>(h->S, h->P, A); break;
+    const int R = A.only_rep >= 0 ? 1 : h->nrep;
+    const bool do_bp = A.term_mask & (1u << ENE_BP);
+    if (do_bp) {
+        cudaEventRecord(h->ev_fork, h->stream);
+        cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+        k_force_bp<<<dim3((std::max(h->nbp_half_max, 1) + 127) / 128, R), 128, 0, h->stream2>>>(h->S, h->P, A);
+        cudaEventRecord(h->ev_join, h->stream2);
+        h->launches++;
     }
-    h->launches++;
+    dim3 grid(A.nblk_pair + A.nblk_loc, R);
+    switch (h->G) {
+    case 4: k_force_local<4><<<grid, 256, 0, h->stream>>>(h->S, h->P, A); break;
+    case 16: k_force_local<16><<<grid, 256, 0, h->stream>>>(h->S, h->P, A); break;
+    case 32: k_force_local<32><<<grid, 256, 0, h->stream>>>(h->S, h->P, A); break;
+    default: k_force_local<8><<<grid, 256, 0, h->stream>>>(h->S, h->P, A); break;
+    }
+    if (do_bp) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+    k_integrate<<<dim3(h->S.nblk, R), 256, 0, h->stream>>>(h->S, h->P, A);
+    h->launches += 2;
 }
 
 // evaluation + MC pruning passes of force_bp_limit_triplet / energy_bp_limit_triplet
@@ -1084,7 +1138,7 @@ int sisgpu_force_terms(sisgpu_t *h, int irep, unsigned mask, double *forces)
         use_mask = 2;
     }
     if (mask & (1u << ENE_RG)) launch_rg(h, irep);
-    launch_step<1>(h, step_args(h, mask, use_mask, irep));
+    enqueue_step(h, step_args(h, mask, use_mask, irep, 0));
     CK(cudaMemcpyAsync(forces, h->S.force + (size_t)irep * h->nmp * 3, 3 * h->nmp * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
@@ -1094,13 +1148,8 @@ int sisgpu_force(sisgpu_t *h, int irep, double *forces) { return sisgpu_force_te
 
 static int energy_launch(sisgpu *h, int only_rep, const RepParams *rp_alt)
 {
-    const int BPB = 256 / h->G;
-    dim3 grid((h->nmp + BPB - 1) / BPB, only_rep >= 0 ? 1 : h->nrep);
-    switch (h->G) {
-    case 8: k_energy<8><<<grid, 256, 0, h->stream>>>(h->S, h->P, rp_alt, only_rep); break;
-    case 16: k_energy<16><<<grid, 256, 0, h->stream>>>(h->S, h->P, rp_alt, only_rep); break;
-    default: k_energy<32><<<grid, 256, 0, h->stream>>>(h->S, h->P, rp_alt, only_rep); break;
-    }
+    dim3 grid(h->S.nblk_ene, only_rep >= 0 ? 1 : h->nrep);
+    k_energy<8><<<grid, 256, 0, h->stream>>>(h->S, h->P, rp_alt, only_rep);
     h->launches++;
     return 0;
 }
@@ -1458,13 +1507,37 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
         }
         int nchunk = (int)std::min<long long>(h->chunk, stop - cur);
         timer_begin(h);
-        for (int s = 0; s < nchunk; s++) {
-            const long long istep = cur + s + 1;
-            bool mc = false;
-            if (h->nstep_bp_MC > 0) mc = (istep % h->nstep_bp_MC == 0) || (s == 0 && force_mc);
-            if (mc) launch_bp_eval<0>(h, -1, true, 0.0, 0, 0, 1, 0);
-            launch_rg(h, -1);
-            launch_step<0>(h, step_args(h, mask_all, h->nstep_bp_MC > 0 ? 1 : 0, -1));
+        const int use_mask = h->nstep_bp_MC > 0 ? 1 : 0;
+        const bool uniform = h->nstep_bp_MC <= 1;   // every step has the same kernel sequence
+        if (h->launch_mode == 1 && uniform && nchunk == h->chunk) {
+            if (!h->graph_chunk || h->graph_chunk_steps != nchunk) {
+                invalidate_graphs(h);
+                cudaGraph_t graph = nullptr;
+                CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                const long long l0 = h->launches;
+                for (int s = 0; s < nchunk; s++) {
+                    if (h->nstep_bp_MC == 1) launch_bp_eval<0>(h, -1, true, 0.0, 0, 0, 1, 0);
+                    launch_rg(h, -1);
+                    enqueue_step(h, step_args(h, mask_all, use_mask, -1, 1));
+                }
+                h->graph_launches_per_chunk = h->launches - l0;
+                h->launches = l0;
+                CK(cudaStreamEndCapture(h->stream, &graph));
+                CK(cudaGraphInstantiate(&h->graph_chunk, graph, 0));
+                CK(cudaGraphDestroy(graph));
+                h->graph_chunk_steps = nchunk;
+            }
+            CK(cudaGraphLaunch(h->graph_chunk, h->stream));
+            h->launches += h->graph_launches_per_chunk;
+        } else {
+            for (int s = 0; s < nchunk; s++) {
+                const long long istep = cur + s + 1;
+                bool mc = false;
+                if (h->nstep_bp_MC > 0) mc = (istep % h->nstep_bp_MC == 0) || (s == 0 && force_mc);
+                if (mc) launch_bp_eval<0>(h, -1, true, 0.0, 0, 0, 1, 0);
+                launch_rg(h, -1);
+                enqueue_step(h, step_args(h, mask_all, use_mask, -1, 1));
+            }
         }
         force_mc = false;
         TRY(sync_ctl(h));
@@ -1532,13 +1605,13 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
 {
     std::string s(name);
     if (s == "launch_mode") h->launch_mode = (int)value;
-    else if (s == "chunk") h->chunk = std::max(1, (int)value);
+    else if (s == "chunk") { h->chunk = std::max(1, (int)value); invalidate_graphs(h); }
     else if (s == "timing") h->timing = (int)value;
     else if (s == "threads_per_bead") {
         int g = (int)value;
-        if (g != 8 && g != 16 && g != 32) return set_err("threads_per_bead must be 8, 16 or 32");
-        if (h->finalized) return set_err("threads_per_bead must be set before finalize_setup");
+        if (g != 4 && g != 8 && g != 16 && g != 32) return set_err("threads_per_bead must be 4, 8, 16 or 32");
         h->G = g;
+        invalidate_graphs(h);
     } else return set_err("unknown option %s", name);
     return 0;
 }

@@ -2,7 +2,7 @@
 //
 // There is no GPU in the build container, so the kernels cannot run there.  This file compiles
 // the product sources (sis_b200/csrc/sisgpu.cu and the __host__ __device__ math / gather code in
-// sis_kernels.cuh) for the HOST and drives `bead_force<1>` and the list predicates serially, so
+// sis_kernels.cuh) for the HOST and drives the force task code (`pair_force<1>`, `local_force<1>`, `bp_pair_force`) and the list predicates serially, so
 // the CPU test-suite can compare the product's arithmetic, term roles and exclusion rules with
 // the oracle before any GPU time is spent.  It is not linked into libsisgpu.so and nothing in
 // sis_b200/ loads it.
@@ -159,16 +159,28 @@ int hc_get_lists(HostCheck *c, int *wca, int *ele, int *bp, double *coef)
     return 0;
 }
 
-// the product's gather force code, one "lane" per bead
+// the product's force tasks run serially: pair + local per bead, bp per half-list candidate
 int hc_force(HostCheck *c, const double *xyz, unsigned mask, double *forces)
 {
     const int N = c->h->nmp;
     c->pos.resize(N);
     for (int i = 0; i < N; i++) c->pos[i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0);
     for (int k = 0; k < N; k++) {
-        Vec3 F = bead_force<1>(c->S, c->h->P, c->rp, c->pos.data(), 0, k, 0, mask, 0, 0ull, 1);
+        Vec3 F = pair_force<1>(c->S, c->h->P, c->rp, c->pos.data(), 0, k, 0, mask);
+        F += local_force<1>(c->S, c->h->P, c->rp, c->pos.data(), 0, k, 0, mask, 0ull);
         forces[3 * k] = F.x; forces[3 * k + 1] = F.y; forces[3 * k + 2] = F.z;
     }
+    if (mask & (1u << ENE_BP))
+        for (int k = 0; k < N; k++)
+            for (int e = 0; e < c->nbp_row[k]; e++) {
+                if (c->bprow[(size_t)k * c->KB + e].x < k) continue;
+                int beads[6];
+                Vec3 f[6];
+                const int n = bp_pair_force(c->S, c->h->P, c->rp, c->pos.data(), 0, k, e, 0, 1, beads, f);
+                for (int s = 0; s < n; s++) {
+                    forces[3 * beads[s]] += f[s].x; forces[3 * beads[s] + 1] += f[s].y; forces[3 * beads[s] + 2] += f[s].z;
+                }
+            }
     return 0;
 }
 

@@ -147,7 +147,9 @@ def test_c4_properties_long_run():
     assert np.isfinite(x).all() and np.isfinite(v).all()
     f = g.force(0)
     assert np.abs(f.sum(axis=0)).max() < 1e-7
-    d = np.linalg.norm(np.diff(x.reshape(64, 141, 3), axis=1), axis=2)
+    dv = np.diff(x.reshape(64, 141, 3), axis=1)
+    dv -= 809.972 * np.round(dv / 809.972)      # minimum image: chains are wrapped bead by bead
+    d = np.linalg.norm(dv, axis=2)
     assert d.min() > 4.0 and d.max() < 8.0
     # temperature from kinetic energy (GJF-2GJ half-step velocity): within 10 % of 310.15 K
     ek = g.energy_kinetic(0)
