@@ -122,6 +122,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=None)
     ap.add_argument("--tpb", type=int, default=None, help="lanes per bead in the pair task")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="phase clocks of the persistent kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -142,6 +143,8 @@ def main():
         if val is not None:
             g.set_option(name, val)
     spec.configure(g)
+    if args.profile:
+        g.set_option("profile", 1)
     if world > 1:
         temps = [spec.tempK + 2.0 * k for k in range(world)]
         g.remd_setup([world, 1, 1, 1], [temps, [], [], []], args.md_steps, rank, world)

@@ -148,7 +148,9 @@ int sisgpu_launch_count(sisgpu_t *h, int64_t *n);
 /* options: name = "launch_mode" (0 stream, 1 graph), "threads_per_bead", "timing" */
 int sisgpu_set_option(sisgpu_t *h, const char *name, double value);
 /* CUDA-event time (ms) accumulated per kernel family since the last reset:
- * out[0] step kernels, out[1] neighbour list, out[2] energy, out[3] exchange */
+ * out[0] step kernels, out[1] neighbour list, out[2] energy, out[3] exchange;
+ * out[4..7] SM clocks block 0 of the persistent kernel spent in force phase, barrier, integrate
+ * phase, barrier, out[8] steps counted (option "profile"); out must hold 9 doubles */
 int sisgpu_get_timers(sisgpu_t *h, double *out, int reset);
 
 /* ---- REMD ------------------------------------------------------------------- */

@@ -68,9 +68,13 @@ class SisGpu(CApi):
         return n.value
 
     def get_timers(self, reset=False) -> dict:
-        out = np.zeros(4)
+        out = np.zeros(9)
         self._call("get_timers", _d(out), C.c_int(int(reset)))
-        return dict(zip(["step_ms", "nl_ms", "energy_ms", "exchange_ms"], out.tolist()))
+        d = dict(zip(["step_ms", "nl_ms", "energy_ms", "exchange_ms"], out[:4].tolist()))
+        if out[8] > 0:
+            d["persistent_clk_per_step"] = dict(zip(["force", "barrier1", "integrate", "barrier2"],
+                                                    (out[4:8] / out[8]).round(1).tolist()))
+        return d
 
     # ---- REMD ------------------------------------------------------------------------
     def remd_setup(self, nrep, values, nstep_exchange, rank=0, nranks=1):

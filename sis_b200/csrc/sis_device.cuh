@@ -226,7 +226,12 @@ SIS_HD double wca_scalar(const FFParams &P, double d2)
 // src/force_ele_DH.F90:39-81: F_k = C/r^2 (1/r + 1/lambda) exp(-r/lambda) * v, d2 <= cutoff^2
 SIS_HD double dh_scalar(double ele_coef, double inv_lambdaD, double d2)
 {
-    double dist1 = sqrt(d2), rdist1 = 1.0 / dist1;
+#ifdef __CUDA_ARCH__
+    const double rdist1 = rsqrt(d2);      // 1/r directly; r = d2 * (1/r)
+#else
+    const double rdist1 = 1.0 / sqrt(d2);
+#endif
+    const double dist1 = d2 * rdist1;
     return ele_coef * rdist1 * rdist1 * (rdist1 + inv_lambdaD) * exp(-dist1 * inv_lambdaD);
 }
 // src/energy_wca.F90:19-35, src/energy_ele_DH.F90:20-40

@@ -10,20 +10,31 @@
 
 #include "sis_device.cuh"
 
+#ifdef __CUDACC__
+#include <cooperative_groups.h>
+#endif
+
+// Step bookkeeping lives on the device so that a whole chunk of steps can be replayed as one
+// CUDA graph (or one persistent launch) without host-supplied per-step arguments.
+// S.ctl[0] ("A") is read by the force-phase kernels and written only by the integrate kernel;
+// S.ctl[1] ("B") is read by the integrate kernel and written only by the force phase -- no kernel
+// ever writes the copy its own blocks read, so no "last block" hand-off is needed.
 struct DevCtl {
-    unsigned long long step;   // istep of the NEXT step to execute minus 1 (job_md istep)
-    int cur;                   // which position buffer holds the current coordinates
-    int nl_overflow;           // max row length seen by the last list build
-    int bp_overflow;
-    unsigned long long steps_done;
-    // 0 = none; else the istep whose position update pushed some replica past the list margin.
-    // Kernels queued behind it see abort_word <= step and return without touching the state;
-    // blocks of the launch that raised it see abort_word > step and finish normally.
-    unsigned long long abort_word;
-    int max_force_flag;        // src/job_md.F90:403-407 (forces > 100 warning)
+    unsigned long long step;   // completed MD steps (job_md's istep)
+    int cur;                   // position buffer that holds the current coordinates
+    int blocked;               // B only: some replica is past the list margin, step not executed
+};
+struct DevMisc {
+    int nl_overflow, bp_overflow;   // longest rows seen by the last list build
+    int max_force_flag;             // src/job_md.F90:403-407 (forces > 100 warning); bit1: stage abort
     int pad;
 };
-SIS_D bool ctl_aborted(const DevCtl &c) { return c.abort_word != 0ull && c.abort_word <= c.step; }
+
+// one contiguous device block the host mirrors with a single copy: header + top2[nrep][2][2]
+struct DevSyncHdr {
+    DevCtl ctl[2];
+    DevMisc misc;
+};
 
 struct GridInfo {
     double origin[3], inv_cell[3];
@@ -65,10 +76,13 @@ struct DevSys {
     int ncell_cap;
     // parameters
     RepParams *rp;
-    DevCtl *ctl;
-    int *need_rebuild;            // [rep]
-    double *blk_top2;             // [rep][nblk][2]
-    unsigned int *blk_counter;    // [rep]
+    DevCtl *ctl;                  // [2]: A, B
+    DevMisc *misc;
+    // displacement top-2 (src/job_md.F90:376-388) as order-preserving bit patterns of |move|^2:
+    // [rep][slot = istep & 1][0 = max, 1 = second max]
+    unsigned long long *top2;
+    double nl_margin;             // 1e300 with the cutoff-free lists (no rebuild trigger)
+    unsigned long long *prof;     // optional phase clocks of the persistent kernel (block 0), or null
     double *ene_partial;          // [rep][nblk][ENE_N]
     unsigned int *ene_counter;    // [rep]
     double *ene_out;              // [rep][ENE_N]
@@ -83,12 +97,11 @@ struct DevSys {
 
 struct StepArgs {
     unsigned long long seed;
-    double nl_margin;
     unsigned term_mask;   // bit k = energies index k
     int use_mask;         // 0 all pairs; 1 only bp_status_MC (nstep_bp_MC > 0); 2 only bp_status
     int only_rep;         // >= 0: single replica (per-irep API); -1: all (grid.y)
     int integrate;        // 1: MD step (job_md loop body); 0: force() only
-    int nblk_pair, nblk_loc;
+    int nblk_pair, nblk_loc, nblk_bp;   // per-replica block counts of the three force roles
 };
 
 // sum over the G lanes that own one bead.  Host builds (tests/csrc/hostcheck.cu) run the same
@@ -126,14 +139,27 @@ SIS_HD Vec3 pair_force(const DevSys &S, const FFParams &P, const RepParams &R, c
     const double cut2 = R.ele_cutoff * R.ele_cutoff;
     const bool do_wca = term_mask & (1u << ENE_EXV);
     const bool do_ele = (term_mask & (1u << ENE_ELE)) && P.flg_ele;
-    for (int e = lane; e < nn; e += G) {
-        const uint32_t ent = row[e];
-        const Vec3 v = pbc_vec_d(P, xk, v3(pos[ent & NB_IDX]));
-        const double d2 = dot(v, v);
-        double s = 0.0;
-        if (do_wca && (ent & NB_WCA) && d2 < P.wca_sigma2) s += wca_scalar(P, d2);
-        if (do_ele && (ent & NB_ELE) && d2 <= cut2) s += dh_scalar(R.ele_coef, R.inv_lambdaD, d2);
-        F += s * v;
+    // batches of 4 entries per lane: the 4 row loads, then the 4 position gathers, are issued
+    // back to back so that a bead costs ~2 dependent L2 round trips instead of 2 per entry
+    for (int e0 = lane; e0 < nn; e0 += 4 * G) {
+        uint32_t ent[4];
+        Vec3 xj[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + u * G;
+            ent[u] = e < nn ? row[e] : (uint32_t)k;   // padding: self index, no list flags
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) xj[u] = v3(pos[ent[u] & NB_IDX]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const Vec3 v = pbc_vec_d(P, xk, xj[u]);
+            const double d2 = dot(v, v);
+            double s = 0.0;
+            if (do_wca && (ent[u] & NB_WCA) && d2 < P.wca_sigma2) s += wca_scalar(P, d2);
+            if (do_ele && (ent[u] & NB_ELE) && d2 <= cut2) s += dh_scalar(R.ele_coef, R.inv_lambdaD, d2);
+            F += s * v;
+        }
     }
     return F;
 }
@@ -283,54 +309,60 @@ SIS_D void top2_merge(double &a1, double &a2, double b1, double b2)
     a1 = m1; a2 = m2;
 }
 
-// pair + local task kernel: blocks [0, nblk_pair) run the pair role with GP lanes per bead,
-// blocks [nblk_pair, nblk_pair + nblk_loc) the local role with 8 lanes per bead
-template <int GP>
-__global__ void __launch_bounds__(256, 4) k_force_local(DevSys S, FFParams P, StepArgs A)
+// the rebuild test of src/job_md.F90:388 on the displacements left by step `step`:
+// sqrt(d2max) + sqrt(d2max_2nd) > nl_margin for any replica of this launch
+SIS_D bool step_blocked(const DevSys &S, unsigned long long step, int only_rep)
 {
-    const DevCtl ctl = *S.ctl;
-    if (A.integrate && ctl_aborted(ctl)) return;
-    const int rep = (A.only_rep >= 0) ? A.only_rep : blockIdx.y;
-    const int nmp = S.nmp;
-    const double4 *pos = S.pos[ctl.cur] + (size_t)rep * nmp;
-    const RepParams R = S.rp[rep];
-    const unsigned long long istep = ctl.step + (A.integrate ? 1ull : 0ull);
-    if ((int)blockIdx.x < A.nblk_pair) {
-        constexpr int BPB = 256 / GP;
-        const int lane = threadIdx.x % GP;
-        const int kraw = blockIdx.x * BPB + threadIdx.x / GP;
-        const bool valid = kraw < nmp;
-        const int k = valid ? kraw : nmp - 1;   // tail groups shadow the last bead (no writes)
-        Vec3 F = pair_force<GP>(S, P, R, pos, rep, k, lane, A.term_mask);
-        F.x = group_sum<GP>(F.x); F.y = group_sum<GP>(F.y); F.z = group_sum<GP>(F.z);
-        if (valid && lane < 3) S.f_pair[((size_t)rep * nmp + k) * 3 + lane] = lane == 0 ? F.x : lane == 1 ? F.y : F.z;
-    } else {
-        constexpr int GL = 8, BPB = 256 / GL;
-        const int lane = threadIdx.x % GL;
-        const int kraw = (blockIdx.x - A.nblk_pair) * BPB + threadIdx.x / GL;
-        const bool valid = kraw < nmp;
-        const int k = valid ? kraw : nmp - 1;
-        Vec3 F = local_force<GL>(S, P, R, pos, rep, k, lane, A.term_mask, istep);
-        F.x = group_sum<GL>(F.x); F.y = group_sum<GL>(F.y); F.z = group_sum<GL>(F.z);
-        if (valid && lane < 3) S.f_loc[((size_t)rep * nmp + k) * 3 + lane] = lane == 0 ? F.x : lane == 1 ? F.y : F.z;
+    const int r0 = only_rep >= 0 ? only_rep : 0, r1 = only_rep >= 0 ? only_rep + 1 : S.nrep;
+    bool blocked = false;
+    for (int r = r0; r < r1; r++) {
+        const unsigned long long *t = S.top2 + ((size_t)r * 2 + (step & 1ull)) * 2;
+        const double m1 = __longlong_as_double((long long)t[0]), m2 = __longlong_as_double((long long)t[1]);
+        blocked |= (sqrt(m1) + sqrt(m2) > S.nl_margin);
     }
+    return blocked;
 }
 
-// bp task kernel: one thread per half-list candidate
-__global__ void __launch_bounds__(128) k_force_bp(DevSys S, FFParams P, StepArgs A)
+// ---- force phase, one block's share -----------------------------------------------------------
+// pair role: GP lanes per bead, beads [blk*256/GP, ...)
+template <int GP>
+SIS_D void phase_pair(const DevSys &S, const FFParams &P, const StepArgs &A, const double4 *pos, int rep, int blk)
 {
-    const DevCtl ctl = *S.ctl;
-    if (A.integrate && ctl_aborted(ctl)) return;
-    const int rep = (A.only_rep >= 0) ? A.only_rep : blockIdx.y;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int BPB = 256 / GP;
+    const int nmp = S.nmp;
+    const int lane = threadIdx.x % GP;
+    const int kraw = blk * BPB + threadIdx.x / GP;
+    const bool valid = kraw < nmp;
+    const int k = valid ? kraw : nmp - 1;   // tail groups shadow the last bead (no writes)
+    const RepParams &R = S.rp[rep];
+    Vec3 F = pair_force<GP>(S, P, R, pos, rep, k, lane, A.term_mask);
+    F.x = group_sum<GP>(F.x); F.y = group_sum<GP>(F.y); F.z = group_sum<GP>(F.z);
+    if (valid && lane < 3) S.f_pair[((size_t)rep * nmp + k) * 3 + lane] = lane == 0 ? F.x : lane == 1 ? F.y : F.z;
+}
+// local role: 8 lanes per bead
+SIS_D void phase_local(const DevSys &S, const FFParams &P, const StepArgs &A, const double4 *pos, int rep, int blk,
+                       unsigned long long istep)
+{
+    constexpr int GL = 8, BPB = 256 / GL;
+    const int nmp = S.nmp;
+    const int lane = threadIdx.x % GL;
+    const int kraw = blk * BPB + threadIdx.x / GL;
+    const bool valid = kraw < nmp;
+    const int k = valid ? kraw : nmp - 1;
+    const RepParams &R = S.rp[rep];
+    Vec3 F = local_force<GL>(S, P, R, pos, rep, k, lane, A.term_mask, istep);
+    F.x = group_sum<GL>(F.x); F.y = group_sum<GL>(F.y); F.z = group_sum<GL>(F.z);
+    if (valid && lane < 3) S.f_loc[((size_t)rep * nmp + k) * 3 + lane] = lane == 0 ? F.x : lane == 1 ? F.y : F.z;
+}
+// bp role: one thread per half-list candidate t
+SIS_D void phase_bp(const DevSys &S, const FFParams &P, const StepArgs &A, const double4 *pos, int rep, int t)
+{
     if (t >= S.nbp_half[rep]) return;
     const int nmp = S.nmp;
     const int ibp = S.bp_half[(size_t)rep * S.bp_half_cap + t];
-    const double4 *pos = S.pos[ctl.cur] + (size_t)rep * nmp;
-    const RepParams R = S.rp[rep];
     int beads[6];
     Vec3 f[6];
-    const int n = bp_pair_force(S, P, R, pos, rep, ibp / S.KB, ibp % S.KB, A.use_mask, A.use_mask != 2, beads, f);
+    const int n = bp_pair_force(S, P, S.rp[rep], pos, rep, ibp / S.KB, ibp % S.KB, A.use_mask, A.use_mask != 2, beads, f);
     double *fb = S.f_bp + (size_t)rep * nmp * 3;
     for (int s = 0; s < n; s++) {
         atomicAdd(fb + 3 * beads[s], f[s].x);
@@ -338,22 +370,17 @@ __global__ void __launch_bounds__(128) k_force_bp(DevSys S, FFParams P, StepArgs
         atomicAdd(fb + 3 * beads[s] + 2, f[s].z);
     }
 }
-
-// integrate (src/job_md.F90:409-456) + displacement top-2 (src/job_md.F90:376-388).
-// 4 lanes per bead, lanes 0..2 own x, y, z.  integrate == 0: only sums the partial forces into
-// S.force (the per-irep force() API).  Consumes and clears the bp scatter buffer.
-__global__ void __launch_bounds__(256) k_integrate(DevSys S, FFParams P, StepArgs A)
+// integrate (src/job_md.F90:409-456) for the 64 beads of block `blk`; 4 lanes per bead, lanes 0..2
+// own x, y, z.  Consumes and clears the bp scatter buffer, pushes the block's displacement top-2
+// into the slot of `istep`.
+SIS_D void phase_integrate(const DevSys &S, const FFParams &P, const StepArgs &A, int cur, int rep, int blk,
+                           unsigned long long istep)
 {
-    const DevCtl ctl = *S.ctl;
-    if (A.integrate && ctl_aborted(ctl)) return;
-    const int rep = (A.only_rep >= 0) ? A.only_rep : blockIdx.y;
     const int lane = threadIdx.x % 4;
-    const int k = blockIdx.x * 64 + threadIdx.x / 4;
+    const int k = blk * 64 + threadIdx.x / 4;
     const int nmp = S.nmp;
     const bool valid = k < nmp;
-    const double4 *pos = S.pos[ctl.cur] + (size_t)rep * nmp;
-    const RepParams R = S.rp[rep];
-    const unsigned long long istep = ctl.step + 1ull;
+    const double4 *pos = S.pos[cur] + (size_t)rep * nmp;
     double xnew = 0.0, mv = 0.0;
     if (valid && lane < 3) {
         const size_t o = ((size_t)rep * nmp + k) * 3 + lane;
@@ -362,6 +389,7 @@ __global__ void __launch_bounds__(256) k_integrate(DevSys S, FFParams P, StepArg
         if (!A.integrate) {
             S.force[o] = f;
         } else {
+            const RepParams &R = S.rp[rep];
             const double4 xo = pos[k];
             const double4 c = S.coef[k];
             const double x = lane == 0 ? xo.x : lane == 1 ? xo.y : xo.z;
@@ -379,7 +407,7 @@ __global__ void __launch_bounds__(256) k_integrate(DevSys S, FFParams P, StepArg
             xnew = x + dx;
             mv = S.move[o] + dx;
             S.move[o] = mv;
-            if (f > 100.0) S.ctl->max_force_flag = 1;
+            if (f > 100.0) S.misc->max_force_flag |= 1;
         }
     }
     if (!A.integrate) return;
@@ -390,61 +418,127 @@ __global__ void __launch_bounds__(256) k_integrate(DevSys S, FFParams P, StepArg
     const double s1 = __shfl_sync(0xffffffffu, mv, 1, 4);
     const double s2 = __shfl_sync(0xffffffffu, mv, 2, 4);
     const double d2 = s0 * s0 + s1 * s1 + s2 * s2;
-    if (valid && lane == 0) S.pos[ctl.cur ^ 1][(size_t)rep * nmp + k] = make_double4(nx, ny, nz, 0.0);
-
-    // displacement top-2 -> rebuild request for the NEXT step
-    __shared__ double s_t1[8], s_t2[8];
-    __shared__ bool s_last;
+    if (valid && lane == 0) S.pos[cur ^ 1][(size_t)rep * nmp + k] = make_double4(nx, ny, nz, 0.0);
+    // warp top-2, then two order-preserving integer atomic maxima per warp:
+    //   old = atomicMax(m1, a1);  atomicMax(m2, max(min(old, a1), a2))
+    // leaves (m1, m2) = the two largest |move|^2 of the replica whatever the arrival order
     double t1 = (valid && lane == 0) ? d2 : 0.0, t2 = 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         double b1 = __shfl_xor_sync(0xffffffffu, t1, o), b2 = __shfl_xor_sync(0xffffffffu, t2, o);
         top2_merge(t1, t2, b1, b2);
     }
-    const int warp = threadIdx.x / 32;
-    if (threadIdx.x % 32 == 0) { s_t1[warp] = t1; s_t2[warp] = t2; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; w++) top2_merge(t1, t2, s_t1[w], s_t2[w]);
-        double *bt = S.blk_top2 + ((size_t)rep * S.nblk + blockIdx.x) * 2;
-        bt[0] = t1; bt[1] = t2;
-        __threadfence();
-        unsigned int done = atomicAdd(&S.blk_counter[rep], 1u);
-        s_last = (done == (unsigned)S.nblk - 1);
+    if (threadIdx.x % 32 == 0 && t1 > 0.0) {
+        unsigned long long *t = S.top2 + ((size_t)rep * 2 + (istep & 1ull)) * 2;
+        const unsigned long long old = atomicMax(t, (unsigned long long)__double_as_longlong(t1));
+        const double oldd = __longlong_as_double((long long)old);
+        const double c2 = fmax(fmin(oldd, t1), t2);
+        if (c2 > 0.0) atomicMax(t + 1, (unsigned long long)__double_as_longlong(c2));
     }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        t1 = 0.0; t2 = 0.0;
-        const volatile double *bt = S.blk_top2 + (size_t)rep * S.nblk * 2;
-        for (int b = threadIdx.x; b < S.nblk; b += blockDim.x) top2_merge(t1, t2, bt[2 * b], bt[2 * b + 1]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double b1 = __shfl_xor_sync(0xffffffffu, t1, o), b2 = __shfl_xor_sync(0xffffffffu, t2, o);
-            top2_merge(t1, t2, b1, b2);
+}
+
+// pair + local task kernel: blocks [0, nblk_pair) run the pair role with GP lanes per bead,
+// blocks [nblk_pair, nblk_pair + nblk_loc) the local role with 8 lanes per bead
+template <int GP>
+__global__ void __launch_bounds__(256, 4) k_force_local(DevSys S, FFParams P, StepArgs A)
+{
+    const DevCtl ctl = S.ctl[0];
+    const int rep = (A.only_rep >= 0) ? A.only_rep : blockIdx.y;
+    bool blocked = false;
+    if (A.integrate) {
+        blocked = step_blocked(S, ctl.step, A.only_rep);
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+            DevCtl b; b.step = ctl.step; b.cur = ctl.cur; b.blocked = blocked;
+            S.ctl[1] = b;
         }
-        __syncthreads();
-        if (threadIdx.x % 32 == 0) { s_t1[warp] = t1; s_t2[warp] = t2; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < 8; w++) top2_merge(t1, t2, s_t1[w], s_t2[w]);
-            S.blk_counter[rep] = 0;
-            if (sqrt(t1) + sqrt(t2) > A.nl_margin) {
-                S.need_rebuild[rep] = 1;
-                atomicExch(&S.ctl->abort_word, ctl.step + 1);
-            }
-            // the last replica to finish advances the step counter and flips the buffers
-            __threadfence();
-            unsigned int r = atomicAdd(&S.blk_counter[S.nrep], 1u);
-            const unsigned int nr = (A.only_rep >= 0) ? 1u : (unsigned)S.nrep;
-            if (r == nr - 1) {
-                S.blk_counter[S.nrep] = 0;
-                S.ctl->step = ctl.step + 1;
-                S.ctl->cur = ctl.cur ^ 1;
-                S.ctl->steps_done = ctl.steps_done + 1;
-                __threadfence();
+        if (blocked) return;
+    }
+    const double4 *pos = S.pos[ctl.cur] + (size_t)rep * S.nmp;
+    if ((int)blockIdx.x < A.nblk_pair) phase_pair<GP>(S, P, A, pos, rep, blockIdx.x);
+    else phase_local(S, P, A, pos, rep, blockIdx.x - A.nblk_pair, ctl.step + (A.integrate ? 1ull : 0ull));
+}
+
+// bp task kernel: one thread per half-list candidate
+__global__ void __launch_bounds__(128) k_force_bp(DevSys S, FFParams P, StepArgs A)
+{
+    const DevCtl ctl = S.ctl[0];
+    if (A.integrate && step_blocked(S, ctl.step, A.only_rep)) return;
+    const int rep = (A.only_rep >= 0) ? A.only_rep : blockIdx.y;
+    phase_bp(S, P, A, S.pos[ctl.cur] + (size_t)rep * S.nmp, rep, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// integrate kernel; integrate == 0: only sums the partial forces into S.force (per-irep force())
+__global__ void __launch_bounds__(256) k_integrate(DevSys S, FFParams P, StepArgs A)
+{
+    const DevCtl ctl = A.integrate ? S.ctl[1] : S.ctl[0];
+    if (A.integrate && ctl.blocked) return;
+    const int rep = (A.only_rep >= 0) ? A.only_rep : blockIdx.y;
+    const unsigned long long istep = ctl.step + 1ull;
+    phase_integrate(S, P, A, ctl.cur, rep, blockIdx.x, istep);
+    if (A.integrate && blockIdx.x == 0 && threadIdx.x == 0) {
+        // clear the slot the NEXT step will accumulate into; publish step / buffer for the next force phase
+        unsigned long long *t = S.top2 + ((size_t)rep * 2 + ((istep + 1ull) & 1ull)) * 2;
+        t[0] = 0ull; t[1] = 0ull;
+        if (blockIdx.y == 0) {
+            DevCtl a; a.step = istep; a.cur = ctl.cur ^ 1; a.blocked = 0;
+            S.ctl[0] = a;
+        }
+    }
+}
+
+// ---- persistent MD kernel ---------------------------------------------------------------------
+// One cooperative launch runs up to `nsteps` steps: force phase, grid barrier, integrate phase,
+// grid barrier.  It leaves as soon as a replica passes the list margin (the host then rebuilds
+// the lists and relaunches), so no launch is wasted and a step costs two grid barriers instead
+// of two kernel launches.  Blocks walk "virtual blocks" of the three force roles; the bp role
+// (longest dependent chain) is scheduled first.
+template <int GP>
+__global__ void __launch_bounds__(256, 2) k_md_persistent(DevSys S, FFParams P, StepArgs A, int nsteps)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const DevCtl ctl = S.ctl[0];
+    unsigned long long step = ctl.step;
+    int cur = ctl.cur;
+    const int R = S.nrep, nmp = S.nmp;
+    const int per_rep = A.nblk_bp + A.nblk_pair + A.nblk_loc;
+    const bool prof = S.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+    for (int n = 0; n < nsteps; n++) {
+        if (step_blocked(S, step, -1)) break;
+        if (prof) c0 = clock64();
+        for (int vb = blockIdx.x; vb < per_rep * R; vb += gridDim.x) {
+            const int rep = vb / per_rep, b = vb % per_rep;
+            const double4 *pos = S.pos[cur] + (size_t)rep * nmp;
+            if (b < A.nblk_bp) phase_bp(S, P, A, pos, rep, b * 256 + threadIdx.x);
+            else if (b < A.nblk_bp + A.nblk_pair) phase_pair<GP>(S, P, A, pos, rep, b - A.nblk_bp);
+            else phase_local(S, P, A, pos, rep, b - A.nblk_bp - A.nblk_pair, step + 1ull);
+        }
+        if (prof) c1 = clock64();
+        grid.sync();
+        if (prof) c2 = clock64();
+        for (int vb = blockIdx.x; vb < S.nblk * R; vb += gridDim.x) {
+            const int rep = vb / S.nblk, b = vb % S.nblk;
+            phase_integrate(S, P, A, cur, rep, b, step + 1ull);
+            if (b == 0 && threadIdx.x == 0) {
+                unsigned long long *t = S.top2 + ((size_t)rep * 2 + ((step + 2ull) & 1ull)) * 2;
+                t[0] = 0ull; t[1] = 0ull;
             }
         }
+        if (prof) c3 = clock64();
+        grid.sync();
+        if (prof) {
+            c4 = clock64();
+            S.prof[0] += (unsigned long long)(c1 - c0); S.prof[1] += (unsigned long long)(c2 - c1);
+            S.prof[2] += (unsigned long long)(c3 - c2); S.prof[3] += (unsigned long long)(c4 - c3);
+            S.prof[4] += 1ull;
+        }
+        step++;
+        cur ^= 1;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        DevCtl a; a.step = step; a.cur = cur; a.blocked = 0;
+        S.ctl[0] = a;
     }
 }
 
@@ -454,9 +548,9 @@ __global__ void __launch_bounds__(256) k_integrate(DevSys S, FFParams P, StepArg
 // count_excess: nt_bp_excess accumulation for the MC pruning
 template <int SIDE>
 __global__ void __launch_bounds__(256) k_bp_eval(DevSys S, FFParams P, int only_rep, double tK_override,
-                                                 int use_override, int use_mask, int count_excess)
+                                                 int use_override, int use_mask, int count_excess, int in_md)
 {
-    if (ctl_aborted(*S.ctl)) return;
+    if (in_md && step_blocked(S, S.ctl[0].step, only_rep)) return;
     const int rep = (only_rep >= 0) ? only_rep : blockIdx.y;
     const int nmp = S.nmp;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over nmp*KB slots
@@ -467,7 +561,7 @@ __global__ void __launch_bounds__(256) k_bp_eval(DevSys S, FFParams P, int only_
     const int2 ent = S.bprow[(rbase + k) * S.KB + e];
     const int j = ent.x, ibp = ent.y;
     if (j < k) return;   // owner = lower bead
-    const double4 *pos = S.pos[S.ctl->cur] + rbase;
+    const double4 *pos = S.pos[S.ctl[0].cur] + rbase;
     const RepParams R = S.rp[rep];
     int st = 0;
     double en = 0.0;
@@ -503,9 +597,9 @@ __global__ void __launch_bounds__(256) k_bp_eval(DevSys S, FFParams P, int only_
     }
 }
 
-__global__ void k_excess_init(DevSys S, int only_rep, int max_bp_per_nt)
+__global__ void k_excess_init(DevSys S, int only_rep, int max_bp_per_nt, int in_md)
 {
-    if (ctl_aborted(*S.ctl)) return;
+    if (in_md && step_blocked(S, S.ctl[0].step, only_rep)) return;
     const int rep = (only_rep >= 0) ? only_rep : blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < S.nmp) S.nt_excess[(size_t)rep * S.nmp + i] = -max_bp_per_nt;
@@ -516,9 +610,9 @@ __global__ void k_excess_init(DevSys S, int only_rep, int max_bp_per_nt)
 // deterministic != 0: temp_independent branch of src/energy_bp_limit_triplet.F90:167-176.
 __global__ void __launch_bounds__(32) k_bp_prune(DevSys S, FFParams P, unsigned long long seed, int only_rep,
                                                   double tK_override, int use_override, int deterministic,
-                                                  int copy_to_mc)
+                                                  int copy_to_mc, int in_md)
 {
-    if (ctl_aborted(*S.ctl)) return;
+    if (in_md && step_blocked(S, S.ctl[0].step, only_rep)) return;
     const int rep = (only_rep >= 0) ? only_rep : blockIdx.x;
     const int lane = threadIdx.x;
     const int nmp = S.nmp, KB = S.KB;
@@ -602,7 +696,7 @@ __global__ void __launch_bounds__(256) k_rg(DevSys S, int only_rep)
 {
     const int rep = (only_rep >= 0) ? only_rep : blockIdx.x;
     const int nmp = S.nmp;
-    const double4 *pos = S.pos[S.ctl->cur] + (size_t)rep * nmp;
+    const double4 *pos = S.pos[S.ctl[0].cur] + (size_t)rep * nmp;
     __shared__ double sh[4][8];
     __shared__ double cm[3];
     double sx = 0, sy = 0, sz = 0;
@@ -649,7 +743,7 @@ __global__ void __launch_bounds__(256) k_energy(DevSys S, FFParams P, const RepP
     const int lane = threadIdx.x % G;
     const int k = blockIdx.x * BPB + threadIdx.x / G;
     const int nmp = S.nmp;
-    const double4 *pos = S.pos[S.ctl->cur] + (size_t)rep * nmp;
+    const double4 *pos = S.pos[S.ctl[0].cur] + (size_t)rep * nmp;
     const RepParams R = rp_alt ? rp_alt[rep] : S.rp[rep];
     double e[ENE_N];
 #pragma unroll
@@ -690,7 +784,7 @@ __global__ void __launch_bounds__(256) k_energy(DevSys S, FFParams P, const RepP
         if (lane == 0 && P.flg_stage) {   // src/energy_stage.F90:28-36
             double z = P.stage_sigma / xk.z;
             e[ENE_STAGE] += 4 * P.stage_eps * (powi(z, 12) - powi(z, 6));
-            if (xk.z < 0.85 * P.stage_sigma) S.ctl->max_force_flag |= 2;   // reference aborts here
+            if (xk.z < 0.85 * P.stage_sigma) S.misc->max_force_flag |= 2;   // reference aborts here
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -800,7 +894,7 @@ __global__ void k_nl_wrap_count(DevSys S, FFParams P, GridInfo Gd, const int *re
     if (!rep_active[rep]) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S.nmp) return;
-    double4 *pos = S.pos[S.ctl->cur] + (size_t)rep * S.nmp;
+    double4 *pos = S.pos[S.ctl[0].cur] + (size_t)rep * S.nmp;
     double4 p = pos[i];
     if (P.flg_pbc) {
         p.x = wrap1(p.x, P.box[0]); p.y = wrap1(p.y, P.box[1]); p.z = wrap1(p.z, P.box[2]);
@@ -950,7 +1044,7 @@ __global__ void __launch_bounds__(256) k_nl_rows(DevSys S, FFParams P, GridInfo 
     const int nmp = S.nmp;
     if (i >= nmp) return;
     const size_t rbase = (size_t)rep * nmp;
-    const double4 *pos = S.pos[S.ctl->cur] + rbase;
+    const double4 *pos = S.pos[S.ctl[0].cur] + rbase;
     const RepParams R = S.rp[rep];
     const int4 mi = S.meta[i];
     const Vec3 xi = v3(pos[i]);
@@ -1027,8 +1121,8 @@ __global__ void __launch_bounds__(256) k_nl_rows(DevSys S, FFParams P, GridInfo 
     if (lane == 0) {
         S.nnbr[rbase + i] = min(nn, S.K);
         S.nbp_row[rbase + i] = min(nb, S.KB);
-        if (nn > S.K) atomicMax(&S.ctl->nl_overflow, nn);
-        if (nb > S.KB) atomicMax(&S.ctl->bp_overflow, nb);
+        if (nn > S.K) atomicMax(&S.misc->nl_overflow, nn);
+        if (nb > S.KB) atomicMax(&S.misc->bp_overflow, nb);
         S.move[(rbase + i) * 3] = 0.0; S.move[(rbase + i) * 3 + 1] = 0.0; S.move[(rbase + i) * 3 + 2] = 0.0;
     }
 }
@@ -1063,9 +1157,10 @@ __global__ void k_nl_begin_slots(DevSys S, const int *rep_active)
     const int rep = blockIdx.x * blockDim.x + threadIdx.x;
     if (rep < S.nrep && rep_active[rep]) S.nbp_half[rep] = 0;
 }
+// a rebuilt replica restarts its displacement bookkeeping (xyz_move = 0, src/job_md.F90:390)
 __global__ void k_nl_finish(DevSys S, const int *rep_active)
 {
     const int rep = blockIdx.x * blockDim.x + threadIdx.x;
-    if (rep < S.nrep && rep_active[rep]) S.need_rebuild[rep] = 0;
-    if (rep == 0) S.ctl->abort_word = 0ull;
+    if (rep < S.nrep && rep_active[rep])
+        for (int q = 0; q < 4; q++) S.top2[(size_t)rep * 4 + q] = 0ull;
 }

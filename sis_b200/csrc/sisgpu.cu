@@ -130,6 +130,7 @@ struct sisgpu {
     bool lists_full = false;   // list_exv/ele/bp mode (no rebuild trigger)
     bool lists_built = false;
     int nbp_half_max = 0;      // max over replicas of the half-list bp candidate count
+    int coop_blocks = 0;       // co-resident grid size of the persistent kernel
     // biases (host copies)
     std::vector<int> twz_pairs, twzfr_pairs, rest_id;
     std::vector<double> twz_dir, twzfr_k, twzfr_init, twzfr_velo, rest_rcut, rest_para;
@@ -153,24 +154,28 @@ struct sisgpu {
     DevSys S{};
     DBuf<int4> d_meta;
     DBuf<int> d_seq, d_hash, d_nnbr, d_nbp_row, d_bp_status, d_bp_status_MC, d_nt_excess, d_cell_of,
-        d_cell_count, d_cell_start, d_cell_cursor, d_cell_beads, d_need_rebuild, d_rep_active, d_twz_pairs,
+        d_cell_count, d_cell_start, d_cell_cursor, d_cell_beads, d_rep_active, d_twz_pairs,
         d_twzfr_pairs, d_rest_id;
     DBuf<double4> d_coef, d_pos0, d_pos1;
     DBuf<double> d_f_pair, d_f_loc, d_f_bp;
     DBuf<int> d_bp_half, d_nbp_half;
-    DBuf<double> d_mass, d_bp3_dH, d_bp3_dS, d_vel, d_acc, d_move, d_force, d_ene_bp, d_blk_top2,
+    DBuf<double> d_mass, d_bp3_dH, d_bp3_dS, d_vel, d_acc, d_move, d_force, d_ene_bp,
         d_ene_partial, d_ene_out, d_kin, d_twz_dir, d_twzfr_k, d_twzfr_init, d_twzfr_velo, d_rest_rcut,
         d_rest_para, d_gather_send, d_gather_recv;
     DBuf<uint32_t> d_nbr;
     DBuf<int2> d_bprow;
     DBuf<signed char> d_bp_type;
     DBuf<double2> d_bp_coef;
-    DBuf<unsigned long long> d_mc_counter;
-    DBuf<unsigned int> d_blk_counter, d_ene_counter;
+    DBuf<unsigned long long> d_mc_counter, d_prof;
+    DBuf<unsigned int> d_ene_counter;
     DBuf<RepParams> d_rp, d_rp_alt;
-    DBuf<DevCtl> d_ctl;
-    DevCtl *h_ctl = nullptr;   // pinned
-    int *h_need = nullptr;     // pinned [nrep]
+    DBuf<unsigned char> d_sync;          // DevSyncHdr + top2[nrep][2][2]
+    unsigned char *h_sync = nullptr;     // pinned mirror
+    size_t sync_bytes = 0;
+    DevCtl *h_ctl = nullptr;             // -> ctl[0] ("A") inside h_sync
+    DevMisc *h_misc = nullptr;
+    unsigned long long *h_top2 = nullptr;
+    std::vector<int> h_need;             // replicas past the list margin (from h_top2)
     int K = 0, KB = 0, G = 8;   // G = lanes per bead in the pair task
     // stats / options
     long long launches = 0, nrebuild = 0, graph_launches_per_chunk = 0;
@@ -213,21 +218,20 @@ int sisgpu_destroy(sisgpu_t *h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
-    if (h->h_ctl) cudaFreeHost(h->h_ctl);
-    if (h->h_need) cudaFreeHost(h->h_need);
+    if (h->h_sync) cudaFreeHost(h->h_sync);
     // DBuf members are released explicitly (no destructors touching CUDA at exit)
     h->d_meta.release(); h->d_seq.release(); h->d_hash.release(); h->d_nnbr.release(); h->d_nbp_row.release();
     h->d_bp_status.release(); h->d_bp_status_MC.release(); h->d_nt_excess.release(); h->d_cell_of.release();
     h->d_cell_count.release(); h->d_cell_start.release(); h->d_cell_cursor.release(); h->d_cell_beads.release();
-    h->d_need_rebuild.release(); h->d_rep_active.release(); h->d_twz_pairs.release(); h->d_twzfr_pairs.release();
+    h->d_rep_active.release(); h->d_twz_pairs.release(); h->d_twzfr_pairs.release();
     h->d_rest_id.release(); h->d_coef.release(); h->d_pos0.release(); h->d_pos1.release(); h->d_mass.release();
     h->d_bp3_dH.release(); h->d_bp3_dS.release(); h->d_vel.release(); h->d_acc.release(); h->d_move.release();
-    h->d_force.release(); h->d_ene_bp.release(); h->d_blk_top2.release(); h->d_ene_partial.release();
+    h->d_force.release(); h->d_ene_bp.release(); h->d_ene_partial.release();
     h->d_ene_out.release(); h->d_kin.release(); h->d_twz_dir.release(); h->d_twzfr_k.release();
     h->d_twzfr_init.release(); h->d_twzfr_velo.release(); h->d_rest_rcut.release(); h->d_rest_para.release();
     h->d_gather_send.release(); h->d_gather_recv.release(); h->d_nbr.release(); h->d_bprow.release();
-    h->d_bp_type.release(); h->d_bp_coef.release(); h->d_mc_counter.release(); h->d_blk_counter.release();
-    h->d_ene_counter.release(); h->d_rp.release(); h->d_rp_alt.release(); h->d_ctl.release();
+    h->d_bp_type.release(); h->d_bp_coef.release(); h->d_mc_counter.release();
+    h->d_ene_counter.release(); h->d_rp.release(); h->d_rp_alt.release(); h->d_sync.release();
     if (h->graph_chunk) cudaGraphExecDestroy(h->graph_chunk);
     h->d_f_pair.release(); h->d_f_loc.release(); h->d_f_bp.release(); h->d_bp_half.release(); h->d_nbp_half.release();
     cudaEventDestroy(h->ev0);
@@ -675,18 +679,24 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     TRY(h->d_vel.alloc(RN * 3)); TRY(h->d_acc.alloc(RN * 3)); TRY(h->d_move.alloc(RN * 3)); TRY(h->d_force.alloc(RN * 3));
     TRY(h->d_nnbr.alloc(RN)); TRY(h->d_nbp_row.alloc(RN)); TRY(h->d_nt_excess.alloc(RN));
     TRY(h->d_cell_of.alloc(RN)); TRY(h->d_cell_beads.alloc(RN));
-    TRY(h->d_mc_counter.alloc(R)); TRY(h->d_need_rebuild.alloc(R)); TRY(h->d_rep_active.alloc(R));
-    TRY(h->d_rp.alloc(R)); TRY(h->d_rp_alt.alloc(R)); TRY(h->d_ctl.alloc(1));
+    TRY(h->d_mc_counter.alloc(R)); TRY(h->d_rep_active.alloc(R));
+    TRY(h->d_rp.alloc(R)); TRY(h->d_rp_alt.alloc(R));
+    h->sync_bytes = sizeof(DevSyncHdr) + (size_t)R * 4 * sizeof(unsigned long long);
+    TRY(h->d_sync.alloc(h->sync_bytes));
     TRY(h->d_kin.alloc(R));
     const int nblk = (N + 63) / 64;            // integrate kernel: 64 beads per block
     const int nblk_ene = (N + 31) / 32;        // energy kernel: 8 lanes per bead
-    TRY(h->d_blk_top2.alloc((size_t)R * nblk * 2)); TRY(h->d_blk_counter.alloc(R + 1));
     TRY(h->d_ene_partial.alloc((size_t)R * nblk_ene * ENE_N)); TRY(h->d_ene_counter.alloc(R)); TRY(h->d_ene_out.alloc((size_t)R * ENE_N));
     TRY(h->d_f_pair.alloc(RN * 3)); TRY(h->d_f_loc.alloc(RN * 3)); TRY(h->d_f_bp.alloc(RN * 3));
     TRY(h->d_nbp_half.alloc(R));
     TRY(h->d_gather_send.alloc(2 * (size_t)R)); TRY(h->d_gather_recv.alloc(2 * (size_t)std::max(h->nrep_all, R)));
-    if (!h->h_ctl) CK(cudaMallocHost(&h->h_ctl, sizeof(DevCtl)));
-    if (!h->h_need) CK(cudaMallocHost(&h->h_need, sizeof(int) * R));
+    if (h->h_sync) cudaFreeHost(h->h_sync);
+    CK(cudaMallocHost(&h->h_sync, h->sync_bytes));
+    memset(h->h_sync, 0, h->sync_bytes);
+    h->h_ctl = &((DevSyncHdr *)h->h_sync)->ctl[0];
+    h->h_misc = &((DevSyncHdr *)h->h_sync)->misc;
+    h->h_top2 = (unsigned long long *)(h->h_sync + sizeof(DevSyncHdr));
+    h->h_need.assign(R, 0);
     DevSys &S = h->S;
     S.nmp = N; S.nrep = R; S.nblk = nblk; S.nblk_ene = nblk_ene;
     S.f_pair = h->d_f_pair.p; S.f_loc = h->d_f_loc.p; S.f_bp = h->d_f_bp.p; S.nbp_half = h->d_nbp_half.p;
@@ -695,8 +705,11 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     S.pos[0] = h->d_pos0.p; S.pos[1] = h->d_pos1.p; S.vel = h->d_vel.p; S.acc = h->d_acc.p; S.move = h->d_move.p;
     S.force = h->d_force.p; S.nnbr = h->d_nnbr.p; S.nbp_row = h->d_nbp_row.p; S.nt_excess = h->d_nt_excess.p;
     S.mc_counter = h->d_mc_counter.p; S.cell_of = h->d_cell_of.p; S.cell_beads = h->d_cell_beads.p;
-    S.rp = h->d_rp.p; S.ctl = h->d_ctl.p; S.need_rebuild = h->d_need_rebuild.p; S.blk_top2 = h->d_blk_top2.p;
-    S.blk_counter = h->d_blk_counter.p; S.ene_partial = h->d_ene_partial.p; S.ene_counter = h->d_ene_counter.p;
+    S.rp = h->d_rp.p;
+    S.ctl = ((DevSyncHdr *)h->d_sync.p)->ctl; S.misc = &((DevSyncHdr *)h->d_sync.p)->misc;
+    S.top2 = (unsigned long long *)(h->d_sync.p + sizeof(DevSyncHdr));
+    S.nl_margin = h->nl_margin;
+    S.ene_partial = h->d_ene_partial.p; S.ene_counter = h->d_ene_counter.p;
     S.ene_out = h->d_ene_out.p;
     S.twz_pairs = h->d_twz_pairs.p; S.twz_dir = h->d_twz_dir.p; S.twzfr_pairs = h->d_twzfr_pairs.p;
     S.twzfr_k = h->d_twzfr_k.p; S.twzfr_init = h->d_twzfr_init.p; S.twzfr_velo = h->d_twzfr_velo.p;
@@ -711,11 +724,19 @@ int sisgpu_finalize_setup(sisgpu_t *h)
 }
 
 // ---- state --------------------------------------------------------------------------------
+// one D2H copy of the step bookkeeping; h_need[r] = replica r is past the list margin
+// (the test of src/job_md.F90:388 on the displacement top-2 of the last completed step)
 static int sync_ctl(sisgpu *h)
 {
-    CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl.p, sizeof(DevCtl), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_need, h->d_need_rebuild.p, sizeof(int) * h->nrep, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_sync, h->d_sync.p, h->sync_bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    const unsigned long long slot = h->h_ctl->step & 1ull;
+    for (int r = 0; r < h->nrep; r++) {
+        double m1, m2;
+        memcpy(&m1, &h->h_top2[((size_t)r * 2 + slot) * 2], 8);
+        memcpy(&m2, &h->h_top2[((size_t)r * 2 + slot) * 2 + 1], 8);
+        h->h_need[r] = (sqrt(m1) + sqrt(m2) > h->S.nl_margin) ? 1 : 0;
+    }
     return 0;
 }
 
@@ -757,7 +778,10 @@ int sisgpu_set_step(sisgpu_t *h, int64_t istep)
 {
     TRY(sync_ctl(h));
     h->h_ctl->step = (unsigned long long)istep;
-    CK(cudaMemcpy(h->d_ctl.p, h->h_ctl, sizeof(DevCtl), cudaMemcpyHostToDevice));
+    // keep the displacement slot of the current step where the new parity expects it
+    CK(cudaMemcpy(h->d_sync.p, h->h_sync, sizeof(DevCtl), cudaMemcpyHostToDevice));
+    // the displacement slots are indexed by step parity: restart them (recomputed every step)
+    CK(cudaMemset(h->S.top2, 0, (size_t)h->nrep * 4 * sizeof(unsigned long long)));
     h->istep_host = istep;
     return 0;
 }
@@ -856,8 +880,8 @@ static int build_lists(sisgpu *h, const std::vector<int> &active, bool all_pairs
     NlArgs A = nl_args(h, brute);
     A.all_pairs = all_pairs ? 1 : (brute ? 2 : 0);
     for (int attempt = 0; attempt < 8; attempt++) {
-        h->h_ctl->nl_overflow = 0; h->h_ctl->bp_overflow = 0;
-        CK(cudaMemcpyAsync(&h->d_ctl.p->nl_overflow, &h->h_ctl->nl_overflow, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        h->h_misc->nl_overflow = 0; h->h_misc->bp_overflow = 0;
+        CK(cudaMemcpyAsync(&h->S.misc->nl_overflow, &h->h_misc->nl_overflow, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         if (!brute) {
             if (attempt == 0) {
                 CK(cudaMemsetAsync(S.cell_count, 0, (size_t)R * S.ncell_cap * sizeof(int), h->stream));
@@ -878,10 +902,10 @@ static int build_lists(sisgpu *h, const std::vector<int> &active, bool all_pairs
         h->launches += 1;
         TRY(sync_ctl(h));
         CK(cudaGetLastError());
-        if (h->h_ctl->nl_overflow > h->K || h->h_ctl->bp_overflow > h->KB) {
+        if (h->h_misc->nl_overflow > h->K || h->h_misc->bp_overflow > h->KB) {
             int K = h->K, KB = h->KB;
-            if (h->h_ctl->nl_overflow > K) K = ((int)(h->h_ctl->nl_overflow * 1.2) + 31) / 32 * 32;   // growth as the reference's x1.2
-            if (h->h_ctl->bp_overflow > KB) KB = ((int)(h->h_ctl->bp_overflow * 1.2) + 7) / 8 * 8;
+            if (h->h_misc->nl_overflow > K) K = ((int)(h->h_misc->nl_overflow * 1.2) + 31) / 32 * 32;   // growth as the reference's x1.2
+            if (h->h_misc->bp_overflow > KB) KB = ((int)(h->h_misc->bp_overflow * 1.2) + 7) / 8 * 8;
             // a capacity change relocates every replica's rows: rebuild all of them
             std::vector<int> all(R, 1);
             bool was_all = true;
@@ -907,6 +931,8 @@ static int build_lists(sisgpu *h, const std::vector<int> &active, bool all_pairs
         timer_end(h, h->t_nl);
         h->lists_full = all_pairs;
         h->lists_built = true;
+        const double margin = all_pairs ? 1e300 : h->nl_margin;
+        if (margin != h->S.nl_margin) { h->S.nl_margin = margin; invalidate_graphs(h); }
         return 0;
     }
     return set_err("neighbour list capacity did not converge");
@@ -1067,10 +1093,11 @@ int sisgpu_set_bp_mc(sisgpu_t *h, int flg) { h->flg_bp_MC = flg; return 0; }
 static StepArgs step_args(const sisgpu *h, unsigned mask, int use_mask, int only_rep, int integrate)
 {
     StepArgs A{};
-    A.seed = h->seed; A.nl_margin = h->lists_full ? 1e300 : h->nl_margin;
+    A.seed = h->seed;
     A.term_mask = mask; A.use_mask = use_mask; A.only_rep = only_rep; A.integrate = integrate;
     A.nblk_pair = (h->nmp + 256 / h->G - 1) / (256 / h->G);
     A.nblk_loc = (h->nmp + 31) / 32;
+    A.nblk_bp = (std::max(h->nbp_half_max, 1) + 255) / 256;
     return A;
 }
 
@@ -1103,18 +1130,18 @@ static void enqueue_step(sisgpu *h, const StepArgs &A)
 // evaluation + MC pruning passes of force_bp_limit_triplet / energy_bp_limit_triplet
 template <int SIDE>
 static void launch_bp_eval(sisgpu *h, int only_rep, bool with_prune, double tK, int use_override, int use_mask,
-                           int copy_to_mc, int deterministic)
+                           int copy_to_mc, int deterministic, int in_md = 0)
 {
     const int R = only_rep >= 0 ? 1 : h->nrep;
     if (with_prune) {
-        k_excess_init<<<dim3((h->nmp + 255) / 256, R), 256, 0, h->stream>>>(h->S, only_rep, h->max_bp_per_nt);
+        k_excess_init<<<dim3((h->nmp + 255) / 256, R), 256, 0, h->stream>>>(h->S, only_rep, h->max_bp_per_nt, in_md);
         h->launches++;
     }
     k_bp_eval<SIDE><<<dim3((h->nmp * h->KB + 255) / 256, R), 256, 0, h->stream>>>(h->S, h->P, only_rep, tK, use_override,
-                                                                                use_mask, with_prune ? 1 : 0);
+                                                                                use_mask, with_prune ? 1 : 0, in_md);
     h->launches++;
     if (with_prune) {
-        k_bp_prune<<<R, 32, 0, h->stream>>>(h->S, h->P, h->seed, only_rep, tK, use_override, deterministic, copy_to_mc);
+        k_bp_prune<<<R, 32, 0, h->stream>>>(h->S, h->P, h->seed, only_rep, tK, use_override, deterministic, copy_to_mc, in_md);
         h->launches++;
     }
 }
@@ -1171,7 +1198,7 @@ int sisgpu_energy_sumup(sisgpu_t *h, int irep, double tempK, int recompute_bp, d
     TRY(sync_ctl(h));
     CK(cudaGetLastError());
     timer_end(h, h->t_ene);
-    if (h->h_ctl->max_force_flag & 2) return set_err("Error: Z-coordinate < 0.85 * stage_sigma in energy_stage. Abort!");
+    if (h->h_misc->max_force_flag & 2) return set_err("Error: Z-coordinate < 0.85 * stage_sigma in energy_stage. Abort!");
     return 0;
 }
 
@@ -1496,8 +1523,6 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
             TRY(build_lists(h, act, false));
             if (h->nstep_bp_MC > 0) force_mc = true;
             TRY(sync_ctl(h));
-        } else if (h->h_ctl->abort_word) {
-            return set_err("internal: abort without rebuild request");
         }
         long long cur = (long long)h->h_ctl->step;
         long long stop = target;
@@ -1509,14 +1534,34 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
         timer_begin(h);
         const int use_mask = h->nstep_bp_MC > 0 ? 1 : 0;
         const bool uniform = h->nstep_bp_MC <= 1;   // every step has the same kernel sequence
-        if (h->launch_mode == 1 && uniform && nchunk == h->chunk) {
+        if (h->launch_mode == 2 && h->nstep_bp_MC == 0 && !h->P.flg_bias_rg) {
+            // persistent cooperative kernel: runs until `stop` or until a replica needs new lists
+            if (h->coop_blocks == 0) {
+                int per_sm = 0, dev_sms = 0;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_md_persistent<8>, 256, 0));
+                CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
+                h->coop_blocks = std::max(1, per_sm) * dev_sms;
+            }
+            StepArgs A = step_args(h, mask_all, 0, -1, 1);
+            int nrun = (int)std::min<long long>(stop - cur, 1 << 20);
+            const int want = (A.nblk_bp + A.nblk_pair + A.nblk_loc) * R;
+            dim3 grid(std::min(h->coop_blocks, want));
+            void *args[] = {&h->S, &h->P, &A, &nrun};
+            switch (h->G) {
+            case 4: CK(cudaLaunchCooperativeKernel((void *)k_md_persistent<4>, grid, dim3(256), args, 0, h->stream)); break;
+            case 16: CK(cudaLaunchCooperativeKernel((void *)k_md_persistent<16>, grid, dim3(256), args, 0, h->stream)); break;
+            case 32: CK(cudaLaunchCooperativeKernel((void *)k_md_persistent<32>, grid, dim3(256), args, 0, h->stream)); break;
+            default: CK(cudaLaunchCooperativeKernel((void *)k_md_persistent<8>, grid, dim3(256), args, 0, h->stream)); break;
+            }
+            h->launches++;
+        } else if (h->launch_mode >= 1 && uniform && nchunk == h->chunk) {
             if (!h->graph_chunk || h->graph_chunk_steps != nchunk) {
                 invalidate_graphs(h);
                 cudaGraph_t graph = nullptr;
                 CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
                 const long long l0 = h->launches;
                 for (int s = 0; s < nchunk; s++) {
-                    if (h->nstep_bp_MC == 1) launch_bp_eval<0>(h, -1, true, 0.0, 0, 0, 1, 0);
+                    if (h->nstep_bp_MC == 1) launch_bp_eval<0>(h, -1, true, 0.0, 0, 0, 1, 0, 1);
                     launch_rg(h, -1);
                     enqueue_step(h, step_args(h, mask_all, use_mask, -1, 1));
                 }
@@ -1534,7 +1579,7 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
                 const long long istep = cur + s + 1;
                 bool mc = false;
                 if (h->nstep_bp_MC > 0) mc = (istep % h->nstep_bp_MC == 0) || (s == 0 && force_mc);
-                if (mc) launch_bp_eval<0>(h, -1, true, 0.0, 0, 0, 1, 0);
+                if (mc) launch_bp_eval<0>(h, -1, true, 0.0, 0, 0, 1, 0, 1);
                 launch_rg(h, -1);
                 enqueue_step(h, step_args(h, mask_all, use_mask, -1, 1));
             }
@@ -1544,7 +1589,7 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
         CK(cudaGetLastError());
         timer_end(h, h->t_step);
         // exchange step (src/job_md.F90:474-481,514-570)
-        if (h->flg_replica && h->nstep_exchange > 0 && !h->h_ctl->abort_word &&
+        if (h->flg_replica && h->nstep_exchange > 0 &&
             (long long)h->h_ctl->step % h->nstep_exchange == 0 && (long long)h->h_ctl->step > cur) {
             std::vector<double> re(2 * (size_t)h->nrep_all);
             const int mc_saved = h->flg_bp_MC;
@@ -1556,10 +1601,10 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
             timer_end(h, h->t_rex);
         }
     }
-    if (h->h_ctl->max_force_flag & 1) {
+    if (h->h_misc->max_force_flag & 1) {
         fprintf(stderr, "Warning: maxval(forces) > 100.0 during the last md_steps call (step %lld)\n", (long long)h->h_ctl->step);
-        h->h_ctl->max_force_flag = 0;
-        CK(cudaMemcpy(&h->d_ctl.p->max_force_flag, &h->h_ctl->max_force_flag, sizeof(int), cudaMemcpyHostToDevice));
+        h->h_misc->max_force_flag = 0;
+        CK(cudaMemcpy(&h->S.misc->max_force_flag, &h->h_misc->max_force_flag, sizeof(int), cudaMemcpyHostToDevice));
     }
     if (nrebuild_out) *nrebuild_out = h->nrebuild - nreb0;
     return 0;
@@ -1607,6 +1652,11 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
     if (s == "launch_mode") h->launch_mode = (int)value;
     else if (s == "chunk") { h->chunk = std::max(1, (int)value); invalidate_graphs(h); }
     else if (s == "timing") h->timing = (int)value;
+    else if (s == "profile") {   // phase clocks of the persistent kernel (block 0): get_timers out[4..8]
+        if (value != 0) { TRY(h->d_prof.alloc(8)); h->S.prof = h->d_prof.p; }
+        else h->S.prof = nullptr;
+        invalidate_graphs(h);
+    }
     else if (s == "threads_per_bead") {
         int g = (int)value;
         if (g != 4 && g != 8 && g != 16 && g != 32) return set_err("threads_per_bead must be 4, 8, 16 or 32");
@@ -1619,6 +1669,13 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
 int sisgpu_get_timers(sisgpu_t *h, double *out, int reset)
 {
     out[0] = h->t_step; out[1] = h->t_nl; out[2] = h->t_ene; out[3] = h->t_rex;
+    for (int i = 4; i < 9; i++) out[i] = 0;
+    if (h->S.prof) {
+        unsigned long long p[8];
+        CK(cudaMemcpy(p, h->d_prof.p, sizeof p, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 5; i++) out[4 + i] = (double)p[i];
+        if (reset) CK(cudaMemset(h->d_prof.p, 0, sizeof p));
+    }
     if (reset) h->t_step = h->t_nl = h->t_ene = h->t_rex = 0;
     return 0;
 }
