@@ -31,8 +31,9 @@ enum { ENE_TOTAL = 0, ENE_BOND, ENE_ANGL, ENE_DIHE, ENE_BP, ENE_EXV, ENE_ELE, EN
 
 // bead meta flags (int4 meta: x = chain start, y = chain length, z = local index, w = flags)
 constexpr int MF_SEQ_MASK = 7, MF_CHARGE = 8, MF_CIRC = 16, MF_FROZEN = 32;
-// neighbour row entry: bit31 = in WCA list, bit30 = in DH list, low 30 bits = partner bead
-constexpr uint32_t NB_WCA = 0x80000000u, NB_ELE = 0x40000000u, NB_IDX = 0x3FFFFFFFu;
+// neighbour row entry: bit31 = in WCA list, bit30 = in DH list, bit29 = the pair may need the
+// periodic image shift before the next rebuild (see nl_needs_image), low 29 bits = partner bead
+constexpr uint32_t NB_WCA = 0x80000000u, NB_ELE = 0x40000000u, NB_IMG = 0x20000000u, NB_IDX = 0x1FFFFFFFu;
 
 // src/var_potential.F90:63-82 (field order kept)
 struct BpPara {
@@ -123,17 +124,24 @@ SIS_HD double powi(double x, int n)
     return r;
 }
 
-// ---- bonded terms: force on the bead at position `pos` of the term -----------------------
-// src/force_bond.F90:34-56
-SIS_HD Vec3 bond_force(const FFParams &P, Vec3 x1, Vec3 x2, int pos)
+// ---- bonded terms --------------------------------------------------------------------------
+// Each term has a "vectors" core that evaluates the term once (used by the once-per-term tables
+// of k_md_fast) and a per-position form (gather form: force on the bead at position `pos`).
+// src/force_bond.F90:34-56: returns f with F1 = -f, F2 = +f
+SIS_HD Vec3 bond_force_vec(const FFParams &P, Vec3 x1, Vec3 x2)
 {
     Vec3 v = pbc_vec_d(P, x1, x2);
     double d = sqrt(dot(v, v));
-    Vec3 f = (P.bond_k * (d - P.bond_r0) / d) * v;
+    return (P.bond_k * (d - P.bond_r0) / d) * v;
+}
+SIS_HD Vec3 bond_force(const FFParams &P, Vec3 x1, Vec3 x2, int pos)
+{
+    Vec3 f = bond_force_vec(P, x1, x2);
     return pos == 0 ? -f : f;
 }
+// angles: F1 = *fa, F3 = *fc, F2 = -(fa + fc)
 // src/force_angl.F90:36-82
-SIS_HD Vec3 angl_force(const FFParams &P, Vec3 x1, Vec3 x2, Vec3 x3, int pos)
+SIS_HD void angl_force_vecs(const FFParams &P, Vec3 x1, Vec3 x2, Vec3 x3, Vec3 *fa, Vec3 *fc)
 {
     Vec3 v21 = pbc_vec_d(P, x2, x1), v32 = pbc_vec_d(P, x3, x2);
     double d21 = dot(v21, v21), d32 = dot(v32, v32), d2132 = dot(v32, v21);
@@ -145,12 +153,19 @@ SIS_HD Vec3 angl_force(const FFParams &P, Vec3 x1, Vec3 x2, Vec3 x3, int pos)
     double f = P.angl_k * delta / sqrt(t);
     Vec3 f21 = f * ((d2132 / d21) * v21 - v32);
     Vec3 f32 = f * ((d2132 / d32) * v32 - v21);
-    if (pos == 0) return -f21;
-    if (pos == 1) return f21 - f32;
-    return f32;
+    *fa = -f21;
+    *fc = f32;
+}
+SIS_HD Vec3 angl_force(const FFParams &P, Vec3 x1, Vec3 x2, Vec3 x3, int pos)
+{
+    Vec3 fa, fc;
+    angl_force_vecs(P, x1, x2, x3, &fa, &fc);
+    if (pos == 0) return fa;
+    if (pos == 1) return -(fa + fc);   // = f21 - f32
+    return fc;
 }
 // src/force_angl_ReB.F90:36-73
-SIS_HD Vec3 angl_ReB_force(const FFParams &P, Vec3 x1, Vec3 x2, Vec3 x3, int pos)
+SIS_HD void angl_ReB_force_vecs(const FFParams &P, Vec3 x1, Vec3 x2, Vec3 x3, Vec3 *fa, Vec3 *fc)
 {
     Vec3 v12 = pbc_vec_d(P, x1, x2), v32 = pbc_vec_d(P, x3, x2);
     double d12 = dot(v12, v12), d32 = dot(v32, v32);
@@ -158,14 +173,19 @@ SIS_HD Vec3 angl_ReB_force(const FFParams &P, Vec3 x1, Vec3 x2, Vec3 x3, int pos
     double c = dot(v12, v32) / a1232;
     double om = 1.0 - c * c;
     double f = -P.angl_k * (c - P.angl_co0) * (1.0 - c * P.angl_co0) / (om * om);
-    Vec3 f1 = f * ((1.0 / a1232) * v32 - (c / d12) * v12);
-    Vec3 f3 = f * ((1.0 / a1232) * v12 - (c / d32) * v32);
-    if (pos == 0) return f1;
-    if (pos == 1) return -(f1 + f3);
-    return f3;
+    *fa = f * ((1.0 / a1232) * v32 - (c / d12) * v12);
+    *fc = f * ((1.0 / a1232) * v12 - (c / d32) * v32);
 }
-// src/force_dih_cos.F90:21-59, src/force_dih_exp.F90:36-94
-SIS_HD Vec3 dih_force(const FFParams &P, Vec3 x1, Vec3 x2, Vec3 x3, Vec3 x4, int pos)
+SIS_HD Vec3 angl_ReB_force(const FFParams &P, Vec3 x1, Vec3 x2, Vec3 x3, int pos)
+{
+    Vec3 fa, fc;
+    angl_ReB_force_vecs(P, x1, x2, x3, &fa, &fc);
+    if (pos == 0) return fa;
+    if (pos == 1) return -(fa + fc);
+    return fc;
+}
+// src/force_dih_cos.F90:21-59, src/force_dih_exp.F90:36-94: forces on the four beads
+SIS_HD void dih_force_vecs(const FFParams &P, Vec3 x1, Vec3 x2, Vec3 x3, Vec3 x4, Vec3 *f)
 {
     Vec3 vij = pbc_vec_d(P, x1, x2), vkj = pbc_vec_d(P, x3, x2), vkl = pbc_vec_d(P, x3, x4);
     Vec3 m = cross(vij, vkj), n = cross(vkj, vkl);
@@ -179,11 +199,17 @@ SIS_HD Vec3 dih_force(const FFParams &P, Vec3 x1, Vec3 x2, Vec3 x3, Vec3 x4, int
     }
     Vec3 fi = (-pre / dot(m, m)) * m;
     Vec3 fl = (pre / dot(n, n)) * n;
-    if (pos == 0) return fi;
-    if (pos == 3) return fl;
     double a = dot(vij, vkj) / akj2, b = dot(vkl, vkj) / akj2;
-    if (pos == 1) return (-1.0 + a) * fi + (-b) * fl;
-    return (-a) * fi + (-1.0 + b) * fl;
+    f[0] = fi;
+    f[1] = (-1.0 + a) * fi + (-b) * fl;
+    f[2] = (-a) * fi + (-1.0 + b) * fl;
+    f[3] = fl;
+}
+SIS_HD Vec3 dih_force(const FFParams &P, Vec3 x1, Vec3 x2, Vec3 x3, Vec3 x4, int pos)
+{
+    Vec3 f[4];
+    dih_force_vecs(P, x1, x2, x3, x4, f);
+    return pos == 0 ? f[0] : pos == 1 ? f[1] : pos == 2 ? f[2] : f[3];
 }
 
 // energies: src/energy_bond.F90:17-28, energy_angl.F90:18-41, energy_angl_ReB.F90:18-29,
@@ -340,6 +366,72 @@ SIS_HD bool bp_force_all(const FFParams &P, const BpPara &p, const Vec3 *x, doub
     f[4] += fl;
     *u_out = u;
     return true;
+}
+
+// The same force-side arithmetic split into seven independent ROLES so that the lanes of a
+// group evaluate one base pair cooperatively (k_md_fused): role 0 = bond 1=2, roles 1..4 = the
+// angles 3-1=2, 1=2-4, 5-1=2, 1=2-6, roles 5..6 = the dihedrals 4-2=1-3 and 6-2=1-5.
+// A role touches beads 0 (i), 1 (j) and at most two more: bead bp_role_A(role) receives `ca`,
+// bead bp_role_B(role) (dihedral roles only) receives `cb`.  Summing u and the contributions
+// over the roles reproduces bp_force_all term by term (same expressions, other summation order).
+struct BpSub {
+    double u;
+    Vec3 c0, c1, ca, cb;
+};
+SIS_HD int bp_role_A(int role) { return role == 1 ? 2 : role == 2 ? 3 : role == 3 ? 4 : role == 4 ? 5 : role == 5 ? 3 : role == 6 ? 5 : -1; }
+SIS_HD int bp_role_B(int role) { return role == 5 ? 2 : role == 6 ? 4 : -1; }
+// xa = position of bead bp_role_A(role), xb = position of bead bp_role_B(role) (dihedral roles)
+SIS_HD BpSub bp_force_role(const FFParams &P, const BpPara &p, int role, Vec3 x0, Vec3 x1, Vec3 xa, Vec3 xb,
+                           Vec3 v12, double d1212, double a12)
+{
+    BpSub o;
+    o.u = 0.0;
+    o.c0 = o.c1 = o.ca = o.cb = mk(0.0, 0.0, 0.0);
+    if (role == 0) {
+        const double d = a12 - p.bond_r;
+        o.u = p.bond_k * d * d;
+        const Vec3 fi = (2.0 * p.bond_k * d / a12) * v12;
+        o.c0 = fi;
+        o.c1 = -fi;
+    } else if (role <= 4) {
+        // angle between v12 and w; odd roles: w = x0 - xa (vertex i), even roles: w = xa - x1 (vertex j)
+        const bool at_i = role & 1;
+        const Vec3 w = at_i ? pbc_vec_d(P, x0, xa) : pbc_vec_d(P, xa, x1);
+        const double k = role == 1 ? p.angl_k2 : role == 2 ? p.angl_k1 : role == 3 ? p.angl_k4 : p.angl_k3;
+        const double th = role == 1 ? p.angl_theta2 : role == 2 ? p.angl_theta1 : role == 3 ? p.angl_theta4 : p.angl_theta3;
+        const double dww = dot(w, w), d12w = dot(v12, w);
+        const double cosine = at_i ? d12w / (sqrt(dww) * a12) : d12w / (a12 * sqrt(dww));
+        const double d = acos(cosine) - th;
+        o.u = k * d * d;
+        const double pre = 2.0 * k * d / sqrt(at_i ? dww * d1212 - d12w * d12w : d1212 * dww - d12w * d12w);
+        const double r12w = d12w / d1212;
+        if (at_i) {
+            const Vec3 fi = pre * (v12 - (d12w / dww) * w);
+            const Vec3 fk = pre * (w - r12w * v12);
+            o.c0 = -fi - fk; o.c1 = fk; o.ca = fi;
+        } else {
+            const Vec3 fi = (-pre) * (w - r12w * v12);
+            const Vec3 fk = (-pre) * (v12 - (d12w / dww) * w);
+            o.c0 = fi; o.c1 = -fi - fk; o.ca = fk;
+        }
+    } else if (role <= 6) {
+        // dihedral a-2=1-b: a on the j side (bead 3 or 5), b on the i side (bead 2 or 4)
+        const Vec3 va2 = pbc_vec_d(P, xa, x1), v1b = pbc_vec_d(P, x0, xb);
+        const double ra = dot(v12, va2) / d1212, rb = dot(v12, v1b) / d1212;
+        const Vec3 m = cross(va2, v12), n = cross(v12, v1b);
+        const double dih = atan2(dot(va2, n) * a12, dot(m, n));
+        const double kk = role == 5 ? p.dihd_k1 : p.dihd_k2;
+        const double d = dih + (role == 5 ? p.dihd_phi1 : p.dihd_phi2);
+        o.u = kk * (1.0 + cos(d));
+        const double pre = -kk * sin(d) * a12;
+        const Vec3 fi = (pre / dot(m, m)) * m;
+        const Vec3 fl = (-pre / dot(n, n)) * n;
+        o.ca = fi;
+        o.c1 = (-1.0 + ra) * fi - rb * fl;
+        o.c0 = (-1.0 + rb) * fl - ra * fi;
+        o.cb = fl;
+    }
+    return o;
 }
 
 // Energy side: src/energy_bp.F90:40-62,76-118 (clamped acos, mp_dihedral)

@@ -83,6 +83,8 @@ struct DevSys {
     unsigned long long *top2;
     double nl_margin;             // 1e300 with the cutoff-free lists (no rebuild trigger)
     unsigned long long *prof;     // optional phase clocks of the persistent kernel (block 0), or null
+    unsigned int *bar;            // grid-barrier counters of k_md_fused: [0] bp done, [32] positions written
+    double2 *top2_slots;          // k_md_fast: per-CTA (max, 2nd max) |xyz_move|^2, [2][FAST_MAX_CTA]
     double *ene_partial;          // [rep][nblk][ENE_N]
     unsigned int *ene_counter;    // [rep]
     double *ene_out;              // [rep][ENE_N]
@@ -483,62 +485,6 @@ __global__ void __launch_bounds__(256) k_integrate(DevSys S, FFParams P, StepArg
             DevCtl a; a.step = istep; a.cur = ctl.cur ^ 1; a.blocked = 0;
             S.ctl[0] = a;
         }
-    }
-}
-
-// ---- persistent MD kernel ---------------------------------------------------------------------
-// One cooperative launch runs up to `nsteps` steps: force phase, grid barrier, integrate phase,
-// grid barrier.  It leaves as soon as a replica passes the list margin (the host then rebuilds
-// the lists and relaunches), so no launch is wasted and a step costs two grid barriers instead
-// of two kernel launches.  Blocks walk "virtual blocks" of the three force roles; the bp role
-// (longest dependent chain) is scheduled first.
-template <int GP>
-__global__ void __launch_bounds__(256, 2) k_md_persistent(DevSys S, FFParams P, StepArgs A, int nsteps)
-{
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
-    const DevCtl ctl = S.ctl[0];
-    unsigned long long step = ctl.step;
-    int cur = ctl.cur;
-    const int R = S.nrep, nmp = S.nmp;
-    const int per_rep = A.nblk_bp + A.nblk_pair + A.nblk_loc;
-    const bool prof = S.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
-    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
-    for (int n = 0; n < nsteps; n++) {
-        if (step_blocked(S, step, -1)) break;
-        if (prof) c0 = clock64();
-        for (int vb = blockIdx.x; vb < per_rep * R; vb += gridDim.x) {
-            const int rep = vb / per_rep, b = vb % per_rep;
-            const double4 *pos = S.pos[cur] + (size_t)rep * nmp;
-            if (b < A.nblk_bp) phase_bp(S, P, A, pos, rep, b * 256 + threadIdx.x);
-            else if (b < A.nblk_bp + A.nblk_pair) phase_pair<GP>(S, P, A, pos, rep, b - A.nblk_bp);
-            else phase_local(S, P, A, pos, rep, b - A.nblk_bp - A.nblk_pair, step + 1ull);
-        }
-        if (prof) c1 = clock64();
-        grid.sync();
-        if (prof) c2 = clock64();
-        for (int vb = blockIdx.x; vb < S.nblk * R; vb += gridDim.x) {
-            const int rep = vb / S.nblk, b = vb % S.nblk;
-            phase_integrate(S, P, A, cur, rep, b, step + 1ull);
-            if (b == 0 && threadIdx.x == 0) {
-                unsigned long long *t = S.top2 + ((size_t)rep * 2 + ((step + 2ull) & 1ull)) * 2;
-                t[0] = 0ull; t[1] = 0ull;
-            }
-        }
-        if (prof) c3 = clock64();
-        grid.sync();
-        if (prof) {
-            c4 = clock64();
-            S.prof[0] += (unsigned long long)(c1 - c0); S.prof[1] += (unsigned long long)(c2 - c1);
-            S.prof[2] += (unsigned long long)(c3 - c2); S.prof[3] += (unsigned long long)(c4 - c3);
-            S.prof[4] += 1ull;
-        }
-        step++;
-        cur ^= 1;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        DevCtl a; a.step = step; a.cur = cur; a.blocked = 0;
-        S.ctl[0] = a;
     }
 }
 
@@ -1030,6 +976,18 @@ SIS_HD uint32_t nl_pair_flags(const NlArgs &A, const FFParams &P, int4 mi, int4 
     }
     return ent;
 }
+// A listed pair can need the periodic image shift of pbc_vec_d before the next rebuild only if a
+// raw coordinate difference can reach L/2: both beads together move at most nl_margin between
+// rebuilds (the trigger of src/job_md.F90:388), so |raw| + margin < L/2 on every axis proves
+// that v = x_i - x_j is already the minimum image for the whole life of the list.
+SIS_HD bool nl_needs_image(const FFParams &P, const NlArgs &A, Vec3 xi, Vec3 xj)
+{
+    if (!P.flg_pbc) return false;
+    if (A.all_pairs == 1) return true;   // cutoff-free lists are never rebuilt
+    const double m = A.nl_margin * 1.0001 + 1.0e-9;
+    return !(fabs(xi.x - xj.x) + m < P.box_half[0] && fabs(xi.y - xj.y) + m < P.box_half[1] &&
+             fabs(xi.z - xj.z) + m < P.box_half[2]);
+}
 // distance / index gate of the bp list: src/neighbor_list.F90:183, src/list_bp.F90:57
 SIS_HD bool nl_bp_geometry(const NlArgs &A, int i, int j, double d2)
 {
@@ -1084,8 +1042,10 @@ __global__ void __launch_bounds__(256) k_nl_rows(DevSys S, FFParams P, GridInfo 
                         j = sweep_all ? q : cbeads[q];
                         if (j != i) {
                             const int4 mj = S.meta[j];
-                            Vec3 v = pbc_vec_d(P, xi, v3(pos[j]));
+                            const Vec3 xj = v3(pos[j]);
+                            Vec3 v = pbc_vec_d(P, xi, xj);
                             ent = nl_pair_flags(A, P, mi, mj, i, j, dot(v, v), ele_nl_cut2);
+                            if (ent && nl_needs_image(P, A, xi, xj)) ent |= NB_IMG;
                             if (nl_bp_geometry(A, i, j, dot(v, v))) {
                                 if (i < j) bp3 = bp_lookup(A.bp_model, A.bp_min_loop, S.hash, S.seq, i, mi, j, mj, &bptype);
                                 else bp3 = bp_lookup(A.bp_model, A.bp_min_loop, S.hash, S.seq, j, mj, i, mi, &bptype);

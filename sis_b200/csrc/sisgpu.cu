@@ -7,6 +7,8 @@
 // that computes runs CUDA kernels or fails.
 #include "../../include/sisgpu.h"
 #include "sis_kernels.cuh"
+#include "sis_fused.cuh"
+#include "sis_fast.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -131,6 +133,9 @@ struct sisgpu {
     bool lists_built = false;
     int nbp_half_max = 0;      // max over replicas of the half-list bp candidate count
     int coop_blocks = 0;       // co-resident grid size of the persistent kernel
+    int fast_kernel = 1;       // option "fast_kernel": 0 forces the general k_md_fused
+    size_t fast_smem_set = 0;
+    std::vector<int> nbp_half_rep;   // half-list bp candidate count per replica (last build)
     // biases (host copies)
     std::vector<int> twz_pairs, twzfr_pairs, rest_id;
     std::vector<double> twz_dir, twzfr_k, twzfr_init, twzfr_velo, rest_rcut, rest_para;
@@ -165,9 +170,9 @@ struct sisgpu {
     DBuf<uint32_t> d_nbr;
     DBuf<int2> d_bprow;
     DBuf<signed char> d_bp_type;
-    DBuf<double2> d_bp_coef;
+    DBuf<double2> d_bp_coef, d_top2_slots;
     DBuf<unsigned long long> d_mc_counter, d_prof;
-    DBuf<unsigned int> d_ene_counter;
+    DBuf<unsigned int> d_ene_counter, d_bar;
     DBuf<RepParams> d_rp, d_rp_alt;
     DBuf<unsigned char> d_sync;          // DevSyncHdr + top2[nrep][2][2]
     unsigned char *h_sync = nullptr;     // pinned mirror
@@ -231,7 +236,7 @@ int sisgpu_destroy(sisgpu_t *h)
     h->d_twzfr_init.release(); h->d_twzfr_velo.release(); h->d_rest_rcut.release(); h->d_rest_para.release();
     h->d_gather_send.release(); h->d_gather_recv.release(); h->d_nbr.release(); h->d_bprow.release();
     h->d_bp_type.release(); h->d_bp_coef.release(); h->d_mc_counter.release();
-    h->d_ene_counter.release(); h->d_rp.release(); h->d_rp_alt.release(); h->d_sync.release();
+    h->d_ene_counter.release(); h->d_bar.release(); h->d_top2_slots.release(); h->d_rp.release(); h->d_rp_alt.release(); h->d_sync.release();
     if (h->graph_chunk) cudaGraphExecDestroy(h->graph_chunk);
     h->d_f_pair.release(); h->d_f_loc.release(); h->d_f_bp.release(); h->d_bp_half.release(); h->d_nbp_half.release();
     cudaEventDestroy(h->ev0);
@@ -256,7 +261,7 @@ int sisgpu_set_topology(sisgpu_t *h, int nmp, int nchains, const int *nmp_chain,
                         const int *seq, const int *has_charge, const int *is_frozen, const double *mass)
 {
     if (nmp <= 0 || nchains <= 0) return set_err("empty system");
-    if (nmp >= (1 << 30)) return set_err("nmp too large for 30-bit row entries");
+    if (nmp >= (1 << 29)) return set_err("nmp too large for 29-bit row entries");
     int tot = 0;
     for (int c = 0; c < nchains; c++) tot += nmp_chain[c];
     if (tot != nmp) return set_err("sum(nmp_chain)=%d != nmp=%d", tot, nmp);
@@ -684,6 +689,8 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     h->sync_bytes = sizeof(DevSyncHdr) + (size_t)R * 4 * sizeof(unsigned long long);
     TRY(h->d_sync.alloc(h->sync_bytes));
     TRY(h->d_kin.alloc(R));
+    TRY(h->d_bar.alloc(64));
+    TRY(h->d_top2_slots.alloc(2 * FAST_MAX_CTA));
     const int nblk = (N + 63) / 64;            // integrate kernel: 64 beads per block
     const int nblk_ene = (N + 31) / 32;        // energy kernel: 8 lanes per bead
     TRY(h->d_ene_partial.alloc((size_t)R * nblk_ene * ENE_N)); TRY(h->d_ene_counter.alloc(R)); TRY(h->d_ene_out.alloc((size_t)R * ENE_N));
@@ -709,6 +716,8 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     S.ctl = ((DevSyncHdr *)h->d_sync.p)->ctl; S.misc = &((DevSyncHdr *)h->d_sync.p)->misc;
     S.top2 = (unsigned long long *)(h->d_sync.p + sizeof(DevSyncHdr));
     S.nl_margin = h->nl_margin;
+    S.bar = h->d_bar.p;
+    S.top2_slots = h->d_top2_slots.p;
     S.ene_partial = h->d_ene_partial.p; S.ene_counter = h->d_ene_counter.p;
     S.ene_out = h->d_ene_out.p;
     S.twz_pairs = h->d_twz_pairs.p; S.twz_dir = h->d_twz_dir.p; S.twzfr_pairs = h->d_twzfr_pairs.p;
@@ -924,6 +933,7 @@ static int build_lists(sisgpu *h, const std::vector<int> &active, bool all_pairs
             CK(cudaStreamSynchronize(h->stream));
             int mx = 0;
             for (int r = 0; r < R; r++) mx = std::max(mx, nh[r]);
+            h->nbp_half_rep = nh;
             // the bp task grid is sized from this count; regrow (and re-capture) with slack
             if (mx > h->nbp_half_max || mx < h->nbp_half_max / 4) { h->nbp_half_max = mx + mx / 4 + 128; invalidate_graphs(h); }
         }
@@ -1520,6 +1530,9 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
         std::vector<int> act(R, 0);
         for (int r = 0; r < R; r++) if (h->h_need[r]) { act[r] = 1; any = true; h->nrebuild++; }
         if (any) {
+            // a persistent kernel that stopped at the rebuild test may have left the base-pair
+            // scatter of the step it did not execute in f_bp
+            CK(cudaMemsetAsync(h->d_f_bp.p, 0, (size_t)R * h->nmp * 3 * sizeof(double), h->stream));
             TRY(build_lists(h, act, false));
             if (h->nstep_bp_MC > 0) force_mc = true;
             TRY(sync_ctl(h));
@@ -1535,23 +1548,37 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
         const int use_mask = h->nstep_bp_MC > 0 ? 1 : 0;
         const bool uniform = h->nstep_bp_MC <= 1;   // every step has the same kernel sequence
         if (h->launch_mode == 2 && h->nstep_bp_MC == 0 && !h->P.flg_bias_rg) {
-            // persistent cooperative kernel: runs until `stop` or until a replica needs new lists
+            // persistent warp-specialised kernel: runs until `stop` or until a replica needs new lists
             if (h->coop_blocks == 0) {
                 int per_sm = 0, dev_sms = 0;
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_md_persistent<8>, 256, 0));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_md_fused, FUSED_THREADS, 0));
                 CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
-                h->coop_blocks = std::max(1, per_sm) * dev_sms;
+                if (per_sm < 1) return set_err("k_md_fused does not fit on an SM");
+                h->coop_blocks = dev_sms;   // one CTA per SM
             }
             StepArgs A = step_args(h, mask_all, 0, -1, 1);
             int nrun = (int)std::min<long long>(stop - cur, 1 << 20);
-            const int want = (A.nblk_bp + A.nblk_pair + A.nblk_loc) * R;
-            dim3 grid(std::min(h->coop_blocks, want));
+            const long long nitems = (long long)R * h->nmp;
+            CK(cudaMemsetAsync(h->d_bar.p, 0, 64 * sizeof(unsigned), h->stream));
             void *args[] = {&h->S, &h->P, &A, &nrun};
-            switch (h->G) {
-            case 4: CK(cudaLaunchCooperativeKernel((void *)k_md_persistent<4>, grid, dim3(256), args, 0, h->stream)); break;
-            case 16: CK(cudaLaunchCooperativeKernel((void *)k_md_persistent<16>, grid, dim3(256), args, 0, h->stream)); break;
-            case 32: CK(cudaLaunchCooperativeKernel((void *)k_md_persistent<32>, grid, dim3(256), args, 0, h->stream)); break;
-            default: CK(cudaLaunchCooperativeKernel((void *)k_md_persistent<8>, grid, dim3(256), args, 0, h->stream)); break;
+            // k_md_fast: one bead per 8-lane group, rows / candidates / bonded tables on chip
+            const int want_fast = (int)((nitems + FAST_GROUPS - 1) / FAST_GROUPS);
+            const size_t smem_fast = ((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)FAST_GROUPS * h->K * sizeof(uint32_t);
+            long long ncand_total = 0;
+            for (int r = 0; r < R; r++) ncand_total += h->nbp_half_rep.empty() ? h->nbp_half_max : h->nbp_half_rep[r];
+            const bool biases = h->P.flg_stage || h->P.ntwz_DCF || h->P.ntwz_FR || h->P.nrest;
+            const bool fast_ok = h->fast_kernel && want_fast <= std::min(h->coop_blocks, FAST_MAX_CTA) && !biases &&
+                                 smem_fast <= 200 * 1024 && ncand_total / want_fast + 2 <= FAST_BPC;
+            if (fast_ok) {
+                if (smem_fast > h->fast_smem_set) {
+                    CK(cudaFuncSetAttribute(k_md_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
+                    h->fast_smem_set = smem_fast;
+                }
+                CK(cudaLaunchCooperativeKernel((void *)k_md_fast, dim3(want_fast), dim3(FAST_THREADS), args, smem_fast, h->stream));
+            } else {
+                const int want = (int)std::max<long long>(1, (nitems + FUSED_GROUPS - 1) / FUSED_GROUPS);
+                dim3 grid(std::min(h->coop_blocks, want));
+                CK(cudaLaunchCooperativeKernel((void *)k_md_fused, grid, dim3(FUSED_THREADS), args, 0, h->stream));
             }
             h->launches++;
         } else if (h->launch_mode >= 1 && uniform && nchunk == h->chunk) {
@@ -1652,6 +1679,7 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
     if (s == "launch_mode") h->launch_mode = (int)value;
     else if (s == "chunk") { h->chunk = std::max(1, (int)value); invalidate_graphs(h); }
     else if (s == "timing") h->timing = (int)value;
+    else if (s == "fast_kernel") h->fast_kernel = (int)value;
     else if (s == "profile") {   // phase clocks of the persistent kernel (block 0): get_timers out[4..8]
         if (value != 0) { TRY(h->d_prof.alloc(8)); h->S.prof = h->d_prof.p; }
         else h->S.prof = nullptr;

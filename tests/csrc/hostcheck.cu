@@ -184,6 +184,54 @@ int hc_force(HostCheck *c, const double *xyz, unsigned mask, double *forces)
     return 0;
 }
 
+// the role-split base-pair evaluation of k_md_fused (bp_force_role), roles combined serially
+// with the same bead routing the device lanes use
+int hc_force_bp_roles(HostCheck *c, const double *xyz, double *forces)
+{
+    const int N = c->h->nmp;
+    const FFParams &P = c->h->P;
+    c->pos.resize(N);
+    for (int i = 0; i < N; i++) c->pos[i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0);
+    for (int i = 0; i < 3 * N; i++) forces[i] = 0.0;
+    for (int k = 0; k < N; k++)
+        for (int e = 0; e < c->nbp_row[k]; e++) {
+            const int2 ent = c->bprow[(size_t)k * c->KB + e];
+            const int j = ent.x, ibp = ent.y;
+            if (j < k) continue;
+            const int type = c->bp_type[ibp];
+            double dG = 1.0;
+            if (P.bp_triplet) {
+                dG = c->bp_coef[ibp].x - c->rp.tempK * c->bp_coef[ibp].y;
+                if (dG >= 0.0) continue;
+            }
+            const BpPara &p = P.bp[type];
+            const int4 mi = c->meta[k], mj = c->meta[j];
+            const int beads[6] = {k, j, chain_nb(mi, -1), chain_nb(mj, -1), chain_nb(mi, +1), chain_nb(mj, +1)};
+            const Vec3 x0 = v3(c->pos[k]), x1 = v3(c->pos[j]);
+            const Vec3 v12 = pbc_vec_d(P, x0, x1);
+            const double d1212 = dot(v12, v12), a12 = sqrt(d1212);
+            if (fabs(a12 - p.bond_r) > p.cutoff_ddist) continue;
+            double u = 0.0;
+            Vec3 F[6];
+            for (int s = 0; s < 6; s++) F[s] = mk(0.0, 0.0, 0.0);
+            for (int role = 0; role < 8; role++) {
+                const int tA = bp_role_A(role), tB = bp_role_B(role);
+                const Vec3 xa = tA >= 0 ? v3(c->pos[beads[tA]]) : x0, xb = tB >= 0 ? v3(c->pos[beads[tB]]) : x0;
+                const BpSub o = bp_force_role(P, p, role, x0, x1, xa, xb, v12, d1212, a12);
+                u += o.u;
+                F[0] += o.c0; F[1] += o.c1;
+                if (tA >= 0) F[tA] += o.ca;
+                if (tB >= 0) F[tB] += o.cb;
+            }
+            const double ene = P.bp_triplet ? p.U0 * dG * exp(-u) : p.U0 * exp(-u);
+            if (ene > P.bp_cutoff_energy) continue;
+            for (int s = 0; s < 6; s++) {
+                forces[3 * beads[s]] += ene * F[s].x; forces[3 * beads[s] + 1] += ene * F[s].y; forces[3 * beads[s] + 2] += ene * F[s].z;
+            }
+        }
+    return 0;
+}
+
 double hc_gauss(unsigned long long seed, unsigned stream, unsigned long long step, unsigned bead, int comp)
 {
     return gauss_component(seed, stream, step, bead, comp);

@@ -59,6 +59,11 @@ class HostCheck(CApi):
         self.lib.hc_force(self.hc, _d(self.xyz)[0], C.c_uint(mask), _d(f)[0])
         return f
 
+    def force_bp_roles(self):
+        f = np.zeros((self.nmp, 3))
+        self.lib.hc_force_bp_roles(self.hc, _d(self.xyz)[0], _d(f)[0])
+        return f
+
     def gauss(self, seed, stream, step, bead):
         self.lib.hc_gauss.restype = C.c_double
         return np.array([self.lib.hc_gauss(C.c_uint64(seed), C.c_uint(stream), C.c_uint64(step), C.c_uint(bead), c)

@@ -182,3 +182,55 @@ def test_c4_properties_long_run():
     assert g.get_list_sizes(0) == o.get_list_sizes(0)
     assert rel(g.force(0), o.force(0)) < FORCE_TOL
     assert nreb >= 1
+
+
+def _run_mode(spec, nsteps, **opts):
+    from sis_b200.api import SisGpu
+    g = SisGpu(0, **opts)
+    spec.configure(g)
+    g.init_velocities(0)
+    g.neighbor_list(0)
+    nreb = g.md_steps(nsteps)
+    x, v, a = g.get_state(0)
+    return g, nreb, x, v, a
+
+
+@pytest.mark.parametrize("name", ["t2s2hp", "cag47_4_pbc", "circ"])
+def test_persistent_kernels_match_stream_path(name):
+    """k_md_fast (on-chip rows / tables, role-split base pairs) and the general k_md_fused run the
+    same trajectory as the per-phase stream launches (dihedral tables, circRNA closure terms and
+    PBC image flags included)."""
+    spec = SPECS[name]()
+    spec.nl_margin = 3.0
+    _, r0, x0, v0, a0 = _run_mode(spec, 60, launch_mode=0)
+    g1, r1, x1, v1, a1 = _run_mode(spec, 60, launch_mode=2, fast_kernel=1)
+    _, r2, x2, v2, a2 = _run_mode(spec, 60, launch_mode=2, fast_kernel=0)
+    assert r0 == r1 == r2
+    for x, v, a in ((x1, v1, a1), (x2, v2, a2)):
+        assert np.abs(x - x0).max() < 1e-7
+        assert np.abs(v - v0).max() < 1e-8
+        assert np.abs(a - a0).max() < 1e-12
+    assert g1.get_step() == 60
+    # cached bp state of the last force evaluation (write_bp / flg_bp_energy semantics)
+    s_ref, e_ref = _run_mode(spec, 60, launch_mode=0)[0].get_bp_state(0)
+    s_fast, e_fast = g1.get_bp_state(0)
+    assert np.array_equal(s_ref, s_fast)
+    assert np.allclose(e_ref, e_fast, rtol=1e-7, atol=1e-10)
+
+
+def test_persistent_kernel_multi_replica():
+    """Several replicas batched into one persistent launch give the stream-path trajectories."""
+    from sis_b200.api import SisGpu
+    spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=0).replicated(4, temps=[290.0, 300.0, 310.0, 320.0])
+    outs = []
+    for mode in (0, 2):
+        g = SisGpu(0, launch_mode=mode)
+        spec.configure(g)
+        for r in range(4):
+            g.init_velocities(r)
+            g.neighbor_list(r)
+        g.md_steps(80)
+        outs.append([g.get_state(r)[0] for r in range(4)])
+    for r in range(4):
+        assert np.abs(outs[0][r] - outs[1][r]).max() < 1e-7
+    assert np.abs(outs[0][0] - outs[0][3]).max() > 1e-3   # the replicas really differ

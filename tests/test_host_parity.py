@@ -93,6 +93,20 @@ def test_forces_per_term(name):
     assert np.abs(fo - fh).max() / np.abs(fo).max() < 1e-10
 
 
+@pytest.mark.parametrize("name", list(SPECS))
+def test_bp_role_split_matches_oracle(name):
+    """k_md_fused evaluates a base pair with one role per lane (bond, 4 angles, 2 dihedrals):
+    the role arithmetic and bead routing summed serially must reproduce force_bp*."""
+    spec = SPECS[name]()
+    o, hcx = both(spec)
+    o.neighbor_list(0)
+    hcx.build_lists(False)
+    fo = o.force_terms(0, 1 << TERMS["bp"])
+    fh = hcx.force_bp_roles()
+    assert np.abs(fo).max() > 0
+    assert np.abs(fo - fh).max() / np.abs(fo).max() < 1e-10
+
+
 def test_bp3_table_matches_oracle():
     spec = fx.t2s2hp()
     o, hcx = both(spec)
