@@ -122,6 +122,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=None)
     ap.add_argument("--tpb", type=int, default=None, help="lanes per bead in the pair task")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (repeatable)")
     ap.add_argument("--profile", action="store_true", help="phase clocks of the persistent kernel")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -142,6 +143,9 @@ def main():
     for name, val in (("launch_mode", args.launch_mode), ("chunk", args.chunk), ("threads_per_bead", args.tpb)):
         if val is not None:
             g.set_option(name, val)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        g.set_option(name, float(val))
     spec.configure(g)
     if args.profile:
         g.set_option("profile", 1)
@@ -177,7 +181,12 @@ def main():
     barrier()
     dt = time.perf_counter() - t0
     launches = g.launch_count() - l0
-    timers = g.get_timers(reset=True)
+    timers = g.get_timers(reset=False)
+    if args.profile and os.environ.get("SIS_CTA_PROFILE"):
+        cp = g.cta_profile(148)
+        nst = max(1.0, timers.get("persistent_clk_per_step") and args.md_steps * args.steps or 1.0)
+        np.save(os.environ["SIS_CTA_PROFILE"], cp / nst)
+    g.get_timers(reset=True)
     g.set_option("timing", 0)
     tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:

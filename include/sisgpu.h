@@ -145,13 +145,19 @@ int sisgpu_check_force(sisgpu_t *h, double tempK, double *f_energy, double *f_fo
                        double *maxdiff);
 /* launch statistics: kernels launched by this handle since creation */
 int sisgpu_launch_count(sisgpu_t *h, int64_t *n);
-/* options: name = "launch_mode" (0 stream, 1 graph), "threads_per_bead", "timing" */
+/* options: name = "launch_mode" (0 stream launches, 1 CUDA-graph chunks, 2 persistent kernels =
+ * default), "fast_kernel" (0: never use k_md_fast), "chunk", "threads_per_bead", "timing", "profile" */
 int sisgpu_set_option(sisgpu_t *h, const char *name, double value);
 /* CUDA-event time (ms) accumulated per kernel family since the last reset:
  * out[0] step kernels, out[1] neighbour list, out[2] energy, out[3] exchange;
  * out[4..7] SM clocks block 0 of the persistent kernel spent in force phase, barrier, integrate
- * phase, barrier, out[8] steps counted (option "profile"); out must hold 9 doubles */
+ * phase, barrier, out[8] steps counted, out[9..11] base-pair warps (gate, evaluate, arrive),
+ * out[12..13] bonded-table warps (tables, Gaussians) (option "profile"); out must hold 16 doubles */
 int sisgpu_get_timers(sisgpu_t *h, double *out, int reset);
+/* diagnostic: accumulated SM clocks of CTA c of k_md_fast in out[8c..8c+7] = pair units, wait for
+ * tables / base pairs, integrate, position barrier, base-pair warps total, wait for the CTA's own
+ * warps, active base pairs, spare (option "profile") */
+int sisgpu_get_cta_profile(sisgpu_t *h, int ncta, double *out);
 
 /* ---- REMD ------------------------------------------------------------------- */
 /* init_replica (src/init_replica.F90) + make_replica_exchange_pair_tb

@@ -68,13 +68,20 @@ class SisGpu(CApi):
         return n.value
 
     def get_timers(self, reset=False) -> dict:
-        out = np.zeros(9)
+        out = np.zeros(16)
         self._call("get_timers", _d(out), C.c_int(int(reset)))
         d = dict(zip(["step_ms", "nl_ms", "energy_ms", "exchange_ms"], out[:4].tolist()))
         if out[8] > 0:
             d["persistent_clk_per_step"] = dict(zip(["force", "barrier1", "integrate", "barrier2"],
                                                     (out[4:8] / out[8]).round(1).tolist()))
+            d["persistent_clk_per_step"].update(zip(["bp_gate", "bp_eval", "bp_arrive", "loc_tables", "loc_gauss"],
+                                                    (out[9:14] / out[8]).round(1).tolist()))
         return d
+
+    def cta_profile(self, ncta: int) -> np.ndarray:
+        out = np.zeros((ncta, 8))
+        self._call("get_cta_profile", C.c_int(ncta), _d(out))
+        return out
 
     # ---- REMD ------------------------------------------------------------------------
     def remd_setup(self, nrep, values, nstep_exchange, rank=0, nranks=1):

@@ -7,22 +7,24 @@
 //         shared memory, its position / velocity / beta / displacement / coefficients in
 //         registers.  Per step: pair loop (src/force_wca.F90, src/force_ele_DH.F90), then the
 //         integrator (src/job_md.F90:409-456) as soon as the other force parts are complete.
-//   BP    (2 warps): candidate data (six bead ids, type, dG) cached in shared memory; one
-//         thread per candidate applies the distance gate, 8-lane groups evaluate the survivors
-//         (one role per lane, bp_force_role) and scatter with fp64 atomics.
-//   LOC   (6 warps): every bonded term the CTA's beads take part in is evaluated ONCE
+//   BP    (4 warps): every base-pair candidate that touches one of the CTA's beads is cached in
+//         shared memory (six bead ids, type, dG); one thread per candidate applies the distance
+//         gate, 8-lane groups evaluate the survivors (one role per lane, bp_force_role) and add
+//         the parts acting on the CTA's own beads to a shared-memory force array -- pairs are
+//         evaluated redundantly by the 2-3 CTAs owning their beads, so the base-pair term needs no
+//         global atomics and no grid barrier.
+//   LOC   (4 warps): every bonded term the CTA's beads take part in is evaluated ONCE
 //         (src/force_bond.F90, force_angl*.F90, force_dih_*.F90) into shared tables the MAIN
 //         groups read; then the Gaussians of the NEXT step (Philox + Box-Muller) into a
 //         double-buffered shared array; one LOC warp also evaluates the rebuild test.
-// Grid barriers: bar[0] "bp scatter done" (arrive: BP warps, wait: MAIN after the pair loop) and
-// bar[32] "positions written" (the one exposed barrier per step).  The rebuild test of
+// One grid barrier per step: bar[32] "positions written".  The rebuild test of
 // src/job_md.F90:376-388 for R == 1 goes through per-CTA (max, 2nd max) slots read after the
 // position barrier, off the critical path; with R > 1 through the atomic top-2 of k_md_fused.
 #pragma once
 
 #include "sis_fused.cuh"
 
-constexpr int FAST_MAIN_WARPS = 16, FAST_BP_WARPS = 2, FAST_LOC_WARPS = 6;
+constexpr int FAST_MAIN_WARPS = 16, FAST_BP_WARPS = 4, FAST_LOC_WARPS = 4;
 constexpr int FAST_MAIN = 32 * FAST_MAIN_WARPS, FAST_BP = 32 * FAST_BP_WARPS, FAST_LOC = 32 * FAST_LOC_WARPS;
 constexpr int FAST_THREADS = FAST_MAIN + FAST_BP + FAST_LOC;
 constexpr int FAST_GROUPS = FAST_MAIN / 8;        // beads per CTA
@@ -32,9 +34,22 @@ constexpr int FAST_BPC = 256;                     // cached bp candidates per CT
 constexpr int FAST_MAX_CTA = 1024;                // capacity of the top-2 slot array
 
 struct FastBpCand {
-    int b[6];       // beads i, j, i-1, j-1, i+1, j+1
-    int ibp, type, rep, last;   // last = bp_status last written (-1 unknown)
+    int b[6];       // flattened (replica, bead) items of beads i, j, i-1, j-1, i+1, j+1
+    int type, last; // last = bp_status last written (-1 unknown)
+    int own;        // this CTA owns bead i: it keeps bp_status / ene_bp of the pair up to date
+    int pad;
+    size_t pb;      // index of the pair in bp_status / ene_bp
     double dG;
+};
+constexpr int FAST_NEXTRA = 160;   // chain neighbours of the CTA's beads outside its range
+
+// state of one owned bead, resident in shared memory for the whole launch
+struct FastBead {
+    double x[3], v[3], a[3], m[3];     // position, velocity, beta (accels), xyz_move
+    double ca, cb, cc, noise;          // a, sqrt(b)h/m, sqrt(b)h of set_md_coef; noise coefficient * sqrt(T)
+    double ele_coef, inv_lambdaD, cut2;
+    int4 meta;
+    int rep, k, nn, valid;
 };
 
 struct FastShared {
@@ -43,9 +58,15 @@ struct FastShared {
     Vec3 dihf[FAST_NT][4];      // dihedral starting at slot: F1..F4
     double gauss[2][FAST_GROUPS][3];
     double d2[FAST_GROUPS];
+    int nn[FAST_GROUPS], unit_start[FAST_GROUPS + 1];   // row lengths; first pair unit of each bead
+    FastBead bead[FAST_GROUPS];
     FastBpCand cand[FAST_BPC];
     int active[FAST_BPC];
-    int nactive, ncand;
+    int nactive, ncand, nextra, overflow;
+    int extra[FAST_NEXTRA];
+    double fbp[FAST_GROUPS][3];      // base-pair forces on the CTA's beads (this step)
+    int4 tmeta[FAST_NT];             // bonded-term slots: meta of the first bead
+    int tbead[FAST_NT];              // ... its flattened item, -1 = no such bead
     int blocked[2];             // rebuild verdict, indexed by iteration parity
     double top[2];
 };
@@ -66,12 +87,45 @@ SIS_D void gauss_pair(uint64_t seed, uint32_t stream, uint64_t step, uint32_t be
     *g1 = rad * sn;
 }
 
-// pair loop of one bead over its row in shared memory: U gathers in flight per lane
+// one listed pair: v = x_k - x_j (+ image shift when flagged), WCA and Debye-Hueckel scalars
+SIS_D void fast_pair_one(const FFParams &P, uint32_t ent, Vec3 xk, Vec3 xj, double ele_coef, double inv_lambdaD,
+                         double cut2, Vec3 &F)
+{
+    Vec3 v = xk - xj;
+    if (ent & NB_IMG) {
+        v.x = minimg1(v.x, P.box[0], P.box_half[0]);
+        v.y = minimg1(v.y, P.box[1], P.box_half[1]);
+        v.z = minimg1(v.z, P.box[2], P.box_half[2]);
+    }
+    const double d2 = dot(v, v);
+    double s = 0.0;
+    if ((ent & NB_WCA) && d2 < P.wca_sigma2) s += wca_scalar(P, d2);
+    if ((ent & NB_ELE) && d2 <= cut2) s += dh_scalar(ele_coef, inv_lambdaD, d2);
+    F += s * v;
+}
+// pair loop of one bead over its row in shared memory (8 lanes, entries lane, lane + 8, ...).
+// U >= 2: U gathers in flight per lane.  U == 1: one entry per iteration with the next
+// position gather issued before the current pair is evaluated (rows are sorted by distance in
+// the prologue, so the lanes of a warp leave the Debye-Hueckel branch together).
 template <int U>
 SIS_D Vec3 fast_pair(const FFParams &P, const uint32_t *row, int nn, int lane, Vec3 xk, const double4 *__restrict__ pos,
                      double ele_coef, double inv_lambdaD, double cut2)
 {
     Vec3 F = mk(0.0, 0.0, 0.0);
+    if (U == 1) {
+        int e = lane;
+        uint32_t ent = e < nn ? row[e] : 0u;
+        Vec3 xj = ent ? v3(pos[ent & NB_IDX]) : xk;
+        while (ent) {
+            const int en = e + 8;
+            const uint32_t ent_n = en < nn ? row[en] : 0u;
+            Vec3 xn = xk;
+            if (ent_n) xn = v3(pos[ent_n & NB_IDX]);
+            fast_pair_one(P, ent, xk, xj, ele_coef, inv_lambdaD, cut2, F);
+            e = en; ent = ent_n; xj = xn;
+        }
+        return F;
+    }
     for (int e0 = lane; e0 < nn; e0 += U * 8) {
         uint32_t ent[U];
         Vec3 xj[U];
@@ -84,20 +138,8 @@ SIS_D Vec3 fast_pair(const FFParams &P, const uint32_t *row, int nn, int lane, V
         for (int u = 0; u < U; u++)
             if (ent[u]) xj[u] = v3(pos[ent[u] & NB_IDX]);
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (!ent[u]) continue;
-            Vec3 v = xk - xj[u];
-            if (ent[u] & NB_IMG) {
-                v.x = minimg1(v.x, P.box[0], P.box_half[0]);
-                v.y = minimg1(v.y, P.box[1], P.box_half[1]);
-                v.z = minimg1(v.z, P.box[2], P.box_half[2]);
-            }
-            const double d2 = dot(v, v);
-            double s = 0.0;
-            if ((ent[u] & NB_WCA) && d2 < P.wca_sigma2) s += wca_scalar(P, d2);
-            if ((ent[u] & NB_ELE) && d2 <= cut2) s += dh_scalar(ele_coef, inv_lambdaD, d2);
-            F += s * v;
-        }
+        for (int u = 0; u < U; u++)
+            if (ent[u]) fast_pair_one(P, ent[u], xk, xj[u], ele_coef, inv_lambdaD, cut2, F);
     }
     return F;
 }
@@ -132,21 +174,26 @@ SIS_D double fast_closure_terms(const DevSys &S, const FFParams &P, const double
 
 // common per-launch context of the three roles
 struct FastCtx {
-    int R, nmp, K, nitems, ncta, item0, nsteps;
+    int R, nmp, K, nitems, ncta, item0, nb, nsteps;   // item0 / nb: the CTA's bead range
     unsigned long long step0;
     int cur0;
-    unsigned *bar_bp, *bar_pos;
+    unsigned *bar_pos;
     bool dih_on;
 };
 SIS_D void cta_sync() { named_bar_sync(0, FAST_THREADS); }
 
 // Loop protocol shared by the roles (iteration n, parity q = n & 1):
 //   LOC   : [n > 0: verdict -> sh.blocked[q]]  tables  arrive(3)  gauss  cta_sync  read blocked[q]
-//   MAIN  : pair  sync(3)  read blocked[q] (leave)  wait bar_bp  integrate  arrive+wait bar_pos  cta_sync
-//   BP    : gate  eval  arrive bar_bp  cta_sync  read blocked[q]
+//   MAIN  : pair  sync(3)  read blocked[q] (leave)  integrate  arrive+wait bar_pos  cta_sync
+//   BP    : gate  eval  arrive(3)  cta_sync  read blocked[q]
 // A MAIN thread that leaves at barrier 3 performs the iteration's cta_sync before returning, so
 // every role executes the same number of cta_syncs.  Returns the number of completed steps.
 
+// MAIN role.  The pair work of the CTA is cut into UNITS of eight row entries ("octets"), units are
+// dealt round-robin to the 64 groups (one entry per lane), so every group runs the same number of
+// iterations whatever the row lengths; each unit's force is written to a fixed slot and the bead's
+// owner adds its units in order (deterministic, no atomics).
+template <int U>
 SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, const FastCtx &C, FastShared &sh,
                          uint32_t *s_rows)
 {
@@ -155,53 +202,136 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
     const int nmp = C.nmp, K = C.K, R = C.R;
     unsigned long long step = C.step0;
     int cur = C.cur0;
-    const bool prof = S.prof != nullptr && blockIdx.x == 0 && tid == 0;
-    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+    const bool prof = S.prof != nullptr && tid == 0;   // every CTA's thread 0: per-CTA phase clocks
+    long long c0 = 0, c1 = 0, c1b = 0, c2 = 0, c3 = 0, c4 = 0;
+    // shared-memory regions behind the rows: prologue scratch, later the unit tables
+    uint32_t *tmp_all = s_rows + (size_t)FAST_GROUPS * K;
+    unsigned char *cls_all = reinterpret_cast<unsigned char *>(s_rows + (size_t)2 * FAST_GROUPS * K);
+    Vec3 *unitF = reinterpret_cast<Vec3 *>(tmp_all);                 // [nunit]
+    unsigned char *unit_q = cls_all, *unit_o = cls_all + 8 * K + FAST_GROUPS;   // [nunit] each
 
-    // ---- state of the owned bead (registers for the whole launch) -----------------------------
-    int rep = 0, k = 0, nn = 0;
-    const int item = C.item0 + grp;
-    const bool valid = item < C.nitems;
-    int4 meta = make_int4(0, 1, 0, 0);
-    Vec3 xk = mk(0.0, 0.0, 0.0);
-    double xc = 0.0, vc = 0.0, ac = 0.0, mc = 0.0;     // component `lane` (< 3) of x, v, beta, xyz_move
-    double ca = 0.0, cb = 0.0, cc = 0.0;               // a, sqrt(b)h/m, sqrt(b)h of set_md_coef
-    double ele_coef = 0.0, inv_lambdaD = 0.0, cut2 = -1.0, noise = 0.0;
-    size_t o3 = 0;
-    if (valid) {
-        fast_item(item, nmp, &rep, &k);
-        meta = S.meta[k];
-        nn = S.nnbr[(size_t)rep * nmp + k];
-        const uint32_t *row = S.nbr + ((size_t)rep * nmp + k) * K;
-        for (int e = lane; e < nn; e += 8) s_rows[grp * K + e] = row[e];
+    // ---- prologue: bead `grp` of the CTA's range -> shared memory ---------------------------------
+    FastBead &B = sh.bead[grp];
+    if (grp < C.nb) {
+        int rep, k;
+        fast_item(C.item0 + grp, nmp, &rep, &k);
+        const int nn = S.nnbr[(size_t)rep * nmp + k];
         const double4 p = S.pos[cur][(size_t)rep * nmp + k];
-        xk = v3(p);
+        const Vec3 xk0 = v3(p);
         const RepParams &Rp = S.rp[rep];
-        ele_coef = Rp.ele_coef; inv_lambdaD = Rp.inv_lambdaD;
-        if (P.flg_ele) cut2 = Rp.ele_cutoff * Rp.ele_cutoff;
-        const double4 coef = S.coef[k];
-        ca = coef.x; cb = coef.y; cc = coef.z;
-        noise = coef.w * Rp.sqrt_tempK;
-        if (lane < 3) {
-            o3 = ((size_t)rep * nmp + k) * 3 + lane;
-            xc = lane == 0 ? p.x : lane == 1 ? p.y : p.z;
-            vc = S.vel[o3]; ac = S.acc[o3]; mc = S.move[o3];
+        const double cut2 = P.flg_ele ? Rp.ele_cutoff * Rp.ele_cutoff : -1.0;
+        // row -> shared memory as a stable partition: pairs inside the Debye-Hueckel / WCA range
+        // now first, the margin shell after them (the lanes of a warp then leave the expensive
+        // branch together); bead-id order, i.e. coalesced gathers, is kept inside each class
+        const uint32_t *row = S.nbr + ((size_t)rep * nmp + k) * K;
+        uint32_t *tmp = tmp_all + grp * K;
+        unsigned char *cls = cls_all + grp * K;
+        const double4 *pos0 = S.pos[cur] + (size_t)rep * nmp;
+        for (int e = lane; e < nn; e += 8) {
+            const uint32_t ent = row[e];
+            const Vec3 v = pbc_vec_d(P, xk0, v3(pos0[ent & NB_IDX]));
+            const double d2 = dot(v, v);
+            const bool near = ((ent & NB_ELE) && d2 <= cut2) || ((ent & NB_WCA) && d2 < P.wca_sigma2);
+            tmp[e] = ent;
+            cls[e] = near ? 0 : 1;
         }
+        __syncwarp(0xFFu << ((tid & 31) & ~7));
+        int nnear = 0;
+        for (int o = 0; o < nn; o++) nnear += cls[o] == 0;
+        for (int e = lane; e < nn; e += 8) {
+            const int mycls = cls[e];
+            int before = 0;
+            for (int o = 0; o < e; o++) before += cls[o] == mycls;
+            s_rows[grp * K + (mycls ? nnear + before : before)] = tmp[e];
+        }
+        if (lane == 0) {
+            B.meta = S.meta[k];
+            B.rep = rep; B.k = k; B.nn = nn; B.valid = 1;
+            const double4 coef = S.coef[k];
+            B.ca = coef.x; B.cb = coef.y; B.cc = coef.z;
+            B.noise = coef.w * Rp.sqrt_tempK;
+            B.ele_coef = Rp.ele_coef; B.inv_lambdaD = Rp.inv_lambdaD; B.cut2 = cut2;
+            sh.nn[grp] = nn;
+        }
+        if (lane < 3) {
+            const size_t o3 = ((size_t)rep * nmp + k) * 3 + lane;
+            B.x[lane] = lane == 0 ? p.x : lane == 1 ? p.y : p.z;
+            B.v[lane] = S.vel[o3]; B.a[lane] = S.acc[o3]; B.m[lane] = S.move[o3];
+        }
+    } else if (lane == 0) {
+        B.valid = 0; B.nn = 0; B.rep = 0; B.k = 0;
+        sh.nn[grp] = 0;
+    }
+    named_bar_sync(2, FAST_MAIN);                      // rows sorted, scratch free
+    if (warp == 0) {                                   // unit_start = exclusive scan of ceil(nn / 8)
+        const int a = (sh.nn[2 * tid] + 7) >> 3, b = (sh.nn[2 * tid + 1] + 7) >> 3;
+        int incl = a + b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += t;
+        }
+        sh.unit_start[2 * tid] = incl - a - b;
+        sh.unit_start[2 * tid + 1] = incl - b;
+        if (tid == 31) sh.unit_start[FAST_GROUPS] = incl;
+    }
+    named_bar_sync(2, FAST_MAIN);
+    {
+        const int u0 = sh.unit_start[grp], nu = sh.unit_start[grp + 1] - u0;
+        for (int o = lane; o < nu; o += 8) { unit_q[u0 + o] = (unsigned char)grp; unit_o[u0 + o] = (unsigned char)o; }
     }
     cta_sync();                                        // prologue of all roles complete
-    const bool overflow = sh.ncand > FAST_BPC;
+    const int nunit = sh.unit_start[FAST_GROUPS];
+    const bool overflow = sh.ncand > FAST_BPC || sh.overflow;
+    const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
     int n = 0;
     if (!sh.blocked[0] && !overflow)
     for (; n < C.nsteps; n++) {
         if (prof) c0 = clock64();
-        const double4 *pos = S.pos[cur] + (size_t)rep * nmp;
-        Vec3 F = fast_pair<2>(P, s_rows + grp * K, nn, lane, xk, pos, ele_coef, inv_lambdaD, cut2);
-        F.x = group_sum<8>(F.x); F.y = group_sum<8>(F.y); F.z = group_sum<8>(F.z);
-        double f = lane == 0 ? F.x : lane == 1 ? F.y : F.z;
+        // ---- pair units: software pipeline, the next unit's entry and position are fetched before
+        // the current pair is evaluated --------------------------------------------------------------
+        {
+            const double4 *posb = S.pos[cur];
+            int u = grp;
+            uint32_t ent = 0;
+            Vec3 xj = mk(0.0, 0.0, 0.0);
+            int q = 0;
+            if (u < nunit) {
+                q = unit_q[u];
+                const int e = unit_o[u] * 8 + lane;
+                ent = e < sh.bead[q].nn ? s_rows[q * K + e] : 0u;
+                if (ent) xj = v3(posb[(size_t)sh.bead[q].rep * nmp + (ent & NB_IDX)]);
+            }
+            while (u < nunit) {
+                const int un = u + FAST_GROUPS;
+                uint32_t ent_n = 0;
+                Vec3 xn = mk(0.0, 0.0, 0.0);
+                int qn = 0;
+                if (un < nunit) {
+                    qn = unit_q[un];
+                    const int e = unit_o[un] * 8 + lane;
+                    ent_n = e < sh.bead[qn].nn ? s_rows[qn * K + e] : 0u;
+                    if (ent_n) xn = v3(posb[(size_t)sh.bead[qn].rep * nmp + (ent_n & NB_IDX)]);
+                }
+                Vec3 F = mk(0.0, 0.0, 0.0);
+                if (ent) {
+                    const FastBead &Q = sh.bead[q];
+                    fast_pair_one(P, ent, mk(Q.x[0], Q.x[1], Q.x[2]), xj, Q.ele_coef, Q.inv_lambdaD, Q.cut2, F);
+                }
+                F.x = group_sum_masked(F.x, gmask); F.y = group_sum_masked(F.y, gmask); F.z = group_sum_masked(F.z, gmask);
+                if (lane == 0) unitF[u] = F;
+                u = un; ent = ent_n; xj = xn; q = qn;
+            }
+        }
         if (prof) c1 = clock64();
-        named_bar_sync(3, FAST_MAIN + FAST_LOC);       // bonded tables + rebuild verdict
+        named_bar_sync(3, FAST_MAIN + FAST_LOC + FAST_BP);   // all units, bonded tables, base-pair forces, rebuild verdict
+        if (prof) c1b = clock64();
         if (sh.blocked[n & 1]) { cta_sync(); break; }
+        const bool valid = B.valid != 0;
+        double f = 0.0;
         if (valid && lane < 3) {
+            for (int u = sh.unit_start[grp]; u < sh.unit_start[grp + 1]; u++) f += (&unitF[u].x)[lane];
+            const int4 meta = B.meta;
             const int l = meta.z, len = meta.y, s0 = grp + 3;
             const bool circ = meta.w & MF_CIRC;
             if (circ ? len > 1 : l + 1 < len) f -= (&sh.bondf[s0].x)[lane];
@@ -215,45 +345,39 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
                 if (l >= 2 && (circ ? len > 3 : l + 1 < len)) f += (&sh.dihf[s0 - 2][2].x)[lane];
                 if (l >= 3) f += (&sh.dihf[s0 - 3][3].x)[lane];
             }
-            if (circ && l < 3) f += fast_closure_terms(S, P, pos, meta, k, lane);
+            if (circ && l < 3) f += fast_closure_terms(S, P, S.pos[cur] + (size_t)B.rep * nmp, meta, B.k, lane);
         }
-        if (tid == 0) {                                // base-pair scatter of every CTA complete?
-            const unsigned target = (unsigned)(n + 1) * (unsigned)C.ncta;
-            while (ld_acquire_u32(C.bar_bp) < target) { }
-        }
-        named_bar_sync(2, FAST_MAIN);
         if (prof) c2 = clock64();
         // ---- integrate (src/job_md.F90:415-456) ----------------------------------------------
-        double xnew = 0.0;
+        double mv = 0.0;
         if (valid && lane < 3) {
-            f += __ldcg(S.f_bp + o3);
-            S.f_bp[o3] = 0.0;
+            f += sh.fbp[grp][lane];
+            sh.fbp[grp][lane] = 0.0;
             const double g = sh.gauss[(step + 1ull) & 1][grp][lane];
             double dx;
             if (P.integrator == 1) {
-                const double accels_pre = noise * g;
-                vc = ca * vc + cb * f + (ac + accels_pre);
-                ac = accels_pre;
-                dx = cc * vc;
+                const double accels_pre = B.noise * g;
+                const double v = B.ca * B.v[lane] + B.cb * f + (B.a[lane] + accels_pre);
+                B.v[lane] = v;
+                B.a[lane] = accels_pre;
+                dx = B.cc * v;
             } else {
-                dx = ca * f + noise * g;
+                dx = B.ca * f + B.noise * g;
             }
-            xc += dx;
-            mc += dx;
-            xnew = xc;
+            B.x[lane] += dx;
+            mv = B.m[lane] + dx;
+            B.m[lane] = mv;
             if (f > 100.0) S.misc->max_force_flag |= 1;
         }
-        xk.x = __shfl_sync(0xffffffffu, xnew, 0, 8);
-        xk.y = __shfl_sync(0xffffffffu, xnew, 1, 8);
-        xk.z = __shfl_sync(0xffffffffu, xnew, 2, 8);
-        const double s0 = __shfl_sync(0xffffffffu, mc, 0, 8);
-        const double s1 = __shfl_sync(0xffffffffu, mc, 1, 8);
-        const double s2 = __shfl_sync(0xffffffffu, mc, 2, 8);
+        __syncwarp();
+        const double s0 = __shfl_sync(0xffffffffu, mv, 0, 8);
+        const double s1 = __shfl_sync(0xffffffffu, mv, 1, 8);
+        const double s2 = __shfl_sync(0xffffffffu, mv, 2, 8);
         const double d2 = valid ? s0 * s0 + s1 * s1 + s2 * s2 : 0.0;
         if (lane == 0) {
-            if (valid) S.pos[cur ^ 1][(size_t)rep * nmp + k] = make_double4(xk.x, xk.y, xk.z, 0.0);
+            if (valid) S.pos[cur ^ 1][(size_t)B.rep * nmp + B.k] = make_double4(B.x[0], B.x[1], B.x[2], 0.0);
             if (R == 1) sh.d2[grp] = d2;
-            else if (d2 > 0.0) top2_push(S.top2 + ((size_t)rep * 2 + ((step + 1ull) & 1ull)) * 2, d2, 0.0);
+            else if (d2 > 0.0) top2_push(S.top2 + ((size_t)B.rep * 2 + ((step + 1ull) & 1ull)) * 2, d2, 0.0);
         }
         named_bar_sync(2, FAST_MAIN);
         if (warp == 0) {
@@ -279,9 +403,15 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
                 while (ld_acquire_u32(C.bar_pos) < target) { }
                 if (prof) {
                     c4 = clock64();
-                    S.prof[0] += (unsigned long long)(c1 - c0); S.prof[1] += (unsigned long long)(c2 - c1);
-                    S.prof[2] += (unsigned long long)(c3 - c2); S.prof[3] += (unsigned long long)(c4 - c3);
-                    S.prof[4] += 1ull;
+                    unsigned long long *pc = S.prof + 16 + 8 * blockIdx.x;
+                    pc[0] += (unsigned long long)(c1 - c0); pc[1] += (unsigned long long)(c2 - c1);
+                    pc[2] += (unsigned long long)(c3 - c2); pc[3] += (unsigned long long)(c4 - c3);
+                    pc[5] += (unsigned long long)(c1b - c1);
+                    if (blockIdx.x == 0) {
+                        S.prof[0] += (unsigned long long)(c1 - c0); S.prof[1] += (unsigned long long)(c2 - c1);
+                        S.prof[2] += (unsigned long long)(c3 - c2); S.prof[3] += (unsigned long long)(c4 - c3);
+                        S.prof[4] += 1ull;
+                    }
                 }
             }
         }
@@ -290,67 +420,109 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
         cta_sync();
     }
     cta_sync();                                        // everybody is out of the loop
-    if (valid && lane < 3) { S.vel[o3] = vc; S.acc[o3] = ac; S.move[o3] = mc; }
+    if (B.valid && lane < 3) {
+        const size_t o3 = ((size_t)B.rep * nmp + B.k) * 3 + lane;
+        S.vel[o3] = B.v[lane]; S.acc[o3] = B.a[lane]; S.move[o3] = B.m[lane];
+    }
     return n;
 }
 
+// BP role.  Every CTA evaluates every base-pair candidate that touches one of its beads (as i, j
+// or one of the four chain neighbours) and keeps only the force parts that act on its own beads,
+// in shared memory: no cross-CTA dependency, no global atomics, no grid barrier for the base
+// pairs.  A pair is evaluated by the two or three CTAs that own its six beads; the CTA that owns
+// bead i also maintains bp_status / ene_bp (src/force_bp.F90:191-193).
 SIS_D void fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, FastShared &sh)
 {
     const int tid = threadIdx.x, bt = tid - FAST_MAIN;
-    const int nmp = C.nmp, R = C.R, KB = S.KB;
+    const int nmp = C.nmp, KB = S.KB;
+    const int lo_item = C.item0, hi_item = C.item0 + C.nb;
     int cur = C.cur0;
-    // ---- candidate cache: the CTA's share of the flattened (replica, half-list index) space -----
-    if (bt < 32) {
-        int total = 0;
-        for (int r0 = 0; r0 < R; r0 += 32) total += (r0 + bt < R) ? S.nbp_half[r0 + bt] : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-        const int lo = (int)((long long)total * blockIdx.x / C.ncta);
-        const int hi = (int)((long long)total * (blockIdx.x + 1) / C.ncta);
-        if (bt == 0) { sh.ncand = 0; sh.nactive = 0; }
-        __syncwarp();
-        int base = 0;
-        for (int r = 0; r < R; r++) {
-            const int nb = S.nbp_half[r];
-            const int a = max(lo, base), b = min(hi, base + nb);
-            for (int g = a + bt; g < b; g += 32) {
-                const int ibp = S.bp_half[(size_t)r * S.bp_half_cap + (g - base)];
-                const size_t rbase = (size_t)r * nmp, pbase = rbase * KB;
-                const int ki = ibp / KB, e = ibp - ki * KB;
-                const int j = S.bprow[(rbase + ki) * KB + e].x;
-                double dG = 1.0;
-                if (P.bp_triplet) {
-                    const double2 cf = S.bp_coef[pbase + ibp];
-                    dG = cf.x - S.rp[r].tempK * cf.y;           // src/force_bp_triplet.F90:77
-                    if (dG >= 0.0) {                            // never active at this temperature
-                        S.bp_status[pbase + ibp] = 0;
-                        S.ene_bp[pbase + ibp] = 0.0;
-                        continue;
-                    }
-                }
-                const int slot = atomicAdd(&sh.ncand, 1);
-                if (slot < FAST_BPC) {
-                    FastBpCand &cd = sh.cand[slot];
-                    const int4 mi = S.meta[ki], mj = S.meta[j];
-                    cd.b[0] = ki; cd.b[1] = j;
-                    cd.b[2] = chain_nb(mi, -1); cd.b[3] = chain_nb(mj, -1);
-                    cd.b[4] = chain_nb(mi, +1); cd.b[5] = chain_nb(mj, +1);
-                    cd.ibp = ibp; cd.type = S.bp_type[pbase + ibp]; cd.rep = r; cd.last = -1; cd.dG = dG;
+    auto in_range = [&](int it) { return it >= lo_item && it < hi_item; };
+    // ---- E = the CTA's beads + their chain neighbours outside the range ---------------------------
+    if (bt == 0) { sh.ncand = 0; sh.nactive = 0; sh.nextra = 0; sh.overflow = 0; }
+    for (int i = bt; i < FAST_GROUPS * 3; i += FAST_BP) (&sh.fbp[0][0])[i] = 0.0;
+    named_bar_sync(1, FAST_BP);
+    for (int q = bt; q < C.nb; q += FAST_BP) {
+        int rep, k;
+        fast_item(lo_item + q, nmp, &rep, &k);
+        const int4 m = S.meta[k];
+        for (int d = -1; d <= 1; d += 2) {
+            const int kb = chain_nb(m, d);
+            if (kb < 0) continue;
+            const int it = rep * nmp + kb;
+            if (in_range(it)) continue;
+            const int slot = atomicAdd(&sh.nextra, 1);
+            if (slot < FAST_NEXTRA) sh.extra[slot] = it;
+        }
+    }
+    named_bar_sync(1, FAST_BP);
+    if (bt == 0) {                                     // remove duplicates (a handful of entries)
+        int n = min(sh.nextra, FAST_NEXTRA), m = 0;
+        for (int i = 0; i < n; i++) {
+            const int v = sh.extra[i];
+            bool dup = false;
+            for (int j = 0; j < m; j++) dup |= sh.extra[j] == v;
+            if (!dup) sh.extra[m++] = v;
+        }
+        if (sh.nextra > FAST_NEXTRA) { S.misc->max_force_flag |= 4; sh.overflow = 1; }
+        sh.nextra = m;
+    }
+    named_bar_sync(1, FAST_BP);
+    const int nextra = sh.nextra;
+    auto in_E = [&](int it) {
+        if (in_range(it)) return true;
+        for (int j = 0; j < nextra; j++)
+            if (sh.extra[j] == it) return true;
+        return false;
+    };
+    // ---- candidates: every list pair with a bead in E, taken from the lower E member --------------
+    for (int ei = bt; ei < C.nb + nextra; ei += FAST_BP) {
+        const int b_item = ei < C.nb ? lo_item + ei : sh.extra[ei - C.nb];
+        int rep, k;
+        fast_item(b_item, nmp, &rep, &k);
+        const size_t rbase = (size_t)rep * nmp, pbase = rbase * KB;
+        const int nrow = S.nbp_row[rbase + k];
+        for (int e = 0; e < nrow; e++) {
+            const int2 ent = S.bprow[(rbase + k) * KB + e];
+            const int p_item = rep * nmp + ent.x;
+            if (in_E(p_item) && p_item < b_item) continue;      // enumerated from the partner
+            const int ki = min(k, ent.x), kj = max(k, ent.x), ibp = ent.y;
+            const bool own = in_range(rep * nmp + ki);
+            double dG = 1.0;
+            if (P.bp_triplet) {
+                const double2 cf = S.bp_coef[pbase + ibp];
+                dG = cf.x - S.rp[rep].tempK * cf.y;             // src/force_bp_triplet.F90:77
+                if (dG >= 0.0) {                                // never active at this temperature
+                    if (own) { S.bp_status[pbase + ibp] = 0; S.ene_bp[pbase + ibp] = 0.0; }
+                    continue;
                 }
             }
-            base += nb;
+            const int slot = atomicAdd(&sh.ncand, 1);
+            if (slot < FAST_BPC) {
+                FastBpCand &cd = sh.cand[slot];
+                const int4 mi = S.meta[ki], mj = S.meta[kj];
+                const int base = rep * nmp;
+                cd.b[0] = base + ki; cd.b[1] = base + kj;
+                cd.b[2] = base + chain_nb(mi, -1); cd.b[3] = base + chain_nb(mj, -1);
+                cd.b[4] = base + chain_nb(mi, +1); cd.b[5] = base + chain_nb(mj, +1);
+                cd.type = S.bp_type[pbase + ibp]; cd.last = -1; cd.own = own; cd.pb = pbase + ibp; cd.dG = dG;
+            }
         }
     }
     cta_sync();
     const int ncand = min(sh.ncand, FAST_BPC);
-    if (sh.ncand > FAST_BPC && bt == 0) S.misc->max_force_flag |= 4;   // the host sizes the grid so that this cannot happen
+    if (sh.ncand > FAST_BPC && bt == 0) S.misc->max_force_flag |= 4;   // the host checks the flag after the launch
     const int bl = bt & 7, bg = bt >> 3;
     const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
-    if (!sh.blocked[0] && sh.ncand <= FAST_BPC)
+    const bool prof = S.prof != nullptr && bt == 0;
+    long long b0 = 0, b1 = 0, b2 = 0;
+    if (!sh.blocked[0] && sh.ncand <= FAST_BPC && !sh.overflow)
     for (int n = 0; n < C.nsteps; n++) {
+        if (prof) b0 = clock64();
+        const double4 *pos = S.pos[cur];
         for (int i = bt; i < ncand; i += FAST_BP) {            // distance gate, one thread per candidate
             FastBpCand &cd = sh.cand[i];
-            const double4 *pos = S.pos[cur] + (size_t)cd.rep * nmp;
             const Vec3 v12 = pbc_vec_d(P, v3(pos[cd.b[0]]), v3(pos[cd.b[1]]));
             const double a12 = sqrt(dot(v12, v12));
             const int type = cd.type;
@@ -358,23 +530,27 @@ SIS_D void fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fa
                 sh.active[atomicAdd(&sh.nactive, 1)] = i;
             } else {
                 if (P.bp_triplet && P.flg_bias_ss) {           // src/force_bp_triplet.F90:85-93
-                    const double s = P.bias_ss_force / a12;
-                    double *fi = S.f_bp + ((size_t)cd.rep * nmp + cd.b[0]) * 3, *fj = S.f_bp + ((size_t)cd.rep * nmp + cd.b[1]) * 3;
-                    atomicAdd(fi, -s * v12.x); atomicAdd(fi + 1, -s * v12.y); atomicAdd(fi + 2, -s * v12.z);
-                    atomicAdd(fj, s * v12.x); atomicAdd(fj + 1, s * v12.y); atomicAdd(fj + 2, s * v12.z);
+                    const double sc = P.bias_ss_force / a12;
+                    if (in_range(cd.b[0])) {
+                        double *fi = sh.fbp[cd.b[0] - lo_item];
+                        atomicAdd(fi, -sc * v12.x); atomicAdd(fi + 1, -sc * v12.y); atomicAdd(fi + 2, -sc * v12.z);
+                    }
+                    if (in_range(cd.b[1])) {
+                        double *fj = sh.fbp[cd.b[1] - lo_item];
+                        atomicAdd(fj, sc * v12.x); atomicAdd(fj + 1, sc * v12.y); atomicAdd(fj + 2, sc * v12.z);
+                    }
                 }
-                if (cd.last != 0) {
-                    const size_t pb = (size_t)cd.rep * nmp * KB + cd.ibp;
-                    S.bp_status[pb] = 0; S.ene_bp[pb] = 0.0;
+                if (cd.own && cd.last != 0) {
+                    S.bp_status[cd.pb] = 0; S.ene_bp[cd.pb] = 0.0;
                     cd.last = 0;
                 }
             }
         }
         named_bar_sync(1, FAST_BP);
+        if (prof) b1 = clock64();
         const int nact = sh.nactive;
         for (int a = bg; a < nact; a += FAST_BPGROUPS) {       // survivors: one role per lane
             FastBpCand &cd = sh.cand[sh.active[a]];
-            const double4 *pos = S.pos[cur] + (size_t)cd.rep * nmp;
             const int type = cd.type;
             const Vec3 x0 = v3(pos[cd.b[0]]), x1 = v3(pos[cd.b[1]]);
             const int tA = bp_role_A(bl), tB = bp_role_B(bl);
@@ -398,20 +574,32 @@ SIS_D void fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fa
             Fda.x = __shfl_sync(gmask, o.ca.x, src_dih, 8); Fda.y = __shfl_sync(gmask, o.ca.y, src_dih, 8); Fda.z = __shfl_sync(gmask, o.ca.z, src_dih, 8);
             Fdb.x = __shfl_sync(gmask, o.cb.x, src_dih, 8); Fdb.y = __shfl_sync(gmask, o.cb.y, src_dih, 8); Fdb.z = __shfl_sync(gmask, o.cb.z, src_dih, 8);
             const bool on = ene <= P.bp_cutoff_energy;
-            if (on && bl < 6) {
+            if (on && bl < 6 && in_range(cd.b[bl])) {
                 const Vec3 Ft = bl == 0 ? F0 : bl == 1 ? F1 : Fa + (dih_b ? Fdb : Fda);
-                double *fb = S.f_bp + ((size_t)cd.rep * nmp + cd.b[bl]) * 3;
+                double *fb = sh.fbp[cd.b[bl] - lo_item];
                 atomicAdd(fb, ene * Ft.x); atomicAdd(fb + 1, ene * Ft.y); atomicAdd(fb + 2, ene * Ft.z);
             }
-            if (bl == 0) {
-                const size_t pb = (size_t)cd.rep * nmp * KB + cd.ibp;
-                S.bp_status[pb] = on ? 1 : 0;
-                S.ene_bp[pb] = on ? ene : 0.0;
+            if (bl == 0 && cd.own) {
+                S.bp_status[cd.pb] = on ? 1 : 0;
+                S.ene_bp[cd.pb] = on ? ene : 0.0;
                 cd.last = on ? 1 : 0;
             }
         }
+        if (prof) b2 = clock64();
+        __threadfence_block();
+        __syncwarp();
+        bar_arrive(3, FAST_MAIN + FAST_LOC + FAST_BP);         // base-pair forces of this CTA's beads are in sh.fbp
         named_bar_sync(1, FAST_BP);
-        if (bt == 0) { sh.nactive = 0; red_release_add(C.bar_bp, 1u); }
+        if (bt == 0) sh.nactive = 0;
+        if (prof) {
+            const long long b3 = clock64();
+            S.prof[16 + 8 * blockIdx.x + 4] += (unsigned long long)(b3 - b0);
+            S.prof[16 + 8 * blockIdx.x + 6] += (unsigned long long)nact;
+            if (blockIdx.x == 0) {
+                S.prof[5] += (unsigned long long)(b1 - b0); S.prof[6] += (unsigned long long)(b2 - b1);
+                S.prof[7] += (unsigned long long)(b3 - b2);
+            }
+        }
         cur ^= 1;
         cta_sync();
         if (sh.blocked[n & 1]) break;
@@ -431,7 +619,7 @@ SIS_D void fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
     const int gg = lt >> 1, gdraw = lt & 1, gitem = C.item0 + gg;
     int grep = 0, gk = 0;
     uint32_t gstream = 0;
-    const bool gon = lt < 2 * FAST_GROUPS && gitem < C.nitems;
+    const bool gon = lt < 2 * FAST_GROUPS && gg < C.nb;
     if (gon) {
         fast_item(gitem, nmp, &grep, &gk);
         gstream = (uint32_t)S.rp[grep].stream;
@@ -451,17 +639,26 @@ SIS_D void fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
         b = __any_sync(0xffffffffu, b);
         if (ll == 0) { sh.blocked[0] = b; sh.blocked[1] = 0; }
     }
-    // bonded-term slot of this thread: [0, NT) angle + bond, [NT, 2 NT) dihedral
-    const int kind = lt / FAST_NT, slot = lt - kind * FAST_NT;
-    const int titem = C.item0 - 3 + slot;
-    bool ton = lt < 2 * FAST_NT && titem >= 0 && titem < C.nitems && (kind == 0 || C.dih_on);
-    int trep = 0, tk = 0;
-    int4 tm = make_int4(0, 1, 0, 0);
-    if (ton) { fast_item(titem, nmp, &trep, &tk); tm = S.meta[tk]; }
-    const bool tcirc = tm.w & MF_CIRC;
+    // bonded-term slots: slot s <-> the terms starting at item0 - 3 + s
+    for (int slot = lt; slot < FAST_NT; slot += FAST_LOC) {
+        const int titem = C.item0 - 3 + slot;
+        int4 tm = make_int4(0, 1, 0, 0);
+        int tb = -1;
+        if (titem >= 0 && slot < C.nb + 3) {
+            int trep, tk;
+            fast_item(titem, nmp, &trep, &tk);
+            tm = S.meta[tk];
+            tb = titem;
+        }
+        sh.tmeta[slot] = tm;
+        sh.tbead[slot] = tb;
+    }
     cta_sync();
-    if (!sh.blocked[0] && sh.ncand <= FAST_BPC)
+    const bool prof = S.prof != nullptr && blockIdx.x == 0 && lt == 0;
+    long long l0 = 0, l1 = 0;
+    if (!sh.blocked[0] && sh.ncand <= FAST_BPC && !sh.overflow)
     for (int n = 0; n < C.nsteps; n++) {
+        if (prof) l0 = clock64();
         // rebuild test on the displacements left by the previous step
         if (n > 0 && wwarp) {
             bool b = false;
@@ -488,9 +685,16 @@ SIS_D void fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
             }
             if (ll == 0) sh.blocked[n & 1] = b;
         }
-        // bonded terms, each evaluated once (src/force_bond.F90, force_angl*.F90, force_dih_*.F90)
-        if (ton) {
-            const double4 *pos = S.pos[cur] + (size_t)trep * nmp;
+        // bonded terms, each evaluated once (src/force_bond.F90, force_angl*.F90, force_dih_*.F90):
+        // tasks [0, NT) = bond + angle of a slot (shared loads), [NT, 2 NT) = its dihedral
+        for (int task = lt; task < (C.dih_on ? 2 * FAST_NT : FAST_NT); task += FAST_LOC) {
+            const int kind = task >= FAST_NT, slot = task - kind * FAST_NT;
+            const int tb = sh.tbead[slot];
+            if (tb < 0) continue;
+            const int4 tm = sh.tmeta[slot];
+            const bool tcirc = tm.w & MF_CIRC;
+            const double4 *pos = S.pos[cur] + (tb - (tm.x + tm.z));     // first bead of the replica
+            const int tk = tm.x + tm.z;
             if (kind == 0) {
                 if (tcirc ? tm.y > 1 : tm.z + 1 < tm.y) {
                     const Vec3 x0 = v3(pos[tk]), x1 = v3(pos[chain_nb(tm, 1)]);
@@ -515,7 +719,8 @@ SIS_D void fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
         }
         __threadfence_block();
         __syncwarp();
-        bar_arrive(3, FAST_MAIN + FAST_LOC);
+        bar_arrive(3, FAST_MAIN + FAST_LOC + FAST_BP);
+        if (prof) l1 = clock64();
         // Gaussians of the next step (buffer parity of step + 2)
         if (gon && n + 1 < C.nsteps) {
             double g0, g1;
@@ -523,6 +728,7 @@ SIS_D void fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
             if (gdraw == 0) { sh.gauss[step & 1][gg][0] = g0; sh.gauss[step & 1][gg][1] = g1; }
             else sh.gauss[step & 1][gg][2] = g0;
         }
+        if (prof) { S.prof[8] += (unsigned long long)(l1 - l0); S.prof[9] += (unsigned long long)(clock64() - l1); }
         step++;
         cur ^= 1;
         cta_sync();
@@ -531,6 +737,7 @@ SIS_D void fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
     cta_sync();
 }
 
+template <int U>
 __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams P, StepArgs A, int nsteps)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -539,14 +746,14 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams 
     const DevCtl ctl = S.ctl[0];
     FastCtx C;
     C.R = S.nrep; C.nmp = S.nmp; C.K = S.K; C.nitems = S.nrep * S.nmp; C.ncta = gridDim.x;
-    C.item0 = blockIdx.x * FAST_GROUPS; C.nsteps = nsteps;
+    C.item0 = S.cta_item0[blockIdx.x]; C.nb = S.cta_item0[blockIdx.x + 1] - C.item0; C.nsteps = nsteps;
     C.step0 = ctl.step; C.cur0 = ctl.cur;
-    C.bar_bp = S.bar; C.bar_pos = S.bar + 32;
+    C.bar_pos = S.bar + 32;
     C.dih_on = P.flg_dih_cos || P.flg_dih_exp;
     const int tid = threadIdx.x;
     if (tid >= FAST_MAIN + FAST_BP) { fast_loc_role(S, P, A, C, sh); return; }
     if (tid >= FAST_MAIN) { fast_bp_role(S, P, C, sh); return; }
-    const int n = fast_main_role(S, P, A, C, sh, s_rows);
+    const int n = fast_main_role<U>(S, P, A, C, sh, s_rows);
     // ---- bookkeeping for the host and the other kernels (block 0, warp 0) ---------------------------
     if (blockIdx.x == 0 && tid < 32) {
         const unsigned long long step = C.step0 + (unsigned long long)n;

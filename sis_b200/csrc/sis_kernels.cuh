@@ -85,6 +85,7 @@ struct DevSys {
     unsigned long long *prof;     // optional phase clocks of the persistent kernel (block 0), or null
     unsigned int *bar;            // grid-barrier counters of k_md_fused: [0] bp done, [32] positions written
     double2 *top2_slots;          // k_md_fast: per-CTA (max, 2nd max) |xyz_move|^2, [2][FAST_MAX_CTA]
+    const int *cta_item0;         // k_md_fast: first flattened (replica, bead) item of each CTA, [ncta + 1]
     double *ene_partial;          // [rep][nblk][ENE_N]
     unsigned int *ene_counter;    // [rep]
     double *ene_out;              // [rep][ENE_N]

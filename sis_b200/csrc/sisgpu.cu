@@ -135,7 +135,11 @@ struct sisgpu {
     int coop_blocks = 0;       // co-resident grid size of the persistent kernel
     int fast_kernel = 1;       // option "fast_kernel": 0 forces the general k_md_fused
     size_t fast_smem_set = 0;
+    void *fast_fn_set = nullptr;
+    int fast_unroll = 1;       // option "fast_unroll": position gathers in flight per lane (1 = pipelined, 2, 4)
     std::vector<int> nbp_half_rep;   // half-list bp candidate count per replica (last build)
+    bool partition_dirty = true;     // lists changed since the CTA bead ranges of k_md_fast were computed
+    int fast_ncta = 0;               // number of ranges (0: the system does not fit the fast kernel)
     // biases (host copies)
     std::vector<int> twz_pairs, twzfr_pairs, rest_id;
     std::vector<double> twz_dir, twzfr_k, twzfr_init, twzfr_velo, rest_rcut, rest_para;
@@ -173,6 +177,7 @@ struct sisgpu {
     DBuf<double2> d_bp_coef, d_top2_slots;
     DBuf<unsigned long long> d_mc_counter, d_prof;
     DBuf<unsigned int> d_ene_counter, d_bar;
+    DBuf<int> d_cta_item0;
     DBuf<RepParams> d_rp, d_rp_alt;
     DBuf<unsigned char> d_sync;          // DevSyncHdr + top2[nrep][2][2]
     unsigned char *h_sync = nullptr;     // pinned mirror
@@ -184,7 +189,7 @@ struct sisgpu {
     int K = 0, KB = 0, G = 8;   // G = lanes per bead in the pair task
     // stats / options
     long long launches = 0, nrebuild = 0, graph_launches_per_chunk = 0;
-    int launch_mode = 1, chunk = 16, timing = 0;   // launch_mode 1: CUDA-graph chunks
+    int launch_mode = 2, chunk = 16, timing = 0;   // launch_mode 2: persistent kernels (k_md_fast / k_md_fused); 1: CUDA-graph chunks; 0: stream launches
     double t_step = 0, t_nl = 0, t_ene = 0, t_rex = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long long istep_host = 0;
@@ -236,7 +241,7 @@ int sisgpu_destroy(sisgpu_t *h)
     h->d_twzfr_init.release(); h->d_twzfr_velo.release(); h->d_rest_rcut.release(); h->d_rest_para.release();
     h->d_gather_send.release(); h->d_gather_recv.release(); h->d_nbr.release(); h->d_bprow.release();
     h->d_bp_type.release(); h->d_bp_coef.release(); h->d_mc_counter.release();
-    h->d_ene_counter.release(); h->d_bar.release(); h->d_top2_slots.release(); h->d_rp.release(); h->d_rp_alt.release(); h->d_sync.release();
+    h->d_ene_counter.release(); h->d_bar.release(); h->d_top2_slots.release(); h->d_cta_item0.release(); h->d_rp.release(); h->d_rp_alt.release(); h->d_sync.release();
     if (h->graph_chunk) cudaGraphExecDestroy(h->graph_chunk);
     h->d_f_pair.release(); h->d_f_loc.release(); h->d_f_bp.release(); h->d_bp_half.release(); h->d_nbp_half.release();
     cudaEventDestroy(h->ev0);
@@ -691,6 +696,7 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     TRY(h->d_kin.alloc(R));
     TRY(h->d_bar.alloc(64));
     TRY(h->d_top2_slots.alloc(2 * FAST_MAX_CTA));
+    TRY(h->d_cta_item0.alloc(FAST_MAX_CTA + 1));
     const int nblk = (N + 63) / 64;            // integrate kernel: 64 beads per block
     const int nblk_ene = (N + 31) / 32;        // energy kernel: 8 lanes per bead
     TRY(h->d_ene_partial.alloc((size_t)R * nblk_ene * ENE_N)); TRY(h->d_ene_counter.alloc(R)); TRY(h->d_ene_out.alloc((size_t)R * ENE_N));
@@ -718,6 +724,7 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     S.nl_margin = h->nl_margin;
     S.bar = h->d_bar.p;
     S.top2_slots = h->d_top2_slots.p;
+    S.cta_item0 = h->d_cta_item0.p;
     S.ene_partial = h->d_ene_partial.p; S.ene_counter = h->d_ene_counter.p;
     S.ene_out = h->d_ene_out.p;
     S.twz_pairs = h->d_twz_pairs.p; S.twz_dir = h->d_twz_dir.p; S.twzfr_pairs = h->d_twzfr_pairs.p;
@@ -934,6 +941,7 @@ static int build_lists(sisgpu *h, const std::vector<int> &active, bool all_pairs
             int mx = 0;
             for (int r = 0; r < R; r++) mx = std::max(mx, nh[r]);
             h->nbp_half_rep = nh;
+            h->partition_dirty = true;
             // the bp task grid is sized from this count; regrow (and re-capture) with slack
             if (mx > h->nbp_half_max || mx < h->nbp_half_max / 4) { h->nbp_half_max = mx + mx / 4 + 128; invalidate_graphs(h); }
         }
@@ -1508,6 +1516,48 @@ int sisgpu_replica_exchange(sisgpu_t *h, const double *E, const double *uniforms
     return 0;
 }
 
+// Bead ranges of k_md_fast: contiguous runs of at most FAST_GROUPS flattened (replica, bead) items,
+// one per CTA, chosen so that the largest per-CTA pair work (row entries + a per-bead constant) is
+// minimal for the number of SMs -- the step time is the time of the busiest CTA.
+static int fast_partition(sisgpu *h)
+{
+    const long long nitems = (long long)h->nrep * h->nmp;
+    const int ncta_max = std::min(h->coop_blocks, FAST_MAX_CTA);
+    h->partition_dirty = false;
+    h->fast_ncta = 0;
+    if (nitems > (long long)ncta_max * FAST_GROUPS) return 0;
+    std::vector<int> nn(nitems);
+    CK(cudaMemcpyAsync(nn.data(), h->d_nnbr.p, nitems * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    long long total = 0;
+    int wmax = 0;
+    for (auto &w : nn) { w += 8; total += w; wmax = std::max(wmax, w); }
+    auto parts = [&](long long W, std::vector<int> *out) {
+        int n = 1, cnt = 0;
+        long long s = 0;
+        if (out) { out->clear(); out->push_back(0); }
+        for (long long i = 0; i < nitems; i++) {
+            if (cnt == FAST_GROUPS || s + nn[i] > W) {
+                n++; s = 0; cnt = 0;
+                if (out) out->push_back((int)i);
+            }
+            s += nn[i]; cnt++;
+        }
+        if (out) out->push_back((int)nitems);
+        return n;
+    };
+    long long lo = wmax, hi = total;
+    while (lo < hi) {
+        const long long mid = (lo + hi) / 2;
+        if (parts(mid, nullptr) <= ncta_max) hi = mid; else lo = mid + 1;
+    }
+    std::vector<int> item0;
+    h->fast_ncta = parts(lo, &item0);
+    CK(cudaMemcpyAsync(h->d_cta_item0.p, item0.data(), item0.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // item0 is a local
+    return 0;
+}
+
 // ---- the MD loop --------------------------------------------------------------------------
 int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
 {
@@ -1562,19 +1612,21 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
             CK(cudaMemsetAsync(h->d_bar.p, 0, 64 * sizeof(unsigned), h->stream));
             void *args[] = {&h->S, &h->P, &A, &nrun};
             // k_md_fast: one bead per 8-lane group, rows / candidates / bonded tables on chip
-            const int want_fast = (int)((nitems + FAST_GROUPS - 1) / FAST_GROUPS);
-            const size_t smem_fast = ((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)FAST_GROUPS * h->K * sizeof(uint32_t);
+            if (h->fast_kernel && h->partition_dirty) TRY(fast_partition(h));
+            const int want_fast = h->fast_ncta;
+            const size_t smem_fast = ((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)3 * FAST_GROUPS * h->K * sizeof(uint32_t);   // rows, sort scratch / unit forces, classes / unit tables
             long long ncand_total = 0;
             for (int r = 0; r < R; r++) ncand_total += h->nbp_half_rep.empty() ? h->nbp_half_max : h->nbp_half_rep[r];
             const bool biases = h->P.flg_stage || h->P.ntwz_DCF || h->P.ntwz_FR || h->P.nrest;
-            const bool fast_ok = h->fast_kernel && want_fast <= std::min(h->coop_blocks, FAST_MAX_CTA) && !biases &&
-                                 smem_fast <= 200 * 1024 && ncand_total / want_fast + 2 <= FAST_BPC;
+            const bool fast_ok = h->fast_kernel && want_fast > 0 && !biases && h->K >= 24 && smem_fast <= 200 * 1024 &&
+                                 3 * (ncand_total / want_fast) + 16 <= FAST_BPC;
             if (fast_ok) {
-                if (smem_fast > h->fast_smem_set) {
-                    CK(cudaFuncSetAttribute(k_md_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
-                    h->fast_smem_set = smem_fast;
+                void *fn = (void *)k_md_fast<1>;
+                if (smem_fast > h->fast_smem_set || fn != h->fast_fn_set) {
+                    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
+                    h->fast_smem_set = smem_fast; h->fast_fn_set = fn;
                 }
-                CK(cudaLaunchCooperativeKernel((void *)k_md_fast, dim3(want_fast), dim3(FAST_THREADS), args, smem_fast, h->stream));
+                CK(cudaLaunchCooperativeKernel(fn, dim3(want_fast), dim3(FAST_THREADS), args, smem_fast, h->stream));
             } else {
                 const int want = (int)std::max<long long>(1, (nitems + FUSED_GROUPS - 1) / FUSED_GROUPS);
                 dim3 grid(std::min(h->coop_blocks, want));
@@ -1615,6 +1667,13 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
         TRY(sync_ctl(h));
         CK(cudaGetLastError());
         timer_end(h, h->t_step);
+        if (h->h_misc->max_force_flag & 4) {
+            // k_md_fast found more base-pair candidates or chain neighbours than its shared-memory
+            // tables hold and did not run: use the general kernel from here on
+            h->h_misc->max_force_flag &= ~4;
+            CK(cudaMemcpy(&h->S.misc->max_force_flag, &h->h_misc->max_force_flag, sizeof(int), cudaMemcpyHostToDevice));
+            h->fast_kernel = 0;
+        }
         // exchange step (src/job_md.F90:474-481,514-570)
         if (h->flg_replica && h->nstep_exchange > 0 &&
             (long long)h->h_ctl->step % h->nstep_exchange == 0 && (long long)h->h_ctl->step > cur) {
@@ -1673,6 +1732,15 @@ int sisgpu_check_force(sisgpu_t *h, double tempK, double *f_energy, double *f_fo
 
 int sisgpu_launch_count(sisgpu_t *h, int64_t *n) { *n = h->launches; return 0; }
 
+int sisgpu_get_cta_profile(sisgpu_t *h, int ncta, double *out)
+{
+    if (!h->S.prof) return set_err("option profile is off");
+    std::vector<unsigned long long> p(8 * (size_t)ncta);
+    CK(cudaMemcpy(p.data(), h->d_prof.p + 16, p.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < p.size(); i++) out[i] = (double)p[i];
+    return 0;
+}
+
 int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
 {
     std::string s(name);
@@ -1680,8 +1748,9 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
     else if (s == "chunk") { h->chunk = std::max(1, (int)value); invalidate_graphs(h); }
     else if (s == "timing") h->timing = (int)value;
     else if (s == "fast_kernel") h->fast_kernel = (int)value;
+    else if (s == "fast_unroll") h->fast_unroll = (int)value;
     else if (s == "profile") {   // phase clocks of the persistent kernel (block 0): get_timers out[4..8]
-        if (value != 0) { TRY(h->d_prof.alloc(8)); h->S.prof = h->d_prof.p; }
+        if (value != 0) { TRY(h->d_prof.alloc(16 + 8 * FAST_MAX_CTA)); h->S.prof = h->d_prof.p; }
         else h->S.prof = nullptr;
         invalidate_graphs(h);
     }
@@ -1697,12 +1766,12 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
 int sisgpu_get_timers(sisgpu_t *h, double *out, int reset)
 {
     out[0] = h->t_step; out[1] = h->t_nl; out[2] = h->t_ene; out[3] = h->t_rex;
-    for (int i = 4; i < 9; i++) out[i] = 0;
+    for (int i = 4; i < 16; i++) out[i] = 0;
     if (h->S.prof) {
-        unsigned long long p[8];
+        unsigned long long p[16];
         CK(cudaMemcpy(p, h->d_prof.p, sizeof p, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < 5; i++) out[4 + i] = (double)p[i];
-        if (reset) CK(cudaMemset(h->d_prof.p, 0, sizeof p));
+        for (int i = 0; i < 10; i++) out[4 + i] = (double)p[i];
+        if (reset) CK(cudaMemset(h->d_prof.p, 0, (16 + 8 * FAST_MAX_CTA) * sizeof(unsigned long long)));
     }
     if (reset) h->t_step = h->t_nl = h->t_ene = h->t_rex = 0;
     return 0;
