@@ -60,6 +60,11 @@ class SystemSpec:
     stage: tuple[float, float] | None = None  # sigma, eps
     twz_dcf_pairs: list[tuple[int, int]] = field(default_factory=list)
     twz_dcf_forces: list[tuple[float, float, float]] = field(default_factory=list)  # kcal/mol/A
+    # Force-Ramp traps (src/force_tweezers.F90:37-61): pairs [n][2], k [n][2], init / velo [n][2][3]
+    twz_fr_pairs: list[tuple[int, int]] = field(default_factory=list)
+    twz_fr_k: list[tuple[float, float]] = field(default_factory=list)
+    twz_fr_init: list | None = None
+    twz_fr_velo: list | None = None
     bias_rg: tuple[int, float, float] | None = None  # pott, k, rg0
     restraints: list[tuple[int, int, int, float, float, float, float]] = field(default_factory=list)
     frozen: list[int] = field(default_factory=list)       # 1-based ids
@@ -137,6 +142,12 @@ class SystemSpec:
             # full vector and the magnitude is 1.
             be.set_tweezers_dcf(len(self.twz_dcf_pairs), np.array(self.twz_dcf_pairs, dtype=np.int32), f)
             twz_mag = 1.0
+        if self.twz_fr_pairs:
+            n = len(self.twz_fr_pairs)
+            be.set_tweezers_fr(n, np.array(self.twz_fr_pairs, dtype=np.int32),
+                               np.array(self.twz_fr_k, dtype=np.float64).reshape(n, 2),
+                               np.array(self.twz_fr_init, dtype=np.float64).reshape(n, 6),
+                               np.array(self.twz_fr_velo, dtype=np.float64).reshape(n, 6))
         rg0 = 0.0
         if self.bias_rg is not None:
             be.set_bias_rg(1, self.bias_rg[0], self.bias_rg[1])
