@@ -1289,9 +1289,9 @@ static void apply_label(sisgpu *h, int irep, int label)
     if (h->P.flg_ele) host_set_ele(h, r, T, I);
 }
 
-int sisgpu_remd_setup(sisgpu_t *h, const int nrep[4], const double *values, int nstep_exchange, int rank, int nranks)
+// host part of sisgpu_remd_setup: tables and the parameters of the local replicas
+static int remd_setup_host(sisgpu *h, const int nrep[4], const double *values, int nstep_exchange, int rank, int nranks)
 {
-    if (!h->finalized) return set_err("finalize_setup not called");
     h->flg_replica = true; h->ndim_replica = 0; h->nrep_all = 1;
     for (int v = 0; v < REPT_MAX; v++) {
         h->nrep_dim[v] = nrep[v];
@@ -1351,7 +1351,6 @@ int sisgpu_remd_setup(sisgpu_t *h, const int nrep[4], const double *values, int 
         }
     }
     h->idx_pair = 1;
-    h->d_gather_recv.alloc(2 * (size_t)n);
     for (int irep = 0; irep < h->nrep; irep++) {
         const int grep = rank * h->nrep + irep;
         apply_label(h, irep, h->rep2lab[grep]);
@@ -1361,6 +1360,14 @@ int sisgpu_remd_setup(sisgpu_t *h, const int nrep[4], const double *values, int 
             else r.ele_cutoff = h->ele_cutoff_inp * r.lambdaD;
         }
     }
+    return 0;
+}
+
+int sisgpu_remd_setup(sisgpu_t *h, const int nrep[4], const double *values, int nstep_exchange, int rank, int nranks)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    TRY(remd_setup_host(h, nrep, values, nstep_exchange, rank, nranks));
+    TRY(h->d_gather_recv.alloc(2 * (size_t)h->nrep_all));
     return push_rp(h);
 }
 
@@ -1468,19 +1475,15 @@ int sisgpu_energy_replica(sisgpu_t *h, double *energies, double *replica_energie
     return 0;
 }
 
-// replica_exchange (src/replica_exchange.F90:44-154): identical decisions on every rank
-int sisgpu_replica_exchange(sisgpu_t *h, const double *E, const double *uniforms, int *n_attempt, int *n_accept)
+// replica_exchange (src/replica_exchange.F90:44-154): identical decisions on every rank.
+// Host part: label tables, acceptance, parameter refresh of the local replicas (src/job_md.F90:538-567).
+// The velocity rescaling of accepted temperature swaps (scale_velo, :175-213) is returned as
+// (local replica, factor) pairs for the caller to apply on the device.
+struct VelScale { int irep; double factor; };
+static void remd_decide(sisgpu *h, const double *E, const double *u, int *n_attempt, int *n_accept, std::vector<VelScale> &scales)
 {
-    if (!h->flg_replica) return set_err("REMD not configured");
-    CK(cudaSetDevice(h->device));
     const int n = h->nrep_all, R = h->nrep;
     int nrand = 0, natt = 0, nacc = 0;
-    // the reference draws ceil(nrep_all/2) numbers up front from mts_rep (:44-48)
-    const int ndraw = (n + 1) / 2;
-    std::vector<double> u(ndraw);
-    for (int i = 0; i < ndraw; i++)
-        u[i] = uniforms ? uniforms[i] : uniform_counter(h->seed, 0x7fffffffu, h->exchange_counter + i);
-    if (!uniforms) h->exchange_counter += ndraw;
     for (int l_i = 1; l_i <= n; l_i++) {
         const int l_j = get_pair(h, l_i);
         if (l_j < l_i) continue;
@@ -1502,17 +1505,35 @@ int sisgpu_replica_exchange(sisgpu_t *h, const double *E, const double *uniforms
             if (h->flg_repvar[REPT_TEMP]) {   // scale_velo :175-213, only for locally held replicas
                 const double sf = sqrt(temp_n / temp_m);
                 const int li = rep_i - 1 - h->rank * R, lj = rep_j - 1 - h->rank * R;
-                if (li >= 0 && li < R) { k_scale_velocities<<<(3 * h->nmp + 255) / 256, 256, 0, h->stream>>>(h->S, li, sf); h->launches++; }
-                if (lj >= 0 && lj < R) { k_scale_velocities<<<(3 * h->nmp + 255) / 256, 256, 0, h->stream>>>(h->S, lj, 1.0 / sf); h->launches++; }
+                if (li >= 0 && li < R) scales.push_back({li, sf});
+                if (lj >= 0 && lj < R) scales.push_back({lj, 1.0 / sf});
             }
         }
     }
     h->idx_pair = (h->idx_pair == 2 * h->ndim_replica) ? 1 : h->idx_pair + 1;   // set_forward
     for (int irep = 0; irep < R; irep++) apply_label(h, irep, h->rep2lab[h->rank * R + irep]);
-    TRY(push_rp(h));
     h->n_attempt += natt; h->n_accept += nacc;
     if (n_attempt) *n_attempt = natt;
     if (n_accept) *n_accept = nacc;
+}
+
+int sisgpu_replica_exchange(sisgpu_t *h, const double *E, const double *uniforms, int *n_attempt, int *n_accept)
+{
+    if (!h->flg_replica) return set_err("REMD not configured");
+    CK(cudaSetDevice(h->device));
+    // the reference draws ceil(nrep_all/2) numbers up front from mts_rep (:44-48)
+    const int ndraw = (h->nrep_all + 1) / 2;
+    std::vector<double> u(ndraw);
+    for (int i = 0; i < ndraw; i++)
+        u[i] = uniforms ? uniforms[i] : uniform_counter(h->seed, 0x7fffffffu, h->exchange_counter + i);
+    if (!uniforms) h->exchange_counter += ndraw;
+    std::vector<VelScale> scales;
+    remd_decide(h, E, u.data(), n_attempt, n_accept, scales);
+    for (const VelScale &v : scales) {
+        k_scale_velocities<<<(3 * h->nmp + 255) / 256, 256, 0, h->stream>>>(h->S, v.irep, v.factor);
+        h->launches++;
+    }
+    TRY(push_rp(h));
     return 0;
 }
 

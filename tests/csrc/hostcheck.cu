@@ -246,6 +246,26 @@ int hc_coef(HostCheck *c, int imp, double *out)
     out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w * c->rp.sqrt_tempK;
     return 0;
 }
+// REMD host logic (tables, acceptance, label -> parameter refresh) of rank `rank` of `nranks`
+int hc_remd_setup(HostCheck *c, const int *nrep, const double *values, int nstep_exchange, int rank, int nranks)
+{
+    return remd_setup_host(c->h, nrep, values, nstep_exchange, rank, nranks);
+}
+// scale_out[nrep_proc]: product of the velocity factors the exchange applies to each local replica;
+// params_out[nrep_proc][4]: tempK, ionic strength, DCF force, Rg0 after the refresh
+int hc_remd_exchange(HostCheck *c, const double *E, const double *uniforms, int *natt, int *nacc, double *scale_out, double *params_out)
+{
+    sisgpu *h = c->h;
+    std::vector<VelScale> sc;
+    remd_decide(h, E, uniforms, natt, nacc, sc);
+    for (int r = 0; r < h->nrep; r++) scale_out[r] = 1.0;
+    for (const VelScale &v : sc) scale_out[v.irep] *= v.factor;
+    for (int r = 0; r < h->nrep; r++) {
+        params_out[4 * r] = h->rep[r].tempK; params_out[4 * r + 1] = h->rep[r].ionic;
+        params_out[4 * r + 2] = h->rep[r].twz_force; params_out[4 * r + 3] = h->rep[r].rg0;
+    }
+    return 0;
+}
 int hc_rep_params(HostCheck *c, double *out)
 {
     out[0] = c->h->rep[0].ele_coef; out[1] = c->h->rep[0].lambdaD; out[2] = c->h->rep[0].ele_cutoff; out[3] = c->h->rep[0].diele;

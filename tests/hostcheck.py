@@ -73,6 +73,19 @@ class HostCheck(CApi):
         self.lib.hc_uniform.restype = C.c_double
         return self.lib.hc_uniform(C.c_uint64(seed), C.c_uint(stream), C.c_uint64(counter))
 
+    def remd_setup(self, nrep, values, nstep_exchange, rank=0, nranks=1):
+        nr, vals = self._remd_args(nrep, values)
+        if self.lib.hc_remd_setup(self.hc, _i(nr)[0], _d(vals)[0], C.c_int(nstep_exchange), C.c_int(rank), C.c_int(nranks)) != 0:
+            raise RuntimeError(self._err().decode())
+
+    def remd_exchange(self, replica_energies, uniforms):
+        """-> (n_attempt, n_accept, velocity scale per local replica, [tempK, ionic, force, rg0] per local replica)"""
+        na, nc = C.c_int(), C.c_int()
+        scale, par = np.zeros(self.nrep_proc), np.zeros((self.nrep_proc, 4))
+        re, u = np.ascontiguousarray(replica_energies, dtype=np.float64), np.ascontiguousarray(uniforms, dtype=np.float64)
+        assert self.lib.hc_remd_exchange(self.hc, _d(re)[0], _d(u)[0], C.byref(na), C.byref(nc), _d(scale)[0], _d(par)[0]) == 0
+        return na.value, nc.value, scale, par
+
     def coef(self, imp):
         out = np.zeros(4)
         self.lib.hc_coef(self.hc, C.c_int(imp), _d(out)[0])
