@@ -61,6 +61,7 @@ struct RepParams {
     double tempK;          // replica temperature (rep2val(TEMP) or tempK)
     double ele_coef;       // src/set_ele.F90:81-86
     double inv_lambdaD;    // 1 / lambdaD
+    double lambdaD;        // kept beside its inverse: ele_cutoff = cutoff_inp * lambdaD must be bit-identical to the host's
     double ele_cutoff;     // refreshed in neighbor_list only for cutoff_type 2 (quirk 3)
     double diele_dTcoef;
     double sqrt_tempK;     // noise scaling: md_coef_rep(1) = noise0[imp] * sqrt(T)

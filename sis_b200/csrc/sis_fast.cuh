@@ -738,12 +738,16 @@ SIS_D void fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
 }
 
 template <int U>
-__global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams P, StepArgs A, int nsteps)
+__global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams P, StepArgs A, long long target)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastShared &sh = *reinterpret_cast<FastShared *>(smem_raw);
     uint32_t *s_rows = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(FastShared) + 15) & ~size_t(15)));
     const DevCtl ctl = S.ctl[0];
+    // steps to run: up to `target`; nothing on lists a device-side rebuild could not fit (the host
+    // grows them first).  Uniform over the grid: ctl and misc were written by earlier kernels.
+    const int nsteps = md_steps_to_run(S, ctl, target);
+    if (nsteps <= 0) return;
     FastCtx C;
     C.R = S.nrep; C.nmp = S.nmp; C.K = S.K; C.nitems = S.nrep * S.nmp; C.ncta = gridDim.x;
     C.item0 = S.cta_item0[blockIdx.x]; C.nb = S.cta_item0[blockIdx.x + 1] - C.item0; C.nsteps = nsteps;

@@ -179,7 +179,15 @@ SIS_D void top2_push(unsigned long long *t, double t1, double t2)
     if (c2 > 0.0) atomicMax(t + 1, (unsigned long long)__double_as_longlong(c2));
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS, 1) k_md_fused(DevSys S, FFParams P, StepArgs A, int nsteps)
+// number of steps a persistent launch runs: up to step `target`, none on invalid lists
+SIS_D int md_steps_to_run(const DevSys &S, const DevCtl &ctl, long long target)
+{
+    if (S.misc->lists_invalid) return 0;
+    const long long left = target - (long long)ctl.step;
+    return left <= 0 ? 0 : (int)(left < (1ll << 20) ? left : (1ll << 20));
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, 1) k_md_fused(DevSys S, FFParams P, StepArgs A, long long target)
 {
     __shared__ int s_blocked;
     __shared__ double s_top[FUSED_MAIN_WARPS][2];
@@ -190,6 +198,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_md_fused(DevSys S, FFParam
     const int ncta = gridDim.x;
     const int niter = (nitems + ncta * FUSED_GROUPS - 1) / (ncta * FUSED_GROUPS);
     const DevCtl ctl = S.ctl[0];
+    const int nsteps = md_steps_to_run(S, ctl, target);
+    if (nsteps <= 0) return;
     unsigned long long step = ctl.step;
     int cur = ctl.cur;
     unsigned *bar_bp = S.bar, *bar_pos = S.bar + 32;   // separate 128-byte lines

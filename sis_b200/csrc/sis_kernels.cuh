@@ -27,7 +27,11 @@ struct DevCtl {
 struct DevMisc {
     int nl_overflow, bp_overflow;   // longest rows seen by the last list build
     int max_force_flag;             // src/job_md.F90:403-407 (forces > 100 warning); bit1: stage abort
-    int pad;
+    int lists_invalid;              // device-side rebuild: a row / the bp half list overflowed its capacity,
+                                    // the persistent kernels do not run until the host has grown the lists
+    int nrebuild;                   // replica list rebuilds done by the device-side chain (k_nl_plan)
+    int half_overflow;              // largest bp half-list count seen by k_nl_partition
+    int pad[2];
 };
 
 // one contiguous device block the host mirrors with a single copy: header + top2[nrep][2][2]
@@ -73,7 +77,9 @@ struct DevSys {
     unsigned long long *mc_counter;  // [rep]
     // cell grid [rep][...]
     int *cell_of, *cell_count, *cell_start, *cell_cursor, *cell_beads;
+    int *cell_sorted;             // cell_beads with every cell in ascending bead order (k_nl_rank)
     int ncell_cap;
+    GridInfo *grid;               // the cell grid of the current build (host- or k_nl_plan-written)
     // parameters
     RepParams *rp;
     DevCtl *ctl;                  // [2]: A, B
@@ -85,7 +91,7 @@ struct DevSys {
     unsigned long long *prof;     // optional phase clocks of the persistent kernel (block 0), or null
     unsigned int *bar;            // grid-barrier counters of k_md_fused: [0] bp done, [32] positions written
     double2 *top2_slots;          // k_md_fast: per-CTA (max, 2nd max) |xyz_move|^2, [2][FAST_MAX_CTA]
-    const int *cta_item0;         // k_md_fast: first flattened (replica, bead) item of each CTA, [ncta + 1]
+    int *cta_item0;               // k_md_fast: first flattened (replica, bead) item of each CTA, [ncta + 1]
     double *ene_partial;          // [rep][nblk][ENE_N]
     unsigned int *ene_counter;    // [rep]
     double *ene_out;              // [rep][ENE_N]
@@ -834,13 +840,97 @@ __global__ void k_scale_velocities(DevSys S, int rep, double factor)
 }
 
 // ---- neighbour list on a cell grid (replaces the O(N^2) sweep of src/neighbor_list.F90) ------
+// Every kernel of the chain reads the grid (S.grid) and the replica flags (rep_active) from device
+// memory, so the same launches serve the host-driven build (build_lists: flags and grid written by
+// the host) and the device-driven rebuild inside the MD loop (k_nl_plan writes both; a chain whose
+// replicas are all within the list margin falls through in a few microseconds without a host
+// round trip).
+struct NlPlanArgs {
+    double rc;              // cell edge lower bound: largest list cutoff + margin
+    double ele_cutoff_inp;  // cutoff_type 2: ele_cutoff = ele_cutoff_inp * lambdaD, refreshed at every rebuild
+    int ele_cutoff_type, flg_ele, pbc;
+    int force_all;          // rebuild every replica whatever its displacement
+    long long stop;         // no rebuild once this step is reached: the lists of step stop + 1 belong to the next call
+};
+// 0. which replicas rebuild (the test of src/job_md.F90:388 on the displacement top-2 of the last
+//    completed step), the ele_cutoff refresh of src/neighbor_list.F90:80-82, and -- without PBC --
+//    the bounding box of those replicas and the cell grid over it.  One block.
+__global__ void __launch_bounds__(1024) k_nl_plan(DevSys S, NlPlanArgs A, int *rep_active)
+{
+    __shared__ int s_any;
+    __shared__ double s_lo[3][32], s_hi[3][32];
+    const int tid = threadIdx.x, R = S.nrep, nmp = S.nmp;
+    const DevCtl ctl = S.ctl[0];
+    if (tid == 0) { s_any = 0; S.misc->nl_overflow = 0; S.misc->bp_overflow = 0; }
+    __syncthreads();
+    for (int r = tid; r < R; r += blockDim.x) {
+        const unsigned long long *t = S.top2 + ((size_t)r * 2 + (ctl.step & 1ull)) * 2;
+        const double m1 = __longlong_as_double((long long)t[0]), m2 = __longlong_as_double((long long)t[1]);
+        const int need = A.force_all || ((long long)ctl.step < A.stop && sqrt(m1) + sqrt(m2) > S.nl_margin);
+        rep_active[r] = need;
+        if (need) {
+            s_any = 1;
+            S.nbp_half[r] = 0;
+            atomicAdd(&S.misc->nrebuild, 1);
+            if (A.flg_ele && A.ele_cutoff_type == 2) S.rp[r].ele_cutoff = A.ele_cutoff_inp * S.rp[r].lambdaD;
+        }
+    }
+    __syncthreads();
+    if (!s_any || A.pbc) return;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    const double4 *pos = S.pos[ctl.cur];
+    for (int it = tid; it < R * nmp; it += blockDim.x) {
+        if (!rep_active[it / nmp]) continue;
+        const double4 p = pos[it];
+        lo[0] = fmin(lo[0], p.x); hi[0] = fmax(hi[0], p.x);
+        lo[1] = fmin(lo[1], p.y); hi[1] = fmax(hi[1], p.y);
+        lo[2] = fmin(lo[2], p.z); hi[2] = fmax(hi[2], p.z);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fmin(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+        if ((tid & 31) == 0) { s_lo[d][tid >> 5] = lo[d]; s_hi[d][tid >> 5] = hi[d]; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        GridInfo G;
+        G.pbc = 0;
+        long long ncell = 1;
+        for (int d = 0; d < 3; d++) {
+            double l = 1e300, h = -1e300;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) { l = fmin(l, s_lo[d][w]); h = fmax(h, s_hi[d][w]); }
+            const double ext = fmax(h - l, 1e-9);
+            int n = (int)floor(ext / (A.rc * 1.000001));
+            n = max(1, min(n, 128));
+            G.n[d] = n; G.origin[d] = l; G.inv_cell[d] = n / ext;
+            ncell *= n;
+        }
+        while (ncell > S.ncell_cap) {       // stay inside the allocated grid: coarser cells are still exact
+            int d = G.n[0] >= G.n[1] ? (G.n[0] >= G.n[2] ? 0 : 2) : (G.n[1] >= G.n[2] ? 1 : 2);
+            G.n[d]--;
+            ncell = (long long)G.n[0] * G.n[1] * G.n[2];
+        }
+        for (int d = 0; d < 3; d++) {
+            double l = 1e300, h = -1e300;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) { l = fmin(l, s_lo[d][w]); h = fmax(h, s_hi[d][w]); }
+            G.inv_cell[d] = G.n[d] / fmax(h - l, 1e-9);
+        }
+        G.ncell = (int)ncell;
+        *S.grid = G;
+    }
+}
 // 1. wrap (src/pbc.F90:196-226) + cell id + per-cell count
-__global__ void k_nl_wrap_count(DevSys S, FFParams P, GridInfo Gd, const int *rep_active)
+__global__ void k_nl_wrap_count(DevSys S, FFParams P, const int *rep_active)
 {
     const int rep = blockIdx.y;
     if (!rep_active[rep]) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S.nmp) return;
+    const GridInfo &Gd = *S.grid;
     double4 *pos = S.pos[S.ctl[0].cur] + (size_t)rep * S.nmp;
     double4 p = pos[i];
     if (P.flg_pbc) {
@@ -854,37 +944,51 @@ __global__ void k_nl_wrap_count(DevSys S, FFParams P, GridInfo Gd, const int *re
     S.cell_of[(size_t)rep * S.nmp + i] = c;
     atomicAdd(&S.cell_count[(size_t)rep * S.ncell_cap + c], 1);
 }
-// 2. exclusive scan of the cell counts (one block per replica)
-__global__ void __launch_bounds__(1024) k_nl_scan(DevSys S, GridInfo Gd, const int *rep_active)
+// 2. exclusive scan of the cell counts (one block per replica); leaves the counts cleared for
+//    the next build
+__global__ void __launch_bounds__(1024) k_nl_scan(DevSys S, const int *rep_active)
 {
     const int rep = blockIdx.x;
     if (!rep_active[rep]) return;
+    const int ncell = S.grid->ncell;
     int *cnt = S.cell_count + (size_t)rep * S.ncell_cap;
     int *start = S.cell_start + (size_t)rep * (S.ncell_cap + 1);
     int *cur = S.cell_cursor + (size_t)rep * S.ncell_cap;
-    __shared__ int sh[1024];
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
+    __shared__ int wsum[32];
+    __shared__ int carry, chunk_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < Gd.ncell; base += 1024) {
-        int i = base + threadIdx.x;
-        int v = i < Gd.ncell ? cnt[i] : 0;
-        sh[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-            __syncthreads();
-            sh[threadIdx.x] += t;
-            __syncthreads();
+    for (int base = 0; base < ncell; base += 1024) {
+        const int i = base + tid;
+        const int v = i < ncell ? cnt[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        if (i < Gd.ncell) { start[i] = carry + sh[threadIdx.x] - v; cur[i] = 0; }
+        if (lane == 31) wsum[warp] = incl;
         __syncthreads();
-        if (threadIdx.x == 1023) carry += sh[1023];
+        if (warp == 0) {
+            int w = wsum[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            wsum[lane] = wi - w;            // exclusive prefix of the warp totals
+            if (lane == 31) chunk_total = wi;
+        }
+        __syncthreads();
+        if (i < ncell) { start[i] = carry + wsum[warp] + incl - v; cur[i] = 0; cnt[i] = 0; }
+        __syncthreads();
+        if (tid == 0) carry += chunk_total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) start[Gd.ncell] = carry;
+    if (tid == 0) start[ncell] = carry;
 }
-// 3. scatter beads into their cells
+// 3. scatter beads into their cells (arrival order)
 __global__ void k_nl_fill(DevSys S, const int *rep_active)
 {
     const int rep = blockIdx.y;
@@ -895,21 +999,22 @@ __global__ void k_nl_fill(DevSys S, const int *rep_active)
     int slot = S.cell_start[(size_t)rep * (S.ncell_cap + 1) + c] + atomicAdd(&S.cell_cursor[(size_t)rep * S.ncell_cap + c], 1);
     S.cell_beads[(size_t)rep * S.nmp + slot] = i;
 }
-// 4. sort each cell by bead id (deterministic rows); also clears the counts for the next build
-__global__ void k_nl_sort(DevSys S, GridInfo Gd, const int *rep_active)
+// 4. every cell in ascending bead order (deterministic rows): bead i goes to the slot given by
+//    the number of smaller bead ids in its cell
+__global__ void k_nl_rank(DevSys S, const int *rep_active)
 {
     const int rep = blockIdx.y;
     if (!rep_active[rep]) return;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= Gd.ncell) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.nmp) return;
+    const size_t rbase = (size_t)rep * S.nmp;
+    const int c = S.cell_of[rbase + i];
     const int *start = S.cell_start + (size_t)rep * (S.ncell_cap + 1);
-    int *b = S.cell_beads + (size_t)rep * S.nmp;
-    for (int i = start[c] + 1; i < start[c + 1]; i++) {
-        int v = b[i], j = i - 1;
-        while (j >= start[c] && b[j] > v) { b[j + 1] = b[j]; j--; }
-        b[j + 1] = v;
-    }
-    S.cell_count[(size_t)rep * S.ncell_cap + c] = 0;
+    const int s = start[c], e = start[c + 1];
+    const int *b = S.cell_beads + rbase;
+    int rank = 0;
+    for (int q = s; q < e; q++) rank += b[q] < i;
+    S.cell_sorted[rbase + s + rank] = i;
 }
 
 SIS_D int uniq_cells(int c, int n, int pbc, int out[3])
@@ -994,14 +1099,16 @@ SIS_HD bool nl_bp_geometry(const NlArgs &A, int i, int j, double d2)
 {
     return A.all_pairs == 1 ? (abs(i - j) >= A.bp_min_loop + 1) : (d2 <= A.bp_nl_cut2);
 }
-__global__ void __launch_bounds__(256) k_nl_rows(DevSys S, FFParams P, GridInfo Gd, NlArgs A, const int *rep_active)
+__global__ void __launch_bounds__(256) k_nl_rows(DevSys S, FFParams P, NlArgs A, const int *rep_active)
 {
     const int rep = blockIdx.y;
     if (!rep_active[rep]) return;
-    const int lane = threadIdx.x % 32;
-    const int i = blockIdx.x * 8 + threadIdx.x / 32;
+    __shared__ int s_off[8][28], s_beg[8][27];
+    const int lane = threadIdx.x % 32, w = threadIdx.x / 32;
+    const int i = blockIdx.x * 8 + w;
     const int nmp = S.nmp;
     if (i >= nmp) return;
+    const GridInfo &Gd = *S.grid;
     const size_t rbase = (size_t)rep * nmp;
     const double4 *pos = S.pos[S.ctl[0].cur] + rbase;
     const RepParams R = S.rp[rep];
@@ -1013,72 +1120,95 @@ __global__ void __launch_bounds__(256) k_nl_rows(DevSys S, FFParams P, GridInfo 
     int2 *brow = S.bprow + (rbase + i) * S.KB;
     int nn = 0, nb = 0;
     const int *cstart = S.cell_start + (size_t)rep * (S.ncell_cap + 1);
-    const int *cbeads = S.cell_beads + rbase;
+    const int *cbeads = S.cell_sorted + rbase;
 
     const bool sweep_all = A.all_pairs != 0;   // iterate every bead instead of the 27 cells
-    const bool full = A.all_pairs == 1;        // the cutoff-free lists of list_exv/ele/bp
-    int lx[3], ly[3], lz[3], nx, ny, nz;
-    if (sweep_all) { nx = ny = nz = 1; lx[0] = ly[0] = lz[0] = 0; }
-    else {
-        int c = S.cell_of[rbase + i];
-        int cx = c % Gd.n[0], cy = (c / Gd.n[0]) % Gd.n[1], cz = c / (Gd.n[0] * Gd.n[1]);
-        nx = uniq_cells(cx, Gd.n[0], Gd.pbc, lx);
-        ny = uniq_cells(cy, Gd.n[1], Gd.pbc, ly);
-        nz = uniq_cells(cz, Gd.n[2], Gd.pbc, lz);
+    // candidate stream: the beads of the (up to 27) surrounding cells, concatenated in the fixed
+    // order (z, y, x neighbour; ascending bead id inside a cell).  Lane r < nrange holds range r;
+    // a warp scan gives the stream offsets, so every iteration tests 32 candidates whatever the
+    // cell occupancies.
+    int total;
+    if (sweep_all) {
+        total = nmp;
+    } else {
+        int lx[3], ly[3], lz[3];
+        const int c = S.cell_of[rbase + i];
+        const int cx = c % Gd.n[0], cy = (c / Gd.n[0]) % Gd.n[1], cz = c / (Gd.n[0] * Gd.n[1]);
+        const int nx = uniq_cells(cx, Gd.n[0], Gd.pbc, lx);
+        const int ny = uniq_cells(cy, Gd.n[1], Gd.pbc, ly);
+        const int nz = uniq_cells(cz, Gd.n[2], Gd.pbc, lz);
+        const int nrange = nx * ny * nz;
+        int beg = 0, len = 0;
+        if (lane < nrange) {
+            const int ix = lane % nx, iy = (lane / nx) % ny, iz = lane / (nx * ny);
+            const int cell = (lz[iz] * Gd.n[1] + ly[iy]) * Gd.n[0] + lx[ix];
+            beg = cstart[cell];
+            len = cstart[cell + 1] - beg;
+        }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane < 28) s_off[w][lane] = incl - len;   // lanes >= nrange: the total (sentinels)
+        if (lane < 27) s_beg[w][lane] = beg;
+        total = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
     }
-    for (int a = 0; a < nz; a++)
-        for (int b = 0; b < ny; b++)
-            for (int cidx = 0; cidx < nx; cidx++) {
-                int beg, end;
-                if (sweep_all) { beg = 0; end = nmp; }
-                else {
-                    int cell = (lz[a] * Gd.n[1] + ly[b]) * Gd.n[0] + lx[cidx];
-                    beg = cstart[cell]; end = cstart[cell + 1];
+    for (int t0 = 0; t0 < total; t0 += 32) {
+        const int t = t0 + lane;
+        uint32_t ent = 0;
+        int bp3 = 0, bptype = 0, j = -1;
+        if (t < total) {
+            if (sweep_all) j = t;
+            else {
+                // range r with off[r] <= t < off[r + 1] (empty ranges have equal offsets)
+                int lo = 0, hi = 27;
+#pragma unroll
+                for (int s = 0; s < 5; s++) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_off[w][mid] <= t) lo = mid; else hi = mid;
                 }
-                for (int q0 = beg; q0 < end; q0 += 32) {
-                    const int q = q0 + lane;
-                    uint32_t ent = 0;
-                    int bp3 = 0, bptype = 0, j = -1;
-                    if (q < end) {
-                        j = sweep_all ? q : cbeads[q];
-                        if (j != i) {
-                            const int4 mj = S.meta[j];
-                            const Vec3 xj = v3(pos[j]);
-                            Vec3 v = pbc_vec_d(P, xi, xj);
-                            ent = nl_pair_flags(A, P, mi, mj, i, j, dot(v, v), ele_nl_cut2);
-                            if (ent && nl_needs_image(P, A, xi, xj)) ent |= NB_IMG;
-                            if (nl_bp_geometry(A, i, j, dot(v, v))) {
-                                if (i < j) bp3 = bp_lookup(A.bp_model, A.bp_min_loop, S.hash, S.seq, i, mi, j, mj, &bptype);
-                                else bp3 = bp_lookup(A.bp_model, A.bp_min_loop, S.hash, S.seq, j, mj, i, mi, &bptype);
-                            }
-                        }
-                    }
-                    // compacted appends
-                    unsigned m = __ballot_sync(0xffffffffu, ent != 0);
-                    if (ent) {
-                        int p = nn + __popc(m & ((1u << lane) - 1));
-                        if (p < S.K) row[p] = ent | (uint32_t)j;
-                    }
-                    nn += __popc(m);
-                    unsigned mb = __ballot_sync(0xffffffffu, bp3 > 0);
-                    if (bp3 > 0) {
-                        int p = nb + __popc(mb & ((1u << lane) - 1));
-                        if (p < S.KB) {
-                            brow[p] = make_int2(j, -1);
-                            if (i < j) {   // owner stores the pair data at ibp = i*KB + p
-                                const size_t ibp = rbase * S.KB + (size_t)i * S.KB + p;
-                                S.bp_type[ibp] = (signed char)bptype;
-                                S.bp_coef[ibp] = (A.bp_model == 5) ? make_double2(S.bp3_dH[bp3], S.bp3_dS[bp3])
-                                                                   : make_double2(0.0, 0.0);
-                                S.bp_status[ibp] = 0;
-                                S.bp_status_MC[ibp] = 0;
-                                S.ene_bp[ibp] = 0.0;
-                            }
-                        }
-                    }
-                    nb += __popc(mb);
+                j = cbeads[s_beg[w][lo] + (t - s_off[w][lo])];
+            }
+            if (j != i) {
+                const int4 mj = S.meta[j];
+                const Vec3 xj = v3(pos[j]);
+                Vec3 v = pbc_vec_d(P, xi, xj);
+                ent = nl_pair_flags(A, P, mi, mj, i, j, dot(v, v), ele_nl_cut2);
+                if (ent && nl_needs_image(P, A, xi, xj)) ent |= NB_IMG;
+                if (nl_bp_geometry(A, i, j, dot(v, v))) {
+                    if (i < j) bp3 = bp_lookup(A.bp_model, A.bp_min_loop, S.hash, S.seq, i, mi, j, mj, &bptype);
+                    else bp3 = bp_lookup(A.bp_model, A.bp_min_loop, S.hash, S.seq, j, mj, i, mi, &bptype);
                 }
             }
+        }
+        // compacted appends
+        unsigned m = __ballot_sync(0xffffffffu, ent != 0);
+        if (ent) {
+            int p = nn + __popc(m & ((1u << lane) - 1));
+            if (p < S.K) row[p] = ent | (uint32_t)j;
+        }
+        nn += __popc(m);
+        unsigned mb = __ballot_sync(0xffffffffu, bp3 > 0);
+        if (bp3 > 0) {
+            int p = nb + __popc(mb & ((1u << lane) - 1));
+            if (p < S.KB) {
+                brow[p] = make_int2(j, -1);
+                if (i < j) {   // owner stores the pair data at ibp = i*KB + p
+                    const size_t ibp = rbase * S.KB + (size_t)i * S.KB + p;
+                    S.bp_type[ibp] = (signed char)bptype;
+                    S.bp_coef[ibp] = (A.bp_model == 5) ? make_double2(S.bp3_dH[bp3], S.bp3_dS[bp3])
+                                                       : make_double2(0.0, 0.0);
+                    S.bp_status[ibp] = 0;
+                    S.bp_status_MC[ibp] = 0;
+                    S.ene_bp[ibp] = 0.0;
+                }
+            }
+        }
+        nb += __popc(mb);
+    }
     if (lane == 0) {
         S.nnbr[rbase + i] = min(nn, S.K);
         S.nbp_row[rbase + i] = min(nb, S.KB);
@@ -1118,10 +1248,70 @@ __global__ void k_nl_begin_slots(DevSys S, const int *rep_active)
     const int rep = blockIdx.x * blockDim.x + threadIdx.x;
     if (rep < S.nrep && rep_active[rep]) S.nbp_half[rep] = 0;
 }
-// a rebuilt replica restarts its displacement bookkeeping (xyz_move = 0, src/job_md.F90:390)
-__global__ void k_nl_finish(DevSys S, const int *rep_active)
+// 7. end of a build.  (a) a rebuilt replica restarts its displacement bookkeeping (xyz_move = 0,
+//    src/job_md.F90:390); (b) capacity check: a row or the bp half list that did not fit marks the
+//    lists invalid so that no persistent kernel runs on them (the host grows and rebuilds);
+//    (c) the CTA bead ranges of k_md_fast: `ncta` contiguous ranges of at most `per_cta` flattened
+//    (replica, bead) items, cut where the running row weight (nnbr + 8) crosses c * total / ncta.
+//    One block of 1024 threads; nitems <= ncta * per_cta <= PART_MAX_ITEMS when ncta > 0.
+constexpr int PART_MAX_ITEMS = 148 * 64;
+__global__ void __launch_bounds__(1024) k_nl_partition(DevSys S, const int *rep_active, int ncta, int per_cta)
 {
-    const int rep = blockIdx.x * blockDim.x + threadIdx.x;
-    if (rep < S.nrep && rep_active[rep])
-        for (int q = 0; q < 4; q++) S.top2[(size_t)rep * 4 + q] = 0ull;
+    __shared__ int s_w[PART_MAX_ITEMS];          // inclusive prefix of the weights
+    __shared__ int s_part[1024];
+    __shared__ int s_cut[1025];
+    __shared__ int s_any;
+    const int tid = threadIdx.x, R = S.nrep, nitems = R * S.nmp;
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    for (int r = tid; r < R; r += blockDim.x) {
+        if (!rep_active[r]) continue;
+        s_any = 1;
+        for (int q = 0; q < 4; q++) S.top2[(size_t)r * 4 + q] = 0ull;
+        const int nh = S.nbp_half[r];
+        if (nh > S.bp_half_cap) { atomicMax(&S.misc->half_overflow, nh); S.misc->lists_invalid = 1; }
+    }
+    if (tid == 0 && (S.misc->nl_overflow > S.K || S.misc->bp_overflow > S.KB)) S.misc->lists_invalid = 1;
+    __syncthreads();
+    if (!s_any || ncta <= 0) return;
+    // block scan: thread t owns items [t * chunk, (t + 1) * chunk)
+    const int chunk = (nitems + 1023) / 1024;
+    const int i0 = tid * chunk, i1 = min(i0 + chunk, nitems);
+    int sum = 0;
+    for (int i = i0; i < i1; i++) { sum += S.nnbr[i] + 8; s_w[i] = sum; }
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int t = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += t;
+        __syncthreads();
+    }
+    const int base = s_part[tid] - sum;
+    for (int i = i0; i < i1; i++) s_w[i] += base;
+    __syncthreads();
+    const long long total = s_part[1023];
+    // weight cuts: first item whose exclusive prefix reaches c * total / ncta
+    for (int c = tid; c <= ncta; c += blockDim.x) {
+        const long long want = total * c / ncta;
+        int lo = 0, hi = nitems;                 // first i with (i == 0 ? 0 : s_w[i - 1]) >= want
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((mid == 0 ? 0 : s_w[mid - 1]) >= want) hi = mid; else lo = mid + 1;
+        }
+        s_cut[c] = lo;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int b = 0;
+        S.cta_item0[0] = 0;
+        for (int c = 1; c < ncta; c++) {
+            int nb = min(s_cut[c], b + per_cta);
+            nb = max(nb, nitems - (ncta - c) * per_cta);
+            nb = max(nb, b);
+            S.cta_item0[c] = nb;
+            b = nb;
+        }
+        S.cta_item0[ncta] = nitems;
+    }
 }

@@ -177,7 +177,14 @@ struct sisgpu {
     DBuf<double2> d_bp_coef, d_top2_slots;
     DBuf<unsigned long long> d_mc_counter, d_prof;
     DBuf<unsigned int> d_ene_counter, d_bar;
-    DBuf<int> d_cta_item0;
+    DBuf<int> d_cta_item0, d_cell_sorted;
+    DBuf<GridInfo> d_grid;
+    GridInfo grid_host{};                // last grid written to d_grid by the host
+    bool grid_host_valid = false;
+    int dev_nrebuild_seen = 0;           // DevMisc::nrebuild at the last sync
+    int pipeline = 1;                    // option "pipeline": device-driven list rebuilds inside md_steps
+    double est_cycle_steps = 50.0;       // running estimate of MD steps between two list rebuilds
+    std::vector<cudaEvent_t> ev_pool;    // timing of the pipelined loop
     DBuf<RepParams> d_rp, d_rp_alt;
     DBuf<unsigned char> d_sync;          // DevSyncHdr + top2[nrep][2][2]
     unsigned char *h_sync = nullptr;     // pinned mirror
@@ -241,7 +248,10 @@ int sisgpu_destroy(sisgpu_t *h)
     h->d_twzfr_init.release(); h->d_twzfr_velo.release(); h->d_rest_rcut.release(); h->d_rest_para.release();
     h->d_gather_send.release(); h->d_gather_recv.release(); h->d_nbr.release(); h->d_bprow.release();
     h->d_bp_type.release(); h->d_bp_coef.release(); h->d_mc_counter.release();
-    h->d_ene_counter.release(); h->d_bar.release(); h->d_top2_slots.release(); h->d_cta_item0.release(); h->d_rp.release(); h->d_rp_alt.release(); h->d_sync.release();
+    h->d_ene_counter.release(); h->d_bar.release(); h->d_top2_slots.release(); h->d_cta_item0.release(); h->d_cell_sorted.release(); h->d_grid.release();
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
+    h->ev_pool.clear();
+    h->d_rp.release(); h->d_rp_alt.release(); h->d_sync.release();
     if (h->graph_chunk) cudaGraphExecDestroy(h->graph_chunk);
     h->d_f_pair.release(); h->d_f_loc.release(); h->d_f_bp.release(); h->d_bp_half.release(); h->d_nbp_half.release();
     cudaEventDestroy(h->ev0);
@@ -460,6 +470,7 @@ static void fill_rp(const sisgpu *h, int irep, RepParams &R)
     R.tempK = r.tempK;
     R.ele_coef = r.ele_coef;
     R.inv_lambdaD = r.lambdaD != 0.0 ? 1.0 / r.lambdaD : 0.0;
+    R.lambdaD = r.lambdaD;
     R.ele_cutoff = r.ele_cutoff;
     R.diele_dTcoef = r.diele_dTcoef;
     R.sqrt_tempK = sqrt(r.tempK);
@@ -688,7 +699,8 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     TRY(h->d_pos0.alloc(RN)); TRY(h->d_pos1.alloc(RN));
     TRY(h->d_vel.alloc(RN * 3)); TRY(h->d_acc.alloc(RN * 3)); TRY(h->d_move.alloc(RN * 3)); TRY(h->d_force.alloc(RN * 3));
     TRY(h->d_nnbr.alloc(RN)); TRY(h->d_nbp_row.alloc(RN)); TRY(h->d_nt_excess.alloc(RN));
-    TRY(h->d_cell_of.alloc(RN)); TRY(h->d_cell_beads.alloc(RN));
+    TRY(h->d_cell_of.alloc(RN)); TRY(h->d_cell_beads.alloc(RN)); TRY(h->d_cell_sorted.alloc(RN)); TRY(h->d_grid.alloc(1));
+    h->grid_host_valid = false;
     TRY(h->d_mc_counter.alloc(R)); TRY(h->d_rep_active.alloc(R));
     TRY(h->d_rp.alloc(R)); TRY(h->d_rp_alt.alloc(R));
     h->sync_bytes = sizeof(DevSyncHdr) + (size_t)R * 4 * sizeof(unsigned long long);
@@ -718,6 +730,7 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     S.pos[0] = h->d_pos0.p; S.pos[1] = h->d_pos1.p; S.vel = h->d_vel.p; S.acc = h->d_acc.p; S.move = h->d_move.p;
     S.force = h->d_force.p; S.nnbr = h->d_nnbr.p; S.nbp_row = h->d_nbp_row.p; S.nt_excess = h->d_nt_excess.p;
     S.mc_counter = h->d_mc_counter.p; S.cell_of = h->d_cell_of.p; S.cell_beads = h->d_cell_beads.p;
+    S.cell_sorted = h->d_cell_sorted.p; S.grid = h->d_grid.p;
     S.rp = h->d_rp.p;
     S.ctl = ((DevSyncHdr *)h->d_sync.p)->ctl; S.misc = &((DevSyncHdr *)h->d_sync.p)->misc;
     S.top2 = (unsigned long long *)(h->d_sync.p + sizeof(DevSyncHdr));
@@ -733,7 +746,7 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     S.ncell_cap = 0;
     h->K = h->KB = 0;
     TRY(alloc_lists(h, 128, 16));
-    TRY(alloc_cells(h, 64));
+    TRY(alloc_cells(h, 4096));
     h->finalized = true;
     TRY(push_rp(h));
     return 0;
@@ -832,6 +845,94 @@ static NlArgs nl_args(const sisgpu *h, bool all_pairs)
     return A;
 }
 
+// bp half-list counts of the last build -> host (sizes the bp task grid of the stream / graph modes)
+static int refresh_half_counts(sisgpu *h)
+{
+    const int R = h->nrep;
+    std::vector<int> nh(R);
+    CK(cudaMemcpyAsync(nh.data(), h->d_nbp_half.p, R * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int mx = 0;
+    for (int r = 0; r < R; r++) mx = std::max(mx, nh[r]);
+    h->nbp_half_rep = nh;
+    // the bp task grid is sized from this count; regrow (and re-capture) with slack
+    if (mx > h->nbp_half_max || mx < h->nbp_half_max / 4) { h->nbp_half_max = mx + mx / 4 + 128; invalidate_graphs(h); }
+    return 0;
+}
+
+// grid of the persistent kernels: one CTA per SM
+static int ensure_coop_blocks(sisgpu *h)
+{
+    if (h->coop_blocks) return 0;
+    int per_sm = 0, dev_sms = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_md_fused, FUSED_THREADS, 0));
+    CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
+    if (per_sm < 1) return set_err("k_md_fused does not fit on an SM");
+    h->coop_blocks = dev_sms;
+    return 0;
+}
+// number of CTA bead ranges of k_md_fast (0: the system does not fit: more than 64 beads per SM)
+static int fast_ncta_of(sisgpu *h)
+{
+    if (ensure_coop_blocks(h)) return 0;
+    const long long nitems = (long long)h->nrep * h->nmp;
+    const int ncta_max = std::min(std::min(h->coop_blocks, FAST_MAX_CTA), PART_MAX_ITEMS / FAST_GROUPS);
+    if (nitems > (long long)ncta_max * FAST_GROUPS) return 0;
+    return (int)std::min<long long>(ncta_max, nitems);
+}
+
+// cell grid over [lo, hi] with cells of at least rc
+static void make_grid(const double lo[3], const double hi[3], double rc, int pbc, GridInfo &Gd)
+{
+    long long ncell = 1;
+    Gd.pbc = pbc;
+    for (int d = 0; d < 3; d++) {
+        double ext = std::max(hi[d] - lo[d], 1e-9);
+        int n = (int)floor(ext / (rc * 1.000001));
+        n = std::max(1, std::min(n, 128));
+        Gd.n[d] = n;
+        Gd.origin[d] = lo[d];
+        Gd.inv_cell[d] = n / ext;
+        ncell *= n;
+    }
+    Gd.ncell = (int)ncell;
+}
+static int upload_grid(sisgpu *h, const GridInfo &Gd)
+{
+    if (h->grid_host_valid && memcmp(&h->grid_host, &Gd, sizeof Gd) == 0) return 0;
+    h->grid_host = Gd;
+    h->grid_host_valid = true;
+    CK(cudaMemcpyAsync(h->d_grid.p, &h->grid_host, sizeof Gd, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+// the kernels of one list build after the replica flags and the grid are on the device
+static void enqueue_nl_kernels(sisgpu *h, const NlArgs &A, bool grid_pass, bool wrap_only)
+{
+    const int N = h->nmp, R = h->nrep;
+    DevSys &S = h->S;
+    const int *act = h->d_rep_active.p;
+    if (grid_pass) {
+        k_nl_wrap_count<<<dim3((N + 255) / 256, R), 256, 0, h->stream>>>(S, h->P, act);
+        k_nl_scan<<<R, 1024, 0, h->stream>>>(S, act);
+        k_nl_fill<<<dim3((N + 255) / 256, R), 256, 0, h->stream>>>(S, act);
+        k_nl_rank<<<dim3((N + 255) / 256, R), 256, 0, h->stream>>>(S, act);
+        h->launches += 4;
+    } else if (wrap_only) {
+        k_nl_wrap_count<<<dim3((N + 255) / 256, R), 256, 0, h->stream>>>(S, h->P, act);
+        h->launches += 1;
+    }
+    k_nl_rows<<<dim3((N + 7) / 8, R), 256, 0, h->stream>>>(S, h->P, A, act);
+    h->launches += 1;
+}
+static void enqueue_nl_tail(sisgpu *h)
+{
+    const int N = h->nmp, R = h->nrep;
+    k_nl_bp_slots<<<dim3((N * h->KB + 255) / 256, R), 256, 0, h->stream>>>(h->S, h->d_rep_active.p);
+    k_nl_partition<<<1, 1024, 0, h->stream>>>(h->S, h->d_rep_active.p, h->fast_kernel ? fast_ncta_of(h) : 0, FAST_GROUPS);
+    h->launches += 2;
+}
+
 // builds the rows of the replicas flagged in `active`; all_pairs = list_exv/list_ele/list_bp mode
 static int build_lists(sisgpu *h, const std::vector<int> &active, bool all_pairs)
 {
@@ -864,7 +965,8 @@ static int build_lists(sisgpu *h, const std::vector<int> &active, bool all_pairs
         if (h->P.flg_pbc) {
             for (int d = 0; d < 3; d++) { lo[d] = 0.0; hi[d] = h->P.box[d]; }
         } else {
-            // bounding box of the active replicas (host reduction; rebuilds are rare)
+            // bounding box of the active replicas (host reduction; this path is the explicit
+            // sisgpu_neighbor_list call -- rebuilds inside md_steps use k_nl_plan)
             std::vector<double4> p(N);
             for (int d = 0; d < 3; d++) { lo[d] = 1e300; hi[d] = -1e300; }
             for (int r = 0; r < R; r++) {
@@ -877,45 +979,20 @@ static int build_lists(sisgpu *h, const std::vector<int> &active, bool all_pairs
                 }
             }
         }
-        long long ncell = 1;
-        for (int d = 0; d < 3; d++) {
-            double ext = std::max(hi[d] - lo[d], 1e-9);
-            int n = (int)floor(ext / (rc * 1.000001));
-            n = std::max(1, std::min(n, 128));
-            Gd.n[d] = n;
-            Gd.origin[d] = lo[d];
-            Gd.inv_cell[d] = n / ext;
-            ncell *= n;
-        }
-        Gd.ncell = (int)ncell;
+        make_grid(lo, hi, rc, h->P.flg_pbc, Gd);
         TRY(alloc_cells(h, Gd.ncell));
     } else {
         Gd.n[0] = Gd.n[1] = Gd.n[2] = 1; Gd.ncell = 1;
     }
+    TRY(upload_grid(h, Gd));
     CK(cudaMemcpyAsync(h->d_rep_active.p, active.data(), R * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     NlArgs A = nl_args(h, brute);
     A.all_pairs = all_pairs ? 1 : (brute ? 2 : 0);
     for (int attempt = 0; attempt < 8; attempt++) {
         h->h_misc->nl_overflow = 0; h->h_misc->bp_overflow = 0;
         CK(cudaMemcpyAsync(&h->S.misc->nl_overflow, &h->h_misc->nl_overflow, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        if (!brute) {
-            if (attempt == 0) {
-                CK(cudaMemsetAsync(S.cell_count, 0, (size_t)R * S.ncell_cap * sizeof(int), h->stream));
-                k_nl_wrap_count<<<dim3((N + 255) / 256, R), 256, 0, h->stream>>>(S, h->P, Gd, h->d_rep_active.p);
-                k_nl_scan<<<R, 1024, 0, h->stream>>>(S, Gd, h->d_rep_active.p);
-                k_nl_fill<<<dim3((N + 255) / 256, R), 256, 0, h->stream>>>(S, h->d_rep_active.p);
-                k_nl_sort<<<dim3((Gd.ncell + 255) / 256, R), 256, 0, h->stream>>>(S, Gd, h->d_rep_active.p);
-                h->launches += 4;
-            }
-        } else if (h->P.flg_pbc && !all_pairs && attempt == 0) {
-            // Bias_SS with PBC still wraps first (src/neighbor_list.F90:28-30); reuse the wrap kernel on a 1-cell grid
-            TRY(alloc_cells(h, 1));
-            CK(cudaMemsetAsync(S.cell_count, 0, (size_t)R * S.ncell_cap * sizeof(int), h->stream));
-            k_nl_wrap_count<<<dim3((N + 255) / 256, R), 256, 0, h->stream>>>(S, h->P, Gd, h->d_rep_active.p);
-            h->launches += 1;
-        }
-        k_nl_rows<<<dim3((N + 7) / 8, R), 256, 0, h->stream>>>(S, h->P, Gd, A, h->d_rep_active.p);
-        h->launches += 1;
+        // Bias_SS with PBC still wraps first (src/neighbor_list.F90:28-30): wrap kernel on the 1-cell grid
+        enqueue_nl_kernels(h, A, !brute && attempt == 0, brute && h->P.flg_pbc && !all_pairs && attempt == 0);
         TRY(sync_ctl(h));
         CK(cudaGetLastError());
         if (h->h_misc->nl_overflow > h->K || h->h_misc->bp_overflow > h->KB) {
@@ -931,20 +1008,9 @@ static int build_lists(sisgpu *h, const std::vector<int> &active, bool all_pairs
             continue;
         }
         k_nl_begin_slots<<<(R + 63) / 64, 64, 0, h->stream>>>(S, h->d_rep_active.p);
-        k_nl_bp_slots<<<dim3((N * h->KB + 255) / 256, R), 256, 0, h->stream>>>(S, h->d_rep_active.p);
-        k_nl_finish<<<(R + 63) / 64, 64, 0, h->stream>>>(S, h->d_rep_active.p);
-        h->launches += 3;
-        {
-            std::vector<int> nh(R);
-            CK(cudaMemcpyAsync(nh.data(), h->d_nbp_half.p, R * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
-            int mx = 0;
-            for (int r = 0; r < R; r++) mx = std::max(mx, nh[r]);
-            h->nbp_half_rep = nh;
-            h->partition_dirty = true;
-            // the bp task grid is sized from this count; regrow (and re-capture) with slack
-            if (mx > h->nbp_half_max || mx < h->nbp_half_max / 4) { h->nbp_half_max = mx + mx / 4 + 128; invalidate_graphs(h); }
-        }
+        h->launches += 1;
+        enqueue_nl_tail(h);
+        TRY(refresh_half_counts(h));
         CK(cudaGetLastError());
         timer_end(h, h->t_nl);
         h->lists_full = all_pairs;
@@ -954,6 +1020,39 @@ static int build_lists(sisgpu *h, const std::vector<int> &active, bool all_pairs
         return 0;
     }
     return set_err("neighbour list capacity did not converge");
+}
+
+// The device-driven rebuild of the MD loop: k_nl_plan decides on the device which replicas are
+// past the list margin (src/job_md.F90:388), the chain rebuilds exactly those, and k_nl_partition
+// re-cuts the CTA bead ranges of k_md_fast.  Nothing is read back; a chain with no replica to
+// rebuild costs nine empty launches.
+static int enqueue_nl_chain(sisgpu *h, int force_all, long long stop)
+{
+    const int R = h->nrep;
+    NlPlanArgs PA{};
+    double rc = std::max(h->P.wca_sigma, h->bp_cutoff_dist);
+    if (h->P.flg_ele)
+        for (int r = 0; r < R; r++) {
+            rc = std::max(rc, h->rep[r].ele_cutoff);
+            if (h->ele_cutoff_type == 2) rc = std::max(rc, h->ele_cutoff_inp * h->rep[r].lambdaD);
+        }
+    PA.rc = rc + h->nl_margin;
+    PA.ele_cutoff_inp = h->ele_cutoff_inp; PA.ele_cutoff_type = h->ele_cutoff_type; PA.flg_ele = h->P.flg_ele;
+    PA.pbc = h->P.flg_pbc; PA.force_all = force_all; PA.stop = stop;
+    if (h->P.flg_pbc) {
+        double lo[3] = {0.0, 0.0, 0.0}, hi[3] = {h->P.box[0], h->P.box[1], h->P.box[2]};
+        GridInfo Gd{};
+        make_grid(lo, hi, PA.rc, 1, Gd);
+        TRY(alloc_cells(h, Gd.ncell));
+        TRY(upload_grid(h, Gd));
+    } else {
+        h->grid_host_valid = false;   // k_nl_plan writes the grid
+    }
+    k_nl_plan<<<1, 1024, 0, h->stream>>>(h->S, PA, h->d_rep_active.p);
+    h->launches += 1;
+    enqueue_nl_kernels(h, nl_args(h, false), true, false);
+    enqueue_nl_tail(h);
+    return 0;
 }
 
 int sisgpu_neighbor_list(sisgpu_t *h, int irep)
@@ -1540,42 +1639,118 @@ int sisgpu_replica_exchange(sisgpu_t *h, const double *E, const double *uniforms
 // Bead ranges of k_md_fast: contiguous runs of at most FAST_GROUPS flattened (replica, bead) items,
 // one per CTA, chosen so that the largest per-CTA pair work (row entries + a per-bead constant) is
 // minimal for the number of SMs -- the step time is the time of the busiest CTA.
-static int fast_partition(sisgpu *h)
+// launch of one persistent kernel that runs until step `stop` or until a replica needs new lists
+static int launch_persistent(sisgpu *h, long long stop)
 {
-    const long long nitems = (long long)h->nrep * h->nmp;
-    const int ncta_max = std::min(h->coop_blocks, FAST_MAX_CTA);
-    h->partition_dirty = false;
-    h->fast_ncta = 0;
-    if (nitems > (long long)ncta_max * FAST_GROUPS) return 0;
-    std::vector<int> nn(nitems);
-    CK(cudaMemcpyAsync(nn.data(), h->d_nnbr.p, nitems * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    long long total = 0;
-    int wmax = 0;
-    for (auto &w : nn) { w += 8; total += w; wmax = std::max(wmax, w); }
-    auto parts = [&](long long W, std::vector<int> *out) {
-        int n = 1, cnt = 0;
-        long long s = 0;
-        if (out) { out->clear(); out->push_back(0); }
-        for (long long i = 0; i < nitems; i++) {
-            if (cnt == FAST_GROUPS || s + nn[i] > W) {
-                n++; s = 0; cnt = 0;
-                if (out) out->push_back((int)i);
-            }
-            s += nn[i]; cnt++;
+    const int R = h->nrep;
+    TRY(ensure_coop_blocks(h));
+    StepArgs A = step_args(h, 0x7FEu, 0, -1, 1);
+    const long long nitems = (long long)R * h->nmp;
+    CK(cudaMemsetAsync(h->d_bar.p, 0, 64 * sizeof(unsigned), h->stream));
+    void *args[] = {&h->S, &h->P, &A, &stop};
+    // k_md_fast: one bead per 8-lane group, rows / candidates / bonded tables on chip
+    const int want_fast = h->fast_kernel ? fast_ncta_of(h) : 0;
+    const size_t smem_fast = ((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)3 * FAST_GROUPS * h->K * sizeof(uint32_t);   // rows, sort scratch / unit forces, classes / unit tables
+    long long ncand_total = 0;
+    for (int r = 0; r < R; r++) ncand_total += h->nbp_half_rep.empty() ? h->nbp_half_max : h->nbp_half_rep[r];
+    const bool biases = h->P.flg_stage || h->P.ntwz_DCF || h->P.ntwz_FR || h->P.nrest;
+    const bool fast_ok = want_fast > 0 && !biases && h->K >= 24 && smem_fast <= 200 * 1024 &&
+                         3 * (ncand_total / want_fast) + 16 <= FAST_BPC;
+    if (fast_ok) {
+        void *fn = (void *)k_md_fast<1>;
+        if (smem_fast > h->fast_smem_set || fn != h->fast_fn_set) {
+            CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
+            h->fast_smem_set = smem_fast; h->fast_fn_set = fn;
         }
-        if (out) out->push_back((int)nitems);
-        return n;
-    };
-    long long lo = wmax, hi = total;
-    while (lo < hi) {
-        const long long mid = (lo + hi) / 2;
-        if (parts(mid, nullptr) <= ncta_max) hi = mid; else lo = mid + 1;
+        CK(cudaLaunchCooperativeKernel(fn, dim3(want_fast), dim3(FAST_THREADS), args, smem_fast, h->stream));
+    } else {
+        // a persistent kernel that stopped at the rebuild test may have left the base-pair
+        // scatter of the step it did not execute in f_bp
+        CK(cudaMemsetAsync(h->d_f_bp.p, 0, (size_t)R * h->nmp * 3 * sizeof(double), h->stream));
+        const int want = (int)std::max<long long>(1, (nitems + FUSED_GROUPS - 1) / FUSED_GROUPS);
+        dim3 grid(std::min(h->coop_blocks, want));
+        CK(cudaLaunchCooperativeKernel((void *)k_md_fused, grid, dim3(FUSED_THREADS), args, 0, h->stream));
     }
-    std::vector<int> item0;
-    h->fast_ncta = parts(lo, &item0);
-    CK(cudaMemcpyAsync(h->d_cta_item0.p, item0.data(), item0.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));   // item0 is a local
+    h->launches++;
+    return 0;
+}
+
+// post-sync bookkeeping shared by the persistent paths
+static int after_persistent_sync(sisgpu *h)
+{
+    h->nrebuild += h->h_misc->nrebuild - h->dev_nrebuild_seen;
+    h->dev_nrebuild_seen = h->h_misc->nrebuild;
+    if (h->h_misc->max_force_flag & 4) {
+        // k_md_fast found more base-pair candidates or chain neighbours than its shared-memory
+        // tables hold and did not run: use the general kernel from here on
+        h->h_misc->max_force_flag &= ~4;
+        CK(cudaMemcpy(&h->S.misc->max_force_flag, &h->h_misc->max_force_flag, sizeof(int), cudaMemcpyHostToDevice));
+        h->fast_kernel = 0;
+    }
+    return 0;
+}
+
+// MD steps up to `stop` with device-driven list rebuilds: [rebuild chain, persistent kernel] cycles
+// are enqueued ahead without reading anything back; one synchronisation per batch.  Kernels
+// enqueued past `stop` (or past an overflow) fall through.
+static int md_run_pipelined(sisgpu *h, long long stop)
+{
+    const int R = h->nrep;
+    while ((long long)h->h_ctl->step < stop) {
+        const long long cur = (long long)h->h_ctl->step;
+        const int nreb_before = h->h_misc->nrebuild;
+        int ncyc = (int)ceil((double)(stop - cur) / std::max(1.0, h->est_cycle_steps) * 1.2) + 1;
+        ncyc = std::max(1, std::min(ncyc, 32));
+        if (h->timing) {
+            while ((int)h->ev_pool.size() < 2 * 32 + 1) {
+                cudaEvent_t e;
+                CK(cudaEventCreate(&e));
+                h->ev_pool.push_back(e);
+            }
+        }
+        for (int c = 0; c < ncyc; c++) {
+            if (h->timing) cudaEventRecord(h->ev_pool[2 * c], h->stream);
+            TRY(enqueue_nl_chain(h, 0, stop));
+            if (h->timing) cudaEventRecord(h->ev_pool[2 * c + 1], h->stream);
+            TRY(launch_persistent(h, stop));
+        }
+        if (h->timing) cudaEventRecord(h->ev_pool[2 * ncyc], h->stream);
+        TRY(sync_ctl(h));
+        CK(cudaGetLastError());
+        if (h->timing) {
+            for (int c = 0; c < ncyc; c++) {
+                float a = 0, b = 0;
+                cudaEventElapsedTime(&a, h->ev_pool[2 * c], h->ev_pool[2 * c + 1]);
+                cudaEventElapsedTime(&b, h->ev_pool[2 * c + 1], h->ev_pool[2 * c + 2]);
+                h->t_nl += a; h->t_step += b;
+            }
+        }
+        const int nreb = h->h_misc->nrebuild - nreb_before;
+        TRY(after_persistent_sync(h));
+        const long long adv = (long long)h->h_ctl->step - cur;
+        if (nreb > 0 && adv > 0) h->est_cycle_steps = 0.5 * h->est_cycle_steps + 0.5 * std::max(1.0, (double)adv / nreb);
+        if (h->ele_cutoff_type == 2 && h->P.flg_ele && nreb > 0) {
+            // k_nl_plan refreshed ele_cutoff of the rebuilt replicas (src/neighbor_list.F90:80-82)
+            std::vector<RepParams> rp(R);
+            CK(cudaMemcpy(rp.data(), h->d_rp.p, R * sizeof(RepParams), cudaMemcpyDeviceToHost));
+            for (int r = 0; r < R; r++) h->rep[r].ele_cutoff = rp[r].ele_cutoff;
+        }
+        if (h->h_misc->lists_invalid) {
+            // a row outgrew its capacity during a device-side rebuild: grow (x1.2, as
+            // src/neighbor_list.F90:247-298) and rebuild every replica through the host path
+            int K = h->K, KB = h->KB;
+            if (h->h_misc->nl_overflow > K) K = ((int)(h->h_misc->nl_overflow * 1.2) + 31) / 32 * 32;
+            if (h->h_misc->bp_overflow > KB) KB = ((int)(h->h_misc->bp_overflow * 1.2) + 7) / 8 * 8;
+            h->h_misc->lists_invalid = 0;
+            CK(cudaMemcpy(&h->S.misc->lists_invalid, &h->h_misc->lists_invalid, sizeof(int), cudaMemcpyHostToDevice));
+            TRY(alloc_lists(h, K, KB));
+            std::vector<int> all(R, 1);
+            TRY(build_lists(h, all, false));
+            TRY(sync_ctl(h));
+        } else if (nreb > 0) {
+            TRY(refresh_half_counts(h));
+        }
+    }
     return 0;
 }
 
@@ -1595,11 +1770,14 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
     bool force_mc = false;
     const int R = h->nrep;
     const unsigned mask_all = 0x7FEu;
+    // launch_mode 2 with device-driven rebuilds (md_run_pipelined) needs no host-side trigger
+    const bool pipelined = h->launch_mode == 2 && h->nstep_bp_MC == 0 && !h->P.flg_bias_rg && h->pipeline && !h->P.flg_bias_ss;
     while ((long long)h->h_ctl->step < target) {
         // rebuild requested by the previous position update (src/job_md.F90:388-395)
         bool any = false;
         std::vector<int> act(R, 0);
-        for (int r = 0; r < R; r++) if (h->h_need[r]) { act[r] = 1; any = true; h->nrebuild++; }
+        if (!pipelined)
+            for (int r = 0; r < R; r++) if (h->h_need[r]) { act[r] = 1; any = true; h->nrebuild++; }
         if (any) {
             // a persistent kernel that stopped at the rebuild test may have left the base-pair
             // scatter of the step it did not execute in f_bp
@@ -1619,41 +1797,15 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
         const int use_mask = h->nstep_bp_MC > 0 ? 1 : 0;
         const bool uniform = h->nstep_bp_MC <= 1;   // every step has the same kernel sequence
         if (h->launch_mode == 2 && h->nstep_bp_MC == 0 && !h->P.flg_bias_rg) {
-            // persistent warp-specialised kernel: runs until `stop` or until a replica needs new lists
-            if (h->coop_blocks == 0) {
-                int per_sm = 0, dev_sms = 0;
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_md_fused, FUSED_THREADS, 0));
-                CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
-                if (per_sm < 1) return set_err("k_md_fused does not fit on an SM");
-                h->coop_blocks = dev_sms;   // one CTA per SM
-            }
-            StepArgs A = step_args(h, mask_all, 0, -1, 1);
-            int nrun = (int)std::min<long long>(stop - cur, 1 << 20);
-            const long long nitems = (long long)R * h->nmp;
-            CK(cudaMemsetAsync(h->d_bar.p, 0, 64 * sizeof(unsigned), h->stream));
-            void *args[] = {&h->S, &h->P, &A, &nrun};
-            // k_md_fast: one bead per 8-lane group, rows / candidates / bonded tables on chip
-            if (h->fast_kernel && h->partition_dirty) TRY(fast_partition(h));
-            const int want_fast = h->fast_ncta;
-            const size_t smem_fast = ((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)3 * FAST_GROUPS * h->K * sizeof(uint32_t);   // rows, sort scratch / unit forces, classes / unit tables
-            long long ncand_total = 0;
-            for (int r = 0; r < R; r++) ncand_total += h->nbp_half_rep.empty() ? h->nbp_half_max : h->nbp_half_rep[r];
-            const bool biases = h->P.flg_stage || h->P.ntwz_DCF || h->P.ntwz_FR || h->P.nrest;
-            const bool fast_ok = h->fast_kernel && want_fast > 0 && !biases && h->K >= 24 && smem_fast <= 200 * 1024 &&
-                                 3 * (ncand_total / want_fast) + 16 <= FAST_BPC;
-            if (fast_ok) {
-                void *fn = (void *)k_md_fast<1>;
-                if (smem_fast > h->fast_smem_set || fn != h->fast_fn_set) {
-                    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
-                    h->fast_smem_set = smem_fast; h->fast_fn_set = fn;
-                }
-                CK(cudaLaunchCooperativeKernel(fn, dim3(want_fast), dim3(FAST_THREADS), args, smem_fast, h->stream));
+            if (pipelined) {
+                // device-driven rebuilds: no host round trip between a rebuild and the next steps
+                timer_end(h, h->t_step);   // (closes the pair opened above; the loop keeps its own events)
+                TRY(md_run_pipelined(h, stop));
+                timer_begin(h);
             } else {
-                const int want = (int)std::max<long long>(1, (nitems + FUSED_GROUPS - 1) / FUSED_GROUPS);
-                dim3 grid(std::min(h->coop_blocks, want));
-                CK(cudaLaunchCooperativeKernel((void *)k_md_fused, grid, dim3(FUSED_THREADS), args, 0, h->stream));
+                // persistent warp-specialised kernel: runs until `stop` or until a replica needs new lists
+                TRY(launch_persistent(h, stop));
             }
-            h->launches++;
         } else if (h->launch_mode >= 1 && uniform && nchunk == h->chunk) {
             if (!h->graph_chunk || h->graph_chunk_steps != nchunk) {
                 invalidate_graphs(h);
@@ -1688,13 +1840,7 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
         TRY(sync_ctl(h));
         CK(cudaGetLastError());
         timer_end(h, h->t_step);
-        if (h->h_misc->max_force_flag & 4) {
-            // k_md_fast found more base-pair candidates or chain neighbours than its shared-memory
-            // tables hold and did not run: use the general kernel from here on
-            h->h_misc->max_force_flag &= ~4;
-            CK(cudaMemcpy(&h->S.misc->max_force_flag, &h->h_misc->max_force_flag, sizeof(int), cudaMemcpyHostToDevice));
-            h->fast_kernel = 0;
-        }
+        TRY(after_persistent_sync(h));
         // exchange step (src/job_md.F90:474-481,514-570)
         if (h->flg_replica && h->nstep_exchange > 0 &&
             (long long)h->h_ctl->step % h->nstep_exchange == 0 && (long long)h->h_ctl->step > cur) {
@@ -1770,6 +1916,7 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
     else if (s == "timing") h->timing = (int)value;
     else if (s == "fast_kernel") h->fast_kernel = (int)value;
     else if (s == "fast_unroll") h->fast_unroll = (int)value;
+    else if (s == "pipeline") h->pipeline = (int)value;
     else if (s == "profile") {   // phase clocks of the persistent kernel (block 0): get_timers out[4..8]
         if (value != 0) { TRY(h->d_prof.alloc(16 + 8 * FAST_MAX_CTA)); h->S.prof = h->d_prof.p; }
         else h->S.prof = nullptr;
