@@ -41,6 +41,7 @@ struct BpPara {
     double angl_k1, angl_k2, angl_k3, angl_k4;
     double angl_theta1, angl_theta2, angl_theta3, angl_theta4;
     double dihd_k1, dihd_k2, dihd_phi1, dihd_phi2;
+    double cos_phi1, sin_phi1, cos_phi2, sin_phi2;   // of dihd_phi1/2: cos(phi + phi0) without atan2 / sincos
 };
 
 // force-field + run constants shared by all replicas (kernel argument, by value)
@@ -420,11 +421,19 @@ SIS_HD BpSub bp_force_role(const FFParams &P, const BpPara &p, int role, Vec3 x0
         const Vec3 va2 = pbc_vec_d(P, xa, x1), v1b = pbc_vec_d(P, x0, xb);
         const double ra = dot(v12, va2) / d1212, rb = dot(v12, v1b) / d1212;
         const Vec3 m = cross(va2, v12), n = cross(v12, v1b);
-        const double dih = atan2(dot(va2, n) * a12, dot(m, n));
+        // phi = atan2(Y, X): cos(phi + phi0) and sin(phi + phi0) from (X, Y) / |(X, Y)| and the
+        // tabulated cos / sin of phi0 (src/force_bp.F90:143-160 evaluates atan2, then cos and sin)
+        const double Y = dot(va2, n) * a12, X = dot(m, n);
         const double kk = role == 5 ? p.dihd_k1 : p.dihd_k2;
-        const double d = dih + (role == 5 ? p.dihd_phi1 : p.dihd_phi2);
-        o.u = kk * (1.0 + cos(d));
-        const double pre = -kk * sin(d) * a12;
+        const double c0 = role == 5 ? p.cos_phi1 : p.cos_phi2, s0 = role == 5 ? p.sin_phi1 : p.sin_phi2;
+#ifdef __CUDA_ARCH__
+        const double rinv = rsqrt(X * X + Y * Y);
+#else
+        const double rinv = 1.0 / sqrt(X * X + Y * Y);
+#endif
+        const double cosd = (X * c0 - Y * s0) * rinv, sind = (Y * c0 + X * s0) * rinv;
+        o.u = kk * (1.0 + cosd);
+        const double pre = -kk * sind * a12;
         const Vec3 fi = (pre / dot(m, m)) * m;
         const Vec3 fl = (-pre / dot(n, n)) * n;
         o.ca = fi;

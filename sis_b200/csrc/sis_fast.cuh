@@ -62,7 +62,8 @@ struct FastShared {
     FastBead bead[FAST_GROUPS];
     FastBpCand cand[FAST_BPC];
     int active[FAST_BPC];
-    int nactive, ncand, nextra, overflow;
+    int nactive[2], bp_next[2];      // survivors of the distance gate / next one to evaluate, by step parity
+    int ncand, nextra, overflow;
     int extra[FAST_NEXTRA];
     double fbp[FAST_GROUPS][3];      // base-pair forces on the CTA's beads (this step)
     int4 tmeta[FAST_NT];             // bonded-term slots: meta of the first bead
@@ -179,8 +180,11 @@ struct FastCtx {
     int cur0;
     unsigned *bar_pos;
     bool dih_on;
+    bool local;      // replica-local mode: the CTA owns every bead of its replica, no grid barrier
 };
 SIS_D void cta_sync() { named_bar_sync(0, FAST_THREADS); }
+SIS_D void fast_bp_eval(const DevSys &S, const FFParams &P, FastShared &sh, const double4 *pos, int lo_item, int hi_item,
+                        int q, int nact);
 
 // Loop protocol shared by the roles (iteration n, parity q = n & 1):
 //   LOC   : [n > 0: verdict -> sh.blocked[q]]  tables  arrive(3)  gauss  cta_sync  read blocked[q]
@@ -324,6 +328,10 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
             }
         }
         if (prof) c1 = clock64();
+        // help the BP warps with the survivors of the distance gate
+        named_bar_sync(4, FAST_MAIN + FAST_BP);
+        fast_bp_eval(S, P, sh, S.pos[cur], C.item0, C.item0 + C.nb, n & 1, sh.nactive[n & 1]);
+        __threadfence_block();
         named_bar_sync(3, FAST_MAIN + FAST_LOC + FAST_BP);   // all units, bonded tables, base-pair forces, rebuild verdict
         if (prof) c1b = clock64();
         if (sh.blocked[n & 1]) { cta_sync(); break; }
@@ -376,12 +384,12 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
         const double d2 = valid ? s0 * s0 + s1 * s1 + s2 * s2 : 0.0;
         if (lane == 0) {
             if (valid) S.pos[cur ^ 1][(size_t)B.rep * nmp + B.k] = make_double4(B.x[0], B.x[1], B.x[2], 0.0);
-            if (R == 1) sh.d2[grp] = d2;
+            if (R == 1 || C.local) sh.d2[grp] = d2;
             else if (d2 > 0.0) top2_push(S.top2 + ((size_t)B.rep * 2 + ((step + 1ull) & 1ull)) * 2, d2, 0.0);
         }
         named_bar_sync(2, FAST_MAIN);
         if (warp == 0) {
-            if (R == 1) {                              // CTA top-2 of |xyz_move|^2 -> this CTA's slot
+            if (R == 1 || C.local) {                   // CTA top-2 of |xyz_move|^2 -> this CTA's slot
                 double t1 = sh.d2[tid], t2 = sh.d2[tid + 32];
                 if (t2 > t1) { const double t = t1; t1 = t2; t2 = t; }
 #pragma unroll
@@ -398,9 +406,16 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
             }
             if (tid == 0) {
                 if (prof) c3 = clock64();
-                red_release_add(C.bar_pos, 1u);
-                const unsigned target = (unsigned)(n + 1) * (unsigned)C.ncta;
-                while (ld_acquire_u32(C.bar_pos) < target) { }
+                if (C.local) {
+                    // no other CTA reads these positions; the acquire drops the SM's stale L1 lines of
+                    // the buffer written two steps ago (positions are gathered through read-only loads)
+                    __threadfence();
+                    (void)ld_acquire_u32(C.bar_pos);
+                } else {
+                    red_release_add(C.bar_pos, 1u);
+                    const unsigned target = (unsigned)(n + 1) * (unsigned)C.ncta;
+                    while (ld_acquire_u32(C.bar_pos) < target) { }
+                }
                 if (prof) {
                     c4 = clock64();
                     unsigned long long *pc = S.prof + 16 + 8 * blockIdx.x;
@@ -427,12 +442,64 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
     return n;
 }
 
+// Evaluation of the base-pair candidates that passed the distance gate: 8-lane groups (one role per
+// lane, bp_force_role) draw survivors from a shared counter.  The BP groups start right after the
+// gate; the MAIN groups join when their pair units are done, so a CTA with many formed base pairs
+// is not held up by its four BP warps.
+SIS_D void fast_bp_eval(const DevSys &S, const FFParams &P, FastShared &sh, const double4 *pos, int lo_item, int hi_item,
+                        int q, int nact)
+{
+    const int bl = threadIdx.x & 7;
+    const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+    auto in_range = [&](int it) { return it >= lo_item && it < hi_item; };
+    for (;;) {
+        int a = 0;
+        if (bl == 0) a = atomicAdd(&sh.bp_next[q], 1);
+        a = __shfl_sync(gmask, a, 0, 8);
+        if (a >= nact) break;
+        FastBpCand &cd = sh.cand[sh.active[a]];
+        const int type = cd.type;
+        const Vec3 x0 = v3(pos[cd.b[0]]), x1 = v3(pos[cd.b[1]]);
+        const int tA = bp_role_A(bl), tB = bp_role_B(bl);
+        Vec3 xa = x0, xb = x0;
+        if (tA >= 0) xa = v3(pos[cd.b[tA]]);
+        if (tB >= 0) xb = v3(pos[cd.b[tB]]);
+        const Vec3 v12 = pbc_vec_d(P, x0, x1);
+        const double d1212 = dot(v12, v12), a12 = sqrt(d1212);
+        const BpSub o = bp_force_role(P, P.bp[type], bl, x0, x1, xa, xb, v12, d1212, a12);
+        const double u = group_sum_masked(o.u, gmask);
+        const double ene = P.bp_triplet ? P.bp[type].U0 * cd.dG * exp(-u) : P.bp[type].U0 * exp(-u);
+        Vec3 F0, F1;
+        F0.x = group_sum_masked(o.c0.x, gmask); F0.y = group_sum_masked(o.c0.y, gmask); F0.z = group_sum_masked(o.c0.z, gmask);
+        F1.x = group_sum_masked(o.c1.x, gmask); F1.y = group_sum_masked(o.c1.y, gmask); F1.z = group_sum_masked(o.c1.z, gmask);
+        // bead t = lane (2..5): ca of its angle role + (ca | cb) of its dihedral role
+        const int src_ang = (bl >= 2 && bl <= 5) ? bl - 1 : 0;
+        const int src_dih = (bl == 2 || bl == 3) ? 5 : 6;
+        const bool dih_b = (bl == 2 || bl == 4);
+        Vec3 Fa, Fda, Fdb;
+        Fa.x = __shfl_sync(gmask, o.ca.x, src_ang, 8); Fa.y = __shfl_sync(gmask, o.ca.y, src_ang, 8); Fa.z = __shfl_sync(gmask, o.ca.z, src_ang, 8);
+        Fda.x = __shfl_sync(gmask, o.ca.x, src_dih, 8); Fda.y = __shfl_sync(gmask, o.ca.y, src_dih, 8); Fda.z = __shfl_sync(gmask, o.ca.z, src_dih, 8);
+        Fdb.x = __shfl_sync(gmask, o.cb.x, src_dih, 8); Fdb.y = __shfl_sync(gmask, o.cb.y, src_dih, 8); Fdb.z = __shfl_sync(gmask, o.cb.z, src_dih, 8);
+        const bool on = ene <= P.bp_cutoff_energy;
+        if (on && bl < 6 && in_range(cd.b[bl])) {
+            const Vec3 Ft = bl == 0 ? F0 : bl == 1 ? F1 : Fa + (dih_b ? Fdb : Fda);
+            double *fb = sh.fbp[cd.b[bl] - lo_item];
+            atomicAdd(fb, ene * Ft.x); atomicAdd(fb + 1, ene * Ft.y); atomicAdd(fb + 2, ene * Ft.z);
+        }
+        if (bl == 0 && cd.own) {
+            S.bp_status[cd.pb] = on ? 1 : 0;
+            S.ene_bp[cd.pb] = on ? ene : 0.0;
+            cd.last = on ? 1 : 0;
+        }
+    }
+}
+
 // BP role.  Every CTA evaluates every base-pair candidate that touches one of its beads (as i, j
 // or one of the four chain neighbours) and keeps only the force parts that act on its own beads,
 // in shared memory: no cross-CTA dependency, no global atomics, no grid barrier for the base
 // pairs.  A pair is evaluated by the two or three CTAs that own its six beads; the CTA that owns
 // bead i also maintains bp_status / ene_bp (src/force_bp.F90:191-193).
-SIS_D void fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, FastShared &sh)
+SIS_D int fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, FastShared &sh)
 {
     const int tid = threadIdx.x, bt = tid - FAST_MAIN;
     const int nmp = C.nmp, KB = S.KB;
@@ -440,7 +507,7 @@ SIS_D void fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fa
     int cur = C.cur0;
     auto in_range = [&](int it) { return it >= lo_item && it < hi_item; };
     // ---- E = the CTA's beads + their chain neighbours outside the range ---------------------------
-    if (bt == 0) { sh.ncand = 0; sh.nactive = 0; sh.nextra = 0; sh.overflow = 0; }
+    if (bt == 0) { sh.ncand = 0; sh.nactive[0] = sh.nactive[1] = 0; sh.bp_next[0] = sh.bp_next[1] = 0; sh.nextra = 0; sh.overflow = 0; }
     for (int i = bt; i < FAST_GROUPS * 3; i += FAST_BP) (&sh.fbp[0][0])[i] = 0.0;
     named_bar_sync(1, FAST_BP);
     for (int q = bt; q < C.nb; q += FAST_BP) {
@@ -513,12 +580,11 @@ SIS_D void fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fa
     cta_sync();
     const int ncand = min(sh.ncand, FAST_BPC);
     if (sh.ncand > FAST_BPC && bt == 0) S.misc->max_force_flag |= 4;   // the host checks the flag after the launch
-    const int bl = bt & 7, bg = bt >> 3;
-    const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
     const bool prof = S.prof != nullptr && bt == 0;
     long long b0 = 0, b1 = 0, b2 = 0;
+    int n = 0;
     if (!sh.blocked[0] && sh.ncand <= FAST_BPC && !sh.overflow)
-    for (int n = 0; n < C.nsteps; n++) {
+    for (; n < C.nsteps; n++) {
         if (prof) b0 = clock64();
         const double4 *pos = S.pos[cur];
         for (int i = bt; i < ncand; i += FAST_BP) {            // distance gate, one thread per candidate
@@ -527,7 +593,7 @@ SIS_D void fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fa
             const double a12 = sqrt(dot(v12, v12));
             const int type = cd.type;
             if (fabs(a12 - P.bp[type].bond_r) <= P.bp[type].cutoff_ddist) {
-                sh.active[atomicAdd(&sh.nactive, 1)] = i;
+                sh.active[atomicAdd(&sh.nactive[n & 1], 1)] = i;
             } else {
                 if (P.bp_triplet && P.flg_bias_ss) {           // src/force_bp_triplet.F90:85-93
                     const double sc = P.bias_ss_force / a12;
@@ -548,49 +614,14 @@ SIS_D void fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fa
         }
         named_bar_sync(1, FAST_BP);
         if (prof) b1 = clock64();
-        const int nact = sh.nactive;
-        for (int a = bg; a < nact; a += FAST_BPGROUPS) {       // survivors: one role per lane
-            FastBpCand &cd = sh.cand[sh.active[a]];
-            const int type = cd.type;
-            const Vec3 x0 = v3(pos[cd.b[0]]), x1 = v3(pos[cd.b[1]]);
-            const int tA = bp_role_A(bl), tB = bp_role_B(bl);
-            Vec3 xa = x0, xb = x0;
-            if (tA >= 0) xa = v3(pos[cd.b[tA]]);
-            if (tB >= 0) xb = v3(pos[cd.b[tB]]);
-            const Vec3 v12 = pbc_vec_d(P, x0, x1);
-            const double d1212 = dot(v12, v12), a12 = sqrt(d1212);
-            const BpSub o = bp_force_role(P, P.bp[type], bl, x0, x1, xa, xb, v12, d1212, a12);
-            const double u = group_sum_masked(o.u, gmask);
-            const double ene = P.bp_triplet ? P.bp[type].U0 * cd.dG * exp(-u) : P.bp[type].U0 * exp(-u);
-            Vec3 F0, F1;
-            F0.x = group_sum_masked(o.c0.x, gmask); F0.y = group_sum_masked(o.c0.y, gmask); F0.z = group_sum_masked(o.c0.z, gmask);
-            F1.x = group_sum_masked(o.c1.x, gmask); F1.y = group_sum_masked(o.c1.y, gmask); F1.z = group_sum_masked(o.c1.z, gmask);
-            // bead t = lane (2..5): ca of its angle role + (ca | cb) of its dihedral role
-            const int src_ang = (bl >= 2 && bl <= 5) ? bl - 1 : 0;
-            const int src_dih = (bl == 2 || bl == 3) ? 5 : 6;
-            const bool dih_b = (bl == 2 || bl == 4);
-            Vec3 Fa, Fda, Fdb;
-            Fa.x = __shfl_sync(gmask, o.ca.x, src_ang, 8); Fa.y = __shfl_sync(gmask, o.ca.y, src_ang, 8); Fa.z = __shfl_sync(gmask, o.ca.z, src_ang, 8);
-            Fda.x = __shfl_sync(gmask, o.ca.x, src_dih, 8); Fda.y = __shfl_sync(gmask, o.ca.y, src_dih, 8); Fda.z = __shfl_sync(gmask, o.ca.z, src_dih, 8);
-            Fdb.x = __shfl_sync(gmask, o.cb.x, src_dih, 8); Fdb.y = __shfl_sync(gmask, o.cb.y, src_dih, 8); Fdb.z = __shfl_sync(gmask, o.cb.z, src_dih, 8);
-            const bool on = ene <= P.bp_cutoff_energy;
-            if (on && bl < 6 && in_range(cd.b[bl])) {
-                const Vec3 Ft = bl == 0 ? F0 : bl == 1 ? F1 : Fa + (dih_b ? Fdb : Fda);
-                double *fb = sh.fbp[cd.b[bl] - lo_item];
-                atomicAdd(fb, ene * Ft.x); atomicAdd(fb + 1, ene * Ft.y); atomicAdd(fb + 2, ene * Ft.z);
-            }
-            if (bl == 0 && cd.own) {
-                S.bp_status[cd.pb] = on ? 1 : 0;
-                S.ene_bp[cd.pb] = on ? ene : 0.0;
-                cd.last = on ? 1 : 0;
-            }
-        }
+        const int nact = sh.nactive[n & 1];
+        bar_arrive(4, FAST_MAIN + FAST_BP);                    // gate complete: the MAIN groups may join the evaluation
+        if (bt == 0) { sh.nactive[(n + 1) & 1] = 0; sh.bp_next[(n + 1) & 1] = 0; }
+        fast_bp_eval(S, P, sh, pos, lo_item, hi_item, n & 1, nact);
         if (prof) b2 = clock64();
         __threadfence_block();
         __syncwarp();
         bar_arrive(3, FAST_MAIN + FAST_LOC + FAST_BP);         // base-pair forces of this CTA's beads are in sh.fbp
-        named_bar_sync(1, FAST_BP);
-        if (bt == 0) sh.nactive = 0;
         if (prof) {
             const long long b3 = clock64();
             S.prof[16 + 8 * blockIdx.x + 4] += (unsigned long long)(b3 - b0);
@@ -605,9 +636,10 @@ SIS_D void fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fa
         if (sh.blocked[n & 1]) break;
     }
     cta_sync();
+    return n;
 }
 
-SIS_D void fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, const FastCtx &C, FastShared &sh)
+SIS_D int fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, const FastCtx &C, FastShared &sh)
 {
     const int tid = threadIdx.x, lt = tid - FAST_MAIN - FAST_BP;
     const int nmp = C.nmp, R = C.R;
@@ -630,7 +662,8 @@ SIS_D void fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
     }
     if (wwarp) {                                       // rebuild test on the state left by the previous launch
         bool b = false;
-        for (int r = ll; r < R; r += 32) {
+        const int rlo = C.local ? C.item0 / nmp : 0, rhi = C.local ? rlo + 1 : R;
+        for (int r = rlo + ll; r < rhi; r += 32) {
             const unsigned long long *t = S.top2 + ((size_t)r * 2 + (step & 1ull)) * 2;
             const double m1 = __longlong_as_double((long long)__ldcg(t));
             const double m2 = __longlong_as_double((long long)__ldcg(t + 1));
@@ -656,15 +689,16 @@ SIS_D void fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
     cta_sync();
     const bool prof = S.prof != nullptr && blockIdx.x == 0 && lt == 0;
     long long l0 = 0, l1 = 0;
+    int n = 0;
     if (!sh.blocked[0] && sh.ncand <= FAST_BPC && !sh.overflow)
-    for (int n = 0; n < C.nsteps; n++) {
+    for (; n < C.nsteps; n++) {
         if (prof) l0 = clock64();
         // rebuild test on the displacements left by the previous step
         if (n > 0 && wwarp) {
             bool b = false;
-            if (R == 1) {
+            if (R == 1 || C.local) {
                 double t1 = 0.0, t2 = 0.0;
-                for (int c = ll; c < C.ncta; c += 32) {
+                for (int c = C.local ? blockIdx.x + ll : ll; c < (C.local ? blockIdx.x + 1 : C.ncta); c += 32) {
                     const double2 s = __ldcg(S.top2_slots + (step & 1ull) * FAST_MAX_CTA + c);
                     top2_merge(t1, t2, s.x, s.y);
                 }
@@ -735,10 +769,46 @@ SIS_D void fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
         if (sh.blocked[n & 1]) break;
     }
     cta_sync();
+    return n;
 }
 
-template <int U>
-__global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams P, StepArgs A, long long target)
+// Replica-local mode: the MAIN warps rebuild the lists of the CTA's replica in place -- pbc_wrap and
+// the predicates of src/neighbor_list.F90:28-229 over all bead pairs (k_nl_rows' all-pairs sweep),
+// the ele_cutoff refresh of :80-82, pair ids, xyz_move = 0 (src/job_md.F90:390) -- and the kernel
+// carries on; nothing leaves the SM.
+SIS_D void fast_local_rebuild(const DevSys &S, const FFParams &P, NlArgs NA, int rep, int cur)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nmp = S.nmp;
+    const size_t rbase = (size_t)rep * nmp;
+    double4 *pos = S.pos[cur] + rbase;
+    if (P.flg_pbc)
+        for (int i = tid; i < nmp; i += FAST_MAIN) {
+            double4 p = pos[i];
+            p.x = wrap1(p.x, P.box[0]); p.y = wrap1(p.y, P.box[1]); p.z = wrap1(p.z, P.box[2]);
+            pos[i] = p;
+        }
+    if (tid == 0) {
+        S.nbp_half[rep] = 0;
+        atomicAdd(&S.misc->nrebuild, 1);
+        if (NA.ele_cutoff_type == 2) S.rp[rep].ele_cutoff = NA.ele_cutoff_inp * S.rp[rep].lambdaD;
+    }
+    __threadfence_block();
+    named_bar_sync(2, FAST_MAIN);
+    NA.all_pairs = 2;
+    for (int i = warp; i < nmp; i += FAST_MAIN_WARPS) nl_rows_bead_at(S, P, NA, rep, i, lane, pos, nullptr, nullptr);
+    __threadfence_block();
+    named_bar_sync(2, FAST_MAIN);
+    for (int idx = tid; idx < nmp * S.KB; idx += FAST_MAIN) nl_bp_slot(S, rep, idx);
+    if (tid < 4) S.top2[(size_t)rep * 4 + tid] = 0ull;
+    if (tid < 2) S.top2_slots[tid * FAST_MAX_CTA + blockIdx.x] = make_double2(0.0, 0.0);
+    __threadfence_block();
+    if (tid == 0) (void)ld_acquire_u32(S.bar + 32);   // drop the SM's L1 copies of the old lists
+    named_bar_sync(2, FAST_MAIN);
+}
+
+template <int U, bool LOCAL>
+__global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams P, StepArgs A, long long target, NlArgs NA)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastShared &sh = *reinterpret_cast<FastShared *>(smem_raw);
@@ -750,19 +820,44 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams 
     if (nsteps <= 0) return;
     FastCtx C;
     C.R = S.nrep; C.nmp = S.nmp; C.K = S.K; C.nitems = S.nrep * S.nmp; C.ncta = gridDim.x;
-    C.item0 = S.cta_item0[blockIdx.x]; C.nb = S.cta_item0[blockIdx.x + 1] - C.item0; C.nsteps = nsteps;
-    C.step0 = ctl.step; C.cur0 = ctl.cur;
+    C.item0 = S.cta_item0[blockIdx.x]; C.nb = S.cta_item0[blockIdx.x + 1] - C.item0;
     C.bar_pos = S.bar + 32;
     C.dih_on = P.flg_dih_cos || P.flg_dih_exp;
+    C.local = LOCAL;
     const int tid = threadIdx.x;
-    if (tid >= FAST_MAIN + FAST_BP) { fast_loc_role(S, P, A, C, sh); return; }
-    if (tid >= FAST_MAIN) { fast_bp_role(S, P, C, sh); return; }
-    const int n = fast_main_role<U>(S, P, A, C, sh, s_rows);
-    // ---- bookkeeping for the host and the other kernels (block 0, warp 0) ---------------------------
-    if (blockIdx.x == 0 && tid < 32) {
-        const unsigned long long step = C.step0 + (unsigned long long)n;
-        const int cur = C.cur0 ^ (n & 1);
-        if (C.R == 1 && n > 0) {
+    // A launch is one segment (prologue, step loop) unless the CTA rebuilds its own lists (LOCAL):
+    // then a segment ends at the rebuild test and the next one starts on the new lists.
+    int done = 0;
+    for (;;) {
+        C.nsteps = nsteps - done;
+        C.step0 = ctl.step + (unsigned long long)done;
+        C.cur0 = ctl.cur ^ (done & 1);
+        int n;
+        if (tid >= FAST_MAIN + FAST_BP) n = fast_loc_role(S, P, A, C, sh);
+        else if (tid >= FAST_MAIN) n = fast_bp_role(S, P, C, sh);
+        else n = fast_main_role<U>(S, P, A, C, sh, s_rows);
+        done += n;
+        if (!LOCAL || done >= nsteps) break;
+        if (sh.ncand > FAST_BPC || sh.overflow) break;     // tables too small (the host checked: cannot happen)
+        __threadfence_block();
+        cta_sync();                                        // velocities, beta, xyz_move are back in global memory
+        if (tid < FAST_MAIN) fast_local_rebuild(S, P, NA, C.item0 / C.nmp, C.cur0 ^ (n & 1));
+        cta_sync();
+    }
+    if (tid >= FAST_MAIN) return;
+    // ---- bookkeeping for the host and the other kernels (warp 0) ------------------------------------
+    const unsigned long long step = ctl.step + (unsigned long long)done;
+    const int cur = ctl.cur ^ (done & 1);
+    if (LOCAL) {
+        if (tid == 0 && done > 0) {                        // this replica's displacement top-2 (src/job_md.F90:376-388)
+            const double2 s = __ldcg(S.top2_slots + (step & 1ull) * FAST_MAX_CTA + blockIdx.x);
+            unsigned long long *t = S.top2 + ((size_t)(C.item0 / C.nmp) * 2 + (step & 1ull)) * 2;
+            t[0] = (unsigned long long)__double_as_longlong(s.x); t[1] = (unsigned long long)__double_as_longlong(s.y);
+            t = S.top2 + ((size_t)(C.item0 / C.nmp) * 2 + ((step + 1ull) & 1ull)) * 2;
+            t[0] = 0ull; t[1] = 0ull;
+        }
+    } else if (blockIdx.x == 0 && tid < 32) {
+        if (C.R == 1 && done > 0) {
             double t1 = 0.0, t2 = 0.0;
             for (int c = tid; c < C.ncta; c += 32) {
                 const double2 s = __ldcg(S.top2_slots + (step & 1ull) * FAST_MAX_CTA + c);
@@ -780,9 +875,19 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams 
                 t[0] = 0ull; t[1] = 0ull;
             }
         }
+    }
+    if (LOCAL) {
+        // without grid barriers a CTA may finish before another one has read ctl: the last CTA to
+        // finish publishes the new step (S.bar[0] is zeroed by the host before every launch)
         if (tid == 0) {
-            DevCtl a; a.step = step; a.cur = cur; a.blocked = 0;
-            S.ctl[0] = a;
+            __threadfence();
+            if (atomicAdd(S.bar, 1u) == gridDim.x - 1) {
+                DevCtl a; a.step = step; a.cur = cur; a.blocked = 0;
+                S.ctl[0] = a;
+            }
         }
+    } else if (blockIdx.x == 0 && tid == 0) {
+        DevCtl a; a.step = step; a.cur = cur; a.blocked = 0;
+        S.ctl[0] = a;
     }
 }

@@ -1039,6 +1039,8 @@ struct NlArgs {
     double wca_nl_cut2, bp_nl_cut2, nl_margin;
     int excl_bond, excl_angle, bp_model, bp_min_loop;
     int all_pairs;   // 0 cell grid; 1 list_exv/ele/bp (no cutoffs); 2 all-pairs sweep with cutoffs
+    int ele_cutoff_type;     // in-kernel rebuilds (k_md_fast, replica-local mode): the ele_cutoff refresh
+    double ele_cutoff_inp;   // of src/neighbor_list.F90:80-82
 };
 // the list predicates of src/neighbor_list.F90:122-180 (and of src/list_exv.F90:36-52,
 // src/list_ele.F90:36-56 when A.all_pairs == 1) for the unordered bead pair {i, j}
@@ -1099,18 +1101,11 @@ SIS_HD bool nl_bp_geometry(const NlArgs &A, int i, int j, double d2)
 {
     return A.all_pairs == 1 ? (abs(i - j) >= A.bp_min_loop + 1) : (d2 <= A.bp_nl_cut2);
 }
-__global__ void __launch_bounds__(256) k_nl_rows(DevSys S, FFParams P, NlArgs A, const int *rep_active)
+SIS_D void nl_rows_bead_at(const DevSys &S, const FFParams &P, const NlArgs &A, int rep, int i, int lane,
+                           const double4 *pos, int *s_off, int *s_beg)
 {
-    const int rep = blockIdx.y;
-    if (!rep_active[rep]) return;
-    __shared__ int s_off[8][28], s_beg[8][27];
-    const int lane = threadIdx.x % 32, w = threadIdx.x / 32;
-    const int i = blockIdx.x * 8 + w;
     const int nmp = S.nmp;
-    if (i >= nmp) return;
-    const GridInfo &Gd = *S.grid;
     const size_t rbase = (size_t)rep * nmp;
-    const double4 *pos = S.pos[S.ctl[0].cur] + rbase;
     const RepParams R = S.rp[rep];
     const int4 mi = S.meta[i];
     const Vec3 xi = v3(pos[i]);
@@ -1131,6 +1126,7 @@ __global__ void __launch_bounds__(256) k_nl_rows(DevSys S, FFParams P, NlArgs A,
     if (sweep_all) {
         total = nmp;
     } else {
+        const GridInfo &Gd = *S.grid;
         int lx[3], ly[3], lz[3];
         const int c = S.cell_of[rbase + i];
         const int cx = c % Gd.n[0], cy = (c / Gd.n[0]) % Gd.n[1], cz = c / (Gd.n[0] * Gd.n[1]);
@@ -1151,8 +1147,8 @@ __global__ void __launch_bounds__(256) k_nl_rows(DevSys S, FFParams P, NlArgs A,
             const int t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        if (lane < 28) s_off[w][lane] = incl - len;   // lanes >= nrange: the total (sentinels)
-        if (lane < 27) s_beg[w][lane] = beg;
+        if (lane < 28) s_off[lane] = incl - len;   // lanes >= nrange: the total (sentinels)
+        if (lane < 27) s_beg[lane] = beg;
         total = __shfl_sync(0xffffffffu, incl, 31);
         __syncwarp();
     }
@@ -1168,9 +1164,9 @@ __global__ void __launch_bounds__(256) k_nl_rows(DevSys S, FFParams P, NlArgs A,
 #pragma unroll
                 for (int s = 0; s < 5; s++) {
                     const int mid = (lo + hi) >> 1;
-                    if (s_off[w][mid] <= t) lo = mid; else hi = mid;
+                    if (s_off[mid] <= t) lo = mid; else hi = mid;
                 }
-                j = cbeads[s_beg[w][lo] + (t - s_off[w][lo])];
+                j = cbeads[s_beg[lo] + (t - s_off[lo])];
             }
             if (j != i) {
                 const int4 mj = S.meta[j];
@@ -1217,14 +1213,20 @@ __global__ void __launch_bounds__(256) k_nl_rows(DevSys S, FFParams P, NlArgs A,
         S.move[(rbase + i) * 3] = 0.0; S.move[(rbase + i) * 3 + 1] = 0.0; S.move[(rbase + i) * 3 + 2] = 0.0;
     }
 }
-// 6. pair ids: ibp = owner*KB + slot-in-owner-row, resolved for both directions
-__global__ void k_nl_bp_slots(DevSys S, const int *rep_active)
+__global__ void __launch_bounds__(256) k_nl_rows(DevSys S, FFParams P, NlArgs A, const int *rep_active)
 {
     const int rep = blockIdx.y;
     if (!rep_active[rep]) return;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int s_off[8][28], s_beg[8][27];
+    const int lane = threadIdx.x % 32, w = threadIdx.x / 32;
+    const int i = blockIdx.x * 8 + w;
+    if (i >= S.nmp) return;
+    nl_rows_bead_at(S, P, A, rep, i, lane, S.pos[S.ctl[0].cur] + (size_t)rep * S.nmp, s_off[w], s_beg[w]);
+}
+// 6. pair ids: ibp = owner*KB + slot-in-owner-row, resolved for both directions
+SIS_D void nl_bp_slot(const DevSys &S, int rep, int idx)
+{
     const int nmp = S.nmp, KB = S.KB;
-    if (idx >= nmp * KB) return;
     const int k = idx / KB, e = idx % KB;
     const size_t rbase = (size_t)rep * nmp;
     if (e >= S.nbp_row[rbase + k]) return;
@@ -1243,6 +1245,13 @@ __global__ void k_nl_bp_slots(DevSys S, const int *rep_active)
         if (jr[q].x == k) { found = q; break; }
     ent->y = j * KB + max(found, 0);
 }
+__global__ void k_nl_bp_slots(DevSys S, const int *rep_active)
+{
+    const int rep = blockIdx.y;
+    if (!rep_active[rep]) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < S.nmp * S.KB) nl_bp_slot(S, rep, idx);
+}
 __global__ void k_nl_begin_slots(DevSys S, const int *rep_active)
 {
     const int rep = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1255,7 +1264,7 @@ __global__ void k_nl_begin_slots(DevSys S, const int *rep_active)
 //    (replica, bead) items, cut where the running row weight (nnbr + 8) crosses c * total / ncta.
 //    One block of 1024 threads; nitems <= ncta * per_cta <= PART_MAX_ITEMS when ncta > 0.
 constexpr int PART_MAX_ITEMS = 148 * 64;
-__global__ void __launch_bounds__(1024) k_nl_partition(DevSys S, const int *rep_active, int ncta, int per_cta)
+__global__ void __launch_bounds__(1024) k_nl_partition(DevSys S, const int *rep_active, int ncta, int per_cta, int local)
 {
     __shared__ int s_w[PART_MAX_ITEMS];          // inclusive prefix of the weights
     __shared__ int s_part[1024];
@@ -1274,6 +1283,10 @@ __global__ void __launch_bounds__(1024) k_nl_partition(DevSys S, const int *rep_
     if (tid == 0 && (S.misc->nl_overflow > S.K || S.misc->bp_overflow > S.KB)) S.misc->lists_invalid = 1;
     __syncthreads();
     if (!s_any || ncta <= 0) return;
+    if (local) {     // replica-local mode of k_md_fast: CTA c owns replica c
+        for (int c = tid; c <= ncta; c += blockDim.x) S.cta_item0[c] = c * S.nmp;
+        return;
+    }
     // block scan: thread t owns items [t * chunk, (t + 1) * chunk)
     const int chunk = (nitems + 1023) / 1024;
     const int i0 = tid * chunk, i1 = min(i0 + chunk, nitems);
@@ -1314,4 +1327,129 @@ __global__ void __launch_bounds__(1024) k_nl_partition(DevSys S, const int *rep_
         }
         S.cta_item0[ncta] = nitems;
     }
+}
+
+// ---- REMD exchange step on the device (src/energy_replica.F90:45-163, src/job_md.F90:531-567,
+// src/replica_exchange.F90:44-154, 175-213) -------------------------------------------------
+// The host tables of var_replica / init_replica are mirrored in RemdDev; a label's parameter block
+// (temperature, Debye-Hueckel coefficients, tweezers force, Rg0) is precomputed per label, so an
+// exchange is a permutation of those blocks.  Every rank replays the same decisions from the
+// all-gathered energies and the shared counter-based uniform stream: no second collective.
+constexpr int REMD_DEV_MAX_LABELS = 4096;   // replicas the device-side exchange handles (shared table of k_remd_exchange)
+struct RemdDev {
+    int n, ncol, idx_pair, R, rank;
+    int flg_temp, flg_ele_var, flg_twz, flg_rg;   // which fields of a label block replace the replica's
+    unsigned long long seed, exchange_counter;
+    long long n_attempt, n_accept;
+    double tempK_default;
+    const int *pair_tb;       // [ncol][n]
+    int *rep2lab, *lab2rep;   // [n], 1-based values
+    const double *lab_temp;   // [n]
+    const RepParams *lab_rp;  // [n]
+    RepParams *rp_alt;        // [R] partner-parameter blocks of the cross-energy pass
+    int *has_opp;             // [R]
+    double *send, *recv;      // [2 R], [2 n]: replica_energies(2, :) of src/job_md.F90:475
+    double *vscale;           // [R]
+};
+SIS_D void remd_apply_label(const RemdDev &D, RepParams &dst, const RepParams &lab)
+{
+    if (D.flg_temp) { dst.tempK = lab.tempK; dst.sqrt_tempK = lab.sqrt_tempK; }
+    if (D.flg_ele_var) {
+        dst.ele_coef = lab.ele_coef; dst.inv_lambdaD = lab.inv_lambdaD; dst.lambdaD = lab.lambdaD;
+        dst.diele_dTcoef = lab.diele_dTcoef;
+    }
+    if (D.flg_twz) dst.twz_force = lab.twz_force;
+    if (D.flg_rg) dst.bias_rg_0 = lab.bias_rg_0;
+}
+// own total energies -> send(1, :); partner blocks for the cross pass (src/energy_replica.F90:76-118)
+__global__ void k_remd_prepare(DevSys S, const RemdDev *Dp)
+{
+    const RemdDev &D = *Dp;
+    const int irep = blockIdx.x * blockDim.x + threadIdx.x;
+    if (irep >= D.R) return;
+    const int label_own = D.rep2lab[D.rank * D.R + irep];
+    const int label_opp = D.pair_tb[(size_t)(D.idx_pair - 1) * D.n + label_own - 1];
+    RepParams alt = S.rp[irep];
+    int has = 0;
+    if (label_opp != 0 && label_opp <= D.n) { has = 1; remd_apply_label(D, alt, D.lab_rp[label_opp - 1]); }
+    D.rp_alt[irep] = alt;
+    D.has_opp[irep] = has;
+    D.send[2 * irep] = S.ene_out[(size_t)irep * ENE_N];
+}
+__global__ void k_remd_pack(DevSys S, const RemdDev *Dp)
+{
+    const RemdDev &D = *Dp;
+    const int irep = blockIdx.x * blockDim.x + threadIdx.x;
+    if (irep < D.R) D.send[2 * irep + 1] = D.has_opp[irep] ? S.ene_out[(size_t)irep * ENE_N] : 0.0;
+}
+// decisions, label tables, parameter refresh of the local replicas, velocity scale factors of
+// accepted temperature swaps.  The pairs of one attempt are disjoint (every label is in at most one
+// pair of the current pair table), so they are decided in parallel, one thread per lower label;
+// pair k in label order uses uniform k of the attempt, as the reference's sequential loop does.
+// One block.
+__global__ void __launch_bounds__(256) k_remd_exchange(DevSys S, RemdDev *Dp)
+{
+    RemdDev &D = *Dp;
+    __shared__ int s_rank[REMD_DEV_MAX_LABELS];
+    __shared__ int s_natt, s_nacc;
+    const int tid = threadIdx.x, n = D.n, R = D.R;
+    const int idx_pair = D.idx_pair;
+    const unsigned long long counter = D.exchange_counter;
+    for (int r = tid; r < R; r += blockDim.x) D.vscale[r] = 1.0;
+    for (int l = tid; l < n; l += blockDim.x) {
+        const int l_j = D.pair_tb[(size_t)(idx_pair - 1) * n + l];
+        s_rank[l] = l_j >= l + 1 ? 1 : 0;
+    }
+    if (tid == 0) { s_natt = 0; s_nacc = 0; }
+    __syncthreads();
+    if (tid == 0) {                      // exclusive scan: index of the pair's uniform
+        int run = 0;
+        for (int l = 0; l < n; l++) { const int v = s_rank[l]; s_rank[l] = v ? run : -1; run += v; }
+    }
+    __syncthreads();
+    for (int l = tid; l < n; l += blockDim.x) {
+        const int nrand = s_rank[l];
+        if (nrand < 0) continue;
+        const int l_i = l + 1, l_j = D.pair_tb[(size_t)(idx_pair - 1) * n + l];
+        const double rnd = uniform_counter(D.seed, 0x7fffffffu, counter + (unsigned long long)nrand);
+        const int rep_i = D.lab2rep[l_i - 1], rep_j = D.lab2rep[l_j - 1];
+        double temp_m, temp_n;
+        if (D.flg_temp) { temp_m = D.lab_temp[l_i - 1]; temp_n = D.lab_temp[l_j - 1]; }
+        else temp_m = temp_n = D.tempK_default;
+        const double *E = D.recv;
+        const double pot_i_m = E[2 * (rep_i - 1)], pot_i_n = E[2 * (rep_i - 1) + 1];
+        const double pot_j_n = E[2 * (rep_j - 1)], pot_j_m = E[2 * (rep_j - 1) + 1];
+        const double delta = ((pot_j_m - pot_i_m) / temp_m - (pot_j_n - pot_i_n) / temp_n) / SIS_BOLTZ_KCAL_MOL;
+        atomicAdd(&s_natt, 1);
+        if (delta < 0.0 || rnd <= exp(-delta)) {
+            atomicAdd(&s_nacc, 1);
+            D.rep2lab[rep_i - 1] = l_j; D.rep2lab[rep_j - 1] = l_i;
+            D.lab2rep[l_i - 1] = rep_j; D.lab2rep[l_j - 1] = rep_i;
+            if (D.flg_temp) {   // scale_velo, src/replica_exchange.F90:175-213
+                const double sf = sqrt(temp_n / temp_m);
+                const int li = rep_i - 1 - D.rank * R, lj = rep_j - 1 - D.rank * R;
+                if (li >= 0 && li < R) D.vscale[li] = sf;
+                if (lj >= 0 && lj < R) D.vscale[lj] = 1.0 / sf;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        D.idx_pair = (idx_pair == D.ncol) ? 1 : idx_pair + 1;
+        D.exchange_counter = counter + (unsigned long long)((n + 1) / 2);   // the reference draws ceil(n/2) numbers up front
+        D.n_attempt += s_natt; D.n_accept += s_nacc;
+    }
+    for (int r = tid; r < R; r += blockDim.x) {
+        RepParams rp = S.rp[r];
+        remd_apply_label(D, rp, D.lab_rp[D.rep2lab[D.rank * R + r] - 1]);
+        S.rp[r] = rp;
+    }
+}
+__global__ void k_remd_scale(DevSys S, const RemdDev *Dp)
+{
+    const int rep = blockIdx.y;
+    const double f = Dp->vscale[rep];
+    if (f == 1.0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S.nmp * 3) S.vel[(size_t)rep * S.nmp * 3 + i] *= f;
 }

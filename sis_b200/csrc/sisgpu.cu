@@ -182,6 +182,20 @@ struct sisgpu {
     GridInfo grid_host{};                // last grid written to d_grid by the host
     bool grid_host_valid = false;
     int dev_nrebuild_seen = 0;           // DevMisc::nrebuild at the last sync
+    bool last_launch_local = false;
+    // device-resident REMD state (exchange steps inside md_steps without host round trips)
+    int remd_device = 1;                 // option "remd_device"
+    double remd_cut_max = 0.0;           // largest ele_cutoff any label can bring to a local replica (cutoff_type 2)
+    DBuf<RemdDev> d_remd;
+    DBuf<int> d_pair_tb, d_rep2lab, d_lab2rep, d_has_opp;
+    DBuf<double> d_lab_temp, d_vscale;
+    DBuf<RepParams> d_lab_rp;
+    // pending device-side timings: (start, end, accumulator), resolved at the next synchronisation
+    struct Pending { cudaEvent_t a, b; double *acc; };
+    std::vector<Pending> ev_pending;
+    std::vector<cudaEvent_t> ev_free;
+    int local_kernel = 1;                // option "local_kernel": replica-local mode of k_md_fast (one CTA per replica)
+    int local_ncand = -1;                // sequence-allowed base pairs of one replica (bound of the per-CTA candidates)
     int pipeline = 1;                    // option "pipeline": device-driven list rebuilds inside md_steps
     double est_cycle_steps = 50.0;       // running estimate of MD steps between two list rebuilds
     std::vector<cudaEvent_t> ev_pool;    // timing of the pipelined loop
@@ -251,6 +265,12 @@ int sisgpu_destroy(sisgpu_t *h)
     h->d_ene_counter.release(); h->d_bar.release(); h->d_top2_slots.release(); h->d_cta_item0.release(); h->d_cell_sorted.release(); h->d_grid.release();
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     h->ev_pool.clear();
+    for (auto &p : h->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    h->ev_pending.clear();
+    for (auto e : h->ev_free) cudaEventDestroy(e);
+    h->ev_free.clear();
+    h->d_remd.release(); h->d_pair_tb.release(); h->d_rep2lab.release(); h->d_lab2rep.release(); h->d_has_opp.release();
+    h->d_lab_temp.release(); h->d_vscale.release(); h->d_lab_rp.release();
     h->d_rp.release(); h->d_rp_alt.release(); h->d_sync.release();
     if (h->graph_chunk) cudaGraphExecDestroy(h->graph_chunk);
     h->d_f_pair.release(); h->d_f_loc.release(); h->d_f_bp.release(); h->d_bp_half.release(); h->d_nbp_half.release();
@@ -348,6 +368,7 @@ int sisgpu_set_ff_bp(sisgpu_t *h, int model, int min_loop, int max_bp_per_nt, in
         b.angl_k1 = v[3]; b.angl_k2 = v[4]; b.angl_k3 = v[5]; b.angl_k4 = v[6];
         b.angl_theta1 = v[7]; b.angl_theta2 = v[8]; b.angl_theta3 = v[9]; b.angl_theta4 = v[10];
         b.dihd_k1 = v[11]; b.dihd_k2 = v[12]; b.dihd_phi1 = v[13]; b.dihd_phi2 = v[14];
+        b.cos_phi1 = cos(b.dihd_phi1); b.sin_phi1 = sin(b.dihd_phi1); b.cos_phi2 = cos(b.dihd_phi2); b.sin_phi2 = sin(b.dihd_phi2);
         P.bp[1 + t] = b;
         BpPara s = b;   // CG / UA / UG: src/read_force_field.F90:203-207
         std::swap(s.angl_k1, s.angl_k2);
@@ -685,6 +706,14 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     const int N = h->nmp, R = h->nrep;
     TRY(h->d_meta.upload(meta));
     TRY(h->d_seq.upload(h->seq));
+    h->local_ncand = -1;
+    if (N <= FAST_GROUPS) {   // bound of the bp candidates k_md_fast can meet in its replica-local mode
+        int cnt = 0, t = 0;
+        for (int i = 0; i < N; i++)
+            for (int j = i + 1; j < N; j++)
+                cnt += bp_lookup(h->bp_model, h->bp_min_loop, h->bp3_hash.data(), h->seq.data(), i, meta[i], j, meta[j], &t) > 0;
+        h->local_ncand = cnt;
+    }
     TRY(h->d_coef.upload(coef));
     TRY(h->d_mass.upload(h->mass));
     TRY(h->d_hash.upload(h->bp3_hash));
@@ -745,7 +774,9 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     S.rest_id = h->d_rest_id.p; S.rest_rcut = h->d_rest_rcut.p; S.rest_para = h->d_rest_para.p;
     S.ncell_cap = 0;
     h->K = h->KB = 0;
-    TRY(alloc_lists(h, 128, 16));
+    // systems of at most 64 beads: rows that can hold every partner, so that an in-kernel rebuild
+    // (k_md_fast, replica-local mode) can never overflow
+    TRY(alloc_lists(h, 128, N <= FAST_GROUPS ? std::max(16, (N + 7) / 8 * 8) : 16));
     TRY(alloc_cells(h, 4096));
     h->finalized = true;
     TRY(push_rp(h));
@@ -833,6 +864,37 @@ static void timer_end(sisgpu *h, double &acc)
     acc += ms;
 }
 
+// device-side interval timing without a synchronisation: span_begin / span_end bracket enqueued
+// work, spans_resolve adds the elapsed times to their accumulators after the next sync
+static int span_begin(sisgpu *h)
+{
+    if (!h->timing) return -1;
+    sisgpu::Pending p{};
+    for (cudaEvent_t *e : {&p.a, &p.b}) {
+        if (!h->ev_free.empty()) { *e = h->ev_free.back(); h->ev_free.pop_back(); }
+        else cudaEventCreate(e);
+    }
+    p.acc = nullptr;
+    cudaEventRecord(p.a, h->stream);
+    h->ev_pending.push_back(p);
+    return (int)h->ev_pending.size() - 1;
+}
+static void span_end(sisgpu *h, int id, double *acc)
+{
+    if (id < 0) return;
+    h->ev_pending[id].acc = acc;
+    cudaEventRecord(h->ev_pending[id].b, h->stream);
+}
+static void spans_resolve(sisgpu *h)   // call after a stream synchronisation
+{
+    for (auto &p : h->ev_pending) {
+        float ms = 0;
+        if (p.acc && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) *p.acc += ms;
+        h->ev_free.push_back(p.a); h->ev_free.push_back(p.b);
+    }
+    h->ev_pending.clear();
+}
+
 static NlArgs nl_args(const sisgpu *h, bool all_pairs)
 {
     NlArgs A{};
@@ -842,6 +904,8 @@ static NlArgs nl_args(const sisgpu *h, bool all_pairs)
     A.excl_bond = h->excl_bond; A.excl_angle = h->excl_angle;
     A.bp_model = h->bp_model; A.bp_min_loop = h->bp_min_loop;
     A.all_pairs = all_pairs;
+    A.ele_cutoff_type = h->P.flg_ele ? h->ele_cutoff_type : 0;
+    A.ele_cutoff_inp = h->ele_cutoff_inp;
     return A;
 }
 
@@ -879,6 +943,16 @@ static int fast_ncta_of(sisgpu *h)
     const int ncta_max = std::min(std::min(h->coop_blocks, FAST_MAX_CTA), PART_MAX_ITEMS / FAST_GROUPS);
     if (nitems > (long long)ncta_max * FAST_GROUPS) return 0;
     return (int)std::min<long long>(ncta_max, nitems);
+}
+
+// replica-local mode of k_md_fast: one CTA owns one whole replica and rebuilds its lists itself
+static bool fast_local_ok(sisgpu *h)
+{
+    if (!h->fast_kernel || !h->local_kernel || ensure_coop_blocks(h)) return false;
+    if (h->nmp > FAST_GROUPS || h->nrep > std::min(h->coop_blocks, FAST_MAX_CTA)) return false;
+    if (h->P.flg_stage || h->P.ntwz_DCF || h->P.ntwz_FR || h->P.nrest || h->P.flg_bias_ss || h->P.flg_bias_rg) return false;
+    if (h->K < h->nmp || h->KB < h->nmp - 1) return false;
+    return h->local_ncand >= 0 && h->local_ncand <= FAST_BPC;
 }
 
 // cell grid over [lo, hi] with cells of at least rc
@@ -929,7 +1003,9 @@ static void enqueue_nl_tail(sisgpu *h)
 {
     const int N = h->nmp, R = h->nrep;
     k_nl_bp_slots<<<dim3((N * h->KB + 255) / 256, R), 256, 0, h->stream>>>(h->S, h->d_rep_active.p);
-    k_nl_partition<<<1, 1024, 0, h->stream>>>(h->S, h->d_rep_active.p, h->fast_kernel ? fast_ncta_of(h) : 0, FAST_GROUPS);
+    const bool local = fast_local_ok(h);
+    k_nl_partition<<<1, 1024, 0, h->stream>>>(h->S, h->d_rep_active.p, local ? h->nrep : (h->fast_kernel ? fast_ncta_of(h) : 0),
+                                              FAST_GROUPS, local ? 1 : 0);
     h->launches += 2;
 }
 
@@ -1036,6 +1112,7 @@ static int enqueue_nl_chain(sisgpu *h, int force_all, long long stop)
             rc = std::max(rc, h->rep[r].ele_cutoff);
             if (h->ele_cutoff_type == 2) rc = std::max(rc, h->ele_cutoff_inp * h->rep[r].lambdaD);
         }
+    if (h->flg_replica) rc = std::max(rc, h->remd_cut_max);   // labels met during an enqueued batch
     PA.rc = rc + h->nl_margin;
     PA.ele_cutoff_inp = h->ele_cutoff_inp; PA.ele_cutoff_type = h->ele_cutoff_type; PA.flg_ele = h->P.flg_ele;
     PA.pbc = h->P.flg_pbc; PA.force_all = force_all; PA.stop = stop;
@@ -1636,6 +1713,96 @@ int sisgpu_replica_exchange(sisgpu_t *h, const double *E, const double *uniforms
     return 0;
 }
 
+// ---- device-resident exchange step ------------------------------------------------------------
+// Host tables -> device (the host copies are authoritative between md_steps calls: the per-call API
+// sisgpu_energy_replica / sisgpu_replica_exchange works on them).
+static int remd_upload(sisgpu *h)
+{
+    const int n = h->nrep_all, R = h->nrep;
+    if (h->d_rep2lab.n != (size_t)n) {
+        TRY(h->d_rep2lab.alloc(n)); TRY(h->d_lab2rep.alloc(n)); TRY(h->d_lab_temp.alloc(n)); TRY(h->d_lab_rp.alloc(n));
+        TRY(h->d_has_opp.alloc(R)); TRY(h->d_vscale.alloc(R)); TRY(h->d_remd.alloc(1));
+    }
+    if (h->d_pair_tb.n != h->pair_tb.size()) TRY(h->d_pair_tb.alloc(h->pair_tb.size()));
+    if (h->d_gather_recv.n < 2 * (size_t)n) TRY(h->d_gather_recv.alloc(2 * (size_t)n));
+    // parameter block of every label: what apply_label + fill_rp give a replica that holds it
+    std::vector<RepParams> lab(n);
+    std::vector<double> ltemp(n);
+    const HostRep saved = h->rep[0];
+    h->remd_cut_max = 0.0;
+    for (int l = 1; l <= n; l++) {
+        apply_label(h, 0, l);
+        fill_rp(h, 0, lab[l - 1]);
+        if (h->P.flg_ele && h->ele_cutoff_type == 2) h->remd_cut_max = std::max(h->remd_cut_max, h->ele_cutoff_inp * h->rep[0].lambdaD);
+        ltemp[l - 1] = h->flg_repvar[REPT_TEMP] ? h->lab2val[(size_t)REPT_TEMP * n + l - 1] : saved.tempK;
+        h->rep[0] = saved;
+    }
+    RemdDev D{};
+    D.n = n; D.ncol = 2 * h->ndim_replica; D.idx_pair = h->idx_pair; D.R = R; D.rank = h->rank;
+    D.flg_temp = h->flg_repvar[REPT_TEMP];
+    D.flg_ele_var = h->P.flg_ele && (h->flg_repvar[REPT_TEMP] || h->flg_repvar[REPT_ION]);
+    D.flg_twz = h->flg_repvar[REPT_TWZDCF]; D.flg_rg = h->flg_repvar[REPT_RG];
+    D.seed = h->seed; D.exchange_counter = h->exchange_counter;
+    D.n_attempt = h->n_attempt; D.n_accept = h->n_accept;
+    D.tempK_default = h->rep[0].tempK;
+    D.pair_tb = h->d_pair_tb.p; D.rep2lab = h->d_rep2lab.p; D.lab2rep = h->d_lab2rep.p;
+    D.lab_temp = h->d_lab_temp.p; D.lab_rp = h->d_lab_rp.p; D.rp_alt = h->d_rp_alt.p; D.has_opp = h->d_has_opp.p;
+    D.send = h->d_gather_send.p; D.recv = h->d_gather_recv.p; D.vscale = h->d_vscale.p;
+    CK(cudaMemcpyAsync(h->d_pair_tb.p, h->pair_tb.data(), h->pair_tb.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_rep2lab.p, h->rep2lab.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_lab2rep.p, h->lab2rep.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_lab_temp.p, ltemp.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_lab_rp.p, lab.data(), n * sizeof(RepParams), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_remd.p, &D, sizeof D, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // the sources are locals
+    return 0;
+}
+// device tables -> host mirrors after the last enqueued exchange (the stream is synchronised)
+static int remd_download(sisgpu *h)
+{
+    const int n = h->nrep_all, R = h->nrep;
+    RemdDev D;
+    CK(cudaMemcpy(&D, h->d_remd.p, sizeof D, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h->rep2lab.data(), h->d_rep2lab.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h->lab2rep.data(), h->d_lab2rep.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    h->idx_pair = D.idx_pair; h->exchange_counter = D.exchange_counter;
+    h->n_attempt = D.n_attempt; h->n_accept = D.n_accept;
+    for (int irep = 0; irep < R; irep++) apply_label(h, irep, h->rep2lab[h->rank * R + irep]);
+    return 0;
+}
+// one exchange step, enqueued: energy_replica (own + partner parameters), the all-gather that
+// replaces MPI_ALLREDUCE (src/job_md.F90:531-533), replica_exchange and the parameter refresh
+static int enqueue_exchange(sisgpu *h)
+{
+    const int R = h->nrep, n = h->nrep_all;
+    const int sp = span_begin(h);
+    launch_rg(h, -1);
+    TRY(energy_launch(h, -1, nullptr));
+    k_remd_prepare<<<(R + 63) / 64, 64, 0, h->stream>>>(h->S, h->d_remd.p);
+    {
+        // cross energies: bp term recomputed with the partner temperature (flg_bp_energy = .False., :72)
+        RepParams *saved = h->S.rp;
+        h->S.rp = h->d_rp_alt.p;
+        launch_bp_eval<1>(h, -1, false, 0.0, 0, 0, 0, h->P.temp_independent);
+        launch_rg(h, -1);
+        TRY(energy_launch(h, -1, nullptr));
+        h->S.rp = saved;
+    }
+    k_remd_pack<<<(R + 63) / 64, 64, 0, h->stream>>>(h->S, h->d_remd.p);
+    if (h->nranks > 1) {
+        if (!h->nccl_comm) return set_err("sisgpu_comm_init not called for a multi-rank REMD");
+        int rc = g_nccl.AllGather(h->d_gather_send.p, h->d_gather_recv.p, 2 * (size_t)R, NCCL_FLOAT64, h->nccl_comm, h->stream);
+        if (rc) return set_err("ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    } else {
+        CK(cudaMemcpyAsync(h->d_gather_recv.p, h->d_gather_send.p, 2 * (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    k_remd_exchange<<<1, 256, 0, h->stream>>>(h->S, h->d_remd.p);
+    k_remd_scale<<<dim3((3 * h->nmp + 255) / 256, R), 256, 0, h->stream>>>(h->S, h->d_remd.p);
+    h->launches += 4;
+    span_end(h, sp, &h->t_rex);
+    return 0;
+}
+
 // Bead ranges of k_md_fast: contiguous runs of at most FAST_GROUPS flattened (replica, bead) items,
 // one per CTA, chosen so that the largest per-CTA pair work (row entries + a per-bead constant) is
 // minimal for the number of SMs -- the step time is the time of the busiest CTA.
@@ -1647,17 +1814,20 @@ static int launch_persistent(sisgpu *h, long long stop)
     StepArgs A = step_args(h, 0x7FEu, 0, -1, 1);
     const long long nitems = (long long)R * h->nmp;
     CK(cudaMemsetAsync(h->d_bar.p, 0, 64 * sizeof(unsigned), h->stream));
-    void *args[] = {&h->S, &h->P, &A, &stop};
+    NlArgs NA = nl_args(h, false);
+    void *args[] = {&h->S, &h->P, &A, &stop, &NA};
     // k_md_fast: one bead per 8-lane group, rows / candidates / bonded tables on chip
-    const int want_fast = h->fast_kernel ? fast_ncta_of(h) : 0;
+    const bool local = fast_local_ok(h);
+    const int want_fast = local ? R : (h->fast_kernel ? fast_ncta_of(h) : 0);
     const size_t smem_fast = ((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)3 * FAST_GROUPS * h->K * sizeof(uint32_t);   // rows, sort scratch / unit forces, classes / unit tables
     long long ncand_total = 0;
     for (int r = 0; r < R; r++) ncand_total += h->nbp_half_rep.empty() ? h->nbp_half_max : h->nbp_half_rep[r];
     const bool biases = h->P.flg_stage || h->P.ntwz_DCF || h->P.ntwz_FR || h->P.nrest;
     const bool fast_ok = want_fast > 0 && !biases && h->K >= 24 && smem_fast <= 200 * 1024 &&
-                         3 * (ncand_total / want_fast) + 16 <= FAST_BPC;
+                         (local || 3 * (ncand_total / want_fast) + 16 <= FAST_BPC);
+    h->last_launch_local = fast_ok && local;
     if (fast_ok) {
-        void *fn = (void *)k_md_fast<1>;
+        void *fn = local ? (void *)k_md_fast<1, true> : (void *)k_md_fast<1, false>;
         if (smem_fast > h->fast_smem_set || fn != h->fast_fn_set) {
             CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
             h->fast_smem_set = smem_fast; h->fast_fn_set = fn;
@@ -1701,30 +1871,21 @@ static int md_run_pipelined(sisgpu *h, long long stop)
         const int nreb_before = h->h_misc->nrebuild;
         int ncyc = (int)ceil((double)(stop - cur) / std::max(1.0, h->est_cycle_steps) * 1.2) + 1;
         ncyc = std::max(1, std::min(ncyc, 32));
-        if (h->timing) {
-            while ((int)h->ev_pool.size() < 2 * 32 + 1) {
-                cudaEvent_t e;
-                CK(cudaEventCreate(&e));
-                h->ev_pool.push_back(e);
-            }
-        }
+        const bool local = fast_local_ok(h) && !(h->h_misc->max_force_flag & 4);
+        if (local) ncyc = 1;      // the kernel rebuilds its own lists and always reaches `stop`
         for (int c = 0; c < ncyc; c++) {
-            if (h->timing) cudaEventRecord(h->ev_pool[2 * c], h->stream);
-            TRY(enqueue_nl_chain(h, 0, stop));
-            if (h->timing) cudaEventRecord(h->ev_pool[2 * c + 1], h->stream);
+            if (!local) {
+                const int sp = span_begin(h);
+                TRY(enqueue_nl_chain(h, 0, stop));
+                span_end(h, sp, &h->t_nl);
+            }
+            const int sp = span_begin(h);
             TRY(launch_persistent(h, stop));
+            span_end(h, sp, &h->t_step);
         }
-        if (h->timing) cudaEventRecord(h->ev_pool[2 * ncyc], h->stream);
         TRY(sync_ctl(h));
         CK(cudaGetLastError());
-        if (h->timing) {
-            for (int c = 0; c < ncyc; c++) {
-                float a = 0, b = 0;
-                cudaEventElapsedTime(&a, h->ev_pool[2 * c], h->ev_pool[2 * c + 1]);
-                cudaEventElapsedTime(&b, h->ev_pool[2 * c + 1], h->ev_pool[2 * c + 2]);
-                h->t_nl += a; h->t_step += b;
-            }
-        }
+        spans_resolve(h);
         const int nreb = h->h_misc->nrebuild - nreb_before;
         TRY(after_persistent_sync(h));
         const long long adv = (long long)h->h_ctl->step - cur;
@@ -1772,6 +1933,53 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
     const unsigned mask_all = 0x7FEu;
     // launch_mode 2 with device-driven rebuilds (md_run_pipelined) needs no host-side trigger
     const bool pipelined = h->launch_mode == 2 && h->nstep_bp_MC == 0 && !h->P.flg_bias_rg && h->pipeline && !h->P.flg_bias_ss;
+    if (pipelined && h->flg_replica && h->nstep_exchange > 0 && h->remd_device && h->nrep_all <= REMD_DEV_MAX_LABELS) {
+        // REMD with the exchange step on the device: MD intervals and exchange chains are enqueued
+        // back to back; the host tables are refreshed once at the end
+        TRY(remd_upload(h));
+        const long long nex = h->nstep_exchange;
+        while ((long long)h->h_ctl->step < target) {
+            const long long cur = (long long)h->h_ctl->step;
+            if (fast_local_ok(h) && !(h->h_misc->max_force_flag & 4)) {
+                long long s = cur;
+                for (int nint = 0; s < target && nint < 64; nint++) {
+                    const long long stop = std::min<long long>(target, (s / nex + 1) * nex);
+                    const int sp = span_begin(h);
+                    TRY(launch_persistent(h, stop));
+                    span_end(h, sp, &h->t_step);
+                    if (!h->last_launch_local) return set_err("internal: replica-local kernel not selected");
+                    if (stop % nex == 0) TRY(enqueue_exchange(h));
+                    s = stop;
+                }
+                TRY(sync_ctl(h));
+                CK(cudaGetLastError());
+                spans_resolve(h);
+                TRY(after_persistent_sync(h));
+                if ((long long)h->h_ctl->step != s) return set_err("internal: replica-local kernel stopped at step %lld, expected %lld", (long long)h->h_ctl->step, s);
+            } else {
+                const long long stop = std::min<long long>(target, (cur / nex + 1) * nex);
+                TRY(md_run_pipelined(h, stop));
+                if (stop % nex == 0) TRY(enqueue_exchange(h));
+            }
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaGetLastError());
+        spans_resolve(h);
+        TRY(remd_download(h));
+        if (h->ele_cutoff_type == 2 && h->P.flg_ele) {   // refreshed by the device-side rebuilds
+            std::vector<RepParams> rp(R);
+            CK(cudaMemcpy(rp.data(), h->d_rp.p, R * sizeof(RepParams), cudaMemcpyDeviceToHost));
+            for (int r = 0; r < R; r++) h->rep[r].ele_cutoff = rp[r].ele_cutoff;
+        }
+        TRY(refresh_half_counts(h));
+        if (h->h_misc->max_force_flag & 1) {
+            fprintf(stderr, "Warning: maxval(forces) > 100.0 during the last md_steps call (step %lld)\n", (long long)h->h_ctl->step);
+            h->h_misc->max_force_flag = 0;
+            CK(cudaMemcpy(&h->S.misc->max_force_flag, &h->h_misc->max_force_flag, sizeof(int), cudaMemcpyHostToDevice));
+        }
+        if (nrebuild_out) *nrebuild_out = h->nrebuild - nreb0;
+        return 0;
+    }
     while ((long long)h->h_ctl->step < target) {
         // rebuild requested by the previous position update (src/job_md.F90:388-395)
         bool any = false;
@@ -1917,6 +2125,8 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
     else if (s == "fast_kernel") h->fast_kernel = (int)value;
     else if (s == "fast_unroll") h->fast_unroll = (int)value;
     else if (s == "pipeline") h->pipeline = (int)value;
+    else if (s == "remd_device") h->remd_device = (int)value;
+    else if (s == "local_kernel") { h->local_kernel = (int)value; h->lists_built = false; }
     else if (s == "profile") {   // phase clocks of the persistent kernel (block 0): get_timers out[4..8]
         if (value != 0) { TRY(h->d_prof.alloc(16 + 8 * FAST_MAX_CTA)); h->S.prof = h->d_prof.p; }
         else h->S.prof = nullptr;
