@@ -234,3 +234,33 @@ def test_persistent_kernel_multi_replica():
     for r in range(4):
         assert np.abs(outs[0][r] - outs[1][r]).max() < 1e-7
     assert np.abs(outs[0][0] - outs[0][3]).max() > 1e-3   # the replicas really differ
+
+
+def test_replica_local_kernel_rebuilds_in_place():
+    """Replica-local mode of k_md_fast (one CTA per replica, lists rebuilt inside the kernel, no
+    grid barrier): same trajectories, same number of rebuilds (src/job_md.F90:388-395) and the
+    same lists as the stream path with host-driven rebuilds, replicas rebuilding at different steps."""
+    from sis_b200.api import SisGpu
+    temps = [290.0, 320.0, 350.0, 380.0]
+    spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=0).replicated(4, temps=temps)
+    spec.nl_margin = 1.5
+    res = []
+    for opts in (dict(launch_mode=0), dict(launch_mode=2, local_kernel=1), dict(launch_mode=2, local_kernel=0)):
+        g = SisGpu(0, **opts)
+        spec.configure(g)
+        for r in range(4):
+            g.init_velocities(r)
+            g.neighbor_list(r)
+        nreb = g.md_steps(150)
+        nreb += g.md_steps(50)
+        res.append((nreb, [g.get_state(r) for r in range(4)], [g.get_lists(r) for r in range(4)], g.get_step()))
+    assert res[0][0] == res[1][0] == res[2][0] and res[0][0] >= 4
+    assert res[0][3] == res[1][3] == 200
+    for other in (res[1], res[2]):
+        for r in range(4):
+            for a, b in zip(res[0][1][r], other[1][r]):
+                assert np.abs(a - b).max() < 1e-6
+            for la, lb in zip(res[0][2][r][:3], other[2][r][:3]):   # wca, ele, bp as index sets
+                ka = np.lexsort(la.T[::-1]) if len(la) else []
+                kb = np.lexsort(lb.T[::-1]) if len(lb) else []
+                assert np.array_equal(la[ka], lb[kb])
