@@ -77,6 +77,16 @@ def algorithmic_bytes_per_step(nmp, st):
     return 272 * nmp + 8 * st["P_wca"] + 8 * st["P_ele"] + 53 * st["P_bp"]
 
 
+def ncu_traffic(workload):
+    """dram bytes (read + write) per MD step of the step kernel from the committed ncu --set full
+    capture of this workload (profiles/r01_traffic.json, written by tools/ncu_traffic.py); None if
+    there is no capture for it."""
+    f = ROOT / "profiles" / "r01_traffic.json"
+    if not f.exists():
+        return None
+    return json.loads(f.read_text()).get(workload, {}).get("dram_bytes_per_md_step")
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (the oracle port: no Fortran compiler exists
     here, so oracle/_ref cannot be built) on the host cores, bounded sample of the same workload."""
@@ -174,12 +184,13 @@ def main():
     g.get_timers(reset=True)
     l0 = g.launch_count()
     barrier()
-    t0 = time.perf_counter()
+    g.mark(0)                      # CUDA events on the library's stream: device-side time of the region
     nreb = 0
     for _ in range(args.steps):
         nreb += g.md_steps(args.md_steps)
+    g.mark(1)
+    dt = 1e-3 * g.elapsed_ms()
     barrier()
-    dt = time.perf_counter() - t0
     launches = g.launch_count() - l0
     timers = g.get_timers(reset=False)
     if args.profile and os.environ.get("SIS_CTA_PROFILE"):
@@ -197,14 +208,15 @@ def main():
     # ---- end to end through the C ABI with host buffers ---------------------------------
     x, v, a = g.get_state(0)
     barrier()
-    t0 = time.perf_counter()
+    g.mark(0)
     for _ in range(args.steps):
         g.set_state(0, x, v, a)
         g.md_steps(args.md_steps)
         x, v, a = g.get_state(0)
         e = g.energy_sumup(0, spec.tempK, False)
+    g.mark(1)
+    dte = 1e-3 * g.elapsed_ms()
     barrier()
-    dte = time.perf_counter() - t0
     tt = torch.tensor([dte], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -234,7 +246,7 @@ def main():
                     "d2h_bytes_per_step": 3 * nmp * 24 + 88},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                         "frac": (achieved / hbm) if achieved else None, "traffic": None,
+                         "frac": (achieved / hbm) if achieved else None, "traffic": ncu_traffic(args.workload),
                          "kernel": "k_step", "algorithmic_bytes_per_launch": bytes_step,
                          "us_per_launch": 1e3 * step_ms / nsteps_total if step_ms else None,
                          "peak_source": "measured" if pk.exists() else "fallback"},

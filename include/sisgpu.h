@@ -146,7 +146,9 @@ int sisgpu_check_force(sisgpu_t *h, double tempK, double *f_energy, double *f_fo
 /* launch statistics: kernels launched by this handle since creation */
 int sisgpu_launch_count(sisgpu_t *h, int64_t *n);
 /* options: name = "launch_mode" (0 stream launches, 1 CUDA-graph chunks, 2 persistent kernels =
- * default), "fast_kernel" (0: never use k_md_fast), "chunk", "threads_per_bead", "timing", "profile" */
+ * default), "fast_kernel" (0: never use k_md_fast), "local_kernel" (0: no replica-local mode of
+ * k_md_fast), "pipeline" (0: host-driven list rebuilds), "remd_device" (0: host-driven exchange
+ * steps), "chunk", "threads_per_bead", "timing", "profile" */
 int sisgpu_set_option(sisgpu_t *h, const char *name, double value);
 /* CUDA-event time (ms) accumulated per kernel family since the last reset:
  * out[0] step kernels, out[1] neighbour list, out[2] energy, out[3] exchange;
@@ -154,6 +156,11 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value);
  * phase, barrier, out[8] steps counted, out[9..11] base-pair warps (gate, evaluate, arrive),
  * out[12..13] bonded-table warps (tables, Gaussians) (option "profile"); out must hold 16 doubles */
 int sisgpu_get_timers(sisgpu_t *h, double *out, int reset);
+/* device-side wall clock of a region of calls: sisgpu_mark(h, 0) / sisgpu_mark(h, 1) record a CUDA
+ * event on the library's stream, sisgpu_elapsed_ms returns the time between the two marks (it
+ * waits for mark 1).  Used by bench.py: torch.cuda.Event only sees torch's own stream */
+int sisgpu_mark(sisgpu_t *h, int which);
+int sisgpu_elapsed_ms(sisgpu_t *h, double *ms);
 /* diagnostic: accumulated SM clocks of CTA c of k_md_fast in out[8c..8c+7] = pair units, wait for
  * tables / base pairs, integrate, position barrier, base-pair warps total, wait for the CTA's own
  * warps, active base pairs, spare (option "profile") */

@@ -78,6 +78,14 @@ class SisGpu(CApi):
                                                     (out[9:14] / out[8]).round(1).tolist()))
         return d
 
+    def mark(self, which: int) -> None:
+        self._call("mark", C.c_int(which))
+
+    def elapsed_ms(self) -> float:
+        ms = C.c_double()
+        self._call("elapsed_ms", C.byref(ms))
+        return ms.value
+
     def cta_profile(self, ncta: int) -> np.ndarray:
         out = np.zeros((ncta, 8))
         self._call("get_cta_profile", C.c_int(ncta), _d(out))

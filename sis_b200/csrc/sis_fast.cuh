@@ -422,6 +422,7 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
                     pc[0] += (unsigned long long)(c1 - c0); pc[1] += (unsigned long long)(c2 - c1);
                     pc[2] += (unsigned long long)(c3 - c2); pc[3] += (unsigned long long)(c4 - c3);
                     pc[5] += (unsigned long long)(c1b - c1);
+                    pc[7] += (unsigned long long)nunit * 1000ull + (unsigned long long)C.nb;   // units, beads of the CTA
                     if (blockIdx.x == 0) {
                         S.prof[0] += (unsigned long long)(c1 - c0); S.prof[1] += (unsigned long long)(c2 - c1);
                         S.prof[2] += (unsigned long long)(c3 - c2); S.prof[3] += (unsigned long long)(c4 - c3);

@@ -213,6 +213,7 @@ struct sisgpu {
     int launch_mode = 2, chunk = 16, timing = 0;   // launch_mode 2: persistent kernels (k_md_fast / k_md_fused); 1: CUDA-graph chunks; 0: stream launches
     double t_step = 0, t_nl = 0, t_ene = 0, t_rex = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_mark[2] = {nullptr, nullptr};
     long long istep_host = 0;
 };
 
@@ -2138,6 +2139,24 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
         h->G = g;
         invalidate_graphs(h);
     } else return set_err("unknown option %s", name);
+    return 0;
+}
+
+int sisgpu_mark(sisgpu_t *h, int which)
+{
+    if (which < 0 || which > 1) return set_err("mark index must be 0 or 1");
+    CK(cudaSetDevice(h->device));
+    if (!h->ev_mark[which]) CK(cudaEventCreate(&h->ev_mark[which]));
+    CK(cudaEventRecord(h->ev_mark[which], h->stream));
+    return 0;
+}
+int sisgpu_elapsed_ms(sisgpu_t *h, double *ms)
+{
+    if (!h->ev_mark[0] || !h->ev_mark[1]) return set_err("sisgpu_mark(0) / sisgpu_mark(1) not called");
+    CK(cudaEventSynchronize(h->ev_mark[1]));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, h->ev_mark[0], h->ev_mark[1]));
+    *ms = f;
     return 0;
 }
 
