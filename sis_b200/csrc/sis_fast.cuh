@@ -27,9 +27,13 @@
 constexpr int FAST_MAIN_WARPS = 16, FAST_BP_WARPS = 4, FAST_LOC_WARPS = 4;
 constexpr int FAST_MAIN = 32 * FAST_MAIN_WARPS, FAST_BP = 32 * FAST_BP_WARPS, FAST_LOC = 32 * FAST_LOC_WARPS;
 constexpr int FAST_THREADS = FAST_MAIN + FAST_BP + FAST_LOC;
-constexpr int FAST_GROUPS = FAST_MAIN / 8;        // beads per CTA
+constexpr int FAST_GROUPS = FAST_MAIN / 8;        // 8-lane groups of the pair loop
+constexpr int FAST_OWN = 2 * FAST_GROUPS;         // owner slots = beads per CTA at most: the two 4-lane halves of a
+                                                  // group each own one bead (x, y, z on three lanes), so the bead
+                                                  // ranges can be cut by pair work instead of by bead count
+constexpr int FAST_EMAX = 8192;                   // row entries (padded to octets) of one CTA held in shared memory
 constexpr int FAST_BPGROUPS = FAST_BP / 8;
-constexpr int FAST_NT = FAST_GROUPS + 3;          // term-table slots: starts at item0-3 .. item0+63
+constexpr int FAST_NT = FAST_OWN + 3;             // term-table slots: starts at item0-3 .. item0+127
 constexpr int FAST_BPC = 256;                     // cached bp candidates per CTA
 constexpr int FAST_MAX_CTA = 1024;                // capacity of the top-2 slot array
 
@@ -56,16 +60,16 @@ struct FastShared {
     Vec3 bondf[FAST_NT];        // bond starting at slot: F(first) = -f, F(second) = +f
     Vec3 angf[FAST_NT][2];      // angle starting at slot: F1, F3; F2 = -(F1 + F3)
     Vec3 dihf[FAST_NT][4];      // dihedral starting at slot: F1..F4
-    double gauss[2][FAST_GROUPS][3];
-    double d2[FAST_GROUPS];
-    int nn[FAST_GROUPS], unit_start[FAST_GROUPS + 1];   // row lengths; first pair unit of each bead
-    FastBead bead[FAST_GROUPS];
+    double gauss[2][FAST_OWN][3];
+    double d2[FAST_OWN];
+    int nn[FAST_OWN], unit_start[FAST_OWN + 1];   // row lengths; first pair unit (octet) of each bead
+    FastBead bead[FAST_OWN];
     FastBpCand cand[FAST_BPC];
     int active[FAST_BPC];
     int nactive[2], bp_next[2];      // survivors of the distance gate / next one to evaluate, by step parity
-    int ncand, nextra, overflow;
+    int ncand, nextra, overflow, overflow_rows;
     int extra[FAST_NEXTRA];
-    double fbp[FAST_GROUPS][3];      // base-pair forces on the CTA's beads (this step)
+    double fbp[FAST_OWN][3];         // base-pair forces on the CTA's beads (this step)
     int4 tmeta[FAST_NT];             // bonded-term slots: meta of the first bead
     int tbead[FAST_NT];              // ... its flattened item, -1 = no such bead
     int blocked[2];             // rebuild verdict, indexed by iteration parity
@@ -193,101 +197,122 @@ SIS_D void fast_bp_eval(const DevSys &S, const FFParams &P, FastShared &sh, cons
 // A MAIN thread that leaves at barrier 3 performs the iteration's cta_sync before returning, so
 // every role executes the same number of cta_syncs.  Returns the number of completed steps.
 
-// MAIN role.  The pair work of the CTA is cut into UNITS of eight row entries ("octets"), units are
+// MAIN role.  The rows of the CTA's beads are packed into shared memory octet-aligned: row of owner
+// slot s starts at entry 8 * unit_start[s], so UNIT u is simply entries [8u, 8u + 8).  Units are
 // dealt round-robin to the 64 groups (one entry per lane), so every group runs the same number of
 // iterations whatever the row lengths; each unit's force is written to a fixed slot and the bead's
-// owner adds its units in order (deterministic, no atomics).
+// owner adds its units in order (deterministic, no atomics).  Owner slot s < nb is held by the
+// 4-lane half (s / 64) of group s % 64.
 template <int U>
 SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, const FastCtx &C, FastShared &sh,
                          uint32_t *s_rows)
 {
     (void)A;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 7, grp = tid >> 3;
-    const int nmp = C.nmp, K = C.K, R = C.R;
+    const int nmp = C.nmp, R = C.R;
     unsigned long long step = C.step0;
     int cur = C.cur0;
     const bool prof = S.prof != nullptr && tid == 0;   // every CTA's thread 0: per-CTA phase clocks
     long long c0 = 0, c1 = 0, c1b = 0, c2 = 0, c3 = 0, c4 = 0;
     // shared-memory regions behind the rows: prologue scratch, later the unit tables
-    uint32_t *tmp_all = s_rows + (size_t)FAST_GROUPS * K;
-    unsigned char *cls_all = reinterpret_cast<unsigned char *>(s_rows + (size_t)2 * FAST_GROUPS * K);
-    Vec3 *unitF = reinterpret_cast<Vec3 *>(tmp_all);                 // [nunit]
-    unsigned char *unit_q = cls_all, *unit_o = cls_all + 8 * K + FAST_GROUPS;   // [nunit] each
+    uint32_t *tmp_all = s_rows + FAST_EMAX;
+    unsigned char *cls_all = reinterpret_cast<unsigned char *>(s_rows + 2 * FAST_EMAX);
+    Vec3 *unitF = reinterpret_cast<Vec3 *>(tmp_all);                 // [nunit] (24 bytes per octet of 32-byte scratch)
+    unsigned char *unit_q = cls_all;                                 // [nunit] owner slot of the unit
 
-    // ---- prologue: bead `grp` of the CTA's range -> shared memory ---------------------------------
-    FastBead &B = sh.bead[grp];
-    if (grp < C.nb) {
-        int rep, k;
-        fast_item(C.item0 + grp, nmp, &rep, &k);
-        const int nn = S.nnbr[(size_t)rep * nmp + k];
-        const double4 p = S.pos[cur][(size_t)rep * nmp + k];
-        const Vec3 xk0 = v3(p);
-        const RepParams &Rp = S.rp[rep];
-        const double cut2 = P.flg_ele ? Rp.ele_cutoff * Rp.ele_cutoff : -1.0;
-        // row -> shared memory as a stable partition: pairs inside the Debye-Hueckel / WCA range
-        // now first, the margin shell after them (the lanes of a warp then leave the expensive
-        // branch together); bead-id order, i.e. coalesced gathers, is kept inside each class
-        const uint32_t *row = S.nbr + ((size_t)rep * nmp + k) * K;
-        uint32_t *tmp = tmp_all + grp * K;
-        unsigned char *cls = cls_all + grp * K;
-        const double4 *pos0 = S.pos[cur] + (size_t)rep * nmp;
-        for (int e = lane; e < nn; e += 8) {
-            const uint32_t ent = row[e];
-            const Vec3 v = pbc_vec_d(P, xk0, v3(pos0[ent & NB_IDX]));
-            const double d2 = dot(v, v);
-            const bool near = ((ent & NB_ELE) && d2 <= cut2) || ((ent & NB_WCA) && d2 < P.wca_sigma2);
-            tmp[e] = ent;
-            cls[e] = near ? 0 : 1;
+    // ---- prologue: the beads of the CTA's range -> shared memory ----------------------------------
+    if (tid < FAST_OWN) {
+        int nn = 0;
+        if (tid < C.nb) {
+            int rep, k;
+            fast_item(C.item0 + tid, nmp, &rep, &k);
+            nn = S.nnbr[(size_t)rep * nmp + k];
         }
-        __syncwarp(0xFFu << ((tid & 31) & ~7));
-        int nnear = 0;
-        for (int o = 0; o < nn; o++) nnear += cls[o] == 0;
-        for (int e = lane; e < nn; e += 8) {
-            const int mycls = cls[e];
-            int before = 0;
-            for (int o = 0; o < e; o++) before += cls[o] == mycls;
-            s_rows[grp * K + (mycls ? nnear + before : before)] = tmp[e];
-        }
-        if (lane == 0) {
-            B.meta = S.meta[k];
-            B.rep = rep; B.k = k; B.nn = nn; B.valid = 1;
-            const double4 coef = S.coef[k];
-            B.ca = coef.x; B.cb = coef.y; B.cc = coef.z;
-            B.noise = coef.w * Rp.sqrt_tempK;
-            B.ele_coef = Rp.ele_coef; B.inv_lambdaD = Rp.inv_lambdaD; B.cut2 = cut2;
-            sh.nn[grp] = nn;
-        }
-        if (lane < 3) {
-            const size_t o3 = ((size_t)rep * nmp + k) * 3 + lane;
-            B.x[lane] = lane == 0 ? p.x : lane == 1 ? p.y : p.z;
-            B.v[lane] = S.vel[o3]; B.a[lane] = S.acc[o3]; B.m[lane] = S.move[o3];
-        }
-    } else if (lane == 0) {
-        B.valid = 0; B.nn = 0; B.rep = 0; B.k = 0;
-        sh.nn[grp] = 0;
+        sh.nn[tid] = nn;
     }
-    named_bar_sync(2, FAST_MAIN);                      // rows sorted, scratch free
+    named_bar_sync(2, FAST_MAIN);
     if (warp == 0) {                                   // unit_start = exclusive scan of ceil(nn / 8)
-        const int a = (sh.nn[2 * tid] + 7) >> 3, b = (sh.nn[2 * tid + 1] + 7) >> 3;
-        int incl = a + b;
+        int a[4], tot = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { a[j] = (sh.nn[4 * tid + j] + 7) >> 3; tot += a[j]; }
+        int incl = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, o);
             if (tid >= o) incl += t;
         }
-        sh.unit_start[2 * tid] = incl - a - b;
-        sh.unit_start[2 * tid + 1] = incl - b;
-        if (tid == 31) sh.unit_start[FAST_GROUPS] = incl;
+        int run = incl - tot;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { sh.unit_start[4 * tid + j] = run; run += a[j]; }
+        if (tid == 31) { sh.unit_start[FAST_OWN] = incl; sh.overflow_rows = incl * 8 > FAST_EMAX; }
     }
     named_bar_sync(2, FAST_MAIN);
-    {
-        const int u0 = sh.unit_start[grp], nu = sh.unit_start[grp + 1] - u0;
-        for (int o = lane; o < nu; o += 8) { unit_q[u0 + o] = (unsigned char)grp; unit_o[u0 + o] = (unsigned char)o; }
+    const bool rows_fit = !sh.overflow_rows;
+    for (int slot = grp; slot < FAST_OWN; slot += FAST_GROUPS) {
+        FastBead &B = sh.bead[slot];
+        if (slot < C.nb && rows_fit) {
+            int rep, k;
+            fast_item(C.item0 + slot, nmp, &rep, &k);
+            const int nn = sh.nn[slot], e0 = 8 * sh.unit_start[slot];
+            const double4 p = S.pos[cur][(size_t)rep * nmp + k];
+            const Vec3 xk0 = v3(p);
+            const RepParams &Rp = S.rp[rep];
+            const double cut2 = P.flg_ele ? Rp.ele_cutoff * Rp.ele_cutoff : -1.0;
+            // row -> shared memory as a stable partition: pairs inside the Debye-Hueckel / WCA range
+            // now first, the margin shell after them (the lanes of a warp then leave the expensive
+            // branch together); bead-id order, i.e. coalesced gathers, is kept inside each class
+            const uint32_t *row = S.nbr + ((size_t)rep * nmp + k) * C.K;
+            uint32_t *tmp = tmp_all + e0;
+            unsigned char *cls = cls_all + e0;
+            const double4 *pos0 = S.pos[cur] + (size_t)rep * nmp;
+            for (int e = lane; e < nn; e += 8) {
+                const uint32_t ent = row[e];
+                const Vec3 v = pbc_vec_d(P, xk0, v3(pos0[ent & NB_IDX]));
+                const double d2 = dot(v, v);
+                const bool near = ((ent & NB_ELE) && d2 <= cut2) || ((ent & NB_WCA) && d2 < P.wca_sigma2);
+                tmp[e] = ent;
+                cls[e] = near ? 0 : 1;
+            }
+            __syncwarp(0xFFu << ((tid & 31) & ~7));
+            int nnear = 0;
+            for (int o = 0; o < nn; o++) nnear += cls[o] == 0;
+            for (int e = lane; e < nn; e += 8) {
+                const int mycls = cls[e];
+                int before = 0;
+                for (int o = 0; o < e; o++) before += cls[o] == mycls;
+                s_rows[e0 + (mycls ? nnear + before : before)] = tmp[e];
+            }
+            if (lane == 0) {
+                B.meta = S.meta[k];
+                B.rep = rep; B.k = k; B.nn = nn; B.valid = 1;
+                const double4 coef = S.coef[k];
+                B.ca = coef.x; B.cb = coef.y; B.cc = coef.z;
+                B.noise = coef.w * Rp.sqrt_tempK;
+                B.ele_coef = Rp.ele_coef; B.inv_lambdaD = Rp.inv_lambdaD; B.cut2 = cut2;
+            }
+            if (lane < 3) {
+                const size_t o3 = ((size_t)rep * nmp + k) * 3 + lane;
+                B.x[lane] = lane == 0 ? p.x : lane == 1 ? p.y : p.z;
+                B.v[lane] = S.vel[o3]; B.a[lane] = S.acc[o3]; B.m[lane] = S.move[o3];
+            }
+        } else if (lane == 0) {
+            B.valid = 0; B.nn = 0; B.rep = 0; B.k = 0;
+        }
     }
+    named_bar_sync(2, FAST_MAIN);                      // rows sorted, scratch free
+    if (rows_fit)
+        for (int slot = grp; slot < C.nb; slot += FAST_GROUPS) {
+            const int u0 = sh.unit_start[slot], nu = sh.unit_start[slot + 1] - u0;
+            for (int o = lane; o < nu; o += 8) unit_q[u0 + o] = (unsigned char)slot;
+        }
+    if (tid == 0 && !rows_fit) S.misc->max_force_flag |= 4;   // the host checks the flag after the launch
     cta_sync();                                        // prologue of all roles complete
-    const int nunit = sh.unit_start[FAST_GROUPS];
-    const bool overflow = sh.ncand > FAST_BPC || sh.overflow;
+    const int nunit = sh.unit_start[FAST_OWN];
+    const bool overflow = sh.ncand > FAST_BPC || sh.overflow || sh.overflow_rows;
     const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
+    // owner slot of this lane: half `lane >> 2` of the group, component `lane & 3` (3 idles)
+    const int sub = lane >> 2, comp = lane & 3, slot = grp + FAST_GROUPS * sub;
+    FastBead &B = sh.bead[slot];
     int n = 0;
     if (!sh.blocked[0] && !overflow)
     for (; n < C.nsteps; n++) {
@@ -302,8 +327,8 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
             int q = 0;
             if (u < nunit) {
                 q = unit_q[u];
-                const int e = unit_o[u] * 8 + lane;
-                ent = e < sh.bead[q].nn ? s_rows[q * K + e] : 0u;
+                const int e = 8 * u + lane;
+                ent = e - 8 * sh.unit_start[q] < sh.bead[q].nn ? s_rows[e] : 0u;
                 if (ent) xj = v3(posb[(size_t)sh.bead[q].rep * nmp + (ent & NB_IDX)]);
             }
             while (u < nunit) {
@@ -313,8 +338,8 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
                 int qn = 0;
                 if (un < nunit) {
                     qn = unit_q[un];
-                    const int e = unit_o[un] * 8 + lane;
-                    ent_n = e < sh.bead[qn].nn ? s_rows[qn * K + e] : 0u;
+                    const int e = 8 * un + lane;
+                    ent_n = e - 8 * sh.unit_start[qn] < sh.bead[qn].nn ? s_rows[e] : 0u;
                     if (ent_n) xn = v3(posb[(size_t)sh.bead[qn].rep * nmp + (ent_n & NB_IDX)]);
                 }
                 Vec3 F = mk(0.0, 0.0, 0.0);
@@ -335,56 +360,57 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
         named_bar_sync(3, FAST_MAIN + FAST_LOC + FAST_BP);   // all units, bonded tables, base-pair forces, rebuild verdict
         if (prof) c1b = clock64();
         if (sh.blocked[n & 1]) { cta_sync(); break; }
-        const bool valid = B.valid != 0;
+        const bool valid = B.valid != 0 && comp < 3;
         double f = 0.0;
-        if (valid && lane < 3) {
-            for (int u = sh.unit_start[grp]; u < sh.unit_start[grp + 1]; u++) f += (&unitF[u].x)[lane];
+        if (valid) {
+            for (int u = sh.unit_start[slot]; u < sh.unit_start[slot + 1]; u++) f += (&unitF[u].x)[comp];
             const int4 meta = B.meta;
-            const int l = meta.z, len = meta.y, s0 = grp + 3;
+            const int l = meta.z, len = meta.y, s0 = slot + 3;
             const bool circ = meta.w & MF_CIRC;
-            if (circ ? len > 1 : l + 1 < len) f -= (&sh.bondf[s0].x)[lane];
-            if (l >= 1) f += (&sh.bondf[s0 - 1].x)[lane];
-            if (circ ? len > 2 : l + 2 < len) f += (&sh.angf[s0][0].x)[lane];
-            if (l >= 1 && (circ ? len > 2 : l + 1 < len)) f -= (&sh.angf[s0 - 1][0].x)[lane] + (&sh.angf[s0 - 1][1].x)[lane];
-            if (l >= 2) f += (&sh.angf[s0 - 2][1].x)[lane];
+            if (circ ? len > 1 : l + 1 < len) f -= (&sh.bondf[s0].x)[comp];
+            if (l >= 1) f += (&sh.bondf[s0 - 1].x)[comp];
+            if (circ ? len > 2 : l + 2 < len) f += (&sh.angf[s0][0].x)[comp];
+            if (l >= 1 && (circ ? len > 2 : l + 1 < len)) f -= (&sh.angf[s0 - 1][0].x)[comp] + (&sh.angf[s0 - 1][1].x)[comp];
+            if (l >= 2) f += (&sh.angf[s0 - 2][1].x)[comp];
             if (C.dih_on) {
-                if (circ ? len > 3 : l + 3 < len) f += (&sh.dihf[s0][0].x)[lane];
-                if (l >= 1 && (circ ? len > 3 : l + 2 < len)) f += (&sh.dihf[s0 - 1][1].x)[lane];
-                if (l >= 2 && (circ ? len > 3 : l + 1 < len)) f += (&sh.dihf[s0 - 2][2].x)[lane];
-                if (l >= 3) f += (&sh.dihf[s0 - 3][3].x)[lane];
+                if (circ ? len > 3 : l + 3 < len) f += (&sh.dihf[s0][0].x)[comp];
+                if (l >= 1 && (circ ? len > 3 : l + 2 < len)) f += (&sh.dihf[s0 - 1][1].x)[comp];
+                if (l >= 2 && (circ ? len > 3 : l + 1 < len)) f += (&sh.dihf[s0 - 2][2].x)[comp];
+                if (l >= 3) f += (&sh.dihf[s0 - 3][3].x)[comp];
             }
-            if (circ && l < 3) f += fast_closure_terms(S, P, S.pos[cur] + (size_t)B.rep * nmp, meta, B.k, lane);
+            if (circ && l < 3) f += fast_closure_terms(S, P, S.pos[cur] + (size_t)B.rep * nmp, meta, B.k, comp);
         }
         if (prof) c2 = clock64();
         // ---- integrate (src/job_md.F90:415-456) ----------------------------------------------
         double mv = 0.0;
-        if (valid && lane < 3) {
-            f += sh.fbp[grp][lane];
-            sh.fbp[grp][lane] = 0.0;
-            const double g = sh.gauss[(step + 1ull) & 1][grp][lane];
+        if (valid) {
+            f += sh.fbp[slot][comp];
+            sh.fbp[slot][comp] = 0.0;
+            const double g = sh.gauss[(step + 1ull) & 1][slot][comp];
             double dx;
             if (P.integrator == 1) {
                 const double accels_pre = B.noise * g;
-                const double v = B.ca * B.v[lane] + B.cb * f + (B.a[lane] + accels_pre);
-                B.v[lane] = v;
-                B.a[lane] = accels_pre;
+                const double v = B.ca * B.v[comp] + B.cb * f + (B.a[comp] + accels_pre);
+                B.v[comp] = v;
+                B.a[comp] = accels_pre;
                 dx = B.cc * v;
             } else {
                 dx = B.ca * f + B.noise * g;
             }
-            B.x[lane] += dx;
-            mv = B.m[lane] + dx;
-            B.m[lane] = mv;
+            B.x[comp] += dx;
+            mv = B.m[comp] + dx;
+            B.m[comp] = mv;
             if (f > 100.0) S.misc->max_force_flag |= 1;
         }
         __syncwarp();
-        const double s0 = __shfl_sync(0xffffffffu, mv, 0, 8);
-        const double s1 = __shfl_sync(0xffffffffu, mv, 1, 8);
-        const double s2 = __shfl_sync(0xffffffffu, mv, 2, 8);
-        const double d2 = valid ? s0 * s0 + s1 * s1 + s2 * s2 : 0.0;
-        if (lane == 0) {
-            if (valid) S.pos[cur ^ 1][(size_t)B.rep * nmp + B.k] = make_double4(B.x[0], B.x[1], B.x[2], 0.0);
-            if (R == 1 || C.local) sh.d2[grp] = d2;
+        const double s0 = __shfl_sync(0xffffffffu, mv, 0, 4);
+        const double s1 = __shfl_sync(0xffffffffu, mv, 1, 4);
+        const double s2 = __shfl_sync(0xffffffffu, mv, 2, 4);
+        const bool owner = B.valid != 0;
+        const double d2 = owner ? s0 * s0 + s1 * s1 + s2 * s2 : 0.0;
+        if (comp == 0) {
+            if (owner) S.pos[cur ^ 1][(size_t)B.rep * nmp + B.k] = make_double4(B.x[0], B.x[1], B.x[2], 0.0);
+            if (R == 1 || C.local) sh.d2[slot] = d2;
             else if (d2 > 0.0) top2_push(S.top2 + ((size_t)B.rep * 2 + ((step + 1ull) & 1ull)) * 2, d2, 0.0);
         }
         named_bar_sync(2, FAST_MAIN);
@@ -392,6 +418,9 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
             if (R == 1 || C.local) {                   // CTA top-2 of |xyz_move|^2 -> this CTA's slot
                 double t1 = sh.d2[tid], t2 = sh.d2[tid + 32];
                 if (t2 > t1) { const double t = t1; t1 = t2; t2 = t; }
+                double t3 = sh.d2[tid + 64], t4 = sh.d2[tid + 96];
+                if (t4 > t3) { const double t = t3; t3 = t4; t4 = t; }
+                top2_merge(t1, t2, t3, t4);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     const double b1 = __shfl_xor_sync(0xffffffffu, t1, o), b2 = __shfl_xor_sync(0xffffffffu, t2, o);
@@ -436,9 +465,9 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
         cta_sync();
     }
     cta_sync();                                        // everybody is out of the loop
-    if (B.valid && lane < 3) {
-        const size_t o3 = ((size_t)B.rep * nmp + B.k) * 3 + lane;
-        S.vel[o3] = B.v[lane]; S.acc[o3] = B.a[lane]; S.move[o3] = B.m[lane];
+    if (B.valid && comp < 3 && rows_fit) {
+        const size_t o3 = ((size_t)B.rep * nmp + B.k) * 3 + comp;
+        S.vel[o3] = B.v[comp]; S.acc[o3] = B.a[comp]; S.move[o3] = B.m[comp];
     }
     return n;
 }
@@ -509,7 +538,7 @@ SIS_D int fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fas
     auto in_range = [&](int it) { return it >= lo_item && it < hi_item; };
     // ---- E = the CTA's beads + their chain neighbours outside the range ---------------------------
     if (bt == 0) { sh.ncand = 0; sh.nactive[0] = sh.nactive[1] = 0; sh.bp_next[0] = sh.bp_next[1] = 0; sh.nextra = 0; sh.overflow = 0; }
-    for (int i = bt; i < FAST_GROUPS * 3; i += FAST_BP) (&sh.fbp[0][0])[i] = 0.0;
+    for (int i = bt; i < FAST_OWN * 3; i += FAST_BP) (&sh.fbp[0][0])[i] = 0.0;
     named_bar_sync(1, FAST_BP);
     for (int q = bt; q < C.nb; q += FAST_BP) {
         int rep, k;
@@ -648,19 +677,19 @@ SIS_D int fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, c
     int cur = C.cur0;
     const bool wwarp = lt >= FAST_LOC - 32;            // the warp that evaluates the rebuild test
     const int ll = lt - (FAST_LOC - 32);
-    // Gaussians of the first step
-    const int gg = lt >> 1, gdraw = lt & 1, gitem = C.item0 + gg;
-    int grep = 0, gk = 0;
-    uint32_t gstream = 0;
-    const bool gon = lt < 2 * FAST_GROUPS && gg < C.nb;
-    if (gon) {
-        fast_item(gitem, nmp, &grep, &gk);
-        gstream = (uint32_t)S.rp[grep].stream;
-        double g0, g1;
-        gauss_pair(A.seed, gstream, step + 1ull, (uint32_t)gk, (uint32_t)gdraw, &g0, &g1);
-        if (gdraw == 0) { sh.gauss[(step + 1ull) & 1][gg][0] = g0; sh.gauss[(step + 1ull) & 1][gg][1] = g1; }
-        else sh.gauss[(step + 1ull) & 1][gg][2] = g0;
-    }
+    // Gaussians of the first step: thread lt draws (x, y) or z of beads lt / 2 and lt / 2 + 64
+    const int gdraw = lt & 1;
+    auto gauss_fill = [&](unsigned long long gstep) {
+        for (int gg = lt >> 1; gg < C.nb; gg += FAST_LOC / 2) {
+            int grep, gk;
+            fast_item(C.item0 + gg, nmp, &grep, &gk);
+            double g0, g1;
+            gauss_pair(A.seed, (uint32_t)S.rp[grep].stream, gstep, (uint32_t)gk, (uint32_t)gdraw, &g0, &g1);
+            if (gdraw == 0) { sh.gauss[gstep & 1][gg][0] = g0; sh.gauss[gstep & 1][gg][1] = g1; }
+            else sh.gauss[gstep & 1][gg][2] = g0;
+        }
+    };
+    gauss_fill(step + 1ull);
     if (wwarp) {                                       // rebuild test on the state left by the previous launch
         bool b = false;
         const int rlo = C.local ? C.item0 / nmp : 0, rhi = C.local ? rlo + 1 : R;
@@ -722,8 +751,9 @@ SIS_D int fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, c
         }
         // bonded terms, each evaluated once (src/force_bond.F90, force_angl*.F90, force_dih_*.F90):
         // tasks [0, NT) = bond + angle of a slot (shared loads), [NT, 2 NT) = its dihedral
-        for (int task = lt; task < (C.dih_on ? 2 * FAST_NT : FAST_NT); task += FAST_LOC) {
-            const int kind = task >= FAST_NT, slot = task - kind * FAST_NT;
+        const int nslot = C.nb + 3;                    // slots in use: terms starting at item0 - 3 .. item0 + nb - 1
+        for (int task = lt; task < (C.dih_on ? 2 * nslot : nslot); task += FAST_LOC) {
+            const int kind = task >= nslot, slot = task - kind * nslot;
             const int tb = sh.tbead[slot];
             if (tb < 0) continue;
             const int4 tm = sh.tmeta[slot];
@@ -757,12 +787,7 @@ SIS_D int fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, c
         bar_arrive(3, FAST_MAIN + FAST_LOC + FAST_BP);
         if (prof) l1 = clock64();
         // Gaussians of the next step (buffer parity of step + 2)
-        if (gon && n + 1 < C.nsteps) {
-            double g0, g1;
-            gauss_pair(A.seed, gstream, step + 2ull, (uint32_t)gk, (uint32_t)gdraw, &g0, &g1);
-            if (gdraw == 0) { sh.gauss[step & 1][gg][0] = g0; sh.gauss[step & 1][gg][1] = g1; }
-            else sh.gauss[step & 1][gg][2] = g0;
-        }
+        if (n + 1 < C.nsteps) gauss_fill(step + 2ull);
         if (prof) { S.prof[8] += (unsigned long long)(l1 - l0); S.prof[9] += (unsigned long long)(clock64() - l1); }
         step++;
         cur ^= 1;

@@ -1261,12 +1261,13 @@ __global__ void k_nl_begin_slots(DevSys S, const int *rep_active)
 //    src/job_md.F90:390); (b) capacity check: a row or the bp half list that did not fit marks the
 //    lists invalid so that no persistent kernel runs on them (the host grows and rebuilds);
 //    (c) the CTA bead ranges of k_md_fast: `ncta` contiguous ranges of at most `per_cta` flattened
-//    (replica, bead) items, cut where the running row weight (nnbr + 8) crosses c * total / ncta.
-//    One block of 1024 threads; nitems <= ncta * per_cta <= PART_MAX_ITEMS when ncta > 0.
-constexpr int PART_MAX_ITEMS = 148 * 64;
+//    (replica, bead) items, cut where the running pair work (2 per row octet + 1 per bead) crosses
+//    c * total / ncta.  One block of 1024 threads, nitems ints of dynamic shared memory;
+//    nitems <= ncta * per_cta <= PART_MAX_ITEMS when ncta > 0.
+constexpr int PART_MAX_ITEMS = 148 * 128;
 __global__ void __launch_bounds__(1024) k_nl_partition(DevSys S, const int *rep_active, int ncta, int per_cta, int local)
 {
-    __shared__ int s_w[PART_MAX_ITEMS];          // inclusive prefix of the weights
+    extern __shared__ int s_w[];                 // [nitems] inclusive prefix of the weights
     __shared__ int s_part[1024];
     __shared__ int s_cut[1025];
     __shared__ int s_any;
@@ -1291,7 +1292,7 @@ __global__ void __launch_bounds__(1024) k_nl_partition(DevSys S, const int *rep_
     const int chunk = (nitems + 1023) / 1024;
     const int i0 = tid * chunk, i1 = min(i0 + chunk, nitems);
     int sum = 0;
-    for (int i = i0; i < i1; i++) { sum += S.nnbr[i] + 8; s_w[i] = sum; }
+    for (int i = i0; i < i1; i++) { sum += 2 * ((S.nnbr[i] + 7) >> 3) + 1; s_w[i] = sum; }
     s_part[tid] = sum;
     __syncthreads();
     for (int o = 1; o < 1024; o <<= 1) {

@@ -134,7 +134,7 @@ struct sisgpu {
     int nbp_half_max = 0;      // max over replicas of the half-list bp candidate count
     int coop_blocks = 0;       // co-resident grid size of the persistent kernel
     int fast_kernel = 1;       // option "fast_kernel": 0 forces the general k_md_fused
-    size_t fast_smem_set = 0;
+    size_t fast_smem_set = 0, part_smem_set = 0;
     void *fast_fn_set = nullptr;
     int fast_unroll = 1;       // option "fast_unroll": position gathers in flight per lane (1 = pipelined, 2, 4)
     std::vector<int> nbp_half_rep;   // half-list bp candidate count per replica (last build)
@@ -941,8 +941,9 @@ static int fast_ncta_of(sisgpu *h)
 {
     if (ensure_coop_blocks(h)) return 0;
     const long long nitems = (long long)h->nrep * h->nmp;
-    const int ncta_max = std::min(std::min(h->coop_blocks, FAST_MAX_CTA), PART_MAX_ITEMS / FAST_GROUPS);
-    if (nitems > (long long)ncta_max * FAST_GROUPS) return 0;
+    const int ncta_max = std::min(std::min(h->coop_blocks, FAST_MAX_CTA), PART_MAX_ITEMS / FAST_OWN);
+    // up to FAST_OWN beads per CTA; beyond ~96 on average the bead ranges can no longer be cut by pair work
+    if (nitems > (long long)ncta_max * (FAST_OWN * 3 / 4)) return 0;
     return (int)std::min<long long>(ncta_max, nitems);
 }
 
@@ -1005,8 +1006,13 @@ static void enqueue_nl_tail(sisgpu *h)
     const int N = h->nmp, R = h->nrep;
     k_nl_bp_slots<<<dim3((N * h->KB + 255) / 256, R), 256, 0, h->stream>>>(h->S, h->d_rep_active.p);
     const bool local = fast_local_ok(h);
-    k_nl_partition<<<1, 1024, 0, h->stream>>>(h->S, h->d_rep_active.p, local ? h->nrep : (h->fast_kernel ? fast_ncta_of(h) : 0),
-                                              FAST_GROUPS, local ? 1 : 0);
+    const int ncta = local ? h->nrep : (h->fast_kernel ? fast_ncta_of(h) : 0);
+    const size_t part_smem = ncta > 0 ? (size_t)h->nrep * h->nmp * sizeof(int) : 0;
+    if (part_smem > h->part_smem_set) {
+        if (cudaFuncSetAttribute((void *)k_nl_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem) == cudaSuccess)
+            h->part_smem_set = part_smem;
+    }
+    k_nl_partition<<<1, 1024, part_smem, h->stream>>>(h->S, h->d_rep_active.p, ncta, FAST_OWN, local ? 1 : 0);
     h->launches += 2;
 }
 
@@ -1820,7 +1826,7 @@ static int launch_persistent(sisgpu *h, long long stop)
     // k_md_fast: one bead per 8-lane group, rows / candidates / bonded tables on chip
     const bool local = fast_local_ok(h);
     const int want_fast = local ? R : (h->fast_kernel ? fast_ncta_of(h) : 0);
-    const size_t smem_fast = ((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)3 * FAST_GROUPS * h->K * sizeof(uint32_t);   // rows, sort scratch / unit forces, classes / unit tables
+    const size_t smem_fast = ((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)3 * FAST_EMAX * sizeof(uint32_t);   // rows, sort scratch / unit forces, classes / unit tables
     long long ncand_total = 0;
     for (int r = 0; r < R; r++) ncand_total += h->nbp_half_rep.empty() ? h->nbp_half_max : h->nbp_half_rep[r];
     const bool biases = h->P.flg_stage || h->P.ntwz_DCF || h->P.ntwz_FR || h->P.nrest;
