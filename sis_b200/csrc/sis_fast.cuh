@@ -265,23 +265,38 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
             uint32_t *tmp = tmp_all + e0;
             unsigned char *cls = cls_all + e0;
             const double4 *pos0 = S.pos[cur] + (size_t)rep * nmp;
-            for (int e = lane; e < nn; e += 8) {
-                const uint32_t ent = row[e];
-                const Vec3 v = pbc_vec_d(P, xk0, v3(pos0[ent & NB_IDX]));
-                const double d2 = dot(v, v);
-                const bool near = ((ent & NB_ELE) && d2 <= cut2) || ((ent & NB_WCA) && d2 < P.wca_sigma2);
-                tmp[e] = ent;
-                cls[e] = near ? 0 : 1;
-            }
-            __syncwarp(0xFFu << ((tid & 31) & ~7));
+            // pass 1: class of every entry (bit c of `mine` = chunk c of this lane is in range), near count
+            const unsigned gm = 0xFFu << ((tid & 31) & ~7);
+            const int gshift = (tid & 31) & ~7;
+            unsigned mine = 0;
             int nnear = 0;
-            for (int o = 0; o < nn; o++) nnear += cls[o] == 0;
-            for (int e = lane; e < nn; e += 8) {
-                const int mycls = cls[e];
-                int before = 0;
-                for (int o = 0; o < e; o++) before += cls[o] == mycls;
-                s_rows[e0 + (mycls ? nnear + before : before)] = tmp[e];
+            const int nchunk = (nn + 7) >> 3;
+            for (int c = 0; c < nchunk; c++) {
+                const int e = 8 * c + lane;
+                bool near = false;
+                if (e < nn) {
+                    const uint32_t ent = row[e];
+                    const Vec3 v = pbc_vec_d(P, xk0, v3(pos0[ent & NB_IDX]));
+                    const double d2 = dot(v, v);
+                    near = ((ent & NB_ELE) && d2 <= cut2) || ((ent & NB_WCA) && d2 < P.wca_sigma2);
+                    tmp[e] = ent;
+                }
+                const unsigned m = (__ballot_sync(gm, near) >> gshift) & 0xFFu;
+                if (near) mine |= 1u << c;
+                nnear += __popc(m);
             }
+            // pass 2: stable placement with running counters (near class first, then the margin shell)
+            int pn = 0, pf = nnear;
+            for (int c = 0; c < nchunk; c++) {
+                const int e = 8 * c + lane;
+                const bool in = e < nn, near = (mine >> c) & 1u;
+                const unsigned mn = (__ballot_sync(gm, in && near) >> gshift) & 0xFFu;
+                const unsigned mf = (__ballot_sync(gm, in && !near) >> gshift) & 0xFFu;
+                const unsigned below = (1u << lane) - 1u;
+                if (in) s_rows[e0 + (near ? pn + __popc(mn & below) : pf + __popc(mf & below))] = tmp[e];
+                pn += __popc(mn); pf += __popc(mf);
+            }
+            (void)cls;
             if (lane == 0) {
                 B.meta = S.meta[k];
                 B.rep = rep; B.k = k; B.nn = nn; B.valid = 1;

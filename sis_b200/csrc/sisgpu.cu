@@ -1830,7 +1830,7 @@ static int launch_persistent(sisgpu *h, long long stop)
     long long ncand_total = 0;
     for (int r = 0; r < R; r++) ncand_total += h->nbp_half_rep.empty() ? h->nbp_half_max : h->nbp_half_rep[r];
     const bool biases = h->P.flg_stage || h->P.ntwz_DCF || h->P.ntwz_FR || h->P.nrest;
-    const bool fast_ok = want_fast > 0 && !biases && h->K >= 24 && smem_fast <= 200 * 1024 &&
+    const bool fast_ok = want_fast > 0 && !biases && h->K >= 24 && h->K <= 256 && smem_fast <= 200 * 1024 &&
                          (local || 3 * (ncand_total / want_fast) + 16 <= FAST_BPC);
     h->last_launch_local = fast_ok && local;
     if (fast_ok) {
