@@ -129,6 +129,11 @@ int sisgpu_energy_sumup(sisgpu_t *h, int irep, double tempK, int recompute_bp,
                         double *energies);
 /* call energy_kinetic: src/job_md.F90:291,501 */
 int sisgpu_energy_kinetic(sisgpu_t *h, int irep, double *ekin);
+/* job_dcd batch mode (src/job_dcd.F90:65-79): energy_sumup with flg_bp_energy = .False. for every
+ * frame of a trajectory, nrep_proc frames per launch through the replica slots (same parameters
+ * in every slot; lists from sisgpu_full_lists as src/main.F90:148-154).  xyz32 = float32
+ * [nframes][nmp][3] as stored in the DCD (src/dcd.F90:584-592); energies = [nframes][11] */
+int sisgpu_dcd_energies(sisgpu_t *h, int nframes, const float *xyz32, double tempK, double *energies);
 /* bp_status / ene_bp for write_bp (src/write_bp.F90:36-49) */
 int sisgpu_get_bp_state(sisgpu_t *h, int irep, int *status, double *ene);
 int sisgpu_get_rg(sisgpu_t *h, int irep, double *rg);

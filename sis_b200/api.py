@@ -78,6 +78,13 @@ class SisGpu(CApi):
                                                     (out[9:14] / out[8]).round(1).tolist()))
         return d
 
+    def dcd_energies(self, frames32: np.ndarray, tempK: float) -> np.ndarray:
+        """job_dcd: the 11 energies of every frame of a float32 trajectory [nframes][nmp][3]."""
+        fr = np.ascontiguousarray(frames32, dtype=np.float32)
+        out = np.zeros((fr.shape[0], 11))
+        self._call("dcd_energies", C.c_int(fr.shape[0]), fr.ctypes.data_as(C.POINTER(C.c_float)), C.c_double(tempK), _d(out))
+        return out
+
     def mark(self, which: int) -> None:
         self._call("mark", C.c_int(which))
 

@@ -1454,3 +1454,13 @@ __global__ void k_remd_scale(DevSys S, const RemdDev *Dp)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < S.nmp * 3) S.vel[(size_t)rep * S.nmp * 3 + i] *= f;
 }
+
+// ---- job_dcd batch mode (src/job_dcd.F90:65-79): frames of a DCD evaluated nrep_proc at a time ----
+// float32 DCD coordinates of `nf` frames -> the double4 positions of replica slots 0 .. nf-1
+__global__ void k_dcd_load(DevSys S, const float *xyz32, int nf)
+{
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf || i >= S.nmp) return;
+    const float *p = xyz32 + ((size_t)f * S.nmp + i) * 3;
+    S.pos[S.ctl[0].cur][(size_t)f * S.nmp + i] = make_double4((double)p[0], (double)p[1], (double)p[2], 0.0);
+}

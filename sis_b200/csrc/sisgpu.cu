@@ -1403,6 +1403,76 @@ int sisgpu_energy_sumup(sisgpu_t *h, int irep, double tempK, int recompute_bp, d
     return 0;
 }
 
+// job_dcd (src/job_dcd.F90:65-79): energy_sumup with flg_bp_energy = .False. for every frame of a
+// trajectory, nrep_proc frames per launch (the replica slots hold frames; all slots must carry the
+// same parameters).  xyz32: float32 [nframes][nmp][3] as read from the DCD (src/dcd.F90:584-592),
+// energies: [nframes][11].  The replica coordinates are overwritten.
+int sisgpu_dcd_energies(sisgpu_t *h, int nframes, const float *xyz32, double tempK, double *energies)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    if (!h->lists_built) return set_err("dcd_energies needs lists (sisgpu_full_lists, as job = DCD does: src/main.F90:148-154)");
+    CK(cudaSetDevice(h->device));
+    const int R = h->nrep, N = h->nmp;
+    const size_t fbytes = (size_t)N * 3 * sizeof(float);
+    float *d_xyz[2] = {nullptr, nullptr}, *h_xyz[2] = {nullptr, nullptr};
+    double *h_ene[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    int rc = 0;
+    auto cleanup = [&]() {
+        for (int b = 0; b < 2; b++) {
+            if (d_xyz[b]) cudaFree(d_xyz[b]);
+            if (h_xyz[b]) cudaFreeHost(h_xyz[b]);
+            if (h_ene[b]) cudaFreeHost(h_ene[b]);
+            if (done[b]) cudaEventDestroy(done[b]);
+        }
+    };
+#define DCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = set_err("CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); cleanup(); return rc; } } while (0)
+    for (int b = 0; b < 2; b++) {
+        DCK(cudaMalloc(&d_xyz[b], fbytes * R));
+        DCK(cudaMallocHost(&h_xyz[b], fbytes * R));
+        DCK(cudaMallocHost(&h_ene[b], (size_t)R * ENE_N * sizeof(double)));
+        DCK(cudaEventCreate(&done[b]));
+    }
+    TRY(sync_ctl(h));
+    timer_begin(h);
+    const bool limit = h->flg_bp_MC != 0;
+    const int nbatch = (nframes + R - 1) / R;
+    // two staging buffers: batch k + 1 is packed on the host while batch k runs; results of batch
+    // k - 1 are unpacked after its event
+    for (int k = 0; k <= nbatch; k++) {
+        const int b = k & 1;
+        if (k < nbatch) {
+            const int f0 = k * R, nf = std::min(R, nframes - f0);
+            if (k >= 2) DCK(cudaEventSynchronize(done[b]));   // the buffer's previous batch has been read back
+            if (k >= 2) {
+                const int g0 = (k - 2) * R, ng = std::min(R, nframes - g0);
+                memcpy(energies + (size_t)g0 * ENE_N, h_ene[b], (size_t)ng * ENE_N * sizeof(double));
+            }
+            memcpy(h_xyz[b], xyz32 + (size_t)f0 * N * 3, fbytes * nf);
+            DCK(cudaMemcpyAsync(d_xyz[b], h_xyz[b], fbytes * nf, cudaMemcpyHostToDevice, h->stream));
+            k_dcd_load<<<dim3((N + 127) / 128, nf), 128, 0, h->stream>>>(h->S, d_xyz[b], nf);
+            h->launches++;
+            launch_bp_eval<1>(h, -1, limit, tempK, 1, (!limit && h->nstep_bp_MC > 0) ? 1 : 0, 0, h->P.temp_independent);
+            launch_rg(h, -1);
+            TRY(energy_launch(h, -1, nullptr));
+            DCK(cudaMemcpyAsync(h_ene[b], h->S.ene_out, (size_t)nf * ENE_N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            DCK(cudaEventRecord(done[b], h->stream));
+        }
+    }
+    for (int k = std::max(0, nbatch - 2); k < nbatch; k++) {
+        const int b = k & 1, g0 = k * R, ng = std::min(R, nframes - g0);
+        DCK(cudaEventSynchronize(done[b]));
+        memcpy(energies + (size_t)g0 * ENE_N, h_ene[b], (size_t)ng * ENE_N * sizeof(double));
+    }
+    DCK(cudaGetLastError());
+#undef DCK
+    timer_end(h, h->t_ene);
+    cleanup();
+    TRY(sync_ctl(h));
+    if (h->h_misc->max_force_flag & 2) return set_err("Error: Z-coordinate < 0.85 * stage_sigma in energy_stage. Abort!");
+    return 0;
+}
+
 int sisgpu_energy_kinetic(sisgpu_t *h, int irep, double *ekin)
 {
     if (!h->finalized) return set_err("finalize_setup not called");

@@ -244,6 +244,15 @@ module sisgpu_mod
          real(c_double), intent(out) :: ekin
          integer(c_int) :: rc
       end function
+      function sisgpu_dcd_energies(h, nframes, xyz32, tempK, energies) bind(C, name='sisgpu_dcd_energies') result(rc)
+         import :: c_ptr, c_int, c_double, c_float
+         type(c_ptr), value :: h
+         integer(c_int), value :: nframes
+         real(c_float), intent(in) :: xyz32(*)
+         real(c_double), value :: tempK
+         real(c_double), intent(out) :: energies(*)
+         integer(c_int) :: rc
+      end function
       function sisgpu_get_bp_state(h, irep, status, ene) bind(C, name='sisgpu_get_bp_state') result(rc)
          import :: c_ptr, c_int, c_double
          type(c_ptr), value :: h
@@ -479,6 +488,16 @@ contains
       integer, intent(in) :: irep
       real(c_double), intent(out) :: Ekin
       call gpu_check(sisgpu_energy_kinetic(h, int(irep - 1, c_int), Ekin), 'energy_kinetic')
+   end subroutine
+
+   ! job_dcd (src/job_dcd.F90:65-79): energies of nframes DCD frames (real(4) coordinates as read by
+   ! src/dcd.F90:584-592), nrep_proc frames per launch; energies(0:10, nframes)
+   subroutine gpu_dcd_energies(nframes, xyz32, tempK_in, energies)
+      integer, intent(in) :: nframes
+      real(c_float), intent(in) :: xyz32(3, *)
+      real(c_double), intent(in) :: tempK_in
+      real(c_double), intent(out) :: energies(0:10, *)
+      call gpu_check(sisgpu_dcd_energies(h, int(nframes, c_int), xyz32, tempK_in, energies), 'dcd_energies')
    end subroutine
 
    ! the loop body of src/job_md.F90:374-460 for every local replica, nsteps times, on the device

@@ -403,3 +403,36 @@ def test_remd_md_steps_with_exchange(mode):
         xo, vo, _ = o.get_state(r)
         assert np.abs(xg - xo).max() < 1e-7
         assert np.abs(vg - vo).max() < 1e-7
+
+
+def test_job_dcd_batch_energies_match_oracle_and_reference_golden():
+    """job_dcd batch mode (src/job_dcd.F90:65-79): the 100 OpenMM frames of
+    check/test_DCD_CAG47/CAG47.dcd evaluated 8 frames per launch through the replica slots.
+    (a) every frame equals the oracle's energy_sumup to 1e-10; (b) the reference's own
+    known-answer file CAG47.energy.out is met within the tolerances of tests/test_oracle_golden.py."""
+    frames32 = fx.array("CAG47_dcd").astype(np.float32)
+    gold = fx.array("CAG47_energy_out")
+    spec = fx.cag47(1)
+    spec.tempK = 295.15
+    g = gpu()
+    spec.replicated(8).configure(g)
+    g.full_lists()
+    e = g.dcd_energies(frames32, 295.15)
+    assert e.shape == (100, 11)
+    o = Oracle()
+    spec.configure(o)
+    o.full_lists()
+    for k in range(0, 100, 9):
+        o.set_state(0, frames32[k].astype(np.float64))
+        eo = o.energy_sumup(0, 295.15, True)
+        assert np.allclose(e[k], eo, rtol=1e-10, atol=1e-10), (k, e[k], eo)
+    assert np.max(np.abs(e[:, 1] - gold[:100, 1]) / np.abs(gold[:100, 1])) < 2e-4      # bond
+    assert np.max(np.abs(e[:, 2] - gold[:100, 2]) / np.abs(gold[:100, 2])) < 2e-4      # angle
+    assert np.max(np.abs(e[:, 5] - gold[:100, 3]) / np.maximum(np.abs(gold[:100, 3]), 1e-3)) < 2e-3   # WCA
+    assert np.max(np.abs(e[:, 6] - gold[:100, 4]) / np.abs(gold[:100, 4])) < 6e-3      # Debye-Hueckel
+    assert np.max(np.abs(e[:, 4] - gold[:100, 6]) / np.maximum(np.abs(gold[:100, 6]), 1.0)) < 2e-2    # base pairs
+    # a batch size that does not divide the frame count gives the same numbers
+    g3 = gpu()
+    spec.replicated(3).configure(g3)
+    g3.full_lists()
+    assert np.array_equal(g3.dcd_energies(frames32[:10], 295.15), e[:10])

@@ -22,6 +22,7 @@ f = Path(__file__).resolve().parent.parent / "profiles" / "r01_traffic.json"
 j = json.loads(f.read_text()) if f.exists() else {}
 j[workload] = {"kernel": d["Kernel Name"], "capture": Path(rep).name, "md_steps_in_launch": nsteps, "dram_read_bytes": rd,
                "dram_write_bytes": wr, "dram_bytes_per_md_step": (rd + wr) / nsteps,
-               "gpu_time_us": float(d["gpu__time_duration.sum"].replace(",", ""))}
+               "gpu_time_us": float(d["gpu__time_duration.sum"].replace(",", "")) *
+               {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3, "second": 1e6, "s": 1e6}.get(u["gpu__time_duration.sum"], 1.0)}
 f.write_text(json.dumps(j, indent=1))
 print(j[workload])
