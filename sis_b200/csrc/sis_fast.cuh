@@ -63,8 +63,6 @@ struct FastShared {
     double gauss[2][FAST_OWN][3];
     double d2[FAST_OWN];
     int nn[FAST_OWN], unit_start[FAST_OWN + 1];   // row lengths; first pair unit (octet) of each bead
-    int nA[FAST_OWN];                             // leading octets of the row whose partners are all owned by this CTA
-    int nA_total;
     FastBead bead[FAST_OWN];
     FastBpCand cand[FAST_BPC];
     int active[FAST_BPC];
@@ -215,7 +213,7 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
     unsigned long long step = C.step0;
     int cur = C.cur0;
     const bool prof = S.prof != nullptr && tid == 0;   // every CTA's thread 0: per-CTA phase clocks
-    long long c0 = 0, c1 = 0, c1b = 0, c2 = 0, c3 = 0, cA = 0, cW = 0;
+    long long c0 = 0, c1 = 0, c1b = 0, c2 = 0, c3 = 0, c4 = 0;
     // shared-memory regions behind the rows: prologue scratch, later the unit tables
     uint32_t *tmp_all = s_rows + FAST_EMAX;
     unsigned char *cls_all = reinterpret_cast<unsigned char *>(s_rows + 2 * FAST_EMAX);
@@ -246,7 +244,7 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
         int run = incl - tot;
 #pragma unroll
         for (int j = 0; j < 4; j++) { sh.unit_start[4 * tid + j] = run; run += a[j]; }
-        if (tid == 31) { sh.unit_start[FAST_OWN] = incl; sh.overflow_rows = incl * 8 > FAST_EMAX || incl > 1024; }
+        if (tid == 31) { sh.unit_start[FAST_OWN] = incl; sh.overflow_rows = incl * 8 > FAST_EMAX; }
     }
     named_bar_sync(2, FAST_MAIN);
     const bool rows_fit = !sh.overflow_rows;
@@ -267,49 +265,37 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
             uint32_t *tmp = tmp_all + e0;
             unsigned char *cls = cls_all + e0;
             const double4 *pos0 = S.pos[cur] + (size_t)rep * nmp;
-            // pass 1: class of every entry.  Order in shared memory: partners owned by this CTA first
-            // (their octets run before the grid barrier of the previous step is awaited, on the
-            // positions held in shared memory), and inside each half the pairs in range first.
+            // pass 1: class of every entry (bit c of `mine` = chunk c of this lane is in range), near count
             const unsigned gm = 0xFFu << ((tid & 31) & ~7);
             const int gshift = (tid & 31) & ~7;
-            unsigned long long mine = 0ull;          // 2 bits per chunk: bit0 = out of range, bit1 = remote
-            int cnt[4] = {0, 0, 0, 0};               // local-near, local-far, remote-near, remote-far
+            unsigned mine = 0;
+            int nnear = 0;
             const int nchunk = (nn + 7) >> 3;
-            const int lo_it = C.item0 - rep * nmp, hi_it = lo_it + C.nb;   // this CTA's beads of replica `rep`
             for (int c = 0; c < nchunk; c++) {
                 const int e = 8 * c + lane;
-                bool near = false, loc = false;
+                bool near = false;
                 if (e < nn) {
                     const uint32_t ent = row[e];
-                    const int j = (int)(ent & NB_IDX);
-                    const Vec3 v = pbc_vec_d(P, xk0, v3(pos0[j]));
+                    const Vec3 v = pbc_vec_d(P, xk0, v3(pos0[ent & NB_IDX]));
                     const double d2 = dot(v, v);
                     near = ((ent & NB_ELE) && d2 <= cut2) || ((ent & NB_WCA) && d2 < P.wca_sigma2);
-                    loc = j >= lo_it && j < hi_it;
                     tmp[e] = ent;
-                    mine |= (unsigned long long)((near ? 0 : 1) | (loc ? 0 : 2)) << (2 * c);
                 }
-                const unsigned in = (__ballot_sync(gm, e < nn) >> gshift) & 0xFFu;
-                const unsigned ml = (__ballot_sync(gm, loc) >> gshift) & 0xFFu;
-                const unsigned mn = (__ballot_sync(gm, near) >> gshift) & 0xFFu;
-                cnt[0] += __popc(ml & mn); cnt[1] += __popc(ml & ~mn & in);
-                cnt[2] += __popc(~ml & mn & in); cnt[3] += __popc(~ml & ~mn & in);
+                const unsigned m = (__ballot_sync(gm, near) >> gshift) & 0xFFu;
+                if (near) mine |= 1u << c;
+                nnear += __popc(m);
             }
-            // pass 2: stable placement with one running counter per class
-            int pc4[4] = {0, cnt[0], cnt[0] + cnt[1], cnt[0] + cnt[1] + cnt[2]};
+            // pass 2: stable placement with running counters (near class first, then the margin shell)
+            int pn = 0, pf = nnear;
             for (int c = 0; c < nchunk; c++) {
                 const int e = 8 * c + lane;
-                const bool in = e < nn;
-                const int cl = (int)((mine >> (2 * c)) & 3ull);
+                const bool in = e < nn, near = (mine >> c) & 1u;
+                const unsigned mn = (__ballot_sync(gm, in && near) >> gshift) & 0xFFu;
+                const unsigned mf = (__ballot_sync(gm, in && !near) >> gshift) & 0xFFu;
                 const unsigned below = (1u << lane) - 1u;
-#pragma unroll
-                for (int k4 = 0; k4 < 4; k4++) {
-                    const unsigned m = (__ballot_sync(gm, in && cl == k4) >> gshift) & 0xFFu;
-                    if (in && cl == k4) s_rows[e0 + pc4[k4] + __popc(m & below)] = tmp[e];
-                    pc4[k4] += __popc(m);
-                }
+                if (in) s_rows[e0 + (near ? pn + __popc(mn & below) : pf + __popc(mf & below))] = tmp[e];
+                pn += __popc(mn); pf += __popc(mf);
             }
-            if (lane == 0) sh.nA[slot] = (cnt[0] + cnt[1]) >> 3;
             (void)cls;
             if (lane == 0) {
                 B.meta = S.meta[k];
@@ -326,37 +312,9 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
             }
         } else if (lane == 0) {
             B.valid = 0; B.nn = 0; B.rep = 0; B.k = 0;
-            sh.nA[slot] = 0;
         }
     }
     named_bar_sync(2, FAST_MAIN);                      // rows sorted, scratch free
-    // unit lists: A = octets with local partners only, B = the rest; positions of a bead's A (B)
-    // units in the lists from exclusive scans of nA (units - nA) over the owner slots
-    unsigned short *list_a = reinterpret_cast<unsigned short *>(cls_all + 2048), *list_b = list_a + 1024;
-    if (warp == 0 && rows_fit) {
-        int a[4], b[4], ta = 0, tb = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int sl = 4 * tid + j;
-            a[j] = sh.nA[sl]; b[j] = sh.unit_start[sl + 1] - sh.unit_start[sl] - a[j];
-            ta += a[j]; tb += b[j];
-        }
-        int ia = ta, ib = tb;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int x = __shfl_up_sync(0xffffffffu, ia, o), y = __shfl_up_sync(0xffffffffu, ib, o);
-            if (tid >= o) { ia += x; ib += y; }
-        }
-        int ra = ia - ta, rb = ib - tb;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int sl = 4 * tid + j, u0 = sh.unit_start[sl];
-            for (int o = 0; o < a[j]; o++) list_a[ra + o] = (unsigned short)(u0 + o);
-            for (int o = 0; o < b[j]; o++) list_b[rb + o] = (unsigned short)(u0 + a[j] + o);
-            ra += a[j]; rb += b[j];
-        }
-        if (tid == 31) sh.nA_total = ia;
-    }
     if (rows_fit)
         for (int slot = grp; slot < C.nb; slot += FAST_GROUPS) {
             const int u0 = sh.unit_start[slot], nu = sh.unit_start[slot + 1] - u0;
@@ -375,51 +333,39 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
     for (; n < C.nsteps; n++) {
         if (prof) c0 = clock64();
         // ---- pair units: software pipeline, the next unit's entry and position are fetched before
-        // the current pair is evaluated.  A units (partners owned by this CTA, positions in shared
-        // memory) run before the positions of the other CTAs are awaited, B units after. ------------
+        // the current pair is evaluated --------------------------------------------------------------
         {
             const double4 *posb = S.pos[cur];
-            const int nA = sh.nA_total, nB = nunit - nA;
-            auto run_units = [&](const unsigned short *list, int cnt, const bool from_shared) {
-                int i = grp, u = 0, q = 0;
-                uint32_t ent = 0;
-                Vec3 xj = mk(0.0, 0.0, 0.0);
-                auto fetch = [&](int ii, int &uu, int &qq, uint32_t &ee, Vec3 &xx) {
-                    uu = list[ii];
-                    qq = unit_q[uu];
-                    const int e = 8 * uu + lane;
-                    ee = e - 8 * sh.unit_start[qq] < sh.bead[qq].nn ? s_rows[e] : 0u;
-                    if (ee) {
-                        if (from_shared) {
-                            const FastBead &J = sh.bead[sh.bead[qq].rep * nmp + (int)(ee & NB_IDX) - C.item0];
-                            xx = mk(J.x[0], J.x[1], J.x[2]);
-                        } else {
-                            xx = v3(posb[(size_t)sh.bead[qq].rep * nmp + (ee & NB_IDX)]);
-                        }
-                    }
-                };
-                if (i < cnt) fetch(i, u, q, ent, xj);
-                while (i < cnt) {
-                    const int in = i + FAST_GROUPS;
-                    int un = 0, qn = 0;
-                    uint32_t ent_n = 0;
-                    Vec3 xn = mk(0.0, 0.0, 0.0);
-                    if (in < cnt) fetch(in, un, qn, ent_n, xn);
-                    Vec3 F = mk(0.0, 0.0, 0.0);
-                    if (ent) {
-                        const FastBead &Q = sh.bead[q];
-                        fast_pair_one(P, ent, mk(Q.x[0], Q.x[1], Q.x[2]), xj, Q.ele_coef, Q.inv_lambdaD, Q.cut2, F);
-                    }
-                    F.x = group_sum_masked(F.x, gmask); F.y = group_sum_masked(F.y, gmask); F.z = group_sum_masked(F.z, gmask);
-                    if (lane == 0) unitF[u] = F;
-                    i = in; u = un; ent = ent_n; xj = xn; q = qn;
+            int u = grp;
+            uint32_t ent = 0;
+            Vec3 xj = mk(0.0, 0.0, 0.0);
+            int q = 0;
+            if (u < nunit) {
+                q = unit_q[u];
+                const int e = 8 * u + lane;
+                ent = e - 8 * sh.unit_start[q] < sh.bead[q].nn ? s_rows[e] : 0u;
+                if (ent) xj = v3(posb[(size_t)sh.bead[q].rep * nmp + (ent & NB_IDX)]);
+            }
+            while (u < nunit) {
+                const int un = u + FAST_GROUPS;
+                uint32_t ent_n = 0;
+                Vec3 xn = mk(0.0, 0.0, 0.0);
+                int qn = 0;
+                if (un < nunit) {
+                    qn = unit_q[un];
+                    const int e = 8 * un + lane;
+                    ent_n = e - 8 * sh.unit_start[qn] < sh.bead[qn].nn ? s_rows[e] : 0u;
+                    if (ent_n) xn = v3(posb[(size_t)sh.bead[qn].rep * nmp + (ent_n & NB_IDX)]);
                 }
-            };
-            run_units(list_a, nA, true);
-            if (prof) cA = clock64();
-            named_bar_sync(6, FAST_MAIN + 32);             // the LOC poller has seen every CTA's positions of the previous step
-            if (prof) cW = clock64();
-            run_units(list_b, nB, false);
+                Vec3 F = mk(0.0, 0.0, 0.0);
+                if (ent) {
+                    const FastBead &Q = sh.bead[q];
+                    fast_pair_one(P, ent, mk(Q.x[0], Q.x[1], Q.x[2]), xj, Q.ele_coef, Q.inv_lambdaD, Q.cut2, F);
+                }
+                F.x = group_sum_masked(F.x, gmask); F.y = group_sum_masked(F.y, gmask); F.z = group_sum_masked(F.z, gmask);
+                if (lane == 0) unitF[u] = F;
+                u = un; ent = ent_n; xj = xn; q = qn;
+            }
         }
         if (prof) c1 = clock64();
         // help the BP warps with the survivors of the distance gate
@@ -504,19 +450,26 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
             }
             if (tid == 0) {
                 if (prof) c3 = clock64();
-                // positions written: arrive only -- the LOC poller awaits the other CTAs at the top
-                // of the next step while the MAIN groups already run their A units
-                if (!C.local) red_release_add(C.bar_pos, 1u);
-                else __threadfence();
+                if (C.local) {
+                    // no other CTA reads these positions; the acquire drops the SM's stale L1 lines of
+                    // the buffer written two steps ago (positions are gathered through read-only loads)
+                    __threadfence();
+                    (void)ld_acquire_u32(C.bar_pos);
+                } else {
+                    red_release_add(C.bar_pos, 1u);
+                    const unsigned target = (unsigned)(n + 1) * (unsigned)C.ncta;
+                    while (ld_acquire_u32(C.bar_pos) < target) { }
+                }
                 if (prof) {
+                    c4 = clock64();
                     unsigned long long *pc = S.prof + 16 + 8 * blockIdx.x;
-                    pc[0] += (unsigned long long)((cA - c0) + (c1 - cW)); pc[1] += (unsigned long long)(c2 - c1);
-                    pc[2] += (unsigned long long)(c3 - c2); pc[3] += (unsigned long long)(cW - cA);
+                    pc[0] += (unsigned long long)(c1 - c0); pc[1] += (unsigned long long)(c2 - c1);
+                    pc[2] += (unsigned long long)(c3 - c2); pc[3] += (unsigned long long)(c4 - c3);
                     pc[5] += (unsigned long long)(c1b - c1);
                     pc[7] += (unsigned long long)nunit * 1000ull + (unsigned long long)C.nb;   // units, beads of the CTA
                     if (blockIdx.x == 0) {
-                        S.prof[0] += (unsigned long long)((cA - c0) + (c1 - cW)); S.prof[1] += (unsigned long long)(c2 - c1);
-                        S.prof[2] += (unsigned long long)(c3 - c2); S.prof[3] += (unsigned long long)(cW - cA);
+                        S.prof[0] += (unsigned long long)(c1 - c0); S.prof[1] += (unsigned long long)(c2 - c1);
+                        S.prof[2] += (unsigned long long)(c3 - c2); S.prof[3] += (unsigned long long)(c4 - c3);
                         S.prof[4] += 1ull;
                     }
                 }
@@ -677,7 +630,6 @@ SIS_D int fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fas
     int n = 0;
     if (!sh.blocked[0] && sh.ncand <= FAST_BPC && !sh.overflow)
     for (; n < C.nsteps; n++) {
-        named_bar_sync(7, FAST_BP + 32);                       // every CTA's positions of the previous step are visible
         if (prof) b0 = clock64();
         const double4 *pos = S.pos[cur];
         for (int i = bt; i < ncand; i += FAST_BP) {            // distance gate, one thread per candidate
@@ -785,18 +737,6 @@ SIS_D int fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, c
     int n = 0;
     if (!sh.blocked[0] && sh.ncand <= FAST_BPC && !sh.overflow)
     for (; n < C.nsteps; n++) {
-        // grid barrier, wait side: one lane per CTA polls the "positions written" counter of the
-        // previous step, then releases the MAIN (after their A units) and BP warps through named barriers
-        if (wwarp) {
-            if (ll == 0) {
-                const unsigned target = C.local ? 0u : (unsigned)n * (unsigned)C.ncta;
-                while (ld_acquire_u32(C.bar_pos) < target) { }
-            }
-            __syncwarp();
-            bar_arrive(6, FAST_MAIN + 32);
-            bar_arrive(7, FAST_BP + 32);
-        }
-        named_bar_sync(5, FAST_LOC);
         if (prof) l0 = clock64();
         // rebuild test on the displacements left by the previous step
         if (n > 0 && wwarp) {
