@@ -161,6 +161,17 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value);
  * phase, barrier, out[8] steps counted, out[9..11] base-pair warps (gate, evaluate, arrive),
  * out[12..13] bonded-table warps (tables, Gaussians) (option "profile"); out must hold 16 doubles */
 int sisgpu_get_timers(sisgpu_t *h, double *out, int reset);
+/* Output staging for a save step (src/job_md.F90:487-509).  _begin reduces on the
+ * device what the writers need -- flags: 1 = float32 DCD frame (src/dcd.F90:584-592), 2 = .bp
+ * records (bp_status and ene_bp <= -kT, src/write_bp.F90:36-49), 4 = .bpall records instead
+ * (:76-88), 8 = the 11 energies of energy_sumup with the cached bp energies + Ekin
+ * (src/write_out.F90:83-110) -- into one of two staging slots and starts the device-to-host copies
+ * on a second stream: sisgpu_md_steps called afterwards overlaps with them.  _end waits for that
+ * slot only; records come back 1-based in the reference's bp_mp order as (imp, jmp, real(ene, 4)).
+ * Any output pointer may be NULL. */
+int sisgpu_snapshot_begin(sisgpu_t *h, int irep, double tempK, int flags, int *slot);
+int sisgpu_snapshot_end(sisgpu_t *h, int slot, float *xyz32, int *nbp, int *bp_i, int *bp_j,
+                        float *bp_e, int cap, double *energies, double *ekin);
 /* device-side wall clock of a region of calls: sisgpu_mark(h, 0) / sisgpu_mark(h, 1) record a CUDA
  * event on the library's stream, sisgpu_elapsed_ms returns the time between the two marks (it
  * waits for mark 1).  Used by bench.py: torch.cuda.Event only sees torch's own stream */

@@ -85,6 +85,22 @@ class SisGpu(CApi):
         self._call("dcd_energies", C.c_int(fr.shape[0]), fr.ctypes.data_as(C.POINTER(C.c_float)), C.c_double(tempK), _d(out))
         return out
 
+    def snapshot_begin(self, irep: int, tempK: float, flags: int = 1 | 2 | 8) -> int:
+        slot = C.c_int()
+        self._call("snapshot_begin", C.c_int(irep), C.c_double(tempK), C.c_int(flags), C.byref(slot))
+        return slot.value
+
+    def snapshot_end(self, slot: int, nmp: int, cap: int = 4096):
+        """-> (xyz32 [nmp][3], (imp, jmp, ene32) records, energies[11], Ekin)"""
+        xyz = np.zeros((nmp, 3), dtype=np.float32)
+        n = C.c_int()
+        bi, bj = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32)
+        be = np.zeros(cap, dtype=np.float32)
+        ene, ek = np.zeros(11), C.c_double()
+        self._call("snapshot_end", C.c_int(slot), xyz.ctypes.data_as(C.POINTER(C.c_float)), C.byref(n), _i(bi), _i(bj),
+                   be.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(cap), _d(ene), C.byref(ek))
+        return xyz, (bi[:n.value], bj[:n.value], be[:n.value]), ene, ek.value
+
     def mark(self, which: int) -> None:
         self._call("mark", C.c_int(which))
 

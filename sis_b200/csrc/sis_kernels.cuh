@@ -1464,3 +1464,88 @@ __global__ void k_dcd_load(DevSys S, const float *xyz32, int nf)
     const float *p = xyz32 + ((size_t)f * S.nmp + i) * 3;
     S.pos[S.ctl[0].cur][(size_t)f * S.nmp + i] = make_double4((double)p[0], (double)p[1], (double)p[2], 0.0);
 }
+
+// ---- output staging: what the writers of a save step need, reduced on the device ----
+// float32 DCD frame (src/dcd.F90:584-592) and the .bp / .bpall records (src/write_bp.F90:36-49,
+// 76-88): base pairs with bp_status and (all or ene_bp <= -kT), as (imp, jmp, real(ene, 4)), 1-based.
+struct SnapDev {
+    float *xyz32;        // [nmp][3]
+    int *bp_cnt;         // [nmp + 1] per-owner record counts, then their exclusive scan
+    int2 *bp_ij;         // [cap]
+    float *bp_e;         // [cap]
+    int *nrec;           // records found (may exceed cap: the host retries with a larger buffer)
+    int cap;
+};
+__global__ void k_snap_frame(DevSys S, SnapDev D, int rep)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.nmp) return;
+    const double4 p = S.pos[S.ctl[0].cur][(size_t)rep * S.nmp + i];
+    D.xyz32[3 * i] = (float)p.x; D.xyz32[3 * i + 1] = (float)p.y; D.xyz32[3 * i + 2] = (float)p.z;
+}
+SIS_D bool snap_bp_keep(const DevSys &S, size_t pbase, int2 ent, int k, double kT, int all)
+{
+    if (ent.x <= k) return false;                       // the owner (lower bead) reports the pair
+    if (!S.bp_status[pbase + ent.y]) return false;
+    return all || S.ene_bp[pbase + ent.y] <= -kT;
+}
+__global__ void k_snap_bp_count(DevSys S, SnapDev D, int rep, double kT, int all)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= S.nmp) return;
+    const size_t rbase = (size_t)rep * S.nmp, pbase = rbase * S.KB;
+    const int2 *row = S.bprow + (rbase + k) * S.KB;
+    int c = 0;
+    for (int e = 0; e < S.nbp_row[rbase + k]; e++) c += snap_bp_keep(S, pbase, row[e], k, kT, all);
+    D.bp_cnt[k] = c;
+}
+__global__ void __launch_bounds__(1024) k_snap_bp_scan(DevSys S, SnapDev D)
+{
+    __shared__ int wsum[32];
+    __shared__ int carry, chunk_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = S.nmp;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const int v = i < n ? D.bp_cnt[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = wsum[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            wsum[lane] = wi - w;
+            if (lane == 31) chunk_total = wi;
+        }
+        __syncthreads();
+        if (i < n) D.bp_cnt[i] = carry + wsum[warp] + incl - v;
+        __syncthreads();
+        if (tid == 0) carry += chunk_total;
+        __syncthreads();
+    }
+    if (tid == 0) { D.bp_cnt[n] = carry; *D.nrec = carry; }
+}
+__global__ void k_snap_bp_fill(DevSys S, SnapDev D, int rep, double kT, int all)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= S.nmp) return;
+    const size_t rbase = (size_t)rep * S.nmp, pbase = rbase * S.KB;
+    const int2 *row = S.bprow + (rbase + k) * S.KB;
+    int o = D.bp_cnt[k];
+    for (int e = 0; e < S.nbp_row[rbase + k]; e++) {
+        const int2 ent = row[e];
+        if (!snap_bp_keep(S, pbase, ent, k, kT, all)) continue;
+        if (o < D.cap) { D.bp_ij[o] = make_int2(k + 1, ent.x + 1); D.bp_e[o] = (float)S.ene_bp[pbase + ent.y]; }
+        o++;
+    }
+}

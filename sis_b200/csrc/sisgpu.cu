@@ -190,6 +190,17 @@ struct sisgpu {
     DBuf<int> d_pair_tb, d_rep2lab, d_lab2rep, d_has_opp;
     DBuf<double> d_lab_temp, d_vscale;
     DBuf<RepParams> d_lab_rp;
+    // output staging (sisgpu_snapshot_begin / _end): two slots of device + pinned buffers, copies on stream2
+    struct SnapSlot {
+        float *d_xyz = nullptr, *d_e = nullptr, *h_xyz = nullptr, *h_e = nullptr;
+        int *d_cnt = nullptr, *d_nrec = nullptr, *h_nrec = nullptr;
+        int2 *d_ij = nullptr, *h_ij = nullptr;
+        double *h_ene = nullptr;          // 11 energies + Ekin
+        int cap = 0, flags = 0, irep = 0;
+        bool busy = false;
+        cudaEvent_t staged = nullptr, copied = nullptr;
+    } snap[2];
+    int snap_next = 0;
     // pending device-side timings: (start, end, accumulator), resolved at the next synchronisation
     struct Pending { cudaEvent_t a, b; double *acc; };
     std::vector<Pending> ev_pending;
@@ -217,7 +228,7 @@ struct sisgpu {
     long long istep_host = 0;
 };
 
-static inline dim3 grid1(int n, int b) { return dim3((unsigned)((n + b - 1) / b)); }
+static void snap_free(sisgpu::SnapSlot &s);
 
 const char *sisgpu_last_error(void) { return g_err; }
 int sisgpu_version(void) { return 100; }
@@ -264,6 +275,7 @@ int sisgpu_destroy(sisgpu_t *h)
     h->d_gather_send.release(); h->d_gather_recv.release(); h->d_nbr.release(); h->d_bprow.release();
     h->d_bp_type.release(); h->d_bp_coef.release(); h->d_mc_counter.release();
     h->d_ene_counter.release(); h->d_bar.release(); h->d_top2_slots.release(); h->d_cta_item0.release(); h->d_cell_sorted.release(); h->d_grid.release();
+    snap_free(h->snap[0]); snap_free(h->snap[1]);
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     h->ev_pool.clear();
     for (auto &p : h->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -707,6 +719,7 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     const int N = h->nmp, R = h->nrep;
     TRY(h->d_meta.upload(meta));
     TRY(h->d_seq.upload(h->seq));
+    snap_free(h->snap[0]); snap_free(h->snap[1]);
     h->local_ncand = -1;
     if (N <= FAST_GROUPS) {   // bound of the bp candidates k_md_fast can meet in its replica-local mode
         int cnt = 0, t = 0;
@@ -2215,6 +2228,128 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
         h->G = g;
         invalidate_graphs(h);
     } else return set_err("unknown option %s", name);
+    return 0;
+}
+
+// ---- output staging ------------------------------------------------------------
+// sisgpu_snapshot_begin reduces what the writers of a save step need (flags: 1 float32 DCD frame,
+// 2 .bp records [ene_bp <= -kT], 4 .bpall records instead, 8 the 11 energies of energy_sumup with
+// the cached bp energies + Ekin) into a staging slot on the device and starts the device-to-host
+// copies on a second stream; MD steps enqueued afterwards run concurrently with the copies.
+// sisgpu_snapshot_end waits for that slot only and hands the data out.
+static void snap_free(sisgpu::SnapSlot &s)
+{
+    if (s.d_xyz) cudaFree(s.d_xyz); if (s.d_e) cudaFree(s.d_e); if (s.d_cnt) cudaFree(s.d_cnt);
+    if (s.d_nrec) cudaFree(s.d_nrec); if (s.d_ij) cudaFree(s.d_ij);
+    if (s.h_xyz) cudaFreeHost(s.h_xyz); if (s.h_e) cudaFreeHost(s.h_e); if (s.h_nrec) cudaFreeHost(s.h_nrec);
+    if (s.h_ij) cudaFreeHost(s.h_ij); if (s.h_ene) cudaFreeHost(s.h_ene);
+    if (s.staged) cudaEventDestroy(s.staged); if (s.copied) cudaEventDestroy(s.copied);
+    s = sisgpu::SnapSlot();
+}
+static int snap_alloc(sisgpu *h, sisgpu::SnapSlot &s, int cap)
+{
+    const int N = h->nmp;
+    if (!s.d_xyz) {
+        CK(cudaMalloc(&s.d_xyz, (size_t)N * 3 * sizeof(float))); CK(cudaMallocHost(&s.h_xyz, (size_t)N * 3 * sizeof(float)));
+        CK(cudaMalloc(&s.d_cnt, (size_t)(N + 1) * sizeof(int)));
+        CK(cudaMalloc(&s.d_nrec, sizeof(int))); CK(cudaMallocHost(&s.h_nrec, sizeof(int)));
+        CK(cudaMallocHost(&s.h_ene, 12 * sizeof(double)));
+        CK(cudaEventCreateWithFlags(&s.staged, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    }
+    if (cap > s.cap) {
+        if (s.d_ij) { cudaFree(s.d_ij); cudaFree(s.d_e); cudaFreeHost(s.h_ij); cudaFreeHost(s.h_e); }
+        CK(cudaMalloc(&s.d_ij, (size_t)cap * sizeof(int2))); CK(cudaMalloc(&s.d_e, (size_t)cap * sizeof(float)));
+        CK(cudaMallocHost(&s.h_ij, (size_t)cap * sizeof(int2))); CK(cudaMallocHost(&s.h_e, (size_t)cap * sizeof(float)));
+        s.cap = cap;
+    }
+    return 0;
+}
+int sisgpu_snapshot_begin(sisgpu_t *h, int irep, double tempK, int flags, int *slot_out)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    if (irep < 0 || irep >= h->nrep) return set_err("irep out of range");
+    CK(cudaSetDevice(h->device));
+    const int si = h->snap_next;
+    sisgpu::SnapSlot &s = h->snap[si];
+    if (s.busy) return set_err("snapshot slot %d still pending: call sisgpu_snapshot_end first", si);
+    const int N = h->nmp;
+    TRY(snap_alloc(h, s, std::max(s.cap, std::max(256, N))));
+    s.flags = flags; s.irep = irep;
+    SnapDev D{s.d_xyz, s.d_cnt, s.d_ij, s.d_e, s.d_nrec, s.cap};
+    const double kT = tempK * SIS_BOLTZ_KCAL_MOL;
+    if (flags & 1) { k_snap_frame<<<(N + 255) / 256, 256, 0, h->stream>>>(h->S, D, irep); h->launches++; }
+    if (flags & 6) {
+        const int all = (flags & 4) ? 1 : 0;
+        k_snap_bp_count<<<(N + 255) / 256, 256, 0, h->stream>>>(h->S, D, irep, kT, all);
+        k_snap_bp_scan<<<1, 1024, 0, h->stream>>>(h->S, D);
+        k_snap_bp_fill<<<(N + 255) / 256, 256, 0, h->stream>>>(h->S, D, irep, kT, all);
+        h->launches += 3;
+    }
+    if (flags & 8) {
+        launch_rg(h, irep);
+        TRY(energy_launch(h, irep, nullptr));
+        k_kinetic<<<1, 256, 0, h->stream>>>(h->S, h->d_kin.p, irep);
+        h->launches++;
+    }
+    CK(cudaEventRecord(s.staged, h->stream));
+    // copies on the second stream: the compute stream is free for the next MD steps.  The energies
+    // live in buffers the next energy call rewrites, so they are copied on the compute stream.
+    if (flags & 8) {
+        CK(cudaMemcpyAsync(s.h_ene, h->S.ene_out + (size_t)irep * ENE_N, ENE_N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(s.h_ene + 11, h->d_kin.p + irep, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(s.staged, h->stream));
+    }
+    CK(cudaStreamWaitEvent(h->stream2, s.staged, 0));
+    if (flags & 1) CK(cudaMemcpyAsync(s.h_xyz, s.d_xyz, (size_t)N * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream2));
+    if (flags & 6) {
+        CK(cudaMemcpyAsync(s.h_nrec, s.d_nrec, sizeof(int), cudaMemcpyDeviceToHost, h->stream2));
+        CK(cudaMemcpyAsync(s.h_ij, s.d_ij, (size_t)s.cap * sizeof(int2), cudaMemcpyDeviceToHost, h->stream2));
+        CK(cudaMemcpyAsync(s.h_e, s.d_e, (size_t)s.cap * sizeof(float), cudaMemcpyDeviceToHost, h->stream2));
+    }
+    CK(cudaEventRecord(s.copied, h->stream2));
+    s.busy = true;
+    h->snap_next ^= 1;
+    if (slot_out) *slot_out = si;
+    return 0;
+}
+int sisgpu_snapshot_end(sisgpu_t *h, int slot, float *xyz32, int *nbp, int *bp_i, int *bp_j, float *bp_e, int cap,
+                        double *energies, double *ekin)
+{
+    if (slot < 0 || slot > 1) return set_err("snapshot slot out of range");
+    sisgpu::SnapSlot &s = h->snap[slot];
+    if (!s.busy) return set_err("snapshot slot %d is not pending", slot);
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(s.copied));
+    s.busy = false;
+    const int N = h->nmp;
+    if ((s.flags & 1) && xyz32) memcpy(xyz32, s.h_xyz, (size_t)N * 3 * sizeof(float));
+    if (s.flags & 6) {
+        const int n = *s.h_nrec;
+        if (nbp) *nbp = n;
+        if (n > s.cap) return set_err("snapshot: %d base-pair records exceed the staging capacity %d", n, s.cap);
+        if (bp_i && bp_j && bp_e) {
+            if (n > cap) return set_err("snapshot: %d base-pair records, caller capacity %d", n, cap);
+            // the reference's record order is bp_mp order: chain pair, then (imp, jmp)
+            std::vector<int> idx(n);
+            for (int k = 0; k < n; k++) idx[k] = k;
+            std::sort(idx.begin(), idx.end(), [&](int a, int b) {
+                const int2 A = s.h_ij[a], B = s.h_ij[b];
+                if (!h->lists_full) {
+                    const int ac = h->ichain[A.x - 1], bc = h->ichain[B.x - 1];
+                    if (ac != bc) return ac < bc;
+                    const int ajc = h->ichain[A.y - 1], bjc = h->ichain[B.y - 1];
+                    if (ajc != bjc) return ajc < bjc;
+                }
+                if (A.x != B.x) return A.x < B.x;
+                return A.y < B.y;
+            });
+            for (int k = 0; k < n; k++) { bp_i[k] = s.h_ij[idx[k]].x; bp_j[k] = s.h_ij[idx[k]].y; bp_e[k] = s.h_e[idx[k]]; }
+        }
+    } else if (nbp) *nbp = 0;
+    if (s.flags & 8) {
+        if (energies) memcpy(energies, s.h_ene, ENE_N * sizeof(double));
+        if (ekin) *ekin = s.h_ene[11];
+    }
     return 0;
 }
 

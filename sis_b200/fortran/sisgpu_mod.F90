@@ -244,6 +244,24 @@ module sisgpu_mod
          real(c_double), intent(out) :: ekin
          integer(c_int) :: rc
       end function
+      function sisgpu_snapshot_begin(h, irep, tempK, flags, slot) bind(C, name='sisgpu_snapshot_begin') result(rc)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: h
+         integer(c_int), value :: irep, flags
+         real(c_double), value :: tempK
+         integer(c_int), intent(out) :: slot
+         integer(c_int) :: rc
+      end function
+      function sisgpu_snapshot_end(h, slot, xyz32, nbp, bp_i, bp_j, bp_e, cap, energies, ekin) &
+            bind(C, name='sisgpu_snapshot_end') result(rc)
+         import :: c_ptr, c_int, c_double, c_float
+         type(c_ptr), value :: h
+         integer(c_int), value :: slot, cap
+         real(c_float), intent(out) :: xyz32(*), bp_e(*)
+         integer(c_int), intent(out) :: nbp, bp_i(*), bp_j(*)
+         real(c_double), intent(out) :: energies(*), ekin
+         integer(c_int) :: rc
+      end function
       function sisgpu_dcd_energies(h, nframes, xyz32, tempK, energies) bind(C, name='sisgpu_dcd_energies') result(rc)
          import :: c_ptr, c_int, c_double, c_float
          type(c_ptr), value :: h

@@ -436,3 +436,42 @@ def test_job_dcd_batch_energies_match_oracle_and_reference_golden():
     spec.replicated(3).configure(g3)
     g3.full_lists()
     assert np.array_equal(g3.dcd_energies(frames32[:10], 295.15), e[:10])
+
+
+def test_snapshot_staging_matches_the_synchronous_getters():
+    """Output staging of a save step: float32 DCD frame, .bp records filtered by
+    bp_status and ene_bp <= -kT in bp_mp order (src/write_bp.F90:36-49), .bpall records, energies
+    + Ekin, staged on the device and copied on a second stream while the next MD steps run."""
+    spec = fx.cag47(4, pbc=True)
+    g = gpu()
+    spec.configure(g)
+    g.init_velocities(0)
+    g.neighbor_list(0)
+    g.md_steps(200)
+    # reference values through the synchronous calls
+    x, v, a = g.get_state(0)
+    wca, ele, bp, coef = g.get_lists(0)
+    st, en = g.get_bp_state(0)
+    e_ref = g.energy_sumup(0, spec.tempK, False)
+    ek_ref = g.energy_kinetic(0)
+    kT = spec.tempK * 0.0019872042586408316
+    slot = g.snapshot_begin(0, spec.tempK, 1 | 2 | 8)
+    g.md_steps(50)                       # overlaps with the copies; must not disturb the staged data
+    xyz32, (bi, bj, be), ene, ek = g.snapshot_end(slot, spec.nmp)
+    assert np.array_equal(xyz32, x.astype(np.float32))
+    keep = (st != 0) & (en <= -kT)
+    assert np.array_equal(bi, bp[keep, 0]) and np.array_equal(bj, bp[keep, 1])
+    assert np.array_equal(be, en[keep].astype(np.float32))
+    assert np.allclose(ene, e_ref, rtol=1e-12, atol=1e-12) and abs(ek - ek_ref) < 1e-9 * abs(ek_ref)
+    assert g.get_step() == 250
+    # .bpall: every pair with bp_status, whatever its energy; two slots can be pending at once
+    st2, en2 = g.get_bp_state(0)
+    bp2 = g.get_lists(0)[2]
+    s1 = g.snapshot_begin(0, spec.tempK, 4)
+    s2 = g.snapshot_begin(0, spec.tempK, 1)
+    _, (ai, aj, ae), _, _ = g.snapshot_end(s1, spec.nmp)
+    x2 = g.snapshot_end(s2, spec.nmp)[0]
+    assert np.array_equal(ai, bp2[st2 != 0, 0]) and np.array_equal(aj, bp2[st2 != 0, 1])
+    assert np.array_equal(ae, en2[st2 != 0].astype(np.float32))
+    assert np.array_equal(x2, g.get_state(0)[0].astype(np.float32))
+    assert keep.sum() > 0
