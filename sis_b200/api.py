@@ -76,6 +76,9 @@ class SisGpu(CApi):
                                                     (out[4:8] / out[8]).round(1).tolist()))
             d["persistent_clk_per_step"].update(zip(["bp_gate", "bp_eval", "bp_arrive", "loc_tables", "loc_gauss"],
                                                     (out[9:14] / out[8]).round(1).tolist()))
+            if out[15] > 0:
+                d["persistent_launch"] = {"launches": int(out[15]), "clk_per_launch": round(out[14] / out[15], 1),
+                                          "steps_per_launch": round(out[8] / out[15], 2)}
         return d
 
     def dcd_energies(self, frames32: np.ndarray, tempK: float) -> np.ndarray:

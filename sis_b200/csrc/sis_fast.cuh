@@ -859,6 +859,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams 
     // grows them first).  Uniform over the grid: ctl and misc were written by earlier kernels.
     const int nsteps = md_steps_to_run(S, ctl, target);
     if (nsteps <= 0) return;
+    const long long k_entry = clock64();
     FastCtx C;
     C.R = S.nrep; C.nmp = S.nmp; C.K = S.K; C.nitems = S.nrep * S.nmp; C.ncta = gridDim.x;
     C.item0 = S.cta_item0[blockIdx.x]; C.nb = S.cta_item0[blockIdx.x + 1] - C.item0;
@@ -886,6 +887,10 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams 
         cta_sync();
     }
     if (tid >= FAST_MAIN) return;
+    if (S.prof != nullptr && blockIdx.x == 0 && tid == 0) {   // whole-launch clocks: prologue share = total - steps * per-step
+        S.prof[10] += (unsigned long long)(clock64() - k_entry);
+        S.prof[11] += 1ull;
+    }
     // ---- bookkeeping for the host and the other kernels (warp 0) ------------------------------------
     const unsigned long long step = ctl.step + (unsigned long long)done;
     const int cur = ctl.cur ^ (done & 1);

@@ -136,10 +136,7 @@ struct sisgpu {
     int fast_kernel = 1;       // option "fast_kernel": 0 forces the general k_md_fused
     size_t fast_smem_set = 0, part_smem_set = 0;
     void *fast_fn_set = nullptr;
-    int fast_unroll = 1;       // option "fast_unroll": position gathers in flight per lane (1 = pipelined, 2, 4)
     std::vector<int> nbp_half_rep;   // half-list bp candidate count per replica (last build)
-    bool partition_dirty = true;     // lists changed since the CTA bead ranges of k_md_fast were computed
-    int fast_ncta = 0;               // number of ranges (0: the system does not fit the fast kernel)
     // biases (host copies)
     std::vector<int> twz_pairs, twzfr_pairs, rest_id;
     std::vector<double> twz_dir, twzfr_k, twzfr_init, twzfr_velo, rest_rcut, rest_para;
@@ -209,7 +206,6 @@ struct sisgpu {
     int local_ncand = -1;                // sequence-allowed base pairs of one replica (bound of the per-CTA candidates)
     int pipeline = 1;                    // option "pipeline": device-driven list rebuilds inside md_steps
     double est_cycle_steps = 50.0;       // running estimate of MD steps between two list rebuilds
-    std::vector<cudaEvent_t> ev_pool;    // timing of the pipelined loop
     DBuf<RepParams> d_rp, d_rp_alt;
     DBuf<unsigned char> d_sync;          // DevSyncHdr + top2[nrep][2][2]
     unsigned char *h_sync = nullptr;     // pinned mirror
@@ -276,8 +272,6 @@ int sisgpu_destroy(sisgpu_t *h)
     h->d_bp_type.release(); h->d_bp_coef.release(); h->d_mc_counter.release();
     h->d_ene_counter.release(); h->d_bar.release(); h->d_top2_slots.release(); h->d_cta_item0.release(); h->d_cell_sorted.release(); h->d_grid.release();
     snap_free(h->snap[0]); snap_free(h->snap[1]);
-    for (auto e : h->ev_pool) cudaEventDestroy(e);
-    h->ev_pool.clear();
     for (auto &p : h->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     h->ev_pending.clear();
     for (auto e : h->ev_free) cudaEventDestroy(e);
@@ -2213,7 +2207,6 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
     else if (s == "chunk") { h->chunk = std::max(1, (int)value); invalidate_graphs(h); }
     else if (s == "timing") h->timing = (int)value;
     else if (s == "fast_kernel") h->fast_kernel = (int)value;
-    else if (s == "fast_unroll") h->fast_unroll = (int)value;
     else if (s == "pipeline") h->pipeline = (int)value;
     else if (s == "remd_device") h->remd_device = (int)value;
     else if (s == "local_kernel") { h->local_kernel = (int)value; h->lists_built = false; }
@@ -2378,7 +2371,7 @@ int sisgpu_get_timers(sisgpu_t *h, double *out, int reset)
     if (h->S.prof) {
         unsigned long long p[16];
         CK(cudaMemcpy(p, h->d_prof.p, sizeof p, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < 10; i++) out[4 + i] = (double)p[i];
+        for (int i = 0; i < 12; i++) out[4 + i] = (double)p[i];
         if (reset) CK(cudaMemset(h->d_prof.p, 0, (16 + 8 * FAST_MAX_CTA) * sizeof(unsigned long long)));
     }
     if (reset) h->t_step = h->t_nl = h->t_ene = h->t_rex = 0;
