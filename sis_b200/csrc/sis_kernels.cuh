@@ -31,7 +31,8 @@ struct DevMisc {
                                     // the persistent kernels do not run until the host has grown the lists
     int nrebuild;                   // replica list rebuilds done by the device-side chain (k_nl_plan)
     int half_overflow;              // largest bp half-list count seen by k_nl_partition
-    int pad[2];
+    int inject_invalid_at;          // test hook (option "inject_invalid"): k_nl_plan marks the lists invalid at this rebuild count
+    int pad;
 };
 
 // one contiguous device block the host mirrors with a single copy: header + top2[nrep][2][2]
@@ -876,6 +877,10 @@ __global__ void __launch_bounds__(1024) k_nl_plan(DevSys S, NlPlanArgs A, int *r
         }
     }
     __syncthreads();
+    if (tid == 0 && s_any && S.misc->inject_invalid_at > 0 && S.misc->nrebuild >= S.misc->inject_invalid_at) {
+        S.misc->lists_invalid = 1;      // exercised by tests: the host must recover exactly as after a row overflow
+        S.misc->inject_invalid_at = 0;
+    }
     if (!s_any || A.pbc) return;
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     const double4 *pos = S.pos[ctl.cur];

@@ -2209,6 +2209,12 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
     else if (s == "fast_kernel") h->fast_kernel = (int)value;
     else if (s == "pipeline") h->pipeline = (int)value;
     else if (s == "remd_device") h->remd_device = (int)value;
+    else if (s == "inject_invalid") {   // test hook: the n-th device-side rebuild from now reports invalid lists
+        if (!h->finalized) return set_err("finalize_setup not called");
+        TRY(sync_ctl(h));
+        const int at = h->h_misc->nrebuild + (int)value;
+        CK(cudaMemcpy(&h->S.misc->inject_invalid_at, &at, sizeof(int), cudaMemcpyHostToDevice));
+    }
     else if (s == "local_kernel") { h->local_kernel = (int)value; h->lists_built = false; }
     else if (s == "profile") {   // phase clocks of the persistent kernel (block 0): get_timers out[4..8]
         if (value != 0) { TRY(h->d_prof.alloc(16 + 8 * FAST_MAX_CTA)); h->S.prof = h->d_prof.p; }

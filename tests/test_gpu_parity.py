@@ -264,3 +264,27 @@ def test_replica_local_kernel_rebuilds_in_place():
                 ka = np.lexsort(la.T[::-1]) if len(la) else []
                 kb = np.lexsort(lb.T[::-1]) if len(lb) else []
                 assert np.array_equal(la[ka], lb[kb])
+
+
+def test_device_side_rebuild_recovers_from_invalid_lists():
+    """A device-side rebuild that cannot fit its rows marks the lists invalid: the persistent kernels
+    enqueued behind it fall through and the host grows the capacities, rebuilds every replica and
+    carries on.  The recovery is exercised with the `inject_invalid` test hook (a real overflow
+    needs a collapsing system); the trajectory must not notice."""
+    from sis_b200.api import SisGpu
+    spec = SPECS["cag47_4_pbc"]()
+    spec.nl_margin = 3.0
+    out = []
+    for inject in (0, 2):
+        g = SisGpu(0)
+        spec.configure(g)
+        g.init_velocities(0)
+        g.neighbor_list(0)
+        if inject:
+            g.set_option("inject_invalid", inject)
+        nreb = g.md_steps(120)
+        out.append((g.get_state(0), nreb, g.get_step()))
+    assert out[0][2] == out[1][2] == 120
+    assert out[1][1] >= 2
+    for a, b in zip(out[0][0], out[1][0]):
+        assert np.abs(a - b).max() < 1e-7
