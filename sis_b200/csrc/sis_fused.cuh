@@ -257,7 +257,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_md_fused(DevSys S, FFParam
                 F += local_force<FUSED_G>(S, P, Rp, pos, rep, k, lane, A.term_mask, step + 1ull);
                 F.x = group_sum<FUSED_G>(F.x); F.y = group_sum<FUSED_G>(F.y); F.z = group_sum<FUSED_G>(F.z);
                 double g = 0.0;
-                if (lane < 3) g = gauss_component(A.seed, (uint32_t)Rp.stream, step + 1ull, (uint32_t)k, lane);
+                // with one bead per group the Gaussian is drawn here, off the critical path of the
+                // integrate phase; otherwise in the integrate loop (once per bead either way)
+                if (niter == 1 && lane < 3) g = gauss_component(A.seed, (uint32_t)Rp.stream, step + 1ull, (uint32_t)k, lane);
                 if (niter == 1) { Freg = F; greg = g; }
                 else if (valid && lane < 3)
                     S.f_pair[((size_t)rep * nmp + k) * 3 + lane] = lane == 0 ? F.x : lane == 1 ? F.y : F.z;

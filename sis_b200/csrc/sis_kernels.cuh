@@ -163,7 +163,12 @@ SIS_HD Vec3 pair_force(const DevSys &S, const FFParams &P, const RepParams &R, c
         for (int u = 0; u < 4; u++) xj[u] = v3(pos[ent[u] & NB_IDX]);
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const Vec3 v = pbc_vec_d(P, xk, xj[u]);
+            Vec3 v = xk - xj[u];
+            if (ent[u] & NB_IMG) {    // only pairs that can cross half a box before the next rebuild (nl_needs_image)
+                v.x = minimg1(v.x, P.box[0], P.box_half[0]);
+                v.y = minimg1(v.y, P.box[1], P.box_half[1]);
+                v.z = minimg1(v.z, P.box[2], P.box_half[2]);
+            }
             const double d2 = dot(v, v);
             double s = 0.0;
             if (do_wca && (ent[u] & NB_WCA) && d2 < P.wca_sigma2) s += wca_scalar(P, d2);

@@ -79,6 +79,7 @@ int hc_build_lists(HostCheck *c, double *xyz, int all_pairs)
             Vec3 v = pbc_vec_d(P, v3(c->pos[i]), v3(c->pos[j]));
             const double d2 = dot(v, v);
             uint32_t ent = nl_pair_flags(A, P, c->meta[i], c->meta[j], i, j, d2, ele_nl_cut2);
+            if (ent && nl_needs_image(P, A, v3(c->pos[i]), v3(c->pos[j]))) ent |= NB_IMG;   // as k_nl_rows
             if (ent) rows[i].push_back(ent | (uint32_t)j);
             if (nl_bp_geometry(A, i, j, d2)) {
                 int bptype = 0, bp3;
