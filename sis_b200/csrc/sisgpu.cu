@@ -182,6 +182,7 @@ struct sisgpu {
     bool last_launch_local = false;
     // device-resident REMD state (exchange steps inside md_steps without host round trips)
     int remd_device = 1;                 // option "remd_device"
+    bool remd_on_device = false;         // inside an md_steps call whose exchange steps run on the device: host tables are stale
     double remd_cut_max = 0.0;           // largest ele_cutoff any label can bring to a local replica (cutoff_type 2)
     DBuf<RemdDev> d_remd;
     DBuf<int> d_pair_tb, d_rep2lab, d_lab2rep, d_has_opp;
@@ -1988,6 +1989,9 @@ static int md_run_pipelined(sisgpu *h, long long stop)
             if (h->h_misc->bp_overflow > KB) KB = ((int)(h->h_misc->bp_overflow * 1.2) + 7) / 8 * 8;
             h->h_misc->lists_invalid = 0;
             CK(cudaMemcpy(&h->S.misc->lists_invalid, &h->h_misc->lists_invalid, sizeof(int), cudaMemcpyHostToDevice));
+            // the host-driven rebuild reads (and may push) the per-replica parameters: bring the host
+            // tables up to date with the exchanges done on the device so far
+            if (h->remd_on_device) TRY(remd_download(h));
             TRY(alloc_lists(h, K, KB));
             std::vector<int> all(R, 1);
             TRY(build_lists(h, all, false));
@@ -2021,6 +2025,7 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
         // REMD with the exchange step on the device: MD intervals and exchange chains are enqueued
         // back to back; the host tables are refreshed once at the end
         TRY(remd_upload(h));
+        h->remd_on_device = true;
         const long long nex = h->nstep_exchange;
         while ((long long)h->h_ctl->step < target) {
             const long long cur = (long long)h->h_ctl->step;
@@ -2050,6 +2055,7 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
         CK(cudaGetLastError());
         spans_resolve(h);
         TRY(remd_download(h));
+        h->remd_on_device = false;
         if (h->ele_cutoff_type == 2 && h->P.flg_ele) {   // refreshed by the device-side rebuilds
             std::vector<RepParams> rp(R);
             CK(cudaMemcpy(rp.data(), h->d_rp.p, R * sizeof(RepParams), cudaMemcpyDeviceToHost));
