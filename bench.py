@@ -147,6 +147,15 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # one block of host cores per rank: the enqueueing thread, the NCCL proxy and the clock sampler of
+        # a rank must not share cores with the spinning threads of the other ranks
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            if not os.environ.get("SIS_NO_PIN"):
+                os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]))
+        except (AttributeError, OSError):
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     spec, wl = build_system(args)
     g = SisGpu(local)
@@ -179,7 +188,8 @@ def main():
         g.md_steps(args.md_steps)
     samples, stop = [], threading.Event()
     th = threading.Thread(target=clocks_sampler, args=(stop, samples), daemon=True)
-    th.start()
+    if not os.environ.get("SIS_NO_SAMPLER"):
+        th.start()
     g.set_option("timing", 1)
     g.get_timers(reset=True)
     l0 = g.launch_count()
@@ -222,7 +232,11 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dte = float(tt.item())
     stop.set()
-    th.join(timeout=2)
+    if th.is_alive():
+        th.join(timeout=2)
+    if os.environ.get("SIS_RANK_DEBUG"):
+        print(f"[rank {rank}] value-loop {dt * 1e3 / args.steps:.2f} ms/chunk, e2e {dte * 1e3 / args.steps:.2f} ms/chunk, "
+              f"timers {timers}, rebuilds {nreb}", file=sys.stderr, flush=True)
     e2e = world * nmp * args.md_steps * args.steps / dte
 
     if rank == 0:

@@ -268,7 +268,7 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
             // pass 1: class of every entry (bit c of `mine` = chunk c of this lane is in range), near count
             const unsigned gm = 0xFFu << ((tid & 31) & ~7);
             const int gshift = (tid & 31) & ~7;
-            unsigned mine = 0;
+            unsigned long long mine = 0ull;   // one bit per octet of the row: up to 512 entries
             int nnear = 0;
             const int nchunk = (nn + 7) >> 3;
             for (int c = 0; c < nchunk; c++) {
@@ -282,14 +282,14 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
                     tmp[e] = ent;
                 }
                 const unsigned m = (__ballot_sync(gm, near) >> gshift) & 0xFFu;
-                if (near) mine |= 1u << c;
+                if (near) mine |= 1ull << c;
                 nnear += __popc(m);
             }
             // pass 2: stable placement with running counters (near class first, then the margin shell)
             int pn = 0, pf = nnear;
             for (int c = 0; c < nchunk; c++) {
                 const int e = 8 * c + lane;
-                const bool in = e < nn, near = (mine >> c) & 1u;
+                const bool in = e < nn, near = (mine >> c) & 1ull;
                 const unsigned mn = (__ballot_sync(gm, in && near) >> gshift) & 0xFFu;
                 const unsigned mf = (__ballot_sync(gm, in && !near) >> gshift) & 0xFFu;
                 const unsigned below = (1u << lane) - 1u;

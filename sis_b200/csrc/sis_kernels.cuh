@@ -867,12 +867,15 @@ __global__ void __launch_bounds__(1024) k_nl_plan(DevSys S, NlPlanArgs A, int *r
     __shared__ double s_lo[3][32], s_hi[3][32];
     const int tid = threadIdx.x, R = S.nrep, nmp = S.nmp;
     const DevCtl ctl = S.ctl[0];
-    if (tid == 0) { s_any = 0; S.misc->nl_overflow = 0; S.misc->bp_overflow = 0; }
+    // lists already marked invalid (a row of an earlier chain of this batch did not fit): nothing is
+    // rebuilt and the overflow marks are kept for the host, which grows the capacities
+    const bool invalid = S.misc->lists_invalid != 0;
+    if (tid == 0) { s_any = 0; if (!invalid) { S.misc->nl_overflow = 0; S.misc->bp_overflow = 0; } }
     __syncthreads();
     for (int r = tid; r < R; r += blockDim.x) {
         const unsigned long long *t = S.top2 + ((size_t)r * 2 + (ctl.step & 1ull)) * 2;
         const double m1 = __longlong_as_double((long long)t[0]), m2 = __longlong_as_double((long long)t[1]);
-        const int need = A.force_all || ((long long)ctl.step < A.stop && sqrt(m1) + sqrt(m2) > S.nl_margin);
+        const int need = !invalid && (A.force_all || ((long long)ctl.step < A.stop && sqrt(m1) + sqrt(m2) > S.nl_margin));
         rep_active[r] = need;
         if (need) {
             s_any = 1;

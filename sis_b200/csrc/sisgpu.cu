@@ -785,7 +785,9 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     h->K = h->KB = 0;
     // systems of at most 64 beads: rows that can hold every partner, so that an in-kernel rebuild
     // (k_md_fast, replica-local mode) can never overflow
-    TRY(alloc_lists(h, 128, N <= FAST_GROUPS ? std::max(16, (N + 7) / 8 * 8) : 16));
+    // K: rows of the C4 system reach ~130 entries once the coils have relaxed; 192 keeps the x1.2 growth
+    // (a reallocation of every list) out of ordinary runs
+    TRY(alloc_lists(h, 192, N <= FAST_GROUPS ? std::max(16, (N + 7) / 8 * 8) : 16));
     TRY(alloc_cells(h, 4096));
     h->finalized = true;
     TRY(push_rp(h));
@@ -896,9 +898,11 @@ static void span_end(sisgpu *h, int id, double *acc)
 }
 static void spans_resolve(sisgpu *h)   // call after a stream synchronisation
 {
+    static const bool dbg = getenv("SIS_SPAN_DEBUG") != nullptr;
     for (auto &p : h->ev_pending) {
         float ms = 0;
         if (p.acc && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) *p.acc += ms;
+        if (dbg && p.acc && ms > 0.3f) fprintf(stderr, "[dev %d] step %lld span %s %.3f ms\n", h->device, (long long)h->h_ctl->step, p.acc == &h->t_nl ? "nl" : p.acc == &h->t_step ? "step" : p.acc == &h->t_rex ? "rex" : "?", ms);
         h->ev_free.push_back(p.a); h->ev_free.push_back(p.b);
     }
     h->ev_pending.clear();
@@ -1908,7 +1912,7 @@ static int launch_persistent(sisgpu *h, long long stop)
     long long ncand_total = 0;
     for (int r = 0; r < R; r++) ncand_total += h->nbp_half_rep.empty() ? h->nbp_half_max : h->nbp_half_rep[r];
     const bool biases = h->P.flg_stage || h->P.ntwz_DCF || h->P.ntwz_FR || h->P.nrest;
-    const bool fast_ok = want_fast > 0 && !biases && h->K >= 24 && h->K <= 256 && smem_fast <= 200 * 1024 &&
+    const bool fast_ok = want_fast > 0 && !biases && h->K >= 24 && h->K <= 512 && smem_fast <= 200 * 1024 &&
                          (local || 3 * (ncand_total / want_fast) + 16 <= FAST_BPC);
     h->last_launch_local = fast_ok && local;
     if (fast_ok) {
@@ -1987,6 +1991,7 @@ static int md_run_pipelined(sisgpu *h, long long stop)
             int K = h->K, KB = h->KB;
             if (h->h_misc->nl_overflow > K) K = ((int)(h->h_misc->nl_overflow * 1.2) + 31) / 32 * 32;
             if (h->h_misc->bp_overflow > KB) KB = ((int)(h->h_misc->bp_overflow * 1.2) + 7) / 8 * 8;
+            if (getenv("SIS_SPAN_DEBUG")) fprintf(stderr, "[dev %d] step %lld lists invalid: K %d -> %d, KB %d -> %d\n", h->device, (long long)h->h_ctl->step, h->K, K, h->KB, KB);
             h->h_misc->lists_invalid = 0;
             CK(cudaMemcpy(&h->S.misc->lists_invalid, &h->h_misc->lists_invalid, sizeof(int), cudaMemcpyHostToDevice));
             // the host-driven rebuild reads (and may push) the per-replica parameters: bring the host
@@ -2215,6 +2220,11 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
     else if (s == "fast_kernel") h->fast_kernel = (int)value;
     else if (s == "pipeline") h->pipeline = (int)value;
     else if (s == "remd_device") h->remd_device = (int)value;
+    else if (s == "list_capacity") {    // row capacity K (tests: a tight K makes device-side rebuilds overflow)
+        if (!h->finalized) return set_err("finalize_setup not called");
+        TRY(alloc_lists(h, std::max(8, (int)value), h->KB));
+        h->lists_built = false;
+    }
     else if (s == "inject_invalid") {   // test hook: the n-th device-side rebuild from now reports invalid lists
         if (!h->finalized) return set_err("finalize_setup not called");
         TRY(sync_ctl(h));

@@ -288,3 +288,32 @@ def test_device_side_rebuild_recovers_from_invalid_lists():
     assert out[1][1] >= 2
     for a, b in zip(out[0][0], out[1][0]):
         assert np.abs(a - b).max() < 1e-7
+
+
+def test_row_overflow_during_device_side_rebuilds_grows_the_lists():
+    """Rows that outgrow their capacity at a device-side rebuild (x1.2 growth of
+    src/neighbor_list.F90:247-298): with a capacity equal to the longest row of the first build the
+    following rebuilds overflow sooner or later; the run must equal the one with ample capacity."""
+    from sis_b200.api import SisGpu
+    spec = SPECS["cag47_4_pbc"]()
+    spec.nl_margin = 3.0
+    g0 = SisGpu(0)
+    spec.configure(g0)
+    g0.neighbor_list(0)
+    wca, ele, bp, _ = g0.get_lists(0)
+    both = np.unique(np.concatenate([wca, ele]), axis=0)          # a pair listed for WCA and DH is one row entry
+    longest = np.bincount(both.ravel() - 1, minlength=spec.nmp).max()
+    out = []
+    for cap in (0, int(longest)):
+        g = SisGpu(0)
+        spec.configure(g)
+        if cap:
+            g.set_option("list_capacity", cap)
+        g.init_velocities(0)
+        g.neighbor_list(0)
+        nreb = g.md_steps(400)
+        out.append((g.get_state(0), nreb, g.get_step(), g.get_list_sizes(0)))
+    assert out[0][2] == out[1][2] == 400 and out[1][1] >= 10
+    assert out[0][3] == out[1][3]
+    for a, b in zip(out[0][0], out[1][0]):
+        assert np.abs(a - b).max() < 1e-6
