@@ -131,8 +131,9 @@ class CApi:
     def set_state(self, irep, xyz=None, velos=None, accels=None):
         self._call("set_state", C.c_int(irep), _d(xyz), _d(velos), _d(accels))
 
-    def get_state(self, irep):
-        x, v, a = (np.zeros((self.nmp, 3)) for _ in range(3))
+    def get_state(self, irep, out=None):
+        """-> xyz, velos, accels ([nmp][3] each); `out` = three caller buffers (e.g. pinned) to fill."""
+        x, v, a = out if out is not None else (np.zeros((self.nmp, 3)) for _ in range(3))
         self._call("get_state", C.c_int(irep), _d(x), _d(v), _d(a))
         return x, v, a
 

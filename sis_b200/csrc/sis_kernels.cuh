@@ -1562,3 +1562,17 @@ __global__ void k_snap_bp_fill(DevSys S, SnapDev D, int rep, double kT, int all)
         o++;
     }
 }
+
+// ---- state transfer: xyz(3, nmp) of the Fortran driver <-> the double4 positions ----------------
+__global__ void k_pos_unpack(DevSys S, const double *xyz, int rep)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S.nmp) S.pos[S.ctl[0].cur][(size_t)rep * S.nmp + i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0);
+}
+__global__ void k_pos_pack(DevSys S, double *xyz, int rep)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.nmp) return;
+    const double4 p = S.pos[S.ctl[0].cur][(size_t)rep * S.nmp + i];
+    xyz[3 * i] = p.x; xyz[3 * i + 1] = p.y; xyz[3 * i + 2] = p.z;
+}

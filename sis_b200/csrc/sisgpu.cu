@@ -175,6 +175,7 @@ struct sisgpu {
     DBuf<unsigned long long> d_mc_counter, d_prof;
     DBuf<unsigned int> d_ene_counter, d_bar;
     DBuf<int> d_cta_item0, d_cell_sorted;
+    DBuf<double> d_xyz_stage;            // [nmp][3] scratch of set_state / get_state
     DBuf<GridInfo> d_grid;
     GridInfo grid_host{};                // last grid written to d_grid by the host
     bool grid_host_valid = false;
@@ -271,7 +272,7 @@ int sisgpu_destroy(sisgpu_t *h)
     h->d_twzfr_init.release(); h->d_twzfr_velo.release(); h->d_rest_rcut.release(); h->d_rest_para.release();
     h->d_gather_send.release(); h->d_gather_recv.release(); h->d_nbr.release(); h->d_bprow.release();
     h->d_bp_type.release(); h->d_bp_coef.release(); h->d_mc_counter.release();
-    h->d_ene_counter.release(); h->d_bar.release(); h->d_top2_slots.release(); h->d_cta_item0.release(); h->d_cell_sorted.release(); h->d_grid.release();
+    h->d_ene_counter.release(); h->d_bar.release(); h->d_top2_slots.release(); h->d_cta_item0.release(); h->d_cell_sorted.release(); h->d_grid.release(); h->d_xyz_stage.release();
     snap_free(h->snap[0]); snap_free(h->snap[1]);
     for (auto &p : h->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     h->ev_pending.clear();
@@ -737,7 +738,7 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     TRY(h->d_pos0.alloc(RN)); TRY(h->d_pos1.alloc(RN));
     TRY(h->d_vel.alloc(RN * 3)); TRY(h->d_acc.alloc(RN * 3)); TRY(h->d_move.alloc(RN * 3)); TRY(h->d_force.alloc(RN * 3));
     TRY(h->d_nnbr.alloc(RN)); TRY(h->d_nbp_row.alloc(RN)); TRY(h->d_nt_excess.alloc(RN));
-    TRY(h->d_cell_of.alloc(RN)); TRY(h->d_cell_beads.alloc(RN)); TRY(h->d_cell_sorted.alloc(RN)); TRY(h->d_grid.alloc(1));
+    TRY(h->d_cell_of.alloc(RN)); TRY(h->d_cell_beads.alloc(RN)); TRY(h->d_cell_sorted.alloc(RN)); TRY(h->d_grid.alloc(1)); TRY(h->d_xyz_stage.alloc((size_t)N * 3));
     h->grid_host_valid = false;
     TRY(h->d_mc_counter.alloc(R)); TRY(h->d_rep_active.alloc(R));
     TRY(h->d_rp.alloc(R)); TRY(h->d_rp_alt.alloc(R));
@@ -811,20 +812,24 @@ static int sync_ctl(sisgpu *h)
     return 0;
 }
 
+// xyz / velos / accels as the Fortran modules hold them ([nmp][3] per replica).  Copies are enqueued
+// on the compute stream (pinned caller buffers make them asynchronous) and the positions are
+// (un)packed on the device through a [nmp][3] scratch; one synchronisation per call.
 int sisgpu_set_state(sisgpu_t *h, int irep, const double *xyz, const double *velos, const double *accels)
 {
     if (!h->finalized) return set_err("finalize_setup not called");
     if (irep < 0 || irep >= h->nrep) return set_err("irep out of range");
     CK(cudaSetDevice(h->device));
-    TRY(sync_ctl(h));
     const int N = h->nmp;
+    const size_t bytes = (size_t)N * 3 * sizeof(double);
     if (xyz) {
-        std::vector<double4> p(N);
-        for (int i = 0; i < N; i++) p[i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0);
-        CK(cudaMemcpy(h->S.pos[h->h_ctl->cur] + (size_t)irep * N, p.data(), N * sizeof(double4), cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(h->d_xyz_stage.p, xyz, bytes, cudaMemcpyHostToDevice, h->stream));
+        k_pos_unpack<<<(N + 255) / 256, 256, 0, h->stream>>>(h->S, h->d_xyz_stage.p, irep);
+        h->launches++;
     }
-    if (velos) CK(cudaMemcpy(h->S.vel + (size_t)irep * N * 3, velos, 3 * N * sizeof(double), cudaMemcpyHostToDevice));
-    if (accels) CK(cudaMemcpy(h->S.acc + (size_t)irep * N * 3, accels, 3 * N * sizeof(double), cudaMemcpyHostToDevice));
+    if (velos) CK(cudaMemcpyAsync(h->S.vel + (size_t)irep * N * 3, velos, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (accels) CK(cudaMemcpyAsync(h->S.acc + (size_t)irep * N * 3, accels, bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // the caller may reuse its buffers
     return 0;
 }
 
@@ -833,15 +838,16 @@ int sisgpu_get_state(sisgpu_t *h, int irep, double *xyz, double *velos, double *
     if (!h->finalized) return set_err("finalize_setup not called");
     if (irep < 0 || irep >= h->nrep) return set_err("irep out of range");
     CK(cudaSetDevice(h->device));
-    TRY(sync_ctl(h));
     const int N = h->nmp;
+    const size_t bytes = (size_t)N * 3 * sizeof(double);
     if (xyz) {
-        std::vector<double4> p(N);
-        CK(cudaMemcpy(p.data(), h->S.pos[h->h_ctl->cur] + (size_t)irep * N, N * sizeof(double4), cudaMemcpyDeviceToHost));
-        for (int i = 0; i < N; i++) { xyz[3 * i] = p[i].x; xyz[3 * i + 1] = p[i].y; xyz[3 * i + 2] = p[i].z; }
+        k_pos_pack<<<(N + 255) / 256, 256, 0, h->stream>>>(h->S, h->d_xyz_stage.p, irep);
+        h->launches++;
+        CK(cudaMemcpyAsync(xyz, h->d_xyz_stage.p, bytes, cudaMemcpyDeviceToHost, h->stream));
     }
-    if (velos) CK(cudaMemcpy(velos, h->S.vel + (size_t)irep * N * 3, 3 * N * sizeof(double), cudaMemcpyDeviceToHost));
-    if (accels) CK(cudaMemcpy(accels, h->S.acc + (size_t)irep * N * 3, 3 * N * sizeof(double), cudaMemcpyDeviceToHost));
+    if (velos) CK(cudaMemcpyAsync(velos, h->S.vel + (size_t)irep * N * 3, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (accels) CK(cudaMemcpyAsync(accels, h->S.acc + (size_t)irep * N * 3, bytes, cudaMemcpyDeviceToHost, h->stream));
+    TRY(sync_ctl(h));
     return 0;
 }
 
