@@ -204,6 +204,7 @@ struct sisgpu {
     struct Pending { cudaEvent_t a, b; double *acc; };
     std::vector<Pending> ev_pending;
     std::vector<cudaEvent_t> ev_free;
+    int fast_max_cta = 0;                // option "fast_max_cta": upper bound of the k_md_fast grid (0 = one CTA per SM)
     int local_kernel = 1;                // option "local_kernel": replica-local mode of k_md_fast (one CTA per replica)
     int local_ncand = -1;                // sequence-allowed base pairs of one replica (bound of the per-CTA candidates)
     int pipeline = 1;                    // option "pipeline": device-driven list rebuilds inside md_steps
@@ -962,7 +963,12 @@ static int fast_ncta_of(sisgpu *h)
     const int ncta_max = std::min(std::min(h->coop_blocks, FAST_MAX_CTA), PART_MAX_ITEMS / FAST_OWN);
     // up to FAST_OWN beads per CTA; beyond ~96 on average the bead ranges can no longer be cut by pair work
     if (nitems > (long long)ncta_max * (FAST_OWN * 3 / 4)) return 0;
-    return (int)std::min<long long>(ncta_max, nitems);
+    // small systems: at least ~6 beads per CTA -- the grid barrier gets slower with the number of CTAs
+    // (measured: one CAG47 chain 8.6 -> 7.2 us per step with 24 instead of 141 CTAs, four chains 9.2 -> 8.2)
+    int ncta = (int)std::min<long long>(ncta_max, (nitems + 5) / 6);
+    if (h->fast_max_cta > 0) ncta = std::min(ncta, h->fast_max_cta);
+    const int ncta_min = (int)((nitems + FAST_OWN * 3 / 4 - 1) / (FAST_OWN * 3 / 4));
+    return std::max(1, std::max(ncta, ncta_min));
 }
 
 // replica-local mode of k_md_fast: one CTA owns one whole replica and rebuilds its lists itself
@@ -1898,9 +1904,6 @@ static int enqueue_exchange(sisgpu *h)
     return 0;
 }
 
-// Bead ranges of k_md_fast: contiguous runs of at most FAST_GROUPS flattened (replica, bead) items,
-// one per CTA, chosen so that the largest per-CTA pair work (row entries + a per-bead constant) is
-// minimal for the number of SMs -- the step time is the time of the busiest CTA.
 // launch of one persistent kernel that runs until step `stop` or until a replica needs new lists
 static int launch_persistent(sisgpu *h, long long stop)
 {
@@ -2237,6 +2240,7 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
         const int at = h->h_misc->nrebuild + (int)value;
         CK(cudaMemcpy(&h->S.misc->inject_invalid_at, &at, sizeof(int), cudaMemcpyHostToDevice));
     }
+    else if (s == "fast_max_cta") { h->fast_max_cta = (int)value; h->lists_built = false; }
     else if (s == "local_kernel") { h->local_kernel = (int)value; h->lists_built = false; }
     else if (s == "profile") {   // phase clocks of the persistent kernel (block 0): get_timers out[4..8]
         if (value != 0) { TRY(h->d_prof.alloc(16 + 8 * FAST_MAX_CTA)); h->S.prof = h->d_prof.p; }
