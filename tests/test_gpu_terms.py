@@ -375,15 +375,16 @@ def test_energy_replica_and_exchange(kind):
     assert nacc_total > 0
 
 
-@pytest.mark.parametrize("mode", [0, 2])
-def test_remd_md_steps_with_exchange(mode):
+@pytest.mark.parametrize("mode,extra", [(0, {}), (2, {}), (2, {"local_kernel": 0}), (2, {"remd_device": 0})],
+                         ids=["stream", "replica-local+device-exchange", "pipelined+device-exchange", "host-exchange"])
+def test_remd_md_steps_with_exchange(mode, extra):
     """sisgpu_md_steps with REMD configured = MD + energy_replica + replica_exchange every
     nstep_exchange steps (src/job_md.F90:474-481,514-570); the oracle is driven through the same
     sequence with the library's counter-based exchange uniforms."""
     n, nex = 4, 10
     temps = [290.0, 310.0, 330.0, 350.0]
     spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=0).replicated(n, temps=temps)
-    g, o = remd_pair([n, 1, 1, 1], [temps, [], [], []], spec, nstep_exchange=nex, launch_mode=mode)
+    g, o = remd_pair([n, 1, 1, 1], [temps, [], [], []], spec, nstep_exchange=nex, launch_mode=mode, **extra)
     for r in range(n):
         g.init_velocities(r); o.init_velocities(r)
         g.neighbor_list(r); o.neighbor_list(r)
