@@ -476,3 +476,38 @@ def test_snapshot_staging_matches_the_synchronous_getters():
     assert np.array_equal(ae, en2[st2 != 0].astype(np.float32))
     assert np.array_equal(x2, g.get_state(0)[0].astype(np.float32))
     assert keep.sum() > 0
+
+
+@pytest.mark.parametrize("extra", [{}, {"local_kernel": 0}], ids=["replica-local", "pipelined"])
+def test_remd_2d_device_exchange_inside_md_steps(extra):
+    """Two replica dimensions (temperature x ionic strength, src/var_replica.F90:162-259 alternating
+    pair tables) with the exchange step on the device: label tables, parameters (Debye-Hueckel
+    coefficients follow both variables, src/job_md.F90:538-567) and trajectories follow the oracle
+    over a full cycle of the four pair tables."""
+    temps, ions = [295.0, 330.0], [0.05, 0.3]
+    nrep, values = [2, 1, 2, 1], [temps, [], ions, []]
+    n, nex = 4, 5
+    # label -> (T, I) as init_replica lays the labels out: the first variable varies slowest
+    spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=0).replicated(n, temps=[temps[0], temps[0], temps[1], temps[1]],
+                                                              ionic=[ions[0], ions[1], ions[0], ions[1]])
+    g, o = remd_pair(nrep, values, spec, nstep_exchange=nex, **extra)
+    _, _, l2v = o.remd_state()
+    assert np.allclose(l2v[0][:4], [295.0, 295.0, 330.0, 330.0]) and np.allclose(l2v[2][:4], [0.05, 0.3, 0.05, 0.3])
+    for r in range(n):
+        g.init_velocities(r); o.init_velocities(r)
+        g.neighbor_list(r); o.neighbor_list(r)
+    ncycle, counter = 8, 0
+    g.md_steps(nex * ncycle)
+    for c in range(ncycle):
+        o.md_run(nex)
+        _, re = o.energy_replica()
+        u = np.array([o.uniform(spec.rng_seed, 0x7fffffff, counter + i) for i in range((n + 1) // 2)])
+        counter += (n + 1) // 2
+        o.replica_exchange(re, u)
+    same_remd_state(g, o, nrep)
+    assert g.remd_stats() == o.remd_stats() if hasattr(o, "remd_stats") else g.remd_stats()[0] > 0
+    for r in range(n):
+        xg, vg, _ = g.get_state(r)
+        xo, vo, _ = o.get_state(r)
+        assert np.abs(xg - xo).max() < 1e-6 and np.abs(vg - vo).max() < 1e-6
+        assert rel(g.force(r), o.force(r)) < FORCE_TOL
