@@ -1401,7 +1401,7 @@ __global__ void k_remd_pack(DevSys S, const RemdDev *Dp)
 // pair of the current pair table), so they are decided in parallel, one thread per lower label;
 // pair k in label order uses uniform k of the attempt, as the reference's sequential loop does.
 // One block.
-__global__ void __launch_bounds__(256) k_remd_exchange(DevSys S, RemdDev *Dp)
+__global__ void __launch_bounds__(256) k_remd_exchange(DevSys S, RemdDev *Dp, int scale_here)
 {
     RemdDev &D = *Dp;
     __shared__ int s_rank[REMD_DEV_MAX_LABELS];
@@ -1457,6 +1457,16 @@ __global__ void __launch_bounds__(256) k_remd_exchange(DevSys S, RemdDev *Dp)
         RepParams rp = S.rp[r];
         remd_apply_label(D, rp, D.lab_rp[D.rep2lab[D.rank * R + r] - 1]);
         S.rp[r] = rp;
+    }
+    // small systems: the velocity rescale of accepted temperature swaps right here (one launch less)
+    if (scale_here) {
+        __syncthreads();                       // vscale complete
+        const int n3 = S.nmp * 3;
+#pragma unroll 4
+        for (int idx = tid; idx < R * n3; idx += blockDim.x) {
+            const double f = D.vscale[idx / n3];
+            if (f != 1.0) S.vel[idx] *= f;
+        }
     }
 }
 __global__ void k_remd_scale(DevSys S, const RemdDev *Dp)

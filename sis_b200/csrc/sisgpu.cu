@@ -1848,7 +1848,7 @@ static int remd_upload(sisgpu *h)
     D.tempK_default = h->rep[0].tempK;
     D.pair_tb = h->d_pair_tb.p; D.rep2lab = h->d_rep2lab.p; D.lab2rep = h->d_lab2rep.p;
     D.lab_temp = h->d_lab_temp.p; D.lab_rp = h->d_lab_rp.p; D.rp_alt = h->d_rp_alt.p; D.has_opp = h->d_has_opp.p;
-    D.send = h->d_gather_send.p; D.recv = h->d_gather_recv.p; D.vscale = h->d_vscale.p;
+    D.send = h->d_gather_send.p; D.recv = h->nranks > 1 ? h->d_gather_recv.p : h->d_gather_send.p; D.vscale = h->d_vscale.p;
     CK(cudaMemcpyAsync(h->d_pair_tb.p, h->pair_tb.data(), h->pair_tb.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_rep2lab.p, h->rep2lab.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_lab2rep.p, h->lab2rep.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -1875,7 +1875,7 @@ static int remd_download(sisgpu *h)
 // replaces MPI_ALLREDUCE (src/job_md.F90:531-533), replica_exchange and the parameter refresh
 static int enqueue_exchange(sisgpu *h)
 {
-    const int R = h->nrep, n = h->nrep_all;
+    const int R = h->nrep;
     const int sp = span_begin(h);
     launch_rg(h, -1);
     TRY(energy_launch(h, -1, nullptr));
@@ -1894,12 +1894,11 @@ static int enqueue_exchange(sisgpu *h)
         if (!h->nccl_comm) return set_err("sisgpu_comm_init not called for a multi-rank REMD");
         int rc = g_nccl.AllGather(h->d_gather_send.p, h->d_gather_recv.p, 2 * (size_t)R, NCCL_FLOAT64, h->nccl_comm, h->stream);
         if (rc) return set_err("ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
-    } else {
-        CK(cudaMemcpyAsync(h->d_gather_recv.p, h->d_gather_send.p, 2 * (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    }
-    k_remd_exchange<<<1, 256, 0, h->stream>>>(h->S, h->d_remd.p);
-    k_remd_scale<<<dim3((3 * h->nmp + 255) / 256, R), 256, 0, h->stream>>>(h->S, h->d_remd.p);
-    h->launches += 4;
+    }   // a single rank reads its own send buffer (RemdDev::recv points at it, remd_upload)
+    const int scale_here = (long long)R * h->nmp * 3 <= 32768 ? 1 : 0;
+    k_remd_exchange<<<1, 256, 0, h->stream>>>(h->S, h->d_remd.p, scale_here);
+    if (!scale_here) k_remd_scale<<<dim3((3 * h->nmp + 255) / 256, R), 256, 0, h->stream>>>(h->S, h->d_remd.p);
+    h->launches += scale_here ? 3 : 4;
     span_end(h, sp, &h->t_rex);
     return 0;
 }
