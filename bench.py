@@ -266,7 +266,8 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": (achieved / hbm) if achieved else None, "traffic": ncu_traffic(args.workload),
-                         "kernel": "k_step", "algorithmic_bytes_per_launch": bytes_step,
+                         "kernel": g.last_step_kernel() + " (one launch = one MD step of the persistent kernel)",
+                         "algorithmic_bytes_per_launch": bytes_step,
                          "us_per_launch": 1e3 * step_ms / nsteps_total if step_ms else None,
                          "peak_source": "measured" if pk.exists() else "fallback"},
             "clocks": summarize_clocks(samples),

@@ -175,6 +175,9 @@ int sisgpu_snapshot_end(sisgpu_t *h, int slot, float *xyz32, int *nbp, int *bp_i
 /* device-side wall clock of a region of calls: sisgpu_mark(h, 0) / sisgpu_mark(h, 1) record a CUDA
  * event on the library's stream, sisgpu_elapsed_ms returns the time between the two marks (it
  * waits for mark 1).  Used by bench.py: torch.cuda.Event only sees torch's own stream */
+/* name of the step kernel the last sisgpu_md_steps call launched (k_md_fast<1,false|true>, k_md_fused,
+ * or the per-phase kernels of launch modes 0 / 1) */
+const char *sisgpu_last_step_kernel(sisgpu_t *h);
 int sisgpu_mark(sisgpu_t *h, int which);
 int sisgpu_elapsed_ms(sisgpu_t *h, double *ms);
 /* diagnostic: accumulated SM clocks of CTA c of k_md_fast in out[8c..8c+7] = pair units, wait for

@@ -104,6 +104,10 @@ class SisGpu(CApi):
                    be.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(cap), _d(ene), C.byref(ek))
         return xyz, (bi[:n.value], bj[:n.value], be[:n.value]), ene, ek.value
 
+    def last_step_kernel(self) -> str:
+        self.lib.sisgpu_last_step_kernel.restype = C.c_char_p
+        return self.lib.sisgpu_last_step_kernel(self.h).decode()
+
     def mark(self, which: int) -> None:
         self._call("mark", C.c_int(which))
 

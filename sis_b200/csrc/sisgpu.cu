@@ -181,6 +181,7 @@ struct sisgpu {
     bool grid_host_valid = false;
     int dev_nrebuild_seen = 0;           // DevMisc::nrebuild at the last sync
     bool last_launch_local = false;
+    const char *last_step_kernel = "k_force_local + k_force_bp + k_integrate";   // what md_steps launched last
     // device-resident REMD state (exchange steps inside md_steps without host round trips)
     int remd_device = 1;                 // option "remd_device"
     bool remd_on_device = false;         // inside an md_steps call whose exchange steps run on the device: host tables are stale
@@ -1923,6 +1924,7 @@ static int launch_persistent(sisgpu *h, long long stop)
     const bool fast_ok = want_fast > 0 && !biases && h->K >= 24 && h->K <= 512 && smem_fast <= 200 * 1024 &&
                          (local || 3 * (ncand_total / want_fast) + 16 <= FAST_BPC);
     h->last_launch_local = fast_ok && local;
+    h->last_step_kernel = fast_ok ? (local ? "k_md_fast<1,true>" : "k_md_fast<1,false>") : "k_md_fused";
     if (fast_ok) {
         void *fn = local ? (void *)k_md_fast<1, true> : (void *)k_md_fast<1, false>;
         if (smem_fast > h->fast_smem_set || fn != h->fast_fn_set) {
@@ -2376,6 +2378,8 @@ int sisgpu_snapshot_end(sisgpu_t *h, int slot, float *xyz32, int *nbp, int *bp_i
     }
     return 0;
 }
+
+const char *sisgpu_last_step_kernel(sisgpu_t *h) { return h->last_step_kernel; }
 
 int sisgpu_mark(sisgpu_t *h, int which)
 {
