@@ -152,8 +152,9 @@ int sisgpu_check_force(sisgpu_t *h, double tempK, double *f_energy, double *f_fo
 int sisgpu_launch_count(sisgpu_t *h, int64_t *n);
 /* options: name = "launch_mode" (0 stream launches, 1 CUDA-graph chunks, 2 persistent kernels =
  * default), "fast_kernel" (0: never use k_md_fast), "local_kernel" (0: no replica-local mode of
- * k_md_fast), "pipeline" (0: host-driven list rebuilds), "remd_device" (0: host-driven exchange
- * steps), "chunk", "threads_per_bead", "timing", "profile" */
+ * k_md_fast), "mc_persistent" (0: Monte-Carlo steps through the per-phase kernels), "pipeline" (0:
+ * host-driven list rebuilds), "remd_device" (0: host-driven exchange steps), "fast_max_cta",
+ * "list_capacity" (row capacity K), "chunk", "threads_per_bead", "timing", "profile" */
 int sisgpu_set_option(sisgpu_t *h, const char *name, double value);
 /* CUDA-event time (ms) accumulated per kernel family since the last reset:
  * out[0] step kernels, out[1] neighbour list, out[2] energy, out[3] exchange;

@@ -185,6 +185,9 @@ struct FastCtx {
     unsigned *bar_pos;
     bool dih_on;
     bool local;      // replica-local mode: the CTA owns every bead of its replica, no grid barrier
+    bool after_rebuild;   // this segment follows an in-kernel list rebuild: its first step is a Monte-Carlo step
+    unsigned long long seed;
+    int max_bp_per_nt;
 };
 SIS_D void cta_sync() { named_bar_sync(0, FAST_THREADS); }
 SIS_D void fast_bp_eval(const DevSys &S, const FFParams &P, FastShared &sh, const double4 *pos, int lo_item, int hi_item,
@@ -539,11 +542,48 @@ SIS_D void fast_bp_eval(const DevSys &S, const FFParams &P, FastShared &sh, cons
     }
 }
 
+// Monte-Carlo step of the BP role (replica-local mode): passes 1-2 of src/force_bp_limit_triplet.F90.
+// Only instantiated in the replica-local kernel (fast_bp_role<true>).
+SIS_D void fast_bp_mc_step(const DevSys &S, const FFParams &P, const FastCtx &C, FastShared &sh,
+                                             const double4 *pos, int ncand)
+{
+    const int bt = threadIdx.x - FAST_MAIN, nmp = C.nmp;
+    const int rep = C.item0 / nmp;
+    const size_t rbase = (size_t)rep * nmp;
+    for (int i = bt; i < nmp; i += FAST_BP) S.nt_excess[rbase + i] = -C.max_bp_per_nt;
+    named_bar_sync(1, FAST_BP);
+    for (int i = bt; i < ncand; i += FAST_BP) {    // pass 1 of force_bp_limit_triplet: k_bp_eval<0>
+        FastBpCand &cd = sh.cand[i];
+        Vec3 xs[6], fr[6], v12;
+#pragma unroll
+        for (int t = 0; t < 6; t++) xs[t] = v3(pos[cd.b[t]]);
+        double u, a12;
+        int st = 0;
+        double en = 0.0;
+        if (bp_force_all(P, P.bp[cd.type], xs, &u, fr, &a12, &v12)) {
+            const double ene = P.bp_triplet ? P.bp[cd.type].U0 * cd.dG * exp(-u) : P.bp[cd.type].U0 * exp(-u);
+            if (ene <= P.bp_cutoff_energy) { st = 1; en = ene; }
+        }
+        S.bp_status[cd.pb] = st; S.ene_bp[cd.pb] = en;
+        cd.last = -1;
+        if (st) { atomicAdd(&S.nt_excess[cd.b[0]], 1); atomicAdd(&S.nt_excess[cd.b[1]], 1); }
+    }
+    __threadfence_block();
+    named_bar_sync(1, FAST_BP);
+    if (bt < 32) bp_prune_warp(S, P, C.seed, rep, 0.0, 0, 0, 0);
+    __threadfence_block();
+    named_bar_sync(1, FAST_BP);
+    for (int i = bt; i < ncand; i += FAST_BP) S.bp_status_MC[sh.cand[i].pb] = S.bp_status[sh.cand[i].pb];
+    __threadfence_block();
+    named_bar_sync(1, FAST_BP);
+}
+
 // BP role.  Every CTA evaluates every base-pair candidate that touches one of its beads (as i, j
 // or one of the four chain neighbours) and keeps only the force parts that act on its own beads,
 // in shared memory: no cross-CTA dependency, no global atomics, no grid barrier for the base
 // pairs.  A pair is evaluated by the two or three CTAs that own its six beads; the CTA that owns
 // bead i also maintains bp_status / ene_bp (src/force_bp.F90:191-193).
+template <bool LOCAL>
 SIS_D int fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, FastShared &sh)
 {
     const int tid = threadIdx.x, bt = tid - FAST_MAIN;
@@ -632,12 +672,24 @@ SIS_D int fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fas
     for (; n < C.nsteps; n++) {
         if (prof) b0 = clock64();
         const double4 *pos = S.pos[cur];
+        // Monte-Carlo limit of base pairs per nucleotide (src/force_bp_limit_triplet.F90:85-328), replica-local
+        // mode only: every nstep_bp_MC steps and right after a rebuild (src/job_md.F90:396-401) all candidates
+        // are evaluated, the per-nucleotide excess is counted, one warp runs the sequential delete loop
+        // (bp_prune_warp, the same code and uniform stream as k_bp_prune) and the survivors become
+        // bp_status_MC; between those steps only pairs with bp_status_MC are evaluated
+        const bool use_mc = LOCAL && P.nstep_bp_MC > 0;
+        if (use_mc) {
+            const unsigned long long istep = C.step0 + (unsigned long long)n + 1ull;
+            const bool mc = (istep % (unsigned long long)P.nstep_bp_MC == 0ull) || (n == 0 && C.after_rebuild);
+            if (LOCAL && mc) fast_bp_mc_step(S, P, C, sh, pos, ncand);
+        }
         for (int i = bt; i < ncand; i += FAST_BP) {            // distance gate, one thread per candidate
             FastBpCand &cd = sh.cand[i];
             const Vec3 v12 = pbc_vec_d(P, v3(pos[cd.b[0]]), v3(pos[cd.b[1]]));
             const double a12 = sqrt(dot(v12, v12));
             const int type = cd.type;
-            if (fabs(a12 - P.bp[type].bond_r) <= P.bp[type].cutoff_ddist) {
+            const bool masked_in = !use_mc || S.bp_status_MC[cd.pb] != 0;   // use_mask = 1 of the stream path
+            if (masked_in && fabs(a12 - P.bp[type].bond_r) <= P.bp[type].cutoff_ddist) {
                 sh.active[atomicAdd(&sh.nactive[n & 1], 1)] = i;
             } else {
                 if (P.bp_triplet && P.flg_bias_ss) {           // src/force_bp_triplet.F90:85-93
@@ -866,6 +918,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams 
     C.bar_pos = S.bar + 32;
     C.dih_on = P.flg_dih_cos || P.flg_dih_exp;
     C.local = LOCAL;
+    C.after_rebuild = false; C.seed = A.seed; C.max_bp_per_nt = A.max_bp_per_nt;
     const int tid = threadIdx.x;
     // A launch is one segment (prologue, step loop) unless the CTA rebuilds its own lists (LOCAL):
     // then a segment ends at the rebuild test and the next one starts on the new lists.
@@ -876,7 +929,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams 
         C.cur0 = ctl.cur ^ (done & 1);
         int n;
         if (tid >= FAST_MAIN + FAST_BP) n = fast_loc_role(S, P, A, C, sh);
-        else if (tid >= FAST_MAIN) n = fast_bp_role(S, P, C, sh);
+        else if (tid >= FAST_MAIN) n = fast_bp_role<LOCAL>(S, P, C, sh);
         else n = fast_main_role<U>(S, P, A, C, sh, s_rows);
         done += n;
         if (!LOCAL || done >= nsteps) break;
@@ -884,6 +937,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams 
         __threadfence_block();
         cta_sync();                                        // velocities, beta, xyz_move are back in global memory
         if (tid < FAST_MAIN) fast_local_rebuild(S, P, NA, C.item0 / C.nmp, C.cur0 ^ (n & 1));
+        C.after_rebuild = true;
         cta_sync();
     }
     if (tid >= FAST_MAIN) return;

@@ -112,6 +112,7 @@ struct StepArgs {
     int only_rep;         // >= 0: single replica (per-irep API); -1: all (grid.y)
     int integrate;        // 1: MD step (job_md loop body); 0: force() only
     int nblk_pair, nblk_loc, nblk_bp;   // per-replica block counts of the three force roles
+    int max_bp_per_nt;                  // Monte-Carlo pruning inside k_md_fast (replica-local mode, nstep_bp_MC > 0)
 };
 
 // sum over the G lanes that own one bead.  Host builds (tests/csrc/hostcheck.cu) run the same
@@ -567,13 +568,10 @@ __global__ void k_excess_init(DevSys S, int only_rep, int max_bp_per_nt, int in_
 // pass 2 of src/force_bp_limit_triplet.F90:260-328: one warp per replica runs the reference's
 // sequential delete loop; uniforms come from the counter-based stream 0x40000000 + grep.
 // deterministic != 0: temp_independent branch of src/energy_bp_limit_triplet.F90:167-176.
-__global__ void __launch_bounds__(32) k_bp_prune(DevSys S, FFParams P, unsigned long long seed, int only_rep,
-                                                  double tK_override, int use_override, int deterministic,
-                                                  int copy_to_mc, int in_md)
+SIS_D void bp_prune_warp(const DevSys &S, const FFParams &P, unsigned long long seed, int rep, double tK_override,
+                         int use_override, int deterministic, int copy_to_mc)
 {
-    if (in_md && step_blocked(S, S.ctl[0].step, only_rep)) return;
-    const int rep = (only_rep >= 0) ? only_rep : blockIdx.x;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const int nmp = S.nmp, KB = S.KB;
     const size_t rbase = (size_t)rep * nmp, pbase = rbase * KB;
     const RepParams R = S.rp[rep];
@@ -640,6 +638,13 @@ __global__ void __launch_bounds__(32) k_bp_prune(DevSys S, FFParams P, unsigned 
     __syncwarp();
     if (copy_to_mc)   // src/job_md.F90:399-401
         for (int i = lane; i < nmp * KB; i += 32) S.bp_status_MC[pbase + i] = S.bp_status[pbase + i];
+}
+__global__ void __launch_bounds__(32) k_bp_prune(DevSys S, FFParams P, unsigned long long seed, int only_rep,
+                                                  double tK_override, int use_override, int deterministic,
+                                                  int copy_to_mc, int in_md)
+{
+    if (in_md && step_blocked(S, S.ctl[0].step, only_rep)) return;
+    bp_prune_warp(S, P, seed, (only_rep >= 0) ? only_rep : blockIdx.x, tK_override, use_override, deterministic, copy_to_mc);
 }
 
 __global__ void k_copy_status_mc(DevSys S, int only_rep)

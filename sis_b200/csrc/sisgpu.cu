@@ -206,6 +206,7 @@ struct sisgpu {
     std::vector<Pending> ev_pending;
     std::vector<cudaEvent_t> ev_free;
     int fast_max_cta = 0;                // option "fast_max_cta": upper bound of the k_md_fast grid (0 = one CTA per SM)
+    int mc_persistent = 1;               // option "mc_persistent": Monte-Carlo base-pair limit inside the replica-local k_md_fast
     int local_kernel = 1;                // option "local_kernel": replica-local mode of k_md_fast (one CTA per replica)
     int local_ncand = -1;                // sequence-allowed base pairs of one replica (bound of the per-CTA candidates)
     int pipeline = 1;                    // option "pipeline": device-driven list rebuilds inside md_steps
@@ -1324,6 +1325,7 @@ static StepArgs step_args(const sisgpu *h, unsigned mask, int use_mask, int only
     A.nblk_pair = (h->nmp + 256 / h->G - 1) / (256 / h->G);
     A.nblk_loc = (h->nmp + 31) / 32;
     A.nblk_bp = (std::max(h->nbp_half_max, 1) + 255) / 256;
+    A.max_bp_per_nt = h->max_bp_per_nt;
     return A;
 }
 
@@ -2035,8 +2037,10 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
     const int R = h->nrep;
     const unsigned mask_all = 0x7FEu;
     // launch_mode 2 with device-driven rebuilds (md_run_pipelined) needs no host-side trigger
-    const bool pipelined = h->launch_mode == 2 && h->nstep_bp_MC == 0 && !h->P.flg_bias_rg && h->pipeline && !h->P.flg_bias_ss;
-    if (pipelined && h->flg_replica && h->nstep_exchange > 0 && h->remd_device && h->nrep_all <= REMD_DEV_MAX_LABELS) {
+    // Monte-Carlo base-pair limit: only the replica-local kernel carries it
+    const bool mc_ok = h->nstep_bp_MC == 0 || (h->mc_persistent && fast_local_ok(h));
+    const bool pipelined = h->launch_mode == 2 && mc_ok && !h->P.flg_bias_rg && h->pipeline && !h->P.flg_bias_ss;
+    if (pipelined && h->flg_replica && h->nstep_exchange > 0 && h->remd_device && h->nstep_bp_MC == 0 && h->nrep_all <= REMD_DEV_MAX_LABELS) {
         // REMD with the exchange step on the device: MD intervals and exchange chains are enqueued
         // back to back; the host tables are refreshed once at the end
         TRY(remd_upload(h));
@@ -2109,7 +2113,7 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
         timer_begin(h);
         const int use_mask = h->nstep_bp_MC > 0 ? 1 : 0;
         const bool uniform = h->nstep_bp_MC <= 1;   // every step has the same kernel sequence
-        if (h->launch_mode == 2 && h->nstep_bp_MC == 0 && !h->P.flg_bias_rg) {
+        if (h->launch_mode == 2 && mc_ok && !h->P.flg_bias_rg) {
             if (pipelined) {
                 // device-driven rebuilds: no host round trip between a rebuild and the next steps
                 timer_end(h, h->t_step);   // (closes the pair opened above; the loop keeps its own events)
@@ -2242,6 +2246,7 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
         CK(cudaMemcpy(&h->S.misc->inject_invalid_at, &at, sizeof(int), cudaMemcpyHostToDevice));
     }
     else if (s == "fast_max_cta") { h->fast_max_cta = (int)value; h->lists_built = false; }
+    else if (s == "mc_persistent") h->mc_persistent = (int)value;
     else if (s == "local_kernel") { h->local_kernel = (int)value; h->lists_built = false; }
     else if (s == "profile") {   // phase clocks of the persistent kernel (block 0): get_timers out[4..8]
         if (value != 0) { TRY(h->d_prof.alloc(16 + 8 * FAST_MAX_CTA)); h->S.prof = h->d_prof.p; }

@@ -105,13 +105,21 @@ def test_bp_mc_prunes_something():
 
 
 @pytest.mark.parametrize("nstep_MC", [1, 5])
-@pytest.mark.parametrize("mode", [0, 2])
-def test_trajectory_with_mc(nstep_MC, mode):
+@pytest.mark.parametrize("mode,extra", [(0, {}), (2, {}), (2, {"mc_persistent": 1})],
+                         ids=["stream", "default", "replica-local-kernel"])
+def test_trajectory_with_mc(nstep_MC, mode, extra):
     """C1 as the reference runs it (check/input_T2S2HP.toml: nstep_MC = 1) and with a sparser MC
-    schedule (bp_status_MC mask between MC steps, src/job_md.F90:365-368,399-401)."""
+    schedule (bp_status_MC mask between MC steps, src/job_md.F90:365-368,399-401); also with the
+    Monte-Carlo pruning inside the replica-local persistent kernel."""
     spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=nstep_MC)
-    g, o = both(spec, launch_mode=mode)
-    run_both(g, o, 30)
+    if extra:
+        spec.nl_margin = 0.5        # in-kernel rebuilds: the step after one is a Monte-Carlo step
+    g, o = both(spec, launch_mode=mode, **extra)
+    if extra:
+        run_both(g, o, 60, xtol=1e-7, vtol=1e-7)
+        assert g.last_step_kernel() == "k_md_fast<1,true>"
+    else:
+        run_both(g, o, 30)
     sg, eg = g.get_bp_state(0)
     so, eo = o.get_bp_state(0)
     assert np.array_equal(sg, so)
@@ -511,3 +519,27 @@ def test_remd_2d_device_exchange_inside_md_steps(extra):
         xo, vo, _ = o.get_state(r)
         assert np.abs(xg - xo).max() < 1e-6 and np.abs(vg - vo).max() < 1e-6
         assert rel(g.force(r), o.force(r)) < FORCE_TOL
+
+
+def test_remd_with_mc_persistent_and_stream_paths_agree():
+    """T-REMD with the Monte-Carlo base-pair limit (nstep_MC = 1): the replica-local persistent kernel
+    (in-kernel pruning, host-driven exchange with flg_bp_MC, src/job_md.F90:476-479) gives the
+    trajectories, label tables and acceptance counts of the per-phase stream path."""
+    n, nex = 4, 10
+    temps = [290.0, 310.0, 330.0, 350.0]
+    spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=1).replicated(n, temps=temps)
+    res = []
+    for opts in (dict(launch_mode=0), dict(launch_mode=2, mc_persistent=1)):
+        g = gpu(**opts)
+        spec.configure(g)
+        g.remd_setup([n, 1, 1, 1], [temps, [], [], []], nex)
+        for r in range(n):
+            g.init_velocities(r)
+            g.neighbor_list(r)
+        g.md_steps(40)
+        res.append(([g.get_state(r) for r in range(n)], g.remd_state(), g.remd_stats(), g.last_step_kernel()))
+    assert res[1][3] == "k_md_fast<1,true>"
+    assert np.array_equal(res[0][1][0], res[1][1][0]) and res[0][2] == res[1][2] and res[0][2][0] > 0
+    for r in range(n):
+        for a, b in zip(res[0][0][r], res[1][0][r]):
+            assert np.abs(a - b).max() < 1e-7
