@@ -20,6 +20,13 @@ elif which == "fused":
     spec.configure(g)
     g.init_velocities(0); g.neighbor_list(0)
     print("rebuilds", g.md_steps(30), "step", g.get_step())
+elif which == "mc":
+    spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=1)
+    spec.nl_margin = 0.5
+    g = SisGpu(0)
+    spec.configure(g)
+    g.init_velocities(0); g.neighbor_list(0)
+    print("rebuilds", g.md_steps(40), "step", g.get_step(), g.last_step_kernel())
 else:
     temps = [290.0, 320.0, 350.0, 380.0]
     spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=0).replicated(4, temps=temps)
