@@ -1880,6 +1880,10 @@ static int enqueue_exchange(sisgpu *h)
 {
     const int R = h->nrep;
     const int sp = span_begin(h);
+    // with the Monte-Carlo base-pair limit the exchange step evaluates with flg_bp_MC set and
+    // flg_bp_energy = .False. (src/job_md.F90:476-479): same launches as sisgpu_energy_replica
+    const bool limit = h->nstep_bp_MC > 0 || h->flg_bp_MC != 0;
+    if (limit && h->nstep_bp_MC > 0) launch_bp_eval<1>(h, -1, true, 0.0, 0, 0, 0, h->P.temp_independent);
     launch_rg(h, -1);
     TRY(energy_launch(h, -1, nullptr));
     k_remd_prepare<<<(R + 63) / 64, 64, 0, h->stream>>>(h->S, h->d_remd.p);
@@ -1887,7 +1891,7 @@ static int enqueue_exchange(sisgpu *h)
         // cross energies: bp term recomputed with the partner temperature (flg_bp_energy = .False., :72)
         RepParams *saved = h->S.rp;
         h->S.rp = h->d_rp_alt.p;
-        launch_bp_eval<1>(h, -1, false, 0.0, 0, 0, 0, h->P.temp_independent);
+        launch_bp_eval<1>(h, -1, limit, 0.0, 0, (!limit && h->nstep_bp_MC > 0) ? 1 : 0, 0, h->P.temp_independent);
         launch_rg(h, -1);
         TRY(energy_launch(h, -1, nullptr));
         h->S.rp = saved;
@@ -2040,7 +2044,7 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
     // Monte-Carlo base-pair limit: only the replica-local kernel carries it
     const bool mc_ok = h->nstep_bp_MC == 0 || (h->mc_persistent && fast_local_ok(h));
     const bool pipelined = h->launch_mode == 2 && mc_ok && !h->P.flg_bias_rg && h->pipeline && !h->P.flg_bias_ss;
-    if (pipelined && h->flg_replica && h->nstep_exchange > 0 && h->remd_device && h->nstep_bp_MC == 0 && h->nrep_all <= REMD_DEV_MAX_LABELS) {
+    if (pipelined && h->flg_replica && h->nstep_exchange > 0 && h->remd_device && h->nrep_all <= REMD_DEV_MAX_LABELS) {
         // REMD with the exchange step on the device: MD intervals and exchange chains are enqueued
         // back to back; the host tables are refreshed once at the end
         TRY(remd_upload(h));

@@ -523,8 +523,9 @@ def test_remd_2d_device_exchange_inside_md_steps(extra):
 
 def test_remd_with_mc_persistent_and_stream_paths_agree():
     """T-REMD with the Monte-Carlo base-pair limit (nstep_MC = 1): the replica-local persistent kernel
-    (in-kernel pruning, host-driven exchange with flg_bp_MC, src/job_md.F90:476-479) gives the
-    trajectories, label tables and acceptance counts of the per-phase stream path."""
+    (in-kernel pruning) with the device-side exchange chain (flg_bp_MC set, bp energies re-evaluated
+    with the limit, src/job_md.F90:476-479) gives the trajectories, label tables and acceptance counts
+    of the per-phase stream path with host-driven exchanges."""
     n, nex = 4, 10
     temps = [290.0, 310.0, 330.0, 350.0]
     spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=1).replicated(n, temps=temps)
