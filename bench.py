@@ -277,6 +277,8 @@ def main():
         try:
             if args.no_cpu:
                 raise RuntimeError("skipped (--no-cpu)")
+            if world > 1:
+                raise RuntimeError("reported at N = 1 only")
             from oracle.oracle import Oracle
             o = Oracle(omp=True)
             spec.configure(o)
