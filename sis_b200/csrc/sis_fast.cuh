@@ -68,6 +68,7 @@ struct FastShared {
     int active[FAST_BPC];
     int nactive[2], bp_next[2];      // survivors of the distance gate / next one to evaluate, by step parity
     int ncand, nextra, overflow, overflow_rows;
+    int gate_done[2];                // step index + 1 of the last completed distance-gate pass, by step parity
     int extra[FAST_NEXTRA];
     double fbp[FAST_OWN][3];         // base-pair forces on the CTA's beads (this step)
     int4 tmeta[FAST_NT];             // bonded-term slots: meta of the first bead
@@ -185,6 +186,7 @@ struct FastCtx {
     unsigned *bar_pos;
     bool dih_on;
     bool local;      // replica-local mode: the CTA owns every bead of its replica, no grid barrier
+    bool no_loc_help;     // option: the LOC warps do not join the base-pair evaluation
     bool after_rebuild;   // this segment follows an in-kernel list rebuild: its first step is a Monte-Carlo step
     unsigned long long seed;
     int max_bp_per_nt;
@@ -592,7 +594,7 @@ SIS_D int fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fas
     int cur = C.cur0;
     auto in_range = [&](int it) { return it >= lo_item && it < hi_item; };
     // ---- E = the CTA's beads + their chain neighbours outside the range ---------------------------
-    if (bt == 0) { sh.ncand = 0; sh.nactive[0] = sh.nactive[1] = 0; sh.bp_next[0] = sh.bp_next[1] = 0; sh.nextra = 0; sh.overflow = 0; }
+    if (bt == 0) { sh.ncand = 0; sh.nactive[0] = sh.nactive[1] = 0; sh.bp_next[0] = sh.bp_next[1] = 0; sh.nextra = 0; sh.overflow = 0; sh.gate_done[0] = sh.gate_done[1] = 0; }
     for (int i = bt; i < FAST_OWN * 3; i += FAST_BP) (&sh.fbp[0][0])[i] = 0.0;
     named_bar_sync(1, FAST_BP);
     for (int q = bt; q < C.nb; q += FAST_BP) {
@@ -712,6 +714,7 @@ SIS_D int fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fas
         named_bar_sync(1, FAST_BP);
         if (prof) b1 = clock64();
         const int nact = sh.nactive[n & 1];
+        if (bt == 0) { __threadfence_block(); *(volatile int *)&sh.gate_done[n & 1] = n + 1; }   // the LOC groups may join
         bar_arrive(4, FAST_MAIN + FAST_BP);                    // gate complete: the MAIN groups may join the evaluation
         if (bt == 0) { sh.nactive[(n + 1) & 1] = 0; sh.bp_next[(n + 1) & 1] = 0; }
         fast_bp_eval(S, P, sh, pos, lo_item, hi_item, n & 1, nact);
@@ -849,6 +852,13 @@ SIS_D int fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, c
                 sh.dihf[slot][0] = f0; sh.dihf[slot][1] = f1; sh.dihf[slot][2] = f2; sh.dihf[slot][3] = f3;
             }
         }
+        // the bonded tables are done: help the BP warps with the survivors of the distance gate before the
+        // Gaussians (a CTA with more formed base pairs than BP groups would otherwise need a second round)
+        if (!C.no_loc_help) {
+            while (*(volatile int *)&sh.gate_done[n & 1] != n + 1) { }
+            __threadfence_block();
+            fast_bp_eval(S, P, sh, S.pos[cur], C.item0, C.item0 + C.nb, n & 1, sh.nactive[n & 1]);
+        }
         __threadfence_block();
         __syncwarp();
         bar_arrive(3, FAST_MAIN + FAST_LOC + FAST_BP);
@@ -918,7 +928,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams 
     C.bar_pos = S.bar + 32;
     C.dih_on = P.flg_dih_cos || P.flg_dih_exp;
     C.local = LOCAL;
-    C.after_rebuild = false; C.seed = A.seed; C.max_bp_per_nt = A.max_bp_per_nt;
+    C.after_rebuild = false; C.seed = A.seed; C.max_bp_per_nt = A.max_bp_per_nt; C.no_loc_help = S.dbg_no_loc_help != 0;
     const int tid = threadIdx.x;
     // A launch is one segment (prologue, step loop) unless the CTA rebuilds its own lists (LOCAL):
     // then a segment ends at the rebuild test and the next one starts on the new lists.

@@ -81,6 +81,7 @@ struct DevSys {
     int *cell_sorted;             // cell_beads with every cell in ascending bead order (k_nl_rank)
     int ncell_cap;
     GridInfo *grid;               // the cell grid of the current build (host- or k_nl_plan-written)
+    int dbg_no_loc_help;          // option "loc_help" = 0: the LOC warps of k_md_fast do not join the base-pair evaluation
     // parameters
     RepParams *rp;
     DevCtl *ctl;                  // [2]: A, B

@@ -2251,6 +2251,7 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
     }
     else if (s == "fast_max_cta") { h->fast_max_cta = (int)value; h->lists_built = false; }
     else if (s == "mc_persistent") h->mc_persistent = (int)value;
+    else if (s == "loc_help") h->S.dbg_no_loc_help = value == 0 ? 1 : 0;
     else if (s == "local_kernel") { h->local_kernel = (int)value; h->lists_built = false; }
     else if (s == "profile") {   // phase clocks of the persistent kernel (block 0): get_timers out[4..8]
         if (value != 0) { TRY(h->d_prof.alloc(16 + 8 * FAST_MAX_CTA)); h->S.prof = h->d_prof.p; }
