@@ -1910,6 +1910,25 @@ static int enqueue_exchange(sisgpu *h)
     return 0;
 }
 
+// which persistent kernel sisgpu_md_steps launches: k_md_fast in its replica-local mode, k_md_fast
+// with a grid barrier, or the general k_md_fused
+static size_t fast_smem_bytes()
+{
+    return ((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)3 * FAST_EMAX * sizeof(uint32_t);   // rows, sort scratch / unit forces, unit tables
+}
+static void persistent_choice(sisgpu *h, bool *local, bool *fast_ok, int *want_fast)
+{
+    const int R = h->nrep;
+    *local = fast_local_ok(h);
+    *want_fast = *local ? R : (h->fast_kernel ? fast_ncta_of(h) : 0);
+    long long ncand_total = 0;
+    for (int r = 0; r < R; r++) ncand_total += h->nbp_half_rep.empty() ? h->nbp_half_max : h->nbp_half_rep[r];
+    const bool biases = h->P.flg_stage || h->P.ntwz_DCF || h->P.ntwz_FR || h->P.nrest;
+    *fast_ok = *want_fast > 0 && !biases && h->K >= 24 && h->K <= 512 && fast_smem_bytes() <= 200 * 1024 &&
+               (*local || 3 * (ncand_total / *want_fast) + 16 <= FAST_BPC);
+    if (!*fast_ok) *local = false;
+}
+
 // launch of one persistent kernel that runs until step `stop` or until a replica needs new lists
 static int launch_persistent(sisgpu *h, long long stop)
 {
@@ -1920,16 +1939,14 @@ static int launch_persistent(sisgpu *h, long long stop)
     CK(cudaMemsetAsync(h->d_bar.p, 0, 64 * sizeof(unsigned), h->stream));
     NlArgs NA = nl_args(h, false);
     void *args[] = {&h->S, &h->P, &A, &stop, &NA};
-    // k_md_fast: one bead per 8-lane group, rows / candidates / bonded tables on chip
-    const bool local = fast_local_ok(h);
-    const int want_fast = local ? R : (h->fast_kernel ? fast_ncta_of(h) : 0);
-    const size_t smem_fast = ((sizeof(FastShared) + 15) & ~size_t(15)) + (size_t)3 * FAST_EMAX * sizeof(uint32_t);   // rows, sort scratch / unit forces, classes / unit tables
-    long long ncand_total = 0;
-    for (int r = 0; r < R; r++) ncand_total += h->nbp_half_rep.empty() ? h->nbp_half_max : h->nbp_half_rep[r];
-    const bool biases = h->P.flg_stage || h->P.ntwz_DCF || h->P.ntwz_FR || h->P.nrest;
-    const bool fast_ok = want_fast > 0 && !biases && h->K >= 24 && h->K <= 512 && smem_fast <= 200 * 1024 &&
-                         (local || 3 * (ncand_total / want_fast) + 16 <= FAST_BPC);
-    h->last_launch_local = fast_ok && local;
+    // k_md_fast: rows / candidates / bonded tables on chip
+    bool local, fast_ok;
+    int want_fast;
+    persistent_choice(h, &local, &fast_ok, &want_fast);
+    const size_t smem_fast = fast_smem_bytes();
+    if (h->nstep_bp_MC > 0 && !(fast_ok && local))
+        return set_err("internal: the Monte-Carlo base-pair limit needs the replica-local kernel");
+    h->last_launch_local = local;
     h->last_step_kernel = fast_ok ? (local ? "k_md_fast<1,true>" : "k_md_fast<1,false>") : "k_md_fused";
     if (fast_ok) {
         void *fn = local ? (void *)k_md_fast<1, true> : (void *)k_md_fast<1, false>;
@@ -1976,7 +1993,10 @@ static int md_run_pipelined(sisgpu *h, long long stop)
         const int nreb_before = h->h_misc->nrebuild;
         int ncyc = (int)ceil((double)(stop - cur) / std::max(1.0, h->est_cycle_steps) * 1.2) + 1;
         ncyc = std::max(1, std::min(ncyc, 32));
-        const bool local = fast_local_ok(h) && !(h->h_misc->max_force_flag & 4);
+        bool local, fast_ok_;
+        int want_;
+        persistent_choice(h, &local, &fast_ok_, &want_);
+        if (h->h_misc->max_force_flag & 4) local = false;
         if (local) ncyc = 1;      // the kernel rebuilds its own lists and always reaches `stop`
         for (int c = 0; c < ncyc; c++) {
             if (!local) {
@@ -2042,7 +2062,10 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
     const unsigned mask_all = 0x7FEu;
     // launch_mode 2 with device-driven rebuilds (md_run_pipelined) needs no host-side trigger
     // Monte-Carlo base-pair limit: only the replica-local kernel carries it
-    const bool mc_ok = h->nstep_bp_MC == 0 || (h->mc_persistent && fast_local_ok(h));
+    bool local_kernel_, fast_ok0_;
+    int want0_;
+    persistent_choice(h, &local_kernel_, &fast_ok0_, &want0_);
+    const bool mc_ok = h->nstep_bp_MC == 0 || (h->mc_persistent && local_kernel_);
     const bool pipelined = h->launch_mode == 2 && mc_ok && !h->P.flg_bias_rg && h->pipeline && !h->P.flg_bias_ss;
     if (pipelined && h->flg_replica && h->nstep_exchange > 0 && h->remd_device && h->nrep_all <= REMD_DEV_MAX_LABELS) {
         // REMD with the exchange step on the device: MD intervals and exchange chains are enqueued
@@ -2052,7 +2075,10 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
         const long long nex = h->nstep_exchange;
         while ((long long)h->h_ctl->step < target) {
             const long long cur = (long long)h->h_ctl->step;
-            if (fast_local_ok(h) && !(h->h_misc->max_force_flag & 4)) {
+            bool local_, fast_ok_;
+            int want_;
+            persistent_choice(h, &local_, &fast_ok_, &want_);
+            if (local_ && !(h->h_misc->max_force_flag & 4)) {
                 long long s = cur;
                 for (int nint = 0; s < target && nint < 64; nint++) {
                     const long long stop = std::min<long long>(target, (s / nex + 1) * nex);
