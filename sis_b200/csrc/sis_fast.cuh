@@ -1,25 +1,33 @@
 // sis_fast.cuh -- k_md_fast: the MD loop body (src/job_md.F90:374-460) for systems with at most
-// one bead per 8-lane group of the grid (R * nmp <= 64 * #SM: BASELINE configs C1..C4).
+// ~96 beads per SM on average (BASELINE configs C1..C4).
 //
-// Same warp-specialised persistent structure as k_md_fused (sis_fused.cuh) with everything that
-// is constant between two list rebuilds held on chip for the whole launch:
-//   MAIN  (16 warps, 64 groups x 8 lanes): group g owns one bead.  Its neighbour row lives in
-//         shared memory, its position / velocity / beta / displacement / coefficients in
-//         registers.  Per step: pair loop (src/force_wca.F90, src/force_ele_DH.F90), then the
-//         integrator (src/job_md.F90:409-456) as soon as the other force parts are complete.
+// Persistent, warp-specialised, one CTA per SM; everything that is constant between two list
+// rebuilds is held on chip for the whole launch:
+//   MAIN  (16 warps = 64 groups x 8 lanes).  The rows of the CTA's beads are packed octet-aligned
+//         in shared memory; a UNIT is one octet of one row.  Units are dealt round-robin to the
+//         groups (src/force_wca.F90, src/force_ele_DH.F90), reduced by shuffles into fixed slots.
+//         Each 4-lane half of a group owns one bead (128 owner slots per CTA): position /
+//         velocity / beta / displacement / coefficients in shared memory, integrated
+//         (src/job_md.F90:409-456) as soon as the other force parts are complete.  Bead ranges are
+//         cut by pair work (k_nl_partition), not by bead count.
 //   BP    (4 warps): every base-pair candidate that touches one of the CTA's beads is cached in
 //         shared memory (six bead ids, type, dG); one thread per candidate applies the distance
-//         gate, 8-lane groups evaluate the survivors (one role per lane, bp_force_role) and add
-//         the parts acting on the CTA's own beads to a shared-memory force array -- pairs are
-//         evaluated redundantly by the 2-3 CTAs owning their beads, so the base-pair term needs no
-//         global atomics and no grid barrier.
+//         gate, 8-lane groups evaluate the survivors (one role per lane, bp_force_role) drawn from a
+//         shared counter and add the parts acting on the CTA's own beads to a shared-memory force
+//         array: pairs are evaluated redundantly by the 2-3 CTAs owning their beads, so the
+//         base-pair term needs no global atomics and no grid barrier.
 //   LOC   (4 warps): every bonded term the CTA's beads take part in is evaluated ONCE
-//         (src/force_bond.F90, force_angl*.F90, force_dih_*.F90) into shared tables the MAIN
-//         groups read; then the Gaussians of the NEXT step (Philox + Box-Muller) into a
-//         double-buffered shared array; one LOC warp also evaluates the rebuild test.
+//         (src/force_bond.F90, force_angl*.F90, force_dih_*.F90) into shared tables the owners
+//         read; then they join the base-pair evaluation (a CTA with more formed base pairs than BP
+//         groups would otherwise need a second round of the ~2 us evaluation chain), as the MAIN
+//         groups do when their units are done; then the Gaussians of the NEXT step (Philox +
+//         Box-Muller) into a double-buffered shared array; one LOC warp also evaluates the rebuild test.
 // One grid barrier per step: bar[32] "positions written".  The rebuild test of
 // src/job_md.F90:376-388 for R == 1 goes through per-CTA (max, 2nd max) slots read after the
 // position barrier, off the critical path; with R > 1 through the atomic top-2 of k_md_fused.
+// Replica-local mode (template LOCAL): one CTA owns one whole replica -- no grid barrier, the lists
+// are rebuilt inside the kernel (fast_local_rebuild) and the Monte-Carlo limit of base pairs per
+// nucleotide (src/force_bp_limit_triplet.F90, nstep_bp_MC > 0) runs in the BP role (fast_bp_mc_step).
 #pragma once
 
 #include "sis_fused.cuh"
@@ -109,47 +117,6 @@ SIS_D void fast_pair_one(const FFParams &P, uint32_t ent, Vec3 xk, Vec3 xj, doub
     if ((ent & NB_ELE) && d2 <= cut2) s += dh_scalar(ele_coef, inv_lambdaD, d2);
     F += s * v;
 }
-// pair loop of one bead over its row in shared memory (8 lanes, entries lane, lane + 8, ...).
-// U >= 2: U gathers in flight per lane.  U == 1: one entry per iteration with the next
-// position gather issued before the current pair is evaluated (rows are sorted by distance in
-// the prologue, so the lanes of a warp leave the Debye-Hueckel branch together).
-template <int U>
-SIS_D Vec3 fast_pair(const FFParams &P, const uint32_t *row, int nn, int lane, Vec3 xk, const double4 *__restrict__ pos,
-                     double ele_coef, double inv_lambdaD, double cut2)
-{
-    Vec3 F = mk(0.0, 0.0, 0.0);
-    if (U == 1) {
-        int e = lane;
-        uint32_t ent = e < nn ? row[e] : 0u;
-        Vec3 xj = ent ? v3(pos[ent & NB_IDX]) : xk;
-        while (ent) {
-            const int en = e + 8;
-            const uint32_t ent_n = en < nn ? row[en] : 0u;
-            Vec3 xn = xk;
-            if (ent_n) xn = v3(pos[ent_n & NB_IDX]);
-            fast_pair_one(P, ent, xk, xj, ele_coef, inv_lambdaD, cut2, F);
-            e = en; ent = ent_n; xj = xn;
-        }
-        return F;
-    }
-    for (int e0 = lane; e0 < nn; e0 += U * 8) {
-        uint32_t ent[U];
-        Vec3 xj[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int e = e0 + u * 8;
-            ent[u] = e < nn ? row[e] : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++)
-            if (ent[u]) xj[u] = v3(pos[ent[u] & NB_IDX]);
-#pragma unroll
-        for (int u = 0; u < U; u++)
-            if (ent[u]) fast_pair_one(P, ent[u], xk, xj[u], ele_coef, inv_lambdaD, cut2, F);
-    }
-    return F;
-}
-
 // (rep, bead) of a flattened item
 SIS_D void fast_item(int item, int nmp, int *rep, int *k) { *rep = item / nmp; *k = item - *rep * nmp; }
 
