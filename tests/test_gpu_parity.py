@@ -317,3 +317,28 @@ def test_row_overflow_during_device_side_rebuilds_grows_the_lists():
     assert out[0][3] == out[1][3]
     for a, b in zip(out[0][0], out[1][0]):
         assert np.abs(a - b).max() < 1e-6
+
+
+def test_gpu_dynamics_match_the_reference_trajectory_statistically():
+    """Same distributional check as tests/test_oracle_golden.py against the reference binary's own
+    trajectory check/test_md.dcd, for the persistent CUDA path (north_star: trajectories agree
+    statistically since the RNG streams differ)."""
+    from tests.test_oracle_golden import chain_statistics
+    from sis_b200.api import SisGpu
+    ref = np.array([chain_statistics(f) for f in fx.array("test_md_dcd")])
+    spec = fx.cag47(4, pbc=True)
+    g = SisGpu(0)
+    spec.configure(g)
+    g.init_velocities(0)
+    g.neighbor_list(0)
+    g.md_steps(3000)
+    ours = []
+    for _ in range(40):
+        g.md_steps(200)
+        ours.append(chain_statistics(g.get_state(0)[0]))
+    ours = np.array(ours)
+    assert abs(ours[:, 0].mean() - ref[:, 0].mean()) < 0.03
+    assert abs(ours[:, 1].mean() - ref[:, 1].mean()) < 0.008
+    assert abs(ours[:, 2].mean() - ref[-4:, 2].mean()) < 0.04
+    ek = g.energy_kinetic(0)
+    assert abs(2.0 * ek / (3 * spec.nmp * 0.0019872042586408316) / spec.tempK - 1.0) < 0.1

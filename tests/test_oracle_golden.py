@@ -119,3 +119,38 @@ def test_list_counts_cag47_4():
     assert nwca == 1572
     assert nele == 18282
     assert nbp == 643
+
+
+def chain_statistics(x, nchain=4, L=809.972):
+    """mean / standard deviation of the bond lengths and mean bond angle of a 4 x CAG47 frame"""
+    x = np.asarray(x, dtype=np.float64).reshape(nchain, -1, 3)
+    d = np.diff(x, axis=1)
+    d -= L * np.round(d / L)
+    b = np.linalg.norm(d, axis=2)
+    v1, v2 = -d[:, :-1], d[:, 1:]
+    c = (v1 * v2).sum(-1) / np.linalg.norm(v1, axis=-1) / np.linalg.norm(v2, axis=-1)
+    return b.mean(), b.std(), np.arccos(c).mean()
+
+
+def test_dynamics_match_the_reference_trajectory_statistically():
+    """check/test_md.dcd is a trajectory of the reference binary itself (4 x CAG47, PBC, 310.15 K,
+    check/input_md.toml).  RNG streams differ, so the comparison is distributional:
+    bond-length mean and thermal width (sqrt(kT / k) = 0.20 A) and the mean bond angle of an
+    equilibrated run of the same system through the integrator + Gaussian generator of this
+    repository must sit where the reference's frames sit."""
+    ref = np.array([chain_statistics(f) for f in fx.array("test_md_dcd")])
+    spec = fx.cag47(4, pbc=True)
+    o = Oracle(omp=True)
+    spec.configure(o)
+    o.init_velocities(0)
+    o.neighbor_list(0)
+    o.md_run(1500)
+    ours = []
+    for _ in range(10):
+        o.md_run(200)
+        ours.append(chain_statistics(o.get_state(0)[0]))
+    ours = np.array(ours)
+    assert abs(ours[:, 0].mean() - ref[:, 0].mean()) < 0.03          # bond mean: 5.91 vs 5.93 A
+    assert abs(ours[:, 1].mean() - ref[:, 1].mean()) < 0.012         # bond width: 0.204 vs 0.204 A
+    assert abs(ours[:, 1].mean() - np.sqrt(0.0019872042586408316 * 310.15 / 15.0)) < 0.012
+    assert abs(ours[:, 2].mean() - ref[-4:, 2].mean()) < 0.04        # mean angle; the reference run is still relaxing
