@@ -66,6 +66,11 @@ int sisgpu_set_ff_bp(sisgpu_t *h, int model, int min_loop, int max_bp_per_nt, in
                      double cutoff_energy, const double *bp_paras);
 /* [NN] tables (21 stacks in NNT order, src/const_idx.F90:96-121) from which the 468-entry
  * bp3 table of src/init_bp.F90:39-172 is rebuilt; replaces the N x N bp_map / bp3_map */
+/* read_ss (src/read_ss.F90) + the restricted branch of init_bp (src/init_bp.F90:178-209): only the
+ * pairs of a ct / bpseq / bpl file may form base pairs.  pairs = 1-based (imp, jmp) [n][2] in any
+ * order; the filters of read_ss (chain ends, minimum loop, isolated pairs, unknown types) are applied
+ * here.  n < 0 removes the restriction.  Call after set_topology and set_ff_bp */
+int sisgpu_set_bp_restrict(sisgpu_t *h, int n, const int *pairs);
 int sisgpu_set_ff_nn(sisgpu_t *h, const double *NN_dH, const double *NN_dS, double dH0,
                      double dS0, int flg_NNend, const double *NNend_dH,
                      const double *NNend_dS, double dHend0, double dSend0);

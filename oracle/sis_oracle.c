@@ -66,6 +66,10 @@ typedef struct {
 } replica;
 
 struct sis_oracle {
+    /* secondary-structure restriction of the bp map (src/read_ss.F90): sorted keys imp * nmp + jmp
+     * (0-based, imp < jmp) of the pairs read_ss accepts; flg_ss = 0: all pairwise */
+    int flg_ss, n_ss;
+    long long *ss_keys;
     /* topology */
     int nmp, nchains;
     int *nmp_chain, *moltypes, *chain_start;
@@ -227,6 +231,7 @@ void oracle_destroy(sis_oracle *o)
         for (int i = 0; i < o->nrep_proc; i++) free_replica(&o->rep[i]);
         free(o->rep);
     }
+    free(o->ss_keys);
     free(o->nmp_chain); free(o->moltypes); free(o->chain_start); free(o->seq);
     free(o->ichain_mp); free(o->lmp_mp); free(o->has_charge); free(o->is_frozen);
     free(o->mass); free(o->bond_mp); free(o->angl_mp); free(o->dih_mp);
@@ -589,11 +594,44 @@ static void init_bp3_table(sis_oracle *o)
 
 /* src/init_bp.F90:184-313 evaluated on the fly for one pair (0-based imp < jmp):
  * returns bp_map (type 1..6) and bp3_map (>0 if the pair enters the bp list) */
+static int ss_has(const sis_oracle *o, int imp, int jmp)
+{
+    const long long key = (long long)imp * o->nmp + jmp;
+    int lo = 0, hi = o->n_ss;
+    while (lo < hi) {
+        const int mid = (lo + hi) / 2;
+        if (o->ss_keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo < o->n_ss && o->ss_keys[lo] == key;
+}
+static int bp_type_seq(int a, int b)
+{
+    if (a == SEQ_G && b == SEQ_C) return BPT_GC;
+    if (a == SEQ_C && b == SEQ_G) return BPT_CG;
+    if (a == SEQ_A && b == SEQ_U) return BPT_AU;
+    if (a == SEQ_U && b == SEQ_A) return BPT_UA;
+    if (a == SEQ_G && b == SEQ_U) return BPT_GU;
+    if (a == SEQ_U && b == SEQ_G) return BPT_UG;
+    return 0;
+}
+
 static void bp_lookup(const sis_oracle *o, int imp, int jmp, int *bptype, int *bp3)
 {
     *bptype = 0;
     *bp3 = 0;
     if (imp >= jmp) return;
+    if (o->flg_ss) {
+        /* src/init_bp.F90:207-209: only the pairs read_ss left in bp_map are visited.  For
+         * bp_model /= 5, bp3_map = bp_map (:315-317) keeps every such pair in the lists, whatever
+         * the loop `cycle`s over afterwards */
+        if (!ss_has(o, imp, jmp)) return;
+        if (o->bp_model != 5) {
+            const int t = bp_type_seq(o->seq[imp], o->seq[jmp]);
+            *bptype = t;
+            *bp3 = t;
+            return;
+        }
+    }
     int ichain = o->ichain_mp[imp], jchain = o->ichain_mp[jmp];
     int i = o->lmp_mp[imp] + 1, j = o->lmp_mp[jmp] + 1; /* 1-based as in the reference */
     int ni = o->nmp_chain[ichain], nj = o->nmp_chain[jchain];
@@ -645,6 +683,41 @@ static void bp_lookup(const sis_oracle *o, int imp, int jmp, int *bptype, int *b
     } else {
         *bp3 = t; /* src/init_bp.F90:315-317 */
     }
+}
+
+/* src/read_ss.F90:120-210: the pairs of a ct / bpseq / bpl file that enter bp_map.  pairs = 1-based
+ * (imp, jmp) in any order; n < 0 removes the restriction.  Call after set_topology and set_ff_bp. */
+static int cmp_ll(const void *a, const void *b)
+{
+    const long long x = *(const long long *)a, y = *(const long long *)b;
+    return x < y ? -1 : x > y;
+}
+int oracle_set_bp_restrict(sis_oracle *o, int n, const int *pairs)
+{
+    free(o->ss_keys);
+    o->ss_keys = NULL; o->n_ss = 0; o->flg_ss = n >= 0;
+    if (n <= 0) return 0;
+    o->ss_keys = (long long *)malloc((size_t)n * sizeof(long long));
+    for (int k = 0; k < n; k++) {
+        int imp = pairs[2 * k] - 1, jmp = pairs[2 * k + 1] - 1;
+        if (imp > jmp) { const int t = imp; imp = jmp; jmp = t; }
+        if (imp < 0 || jmp >= o->nmp || imp == jmp) continue;
+        const int ichain = o->ichain_mp[imp], jchain = o->ichain_mp[jmp];
+        const int i = o->lmp_mp[imp] + 1, j = o->lmp_mp[jmp] + 1;
+        if (i == 1 || i == o->nmp_chain[ichain]) continue;               /* chain ends */
+        if (j == 1 || j == o->nmp_chain[jchain]) continue;
+        if (ichain == jchain && i + o->bp_min_loop >= j) continue;         /* minimum loop length */
+        if (o->bp_model == 3 || o->bp_model == 4 || o->bp_model == 5)      /* isolated base pair */
+            if (!is_complement(o->seq[imp - 1], o->seq[jmp + 1]) && !is_complement(o->seq[imp + 1], o->seq[jmp - 1])) continue;
+        if (!bp_type_seq(o->seq[imp], o->seq[jmp])) continue;              /* no known type */
+        o->ss_keys[o->n_ss++] = (long long)imp * o->nmp + jmp;
+    }
+    qsort(o->ss_keys, (size_t)o->n_ss, sizeof(long long), cmp_ll);
+    int m = 0;
+    for (int k = 0; k < o->n_ss; k++)
+        if (k == 0 || o->ss_keys[k] != o->ss_keys[k - 1]) o->ss_keys[m++] = o->ss_keys[k];
+    o->n_ss = m;
+    return 0;
 }
 
 int oracle_bp_lookup(sis_oracle *o, int imp, int jmp, int *bptype, int *bp3idx)

@@ -93,6 +93,8 @@ int oracle_get_local_lists(sis_oracle *o, int *nbond, int *nangl, int *ndih, int
 int oracle_bp3_table(sis_oracle *o, int *n, int *hash4096, double *dH, double *dS);
 /* on-the-fly bp_map / bp3_map value of src/init_bp.F90:184-313 for a 1-based pair */
 int oracle_bp_lookup(sis_oracle *o, int imp, int jmp, int *bptype, int *bp3idx);
+/* src/read_ss.F90 + src/init_bp.F90:178-209: restrict the bp map to the pairs of a ct/bpseq/bpl file */
+int oracle_set_bp_restrict(sis_oracle *o, int n, const int *pairs /*1-based [n][2]*/);
 
 /* hot path */
 int oracle_set_bp_mc(sis_oracle *o, int flg_bp_MC);         /* job_md.F90:365-368 */

@@ -85,6 +85,14 @@ class CApi:
         self._call("set_ff_bp", C.c_int(model), C.c_int(min_loop), C.c_int(max_bp_per_nt), C.c_int(nstep_MC),
                    C.c_double(cutoff_energy), _d(bp_paras))
 
+    def set_bp_restrict(self, pairs):
+        """ct / bpseq / bpl restriction of the bp map: 1-based (imp, jmp) pairs; None removes it."""
+        if pairs is None:
+            self._call("set_bp_restrict", C.c_int(-1), None)
+            return
+        a = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+        self._call("set_bp_restrict", C.c_int(a.shape[0]), _i(a))
+
     def set_ff_nn(self, NN_dH, NN_dS, dH0, dS0, flg_NNend, NNend_dH, NNend_dS, dHend0, dSend0):
         self._call("set_ff_nn", _d(NN_dH), _d(NN_dS), C.c_double(dH0), C.c_double(dS0), C.c_int(flg_NNend),
                    _d(NNend_dH), _d(NNend_dS), C.c_double(dHend0), C.c_double(dSend0))

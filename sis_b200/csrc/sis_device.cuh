@@ -518,6 +518,40 @@ SIS_HD int chain_nb(int4 m, int off)
 // bp_map / bp3_map of src/init_bp.F90:184-313 evaluated on the fly for beads imp < jmp.
 // seq = per-bead sequence codes.  Returns bp type (1..6) in *bptype and the 1-based bp3 index
 // (model 5) or the type (other models); 0 = pair not allowed.
+// secondary-structure restriction (src/read_ss.F90, src/init_bp.F90:178-209): sorted keys
+// imp * nmp + jmp (0-based, imp < jmp) of the pairs read_ss leaves in bp_map; n_ss < 0: all pairwise
+struct BpRestrict {
+    const unsigned long long *keys;
+    int n_ss, nmp;
+};
+SIS_HD bool bp_restrict_has(const BpRestrict &Rs, int imp, int jmp)
+{
+    const unsigned long long key = (unsigned long long)imp * (unsigned long long)Rs.nmp + (unsigned long long)jmp;
+    int lo = 0, hi = Rs.n_ss;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (Rs.keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo < Rs.n_ss && Rs.keys[lo] == key;
+}
+SIS_HD int bp_lookup(int model, int min_loop, const int *__restrict__ hash, const int *__restrict__ seq,
+                     int imp, int4 mi, int jmp, int4 mj, int *bptype);
+// bp_lookup under a restriction: only listed pairs; for bp_model /= 5, bp3_map = bp_map
+// (src/init_bp.F90:315-317) keeps every listed pair, whatever the rules of :211-266 say
+SIS_HD int bp_lookup_r(const BpRestrict &Rs, int model, int min_loop, const int *__restrict__ hash,
+                       const int *__restrict__ seq, int imp, int4 mi, int jmp, int4 mj, int *bptype)
+{
+    if (Rs.n_ss >= 0) {
+        *bptype = 0;
+        if (!bp_restrict_has(Rs, imp, jmp)) return 0;
+        if (model != 5) {
+            const int t = bp_type_of(seq[mi.x + mi.z], seq[mj.x + mj.z]);
+            *bptype = t;
+            return t;
+        }
+    }
+    return bp_lookup(model, min_loop, hash, seq, imp, mi, jmp, mj, bptype);
+}
 SIS_HD int bp_lookup(int model, int min_loop, const int *__restrict__ hash, const int *__restrict__ seq,
                      int imp, int4 mi, int jmp, int4 mj, int *bptype)
 {

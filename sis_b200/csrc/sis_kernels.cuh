@@ -56,6 +56,7 @@ struct DevSys {
     const double4 *coef;          // a, sqrt(b)h/m, sqrt(b)h (0 if frozen), noise0
     const double *mass;
     const int *hash;              // bp3 hash (4096), 1-based values, 0 = none
+    BpRestrict rs;                // ct / bpseq / bpl restriction of the bp map (n_ss < 0: none)
     const double *bp3_dH, *bp3_dS;  // 1-based (index 0 unused)
     // state [rep][nmp]
     double4 *pos[2];
@@ -1194,8 +1195,8 @@ SIS_D void nl_rows_bead_at(const DevSys &S, const FFParams &P, const NlArgs &A, 
                 ent = nl_pair_flags(A, P, mi, mj, i, j, dot(v, v), ele_nl_cut2);
                 if (ent && nl_needs_image(P, A, xi, xj)) ent |= NB_IMG;
                 if (nl_bp_geometry(A, i, j, dot(v, v))) {
-                    if (i < j) bp3 = bp_lookup(A.bp_model, A.bp_min_loop, S.hash, S.seq, i, mi, j, mj, &bptype);
-                    else bp3 = bp_lookup(A.bp_model, A.bp_min_loop, S.hash, S.seq, j, mj, i, mi, &bptype);
+                    if (i < j) bp3 = bp_lookup_r(S.rs, A.bp_model, A.bp_min_loop, S.hash, S.seq, i, mi, j, mj, &bptype);
+                    else bp3 = bp_lookup_r(S.rs, A.bp_model, A.bp_min_loop, S.hash, S.seq, j, mj, i, mi, &bptype);
                 }
             }
         }

@@ -119,6 +119,10 @@ struct sisgpu {
     int bp_model = 5, bp_min_loop = 3, max_bp_per_nt = 1, nstep_bp_MC = 0;
     double NN_dH[22]{}, NN_dS[22]{}, dH0 = 0, dS0 = 0, NNend_dH[7]{}, NNend_dS[7]{}, dHend0 = 0, dSend0 = 0;
     int flg_NNend = 0, have_nn = 0;
+    // ct / bpseq / bpl restriction (src/read_ss.F90): sorted keys imp * nmp + jmp of the accepted pairs
+    bool flg_ss = false;
+    std::vector<unsigned long long> ss_keys;
+    DBuf<unsigned long long> d_ss_keys;
     std::vector<int> bp3_hash;          // 4096
     std::vector<double> bp3_dH, bp3_dS; // 469 (1-based)
     int bp3_n = 0;
@@ -275,7 +279,7 @@ int sisgpu_destroy(sisgpu_t *h)
     h->d_twzfr_init.release(); h->d_twzfr_velo.release(); h->d_rest_rcut.release(); h->d_rest_para.release();
     h->d_gather_send.release(); h->d_gather_recv.release(); h->d_nbr.release(); h->d_bprow.release();
     h->d_bp_type.release(); h->d_bp_coef.release(); h->d_mc_counter.release();
-    h->d_ene_counter.release(); h->d_bar.release(); h->d_top2_slots.release(); h->d_cta_item0.release(); h->d_cell_sorted.release(); h->d_grid.release(); h->d_xyz_stage.release();
+    h->d_ene_counter.release(); h->d_bar.release(); h->d_top2_slots.release(); h->d_cta_item0.release(); h->d_cell_sorted.release(); h->d_grid.release(); h->d_xyz_stage.release(); h->d_ss_keys.release();
     snap_free(h->snap[0]); snap_free(h->snap[1]);
     for (auto &p : h->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     h->ev_pending.clear();
@@ -388,6 +392,47 @@ int sisgpu_set_ff_bp(sisgpu_t *h, int model, int min_loop, int max_bp_per_nt, in
         P.bp[4 + t] = s;
     }
     return 0;
+}
+
+// host view of the restriction (hostcheck, setup-time counts)
+static BpRestrict host_restrict(const sisgpu *h)
+{
+    BpRestrict r;
+    r.keys = h->ss_keys.data(); r.n_ss = h->flg_ss ? (int)h->ss_keys.size() : -1; r.nmp = h->nmp;
+    return r;
+}
+static int upload_restrict(sisgpu *h)
+{
+    if (!h->finalized) return 0;
+    TRY(h->d_ss_keys.upload(h->ss_keys));
+    h->S.rs.keys = h->d_ss_keys.p; h->S.rs.n_ss = h->flg_ss ? (int)h->ss_keys.size() : -1; h->S.rs.nmp = h->nmp;
+    h->lists_built = false;
+    return 0;
+}
+// src/read_ss.F90:120-210: the pairs of a ct / bpseq / bpl file that enter bp_map (1-based (imp, jmp),
+// any order); n < 0 removes the restriction.  Call after set_topology and set_ff_bp.
+int sisgpu_set_bp_restrict(sisgpu_t *h, int n, const int *pairs)
+{
+    if (h->nmp <= 0) return set_err("set_topology must come first");
+    h->flg_ss = n >= 0;
+    h->ss_keys.clear();
+    for (int k = 0; k < n; k++) {
+        int imp = pairs[2 * k] - 1, jmp = pairs[2 * k + 1] - 1;
+        if (imp > jmp) std::swap(imp, jmp);
+        if (imp < 0 || jmp >= h->nmp || imp == jmp) continue;
+        const int ic = h->ichain[imp], jc = h->ichain[jmp];
+        const int i = h->lmp[imp] + 1, j = h->lmp[jmp] + 1;
+        if (i == 1 || i == h->nmp_chain[ic]) continue;                  // chain ends
+        if (j == 1 || j == h->nmp_chain[jc]) continue;
+        if (ic == jc && i + h->bp_min_loop >= j) continue;               // minimum loop length
+        if (h->bp_model == 3 || h->bp_model == 4 || h->bp_model == 5)    // isolated base pair
+            if (!is_complement(h->seq[imp - 1], h->seq[jmp + 1]) && !is_complement(h->seq[imp + 1], h->seq[jmp - 1])) continue;
+        if (!bp_type_of(h->seq[imp], h->seq[jmp])) continue;             // no known type
+        h->ss_keys.push_back((unsigned long long)imp * h->nmp + jmp);
+    }
+    std::sort(h->ss_keys.begin(), h->ss_keys.end());
+    h->ss_keys.erase(std::unique(h->ss_keys.begin(), h->ss_keys.end()), h->ss_keys.end());
+    return upload_restrict(h);
 }
 
 int sisgpu_set_ff_nn(sisgpu_t *h, const double *NN_dH, const double *NN_dS, double dH0, double dS0,
@@ -724,7 +769,7 @@ int sisgpu_finalize_setup(sisgpu_t *h)
         int cnt = 0, t = 0;
         for (int i = 0; i < N; i++)
             for (int j = i + 1; j < N; j++)
-                cnt += bp_lookup(h->bp_model, h->bp_min_loop, h->bp3_hash.data(), h->seq.data(), i, meta[i], j, meta[j], &t) > 0;
+                cnt += bp_lookup_r(host_restrict(h), h->bp_model, h->bp_min_loop, h->bp3_hash.data(), h->seq.data(), i, meta[i], j, meta[j], &t) > 0;
         h->local_ncand = cnt;
     }
     TRY(h->d_coef.upload(coef));
@@ -794,6 +839,7 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     TRY(alloc_lists(h, 192, N <= FAST_GROUPS ? std::max(16, (N + 7) / 8 * 8) : 16));
     TRY(alloc_cells(h, 4096));
     h->finalized = true;
+    TRY(upload_restrict(h));
     TRY(push_rp(h));
     return 0;
 }

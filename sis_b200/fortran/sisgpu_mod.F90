@@ -244,6 +244,13 @@ module sisgpu_mod
          real(c_double), intent(out) :: ekin
          integer(c_int) :: rc
       end function
+      function sisgpu_set_bp_restrict(h, n, pairs) bind(C, name='sisgpu_set_bp_restrict') result(rc)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: h
+         integer(c_int), value :: n
+         integer(c_int), intent(in) :: pairs(2, *)
+         integer(c_int) :: rc
+      end function
       function sisgpu_snapshot_begin(h, irep, tempK, flags, slot) bind(C, name='sisgpu_snapshot_begin') result(rc)
          import :: c_ptr, c_int, c_double
          type(c_ptr), value :: h

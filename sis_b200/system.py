@@ -43,6 +43,7 @@ class SystemSpec:
     bp_min_loop: int = 3
     max_bp_per_nt: int = 1
     nstep_MC: int = 1
+    bp_restrict: object = None      # ct / bpseq / bpl pairs, 1-based (imp, jmp); None = all pairwise
     # [Electrostatic]
     flg_ele: bool = False
     ionic_strength: float = 0.15
@@ -120,6 +121,8 @@ class SystemSpec:
         be.set_ff_wca(ff.wca_sigma, ff.wca_eps)
         be.set_ff_bp(self.bp_model, self.bp_min_loop, self.max_bp_per_nt if self.nstep_MC > 0 else 0,
                      self.nstep_MC, ff.bp_cutoff_energy, ff.bp_paras)
+        if self.bp_restrict is not None:
+            be.set_bp_restrict(self.bp_restrict)
         if self.bp_model == 5:
             if ff.NN_dH is None or ff.NN_dS is None:
                 raise ValueError("[NN.dH]/[NN.dS] required in FF file for bp model 5")

@@ -83,8 +83,8 @@ int hc_build_lists(HostCheck *c, double *xyz, int all_pairs)
             if (ent) rows[i].push_back(ent | (uint32_t)j);
             if (nl_bp_geometry(A, i, j, d2)) {
                 int bptype = 0, bp3;
-                if (i < j) bp3 = bp_lookup(A.bp_model, A.bp_min_loop, h->bp3_hash.data(), h->seq.data(), i, c->meta[i], j, c->meta[j], &bptype);
-                else bp3 = bp_lookup(A.bp_model, A.bp_min_loop, h->bp3_hash.data(), h->seq.data(), j, c->meta[j], i, c->meta[i], &bptype);
+                if (i < j) bp3 = bp_lookup_r(host_restrict(h), A.bp_model, A.bp_min_loop, h->bp3_hash.data(), h->seq.data(), i, c->meta[i], j, c->meta[j], &bptype);
+                else bp3 = bp_lookup_r(host_restrict(h), A.bp_model, A.bp_min_loop, h->bp3_hash.data(), h->seq.data(), j, c->meta[j], i, c->meta[i], &bptype);
                 if (bp3 > 0) { brows[i].push_back(j); btype[i].push_back(bptype); bidx[i].push_back(bp3); }
             }
         }

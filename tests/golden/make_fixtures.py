@@ -60,3 +60,14 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_ss_pairs():
+    """tests/golden/ss_pairs.json: the base pairs of check/T2S2HP.ct (1-based i < j)."""
+    pairs = []
+    for line in (REF / "check/T2S2HP.ct").read_text().splitlines()[1:]:
+        f = line.split()
+        if len(f) >= 5 and int(f[4]) > int(f[0]):
+            pairs.append([int(f[0]), int(f[4])])
+    (Path(__file__).resolve().parent / "ss_pairs.json").write_text(json.dumps(
+        {"T2S2HP_ct_pairs": pairs, "source": "check/T2S2HP.ct (column 1, column 5), pairs with j > i"}, indent=1))

@@ -41,8 +41,30 @@ def circ_spec():
     return spec
 
 
+def ct_pairs():
+    import json
+    return json.loads((fx.GOLDEN / "ss_pairs.json").read_text())["T2S2HP_ct_pairs"]
+
+
+def t2s2hp_restricted(model5=True):
+    """check/input_T2S2HP_go.toml / _bpl.toml: base pairs only between the pairs of the secondary
+    structure file (src/read_ss.F90); extra listed pairs exercise the filters of read_ss (chain end,
+    minimum loop, isolated pair) and, for bp_model /= 5, the pairs init_bp's loop skips but bp3_map keeps."""
+    pairs = ct_pairs() + [[1, 27], [9, 12], [10, 17], [9, 17], [3, 24]]
+    if model5:
+        spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=0)
+    else:
+        spec = SystemSpec(seqs=fx.seqs("T2S2HP"), ff=fx.force_field("rna_cg1"), xyz=fx.array("T2S2HP_folded"),
+                          tempK=300.0, dt=0.05, bp_model=1, bp_min_loop=4, nstep_MC=0, flg_ele=True,
+                          ionic_strength=0.15, ele_cutoff_type=1, ele_cutoff=50.0, length_per_charge=4.38178046)
+    spec.bp_restrict = pairs
+    return spec
+
+
 SPECS = {
     "t2s2hp": lambda: fx.t2s2hp("T2S2HP_folded", nstep_MC=0),
+    "t2s2hp_ct": lambda: t2s2hp_restricted(True),
+    "t2s2hp_ct_model1": lambda: t2s2hp_restricted(False),
     "cag47_4_pbc": lambda: fx.cag47(4, pbc=True),
     "circ": circ_spec,
 }
