@@ -407,6 +407,8 @@ static int upload_restrict(sisgpu *h)
     TRY(h->d_ss_keys.upload(h->ss_keys));
     h->S.rs.keys = h->d_ss_keys.p; h->S.rs.n_ss = h->flg_ss ? (int)h->ss_keys.size() : -1; h->S.rs.nmp = h->nmp;
     h->lists_built = false;
+    // bound of the base-pair candidates of one replica (replica-local mode of k_md_fast)
+    if (h->flg_ss && h->nmp <= FAST_GROUPS) h->local_ncand = (int)h->ss_keys.size();
     return 0;
 }
 // src/read_ss.F90:120-210: the pairs of a ct / bpseq / bpl file that enter bp_map (1-based (imp, jmp),

@@ -544,3 +544,18 @@ def test_remd_with_mc_persistent_and_stream_paths_agree():
     for r in range(n):
         for a, b in zip(res[0][0][r], res[1][0][r]):
             assert np.abs(a - b).max() < 1e-7
+
+
+def test_md_with_secondary_structure_restriction():
+    """MD of the hairpin with the base pairs restricted to check/T2S2HP.ct (check/input_T2S2HP_go.toml
+    style): the persistent replica-local kernel, in-kernel rebuilds included, follows the oracle."""
+    from tests.test_host_parity import t2s2hp_restricted
+    spec = t2s2hp_restricted(True)
+    spec.nl_margin = 1.0
+    g, o = both(spec)
+    run_both(g, o, 60, xtol=1e-7, vtol=1e-7)
+    assert g.last_step_kernel() == "k_md_fast<1,true>"
+    assert g.get_list_sizes(0) == o.get_list_sizes(0) and g.get_list_sizes(0)[2] <= 7
+    sg, eg = g.get_bp_state(0)
+    so, eo = o.get_bp_state(0)
+    assert np.array_equal(sg, so) and np.allclose(eg, eo, rtol=1e-7, atol=1e-10)
