@@ -227,3 +227,37 @@ def read_input_toml(path: str | Path) -> dict:
     case-sensitive in the reference; no normalisation is done here)."""
     with open(path, "rb") as fh:
         return tomllib.load(fh)
+
+
+def read_ss_pairs(path, kind: str, nmp: int | None = None) -> list[tuple[int, int]]:
+    """Base pairs of a secondary-structure file as `read_ss` reads it (`src/read_ss.F90:28-148`):
+    kind = "ct" (header line with the nucleotide count, then `imp nt _ _ jmp _`), "bpseq"
+    (`imp nt jmp`) or "bpl" (`imp jmp` per line).  Returns 1-based (imp, jmp) with imp < jmp; the
+    filters of read_ss (chain ends, minimum loop, isolated pairs) are applied by the library."""
+    lines = [l.split() for l in Path(path).read_text().splitlines() if l.split()]
+    pairs = []
+    if kind == "ct":
+        n = int(lines[0][0])
+        if nmp is not None and n != nmp:
+            raise ValueError("CT file format error. The total number of nucleotide does not match.")
+        for k, f in enumerate(lines[1:n + 1], start=1):
+            imp, jmp = int(f[0]), int(f[4])
+            if imp != k:
+                raise ValueError(f"CT file format error. Nucleotide number does not match for Nucleotide {k}")
+            if jmp != 0:
+                pairs.append((min(imp, jmp), max(imp, jmp)))
+    elif kind == "bpseq":
+        for k, f in enumerate(lines, start=1):
+            imp, jmp = int(f[0]), int(f[2])
+            if imp != k:
+                raise ValueError(f"BPSEQ file format error. Nucleotide number does not match for Nucleotide {k}")
+            if jmp != 0:
+                pairs.append((min(imp, jmp), max(imp, jmp)))
+    elif kind == "bpl":
+        for f in lines:
+            imp, jmp = int(f[0]), int(f[1])
+            if jmp != 0:
+                pairs.append((min(imp, jmp), max(imp, jmp)))
+    else:
+        raise ValueError(f"unknown secondary-structure file kind {kind}")
+    return sorted(set(pairs))

@@ -186,6 +186,11 @@ def from_input_toml(path: str | Path, ff_override: str | Path | None = None) -> 
     elif "xyz_ini" in fin:
         xyz = read_xyz(base / fin["xyz_ini"])
     spec = SystemSpec(seqs=seqs, ff=ff, xyz=xyz)
+    for kind in ("ct", "bpseq", "bpl"):      # src/read_input.F90 [Files.In]; read_ss takes the first that is set
+        if kind in fin:
+            from .inputs import read_ss_pairs
+            spec.bp_restrict = read_ss_pairs(base / fin[kind], kind, spec.nmp if kind != "bpl" else None)
+            break
     cond = t.get("Condition", {})
     spec.tempK = float(cond.get("tempK", spec.tempK))
     spec.rng_seed = int(cond.get("rng_seed", spec.rng_seed))

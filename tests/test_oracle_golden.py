@@ -154,3 +154,26 @@ def test_dynamics_match_the_reference_trajectory_statistically():
     assert abs(ours[:, 1].mean() - ref[:, 1].mean()) < 0.012         # bond width: 0.204 vs 0.204 A
     assert abs(ours[:, 1].mean() - np.sqrt(0.0019872042586408316 * 310.15 / 15.0)) < 0.012
     assert abs(ours[:, 2].mean() - ref[-4:, 2].mean()) < 0.04        # mean angle; the reference run is still relaxing
+
+
+def test_reference_secondary_structure_inputs():
+    """check/input_T2S2HP_go.toml (bpseq restriction; its [Electrostatic] header is commented out, so the
+    keys below it belong to [MD] and electrostatics stay off) read through the Python mirror of
+    the driver; the ct and bpseq files of the reference name the same seven pairs, which is what the
+    committed fixture tests/golden/ss_pairs.json holds.  Needs /root/reference (build container only)."""
+    import json
+    from pathlib import Path
+    ref = Path("/root/reference/check")
+    if not ref.exists():
+        pytest.skip("reference tree not present")
+    from sis_b200.inputs import read_ss_pairs
+    from sis_b200.system import from_input_toml
+    fixture = [tuple(p) for p in json.loads((fx.GOLDEN / "ss_pairs.json").read_text())["T2S2HP_ct_pairs"]]
+    assert read_ss_pairs(ref / "T2S2HP.ct", "ct", 27) == fixture
+    assert read_ss_pairs(ref / "T2S2HP.bpseq", "bpseq", 27) == fixture
+    spec, _ = from_input_toml(ref / "input_T2S2HP_go.toml")
+    assert spec.bp_restrict == fixture and not spec.flg_ele and spec.bp_model == 5
+    o = make(spec)
+    o.full_lists()
+    bp = o.get_lists(0)[2]
+    assert [tuple(r[:2]) for r in bp.tolist()] == fixture
