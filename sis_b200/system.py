@@ -228,4 +228,35 @@ def from_input_toml(path: str | Path, ff_override: str | Path | None = None) -> 
         spec.bias_ss_force = float(t["Bias_SS"]["force_pN"]) * PN2KCALMOLA
     if "Stage" in t:
         spec.stage = (float(t["Stage"]["sigma"]), float(t["Stage"]["epsilon"]))
+    tw = t.get("Tweezers", {}).get("Dual_Constant_Force")
+    if tw is not None:  # src/read_input.F90 [Tweezers.Dual_Constant_Force]: forces in pN
+        spec.twz_dcf_pairs = [tuple(int(x) for x in p) for p in tw["id_pairs"]]
+        spec.twz_dcf_forces = [tuple(float(x) * PN2KCALMOLA for x in f) for f in tw["forces_pN"]]
     return spec, t
+
+
+def remd_from_toml(t: dict) -> dict | None:
+    """The [Replica] block (`src/read_input.F90:443-620`) in the argument form of `remd_setup`:
+    {"nrep": [TEMP, TWZDCF, ION, RG], "values": [[...], [...], [...], [...]], "nstep_exchange": n}.
+    A variable with nrep_* of 0 or 1 is no replica variable; forces are converted from pN to
+    kcal/mol/A as the reference does (`:552`)."""
+    rep = t.get("Replica")
+    if rep is None:
+        return None
+    keys = [("nrep_temp", "Temperature", 1.0), ("nrep_force", "Force", PN2KCALMOLA),
+            ("nrep_ion", "Ionic_strength", 1.0), ("nrep_rg", "Rg", 1.0)]
+    nrep, values = [], []
+    for nkey, block, unit in keys:
+        n = int(rep.get(nkey, 1))
+        if n > 1:
+            if block not in rep:
+                raise ValueError(f"Error in input file: [Replica.{block}] is required.")
+            values.append([float(rep[block][str(i)]) * unit for i in range(1, n + 1)])
+            nrep.append(n)
+        else:
+            values.append([])
+            nrep.append(1)
+    if all(n == 1 for n in nrep):
+        raise ValueError("Error in input file: [Replica] needs any of nrep_temp, nrep_force, nrep_ion, or nrep_rg.")
+    return {"nrep": nrep, "values": values, "nstep_exchange": int(rep.get("nstep_exchange", 0)),
+            "exchange": bool(rep.get("exchange", True))}

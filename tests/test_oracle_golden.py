@@ -177,3 +177,34 @@ def test_reference_secondary_structure_inputs():
     o.full_lists()
     bp = o.get_lists(0)[2]
     assert [tuple(r[:2]) for r in bp.tolist()] == fixture
+
+
+@pytest.mark.parametrize("case,nrep,first,last", [("T2S2HP_REMD_T", [8, 1, 1, 1], 293.15, 363.15),
+                                                  ("T2S2HP_REMD_F", [1, 8, 1, 1], 0.0, 18.0 * 0.0143932617),
+                                                  ("T2S2HP_REMD_C", [1, 1, 8, 1], 0.02, 0.80)])
+def test_reference_remd_inputs(case, nrep, first, last):
+    """The three REMD inputs of the reference (temperature, tweezers force, ionic strength) through the
+    Python mirror of the driver ([Replica] block, src/read_input.F90:443-620) into remd_setup of the
+    oracle; the force-field file they name is not in the tree, sis_dih_ReB_NN.ff stands in.
+    Needs /root/reference (build container only)."""
+    from pathlib import Path
+    ref = Path("/root/reference/check")
+    if not ref.exists():
+        pytest.skip("reference tree not present")
+    from sis_b200.system import from_input_toml, remd_from_toml
+    spec, t = from_input_toml(ref / case / "input_REMD.toml", ff_override=ref / "sis_dih_ReB_NN.ff")
+    r = remd_from_toml(t)
+    assert r["nrep"] == nrep and r["nstep_exchange"] in (10, 100)
+    v = r["values"][[i for i, n in enumerate(nrep) if n > 1][0]]
+    assert len(v) == 8 and abs(v[0] - first) < 1e-9 and abs(v[-1] - last) < 1e-6
+    n = 8
+    o = Oracle()
+    spec.replicated(n).configure(o)
+    o.remd_setup(r["nrep"], r["values"], r["nstep_exchange"])
+    r2l, l2r, l2v = o.remd_state()
+    assert list(r2l[:n]) == list(range(1, n + 1))
+    for irep in range(n):
+        o.init_velocities(irep)
+        o.neighbor_list(irep)
+    e, re = o.energy_replica()
+    assert np.isfinite(re).all() and e.shape[0] == n
