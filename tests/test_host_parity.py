@@ -50,12 +50,14 @@ def t2s2hp_restricted(model5=True):
     """check/input_T2S2HP_go.toml / _bpl.toml: base pairs only between the pairs of the secondary
     structure file (src/read_ss.F90); extra listed pairs exercise the filters of read_ss (chain end,
     minimum loop, isolated pair) and, for bp_model /= 5, the pairs init_bp's loop skips but bp3_map keeps."""
-    pairs = ct_pairs() + [[1, 27], [9, 12], [10, 17], [9, 17], [3, 24]]
-    if model5:
+    # (2, 19), (2, 21), (9, 26): read_ss accepts them (a complementary neighbour pair exists), the loop
+    # of init_bp skips them (that neighbour is a chain end): listed for bp_model 3, not for 5
+    pairs = ct_pairs() + [[1, 27], [9, 12], [10, 17], [9, 17], [3, 24], [2, 19], [21, 2], [9, 26]]
+    if model5 is True:
         spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=0)
     else:
         spec = SystemSpec(seqs=fx.seqs("T2S2HP"), ff=fx.force_field("rna_cg1"), xyz=fx.array("T2S2HP_folded"),
-                          tempK=300.0, dt=0.05, bp_model=1, bp_min_loop=4, nstep_MC=0, flg_ele=True,
+                          tempK=300.0, dt=0.05, bp_model=model5 if model5 else 1, bp_min_loop=3 if model5 else 4, nstep_MC=0, flg_ele=True,
                           ionic_strength=0.15, ele_cutoff_type=1, ele_cutoff=50.0, length_per_charge=4.38178046)
     spec.bp_restrict = pairs
     return spec
@@ -65,6 +67,7 @@ SPECS = {
     "t2s2hp": lambda: fx.t2s2hp("T2S2HP_folded", nstep_MC=0),
     "t2s2hp_ct": lambda: t2s2hp_restricted(True),
     "t2s2hp_ct_model1": lambda: t2s2hp_restricted(False),
+    "t2s2hp_ct_model3": lambda: t2s2hp_restricted(3),
     "cag47_4_pbc": lambda: fx.cag47(4, pbc=True),
     "circ": circ_spec,
 }
@@ -157,3 +160,16 @@ def test_gauss_statistics():
     g = np.array([hcx.gauss(1, 0, s, b) for s in range(1, 60) for b in range(60)])
     assert abs(g.mean()) < 0.03 and abs(g.std() - 1.0) < 0.03
     assert abs(np.corrcoef(g[:, 0], g[:, 1])[0, 1]) < 0.03
+
+
+def test_restriction_keeps_skipped_pairs_for_models_other_than_5():
+    """src/init_bp.F90:315-317: with a ct / bpseq / bpl restriction and bp_model /= 5, bp3_map = bp_map keeps
+    the pairs read_ss accepted even where the loop of init_bp `cycle`s; bp_model 5 drops them."""
+    quirk = {(2, 19), (2, 21), (9, 26)}
+    for name, expect in (("t2s2hp_ct_model3", True), ("t2s2hp_ct", False)):
+        o, hcx = both(SPECS[name]())
+        o.full_lists()
+        hcx.build_lists(all_pairs=True)
+        po, ph = pairset(o.get_lists(0)[2]), pairset(hcx.lists()[2])
+        assert po == ph
+        assert quirk.issubset(po) == expect and (not expect) == quirk.isdisjoint(po)
