@@ -59,6 +59,15 @@ class Oracle(CApi):
         self._call("md_run", C.c_int(nsteps), C.byref(n))
         return n.value
 
+    def num_threads(self):
+        self.lib.oracle_num_threads.restype = C.c_int
+        return self.lib.oracle_num_threads()
+
+    def nl_seconds(self, reset=False):
+        self.lib.oracle_nl_seconds.restype = C.c_double
+        self.lib.oracle_nl_seconds.argtypes = [C.c_void_p, C.c_int]
+        return self.lib.oracle_nl_seconds(self.h, int(reset))
+
     def md_coef(self, irep, imp):
         c = np.zeros(4)
         self._call("md_coef", C.c_int(irep), C.c_int(imp), _d(c))

@@ -1,5 +1,14 @@
 /*
- * sis_oracle.c -- CPU restatement of the Hori-Lab/SIS per-step hot path (fp64, serial).
+ * sis_oracle.c -- CPU restatement of the Hori-Lab/SIS per-step hot path (fp64).
+ *
+ * Built twice (oracle/Makefile): libsis_oracle.so is serial (the parity checker);
+ * libsis_oracle_omp.so (-fopenmp) carries the reference's OpenMP threading -- one parallel
+ * region in force() with per-thread force buffers and `omp do ... nowait` per term
+ * (src/force.F90:27-69), `parallel do reduction(+)` in the pair / stage / kinetic energies
+ * (src/energy_wca.F90:19-33, energy_ele_DH.F90:20-38, energy_stage.F90:28-37,
+ * energy_kinetic.F90:23-27), `parallel do` in the bp energies (src/energy_bp_triplet.F90:36-87)
+ * and in the integrator loop (src/job_md.F90:416-456); neighbor_list stays serial as in the
+ * reference.  It is the CPU baseline of bench.py.
  *
  * TEST INFRASTRUCTURE ONLY -- see sis_oracle.h.  The product (sis_b200/) never
  * links or calls this.  "parity unpinned" at 1e-10 against the Fortran binary
@@ -8,6 +17,7 @@
  *
  * Citations are file:line relative to /root/reference.
  */
+#define _POSIX_C_SOURCE 200809L
 #include "sis_oracle.h"
 
 #include <math.h>
@@ -15,6 +25,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 /* ---- src/const_phys.F90:5-18 ------------------------------------------------ */
 static const double EPS0 = 8.8541878128e-12;
@@ -130,6 +144,10 @@ struct sis_oracle {
     int nstep_exchange;
     uint64_t exchange_counter;
     int finalized;
+    double t_nl;           /* wall seconds spent in neighbor_list inside oracle_md_step (bench.py) */
+    double *forces_t;      /* forces_t(3, nmp, 0:nthreads-1) of src/force.F90:19 */
+    size_t forces_t_n;
+    int *bp_excess;        /* nt_bp_excess(nmp), shared by the threads of force_bp_limit_triplet */
 };
 
 static char g_err[512];
@@ -239,6 +257,7 @@ void oracle_destroy(sis_oracle *o)
     free(o->twz_FR_k); free(o->twz_FR_init); free(o->twz_FR_velo);
     free(o->rest_id); free(o->rest_rcut); free(o->rest_para);
     free(o->exchange_pair_tb); free(o->rep2lab); free(o->lab2rep); free(o->lab2val);
+    free(o->forces_t); free(o->bp_excess);
     free(o);
 }
 
@@ -1064,6 +1083,7 @@ int oracle_get_lists(sis_oracle *o, int irep, int *wca_mp, int *ele_mp, int *bp_
 /* src/force_bond.F90:34-56 */
 static void force_bond(const sis_oracle *o, const replica *r, double *F)
 {
+#pragma omp for nowait
     for (int ibd = 0; ibd < o->nbond; ibd++) {
         int i1 = o->bond_mp[2 * ibd], i2 = o->bond_mp[2 * ibd + 1];
         double v[3];
@@ -1080,6 +1100,7 @@ static void force_bond(const sis_oracle *o, const replica *r, double *F)
 /* src/force_angl.F90:36-82 */
 static void force_angl(const sis_oracle *o, const replica *r, double *F)
 {
+#pragma omp for nowait
     for (int ia = 0; ia < o->nangl; ia++) {
         int i1 = o->angl_mp[3 * ia], i2 = o->angl_mp[3 * ia + 1], i3 = o->angl_mp[3 * ia + 2];
         double v21[3], v32[3];
@@ -1105,6 +1126,7 @@ static void force_angl(const sis_oracle *o, const replica *r, double *F)
 static void force_angl_ReB(const sis_oracle *o, const replica *r, double *F)
 {
     double co0 = cos(o->angl_t0);
+#pragma omp for nowait
     for (int ia = 0; ia < o->nangl; ia++) {
         int i1 = o->angl_mp[3 * ia], i2 = o->angl_mp[3 * ia + 1], i3 = o->angl_mp[3 * ia + 2];
         double v12[3], v32[3];
@@ -1128,6 +1150,7 @@ static void force_angl_ReB(const sis_oracle *o, const replica *r, double *F)
 static void force_dih(const sis_oracle *o, const replica *r, double *F, int exp_form)
 {
     double coef1 = o->dih_k * o->dih_w, coef2 = -0.5 * o->dih_w;
+#pragma omp for nowait
     for (int id = 0; id < o->ndih; id++) {
         const int *q = o->dih_mp + 4 * id;
         double vij[3], vkj[3], vkl[3], m[3], n[3];
@@ -1164,6 +1187,7 @@ static void force_wca(const sis_oracle *o, const replica *r, double *F)
 {
     double s2 = o->wca_sigma * o->wca_sigma;
     double coef = 12.0 * o->wca_eps / s2;
+#pragma omp for nowait
     for (int k = 0; k < r->nwca; k++) {
         int i1 = r->wca_mp[2 * k], i2 = r->wca_mp[2 * k + 1];
         double v[3];
@@ -1183,6 +1207,7 @@ static void force_ele_DH(const sis_oracle *o, const replica *r, double *F)
 {
     double cutoff2 = r->ele_cutoff * r->ele_cutoff;
     double rcdist = 1.0 / r->lambdaD;
+#pragma omp for nowait
     for (int k = 0; k < r->nele; k++) {
         int i1 = r->ele_mp[2 * k], i2 = r->ele_mp[2 * k + 1];
         double v21[3];
@@ -1412,15 +1437,23 @@ static void bp_mc_prune(const sis_oracle *o, replica *r, int irep, int *nt_bp_ex
 /* src/force_bp.F90, force_bp_triplet.F90, force_bp_limit_triplet.F90 */
 static void force_bp_all(const sis_oracle *o, replica *r, int irep, double *F)
 {
+    /* called by every thread of the parallel region of oracle_force_terms (orphaned worksharing,
+     * as the reference's force_bp* routines are): master resets + barrier
+     * (src/force_bp_triplet.F90:49-55, force_bp_limit_triplet.F90:70-78), `omp do` over the list,
+     * serial Monte-Carlo pruning on the master (:259-333), `omp do` scatter of the survivors */
     int triplet = is_triplet(o), limit = o->flg_bp_MC;
     double tK = r->tempK, beta = 1.0 / (BOLTZ_KCAL_MOL * tK);
-    int *excess = NULL;
-    for (int k = 0; k < r->nbp; k++) { r->bp_status[k] = 0; r->ene_bp[k] = 0.0; }
-    if (limit) {
-        memset(r->for_bp, 0, 18 * (size_t)r->nbp * sizeof(double));
-        excess = (int *)xcalloc(o->nmp, sizeof(int));
-        for (int i = 0; i < o->nmp; i++) excess[i] = -o->max_bp_per_nt;
+    int *excess = o->bp_excess;
+#pragma omp master
+    {
+        for (int k = 0; k < r->nbp; k++) { r->bp_status[k] = 0; r->ene_bp[k] = 0.0; }
+        if (limit) {
+            memset(r->for_bp, 0, 18 * (size_t)r->nbp * sizeof(double));
+            for (int i = 0; i < o->nmp; i++) excess[i] = -o->max_bp_per_nt;
+        }
     }
+#pragma omp barrier
+#pragma omp for nowait
     for (int ibp = 0; ibp < r->nbp; ibp++) {
         if (!limit && o->nstep_bp_MC > 0 && !r->bp_status_MC[ibp]) continue;
         const int *b = r->bp_mp + 7 * ibp;
@@ -1447,7 +1480,9 @@ static void force_bp_all(const sis_oracle *o, replica *r, int irep, double *F)
             if (limit) {
                 for (int s = 0; s < 6; s++)
                     for (int k = 0; k < 3; k++) r->for_bp[18 * ibp + 3 * s + k] = ene * f[s][k];
+#pragma omp atomic
                 excess[b[0]]++;
+#pragma omp atomic
                 excess[b[1]]++;
             } else
                 for (int s = 0; s < 6; s++)
@@ -1455,15 +1490,19 @@ static void force_bp_all(const sis_oracle *o, replica *r, int irep, double *F)
         }
     }
     if (limit) {
+#pragma omp barrier
+#pragma omp master
         bp_mc_prune(o, r, irep, excess, beta, 0);
+#pragma omp barrier
+#pragma omp for nowait
         for (int ibp = 0; ibp < r->nbp; ibp++) {
             if (!r->bp_status[ibp]) continue;
             const int *b = r->bp_mp + 7 * ibp;
             for (int s = 0; s < 6; s++)
                 for (int k = 0; k < 3; k++) F[3 * b[s] + k] += r->for_bp[18 * ibp + 3 * s + k];
         }
-        free(excess);
     }
+#pragma omp master
     r->flg_bp_energy = 1;
 }
 
@@ -1480,6 +1519,7 @@ static double energy_bp_all(const sis_oracle *o, replica *r, int irep, double te
             for (int i = 0; i < o->nmp; i++) excess[i] = -o->max_bp_per_nt;
         }
         for (int k = 0; k < r->nbp; k++) { r->bp_status[k] = 0; r->ene_bp[k] = 0.0; }
+#pragma omp parallel for
         for (int ibp = 0; ibp < r->nbp; ibp++) {
             if (!limit && o->nstep_bp_MC > 0 && !r->bp_status_MC[ibp]) continue;
             const int *b = r->bp_mp + 7 * ibp;
@@ -1494,7 +1534,12 @@ static double energy_bp_all(const sis_oracle *o, replica *r, int irep, double te
             if (u <= o->bp_cutoff_energy) {
                 r->ene_bp[ibp] = u;
                 r->bp_status[ibp] = 1;
-                if (limit) { excess[b[0]]++; excess[b[1]]++; }
+                if (limit) {
+#pragma omp atomic
+                    excess[b[0]]++;
+#pragma omp atomic
+                    excess[b[1]]++;
+                }
             }
         }
         if (limit) {
@@ -1513,6 +1558,7 @@ static double energy_bp_all(const sis_oracle *o, replica *r, int irep, double te
 static void force_stage(const sis_oracle *o, const replica *r, double *F)
 {
     double coef = 24.0 * o->stage_eps / o->stage_sigma;
+#pragma omp for nowait
     for (int imp = 0; imp < o->nmp; imp++) {
         double z = r->xyz[3 * imp + 2];
         if (z < SMALL_VALUE) z = SMALL_VALUE;
@@ -1594,20 +1640,45 @@ int oracle_set_bp_mc(sis_oracle *o, int flg) { o->flg_bp_MC = flg; return 0; }
 int oracle_force_terms(sis_oracle *o, int irep, unsigned mask, double *F)
 {
     replica *r = &o->rep[irep];
-    memset(F, 0, 3 * (size_t)o->nmp * sizeof(double));
-    if (mask & (1u << O_ENE_BOND)) force_bond(o, r, F);
-    if (mask & (1u << O_ENE_ANGL)) {
-        if (o->flg_angl_ReB) force_angl_ReB(o, r, F);
-        else force_angl(o, r, F);
+    const size_t n3 = 3 * (size_t)o->nmp;
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    if (o->forces_t_n < n3 * (size_t)nthreads) {   /* forces_t(3, nmp, 0:nthreads-1), src/force.F90:19 */
+        free(o->forces_t);
+        o->forces_t = (double *)xcalloc(n3 * (size_t)nthreads, sizeof(double));
+        o->forces_t_n = n3 * (size_t)nthreads;
     }
-    if (mask & (1u << O_ENE_DIHE)) {
-        if (o->flg_dih_cos) force_dih(o, r, F, 0);
-        if (o->flg_dih_exp) force_dih(o, r, F, 1);
+    if (!o->bp_excess) o->bp_excess = (int *)xcalloc(o->nmp, sizeof(int));
+    double *forces_t = o->forces_t;
+#pragma omp parallel
+    {
+        int tn = 0;
+#ifdef _OPENMP
+        tn = omp_get_thread_num();
+#endif
+        double *Ft = forces_t + n3 * (size_t)tn;
+        memset(Ft, 0, n3 * sizeof(double));
+        if (mask & (1u << O_ENE_BOND)) force_bond(o, r, Ft);
+        if (mask & (1u << O_ENE_ANGL)) {
+            if (o->flg_angl_ReB) force_angl_ReB(o, r, Ft);
+            else force_angl(o, r, Ft);
+        }
+        if (mask & (1u << O_ENE_DIHE)) {
+            if (o->flg_dih_cos) force_dih(o, r, Ft, 0);
+            if (o->flg_dih_exp) force_dih(o, r, Ft, 1);
+        }
+        if (mask & (1u << O_ENE_BP)) force_bp_all(o, r, irep, Ft);
+        if (mask & (1u << O_ENE_EXV)) force_wca(o, r, Ft);
+        if ((mask & (1u << O_ENE_ELE)) && o->flg_ele) force_ele_DH(o, r, Ft);
+        if ((mask & (1u << O_ENE_STAGE)) && o->flg_stage) force_stage(o, r, Ft);
     }
-    if (mask & (1u << O_ENE_BP)) force_bp_all(o, r, irep, F);
-    if (mask & (1u << O_ENE_EXV)) force_wca(o, r, F);
-    if ((mask & (1u << O_ENE_ELE)) && o->flg_ele) force_ele_DH(o, r, F);
-    if ((mask & (1u << O_ENE_STAGE)) && o->flg_stage) force_stage(o, r, F);
+    /* serial reduction over the threads, src/force.F90:66-69 */
+    for (int tn = 1; tn < nthreads; tn++)
+        for (size_t i = 0; i < n3; i++) forces_t[i] += forces_t[n3 * (size_t)tn + i];
+    memcpy(F, forces_t, n3 * sizeof(double));
+    /* serial biases, src/force.F90:71-75 */
     if ((mask & (1u << O_ENE_TWZ)) && (o->ntwz_DCF + o->ntwz_FR) > 0) force_tweezers(o, r, F);
     if ((mask & (1u << O_ENE_RG)) && o->flg_bias_rg) force_rg(o, r, F);
     if ((mask & (1u << O_ENE_REST)) && o->nrest > 0) force_restraint(o, r, F);
@@ -1666,6 +1737,7 @@ static double energy_dih(const sis_oracle *o, const replica *r)
 static double energy_wca(const sis_oracle *o, const replica *r)
 { /* src/energy_wca.F90:19-35 */
     double e = 0.0;
+#pragma omp parallel for reduction(+ : e)
     for (int k = 0; k < r->nwca; k++) {
         double v[3];
         pbc_vec_d(o, r->xyz + 3 * r->wca_mp[2 * k], r->xyz + 3 * r->wca_mp[2 * k + 1], v);
@@ -1679,6 +1751,7 @@ static double energy_wca(const sis_oracle *o, const replica *r)
 static double energy_ele_DH(const sis_oracle *o, const replica *r)
 { /* src/energy_ele_DH.F90:20-40 */
     double e = 0.0, rcdist = 1.0 / r->lambdaD;
+#pragma omp parallel for reduction(+ : e)
     for (int k = 0; k < r->nele; k++) {
         double v[3];
         pbc_vec_d(o, r->xyz + 3 * r->ele_mp[2 * k], r->xyz + 3 * r->ele_mp[2 * k + 1], v);
@@ -1698,6 +1771,7 @@ static int energy_stage(const sis_oracle *o, const replica *r, double *e_out)
     for (int imp = 0; imp < o->nmp; imp++)
         if (r->xyz[3 * imp + 2] < 0.85 * o->stage_sigma)
             return fail("Z-coordinate < 0.85 * stage_sigma in energy_stage");
+#pragma omp parallel for reduction(+ : e)
     for (int imp = 0; imp < o->nmp; imp++) {
         double z = o->stage_sigma / r->xyz[3 * imp + 2];
         e += 4 * o->stage_eps * (powi(z, 12) - powi(z, 6));
@@ -1763,6 +1837,7 @@ int oracle_energy_kinetic(sis_oracle *o, int irep, double *ekin)
 {
     replica *r = &o->rep[irep];
     double e = 0.0;
+#pragma omp parallel for reduction(+ : e)
     for (int imp = 0; imp < o->nmp; imp++) {
         if (o->is_frozen[imp]) r->velos[3 * imp] = r->velos[3 * imp + 1] = r->velos[3 * imp + 2] = 0.0;
         e += o->mass[imp] * dot3(r->velos + 3 * imp, r->velos + 3 * imp);
@@ -1880,7 +1955,11 @@ int oracle_md_step(sis_oracle *o, int irep, const double *gauss, int *rebuilt)
     int flg_MC_save = o->flg_bp_MC;
     if (rebuilt) *rebuilt = 0;
     if (sqrt(d2max) + sqrt(d2max_2nd) > o->nl_margin) {
+        struct timespec ts0, ts1;
+        clock_gettime(CLOCK_MONOTONIC, &ts0);
         oracle_neighbor_list(o, irep);
+        clock_gettime(CLOCK_MONOTONIC, &ts1);
+        o->t_nl += (double)(ts1.tv_sec - ts0.tv_sec) + 1e-9 * (double)(ts1.tv_nsec - ts0.tv_nsec);
         memset(r->xyz_move, 0, 3 * (size_t)nmp * sizeof(double));
         if (o->nstep_bp_MC > 0) o->flg_bp_MC = 1;
         if (rebuilt) *rebuilt = 1;
@@ -1889,6 +1968,9 @@ int oracle_md_step(sis_oracle *o, int irep, const double *gauss, int *rebuilt)
     oracle_force(o, irep, F);
     if (o->flg_bp_MC) memcpy(r->bp_status_MC, r->bp_status, (size_t)r->nbp * sizeof(int));
     (void)flg_MC_save; /* the reference leaves flg_bp_MC set for the remaining replicas too */
+    /* src/job_md.F90:416-456 `omp parallel do`; the counter-based Gaussians are drawn inside the
+     * loop (the reference draws its 3N Mersenne-Twister normals serially first, :409-413) */
+#pragma omp parallel for
     for (int imp = 0; imp < nmp; imp++) {
         double g[3], c[4];
         if (gauss) memcpy(g, gauss + 3 * imp, sizeof g);
@@ -1910,6 +1992,23 @@ int oracle_md_step(sis_oracle *o, int irep, const double *gauss, int *rebuilt)
     }
     free(F);
     return 0;
+}
+
+/* threads the OpenMP regions use (1 in the serial build) and the wall time spent in the serial
+ * neighbor_list since the last reset: what bench.py prints beside the CPU baseline */
+int oracle_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+double oracle_nl_seconds(sis_oracle *o, int reset)
+{
+    double t = o->t_nl;
+    if (reset) o->t_nl = 0.0;
+    return t;
 }
 
 /* src/job_md.F90:360-460 for all local replicas (no exchange, no output) */

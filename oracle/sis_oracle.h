@@ -16,8 +16,9 @@
  *   - structural invariants (468 bp3 entries, sum F = 0, PBC-shift invariance)
  *
  * Every function cites the reference file:line (relative to /root/reference)
- * it follows.  All arithmetic is fp64, loops are serial and in the
- * reference's order.  Indices are 0-based inside; list getters return the
+ * it follows.  All arithmetic is fp64, loops are in the reference's order; the
+ * serial build (libsis_oracle.so) is the checker, the -fopenmp build
+ * (libsis_oracle_omp.so) threads the loops the reference threads and is the CPU baseline.  Indices are 0-based inside; list getters return the
  * reference's 1-based values.
  */
 #ifndef SIS_ORACLE_H
@@ -112,6 +113,9 @@ int oracle_get_rg(sis_oracle *o, int irep, double *rg);
  * generator shared with the GPU build (oracle_gauss). */
 int oracle_md_step(sis_oracle *o, int irep, const double *gauss, int *rebuilt);
 int oracle_md_run(sis_oracle *o, int nsteps, int64_t *nrebuild);
+/* bench.py: OpenMP threads in use (1 = serial build); wall seconds inside neighbor_list */
+int oracle_num_threads(void);
+double oracle_nl_seconds(sis_oracle *o, int reset);
 int oracle_init_velocities(sis_oracle *o, int irep);        /* job_md.F90:157-176 */
 void oracle_gauss(uint64_t seed, uint32_t stream, uint64_t step, uint32_t bead, double g[3]);
 double oracle_uniform(uint64_t seed, uint32_t stream, uint64_t counter);

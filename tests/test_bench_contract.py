@@ -42,3 +42,38 @@ def test_product_arm_needs_a_gpu():
                        capture_output=True, text=True, timeout=300)
     assert r.returncode != 0          # no CPU fallback
     assert not any(l.startswith("{") for l in r.stdout.splitlines())
+
+
+def test_omp_oracle_is_threaded_and_agrees_with_the_serial_build():
+    """the CPU baseline of bench.py is the -fopenmp build of the oracle: it must really run on more
+    than one thread (the 'OpenMP' baseline was single-threaded) and give the serial
+    build's forces / energies up to summation order"""
+    import os
+    import time
+    import numpy as np
+    from oracle.oracle import Oracle
+    from sis_b200 import fixtures as fx
+    lib = (ROOT / "oracle" / "libsis_oracle_omp.so")
+    assert lib.exists()
+    ldd = subprocess.run(["ldd", str(lib)], capture_output=True, text=True).stdout
+    assert "libgomp" in ldd
+    spec = fx.cag47(4, pbc=True)
+    res = []
+    for omp in (False, True):
+        o = Oracle(omp=omp)
+        spec.configure(o)
+        o.neighbor_list(0)
+        res.append((o.force(0), o.energy_sumup(0, spec.tempK, True), o))
+    assert res[0][2].num_threads() == 1
+    f0, e0, _ = res[0]
+    f1, e1, o = res[1]
+    assert np.abs(f1 - f0).max() <= 1e-12 * np.abs(f0).max()
+    assert np.allclose(e1, e0, rtol=1e-12, atol=1e-12)
+    if (os.cpu_count() or 1) < 2 or len(os.sched_getaffinity(0)) < 2:
+        pytest.skip("one host core")
+    assert o.num_threads() > 1
+    o.init_velocities(0)
+    w0, c0 = time.perf_counter(), time.process_time()
+    o.md_run(300)
+    w, c = time.perf_counter() - w0, time.process_time() - c0
+    assert c / w > 1.5, (c, w)
