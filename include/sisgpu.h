@@ -106,6 +106,16 @@ int sisgpu_set_state(sisgpu_t *h, int irep, const double *xyz, const double *vel
 int sisgpu_get_state(sisgpu_t *h, int irep, double *xyz, double *velos, double *accels);
 int sisgpu_set_step(sisgpu_t *h, int64_t istep);
 int sisgpu_get_step(sisgpu_t *h, int64_t *istep);
+/* Restart payload of the counter-based generators.  The reference writes 643 int32 of
+ * Mersenne-Twister state per stream under the PRNG / PRNGREP tags (src/write_rst.F90:69-131) and reads
+ * them back in src/read_rst.F90:405-600; the device generators are counter-based, so the payload is
+ * state[0] = seed, [1] = istep (the Gaussian counter), [2] = draw counter of the exchange stream
+ * (PRNGREP), [3] = nrep_proc, [4 ..] = draw counters of the Monte-Carlo base-pair pruning per local
+ * replica (PRNG).  get with state == NULL returns the word count in *n.  Together with XYZ / VELO /
+ * ACCEL (sisgpu_get_state), STEP and REPLICA this makes `stop -> restart` continue the trajectory
+ * (src/job_md.F90:642-681). */
+int sisgpu_get_rng_state(sisgpu_t *h, int64_t *state, int cap, int *n);
+int sisgpu_set_rng_state(sisgpu_t *h, const int64_t *state, int n);
 
 /* ---- lists ------------------------------------------------------------------ */
 /* call neighbor_list(irep): src/job_md.F90:197,389,584 -> src/neighbor_list.F90 */
@@ -205,6 +215,10 @@ int sisgpu_comm_init(sisgpu_t *h, int nranks, int rank, const unsigned char *id)
 int sisgpu_remd_pair_table(sisgpu_t *h, int *tb);
 int sisgpu_remd_state(sisgpu_t *h, int *rep2lab, int *lab2rep, double *lab2val);
 int sisgpu_remd_stats(sisgpu_t *h, int64_t *n_attempt, int64_t *n_accept);
+/* REPLICA block of a restart (src/write_rst.F90:41-60, src/read_rst.F90:405-460): the label permutation
+ * rep2lab(1:nrep_all) and the position in the exchange schedule (var_replica's idx_pair) */
+int sisgpu_remd_set_labels(sisgpu_t *h, const int *rep2lab, int idx_pair);
+int sisgpu_remd_get_idx_pair(sisgpu_t *h, int *idx_pair);
 /* call energy_replica(...) on an exchange step: src/energy_replica.F90:45-163;
  * energies [nrep_proc][11], replica_energies [nrep_all][2] after the allgather */
 int sisgpu_energy_replica(sisgpu_t *h, double *energies, double *replica_energies);

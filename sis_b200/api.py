@@ -9,13 +9,15 @@ device construction fails.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 from ._capi import CApi, SisError, _d, _i, load_library
 
-LIB_PATH = Path(__file__).resolve().parent / "libsisgpu.so"
+# SISGPU_LIB: another build of the same library (A/B runs of kernel variants on the GPU box)
+LIB_PATH = Path(os.environ.get("SISGPU_LIB") or Path(__file__).resolve().parent / "libsisgpu.so")
 _lib = None
 
 
@@ -130,6 +132,27 @@ class SisGpu(CApi):
         a, b = C.c_int64(), C.c_int64()
         self._call("remd_stats", C.byref(a), C.byref(b))
         return a.value, b.value
+
+    def get_rng_state(self) -> np.ndarray:
+        """restart payload of the counter-based generators (PRNG / PRNGREP blocks of the .rst)"""
+        n = C.c_int()
+        self._call("get_rng_state", None, C.c_int(0), C.byref(n))
+        st = np.zeros(n.value, dtype=np.int64)
+        self._call("get_rng_state", st.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int(n.value), C.byref(n))
+        return st
+
+    def set_rng_state(self, st: np.ndarray) -> None:
+        st = np.ascontiguousarray(st, dtype=np.int64)
+        self._call("set_rng_state", st.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int(len(st)))
+
+    def remd_set_labels(self, rep2lab, idx_pair: int) -> None:
+        r = np.ascontiguousarray(rep2lab, dtype=np.int32)
+        self._call("remd_set_labels", r.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(idx_pair))
+
+    def remd_idx_pair(self) -> int:
+        v = C.c_int()
+        self._call("remd_get_idx_pair", C.byref(v))
+        return v.value
 
     def comm_init_torch(self):
         """NCCL communicator for the exchange all-gather; the unique id travels over the

@@ -89,6 +89,16 @@ SIS_HD Vec3 cross(Vec3 a, Vec3 b)
     return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 SIS_HD Vec3 v3(double4 p) { return mk(p.x, p.y, p.z); }
+#ifdef __CUDACC__
+// one 256-bit read-only load of a position (LDG.E.ENL2.256.CONSTANT on sm_100a); only for buffers
+// the running kernel never writes (the `cur` position buffer of a step)
+SIS_D double4 ldg_pos(const double4 *p)
+{
+    double4 v;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+#endif
 
 // src/pbc.F90:140-165 pbc_vec_d: single image, strict inequalities
 SIS_HD double minimg1(double v, double L, double Lh)
@@ -262,6 +272,47 @@ SIS_HD double dh_scalar(double ele_coef, double inv_lambdaD, double d2)
     const double dist1 = d2 * rdist1;
     return ele_coef * rdist1 * rdist1 * (rdist1 + inv_lambdaD) * exp(-dist1 * inv_lambdaD);
 }
+#ifdef __CUDACC__
+// Straight-line (branch-free) versions for the pair loop of k_md_big, where four pairs are
+// evaluated side by side and any branch would serialise them.
+// 1 / sqrt(x) for normal x: single-precision seed + two Newton steps (error below 1 ulp of the result)
+SIS_D double rsqrt_sl(double x)
+{
+    double y = (double)rsqrtf((float)x);
+    const double h = 0.5 * x;
+    double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    return fma(y, e, y);
+}
+// exp(-x) for 0 <= x < 700: x = -(k ln2 + r), |r| <= ln2 / 2, degree-13 Taylor polynomial (truncation
+// 4e-18), scaled by 2^k through the exponent field
+SIS_D double exp_neg_sl(double x)
+{
+    const double t = -x;
+    const double magic = 6755399441055744.0;                 // 1.5 * 2^52: round to nearest integer
+    const double kz = fma(t, 1.4426950408889634, magic);
+    const int k = __double2loint(kz);
+    const double kf = kz - magic;
+    double r = fma(kf, -6.93147180369123816490e-01, t);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;                       // 1 / 13!
+    p = fma(p, r, 2.08767569878681e-09);
+    p = fma(p, r, 2.505210838544172e-08);
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.7557319223985893e-06);
+    p = fma(p, r, 2.48015873015873e-05);
+    p = fma(p, r, 1.984126984126984e-04);
+    p = fma(p, r, 1.388888888888889e-03);
+    p = fma(p, r, 8.333333333333333e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+#endif
 // src/energy_wca.F90:19-35, src/energy_ele_DH.F90:20-40
 SIS_HD double wca_energy(const FFParams &P, double d2)
 {

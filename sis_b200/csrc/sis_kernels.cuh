@@ -33,6 +33,7 @@ struct DevMisc {
     int half_overflow;              // largest bp half-list count seen by k_nl_partition
     int inject_invalid_at;          // test hook (option "inject_invalid"): k_nl_plan marks the lists invalid at this rebuild count
     int pad;
+    long long stop_step;            // k_md_big / k_nl_plan inside replayed graphs: no step, no rebuild once this step is reached
 };
 
 // one contiguous device block the host mirrors with a single copy: header + top2[nrep][2][2]
@@ -182,6 +183,58 @@ SIS_HD Vec3 pair_force(const DevSys &S, const FFParams &P, const RepParams &R, c
     return F;
 }
 
+// per-bead biases in gather form (src/force_stage.F90, force_tweezers.F90, force_rg.F90,
+// force_restraint.F90): the force these terms put on bead k
+SIS_HD Vec3 bias_force(const DevSys &S, const FFParams &P, const RepParams &R, const double4 *__restrict__ pos,
+                       int k, Vec3 xk, unsigned term_mask, unsigned long long istep)
+{
+    const int nmp = S.nmp;
+    Vec3 F = mk(0.0, 0.0, 0.0);
+    if ((term_mask & (1u << ENE_STAGE)) && P.flg_stage) {   // src/force_stage.F90:17-37
+        double z = xk.z;
+        if (z < SIS_SMALL_VALUE) z = SIS_SMALL_VALUE;
+        z = P.stage_sigma / z;
+        F.z += (24.0 * P.stage_eps / P.stage_sigma) * (2 * powi(z, 13) - powi(z, 7));
+    }
+    if (term_mask & (1u << ENE_TWZ)) {                      // src/force_tweezers.F90:27-61
+        for (int t = 0; t < P.ntwz_DCF; t++) {
+            Vec3 f = R.twz_force * mk(S.twz_dir[3 * t], S.twz_dir[3 * t + 1], S.twz_dir[3 * t + 2]);
+            if (S.twz_pairs[2 * t] == k) F += f;
+            if (S.twz_pairs[2 * t + 1] == k) F -= f;
+        }
+        for (int t = 0; t < P.ntwz_FR; t++)
+            for (int s = 0; s < 2; s++)
+                if (S.twzfr_pairs[2 * t + s] == k) {
+                    const double *ini = S.twzfr_init + 6 * t + 3 * s, *vel = S.twzfr_velo + 6 * t + 3 * s;
+                    double st = (double)istep;
+                    Vec3 p = mk(ini[0] + vel[0] * st, ini[1] + vel[1] * st, ini[2] + vel[2] * st);
+                    F += S.twzfr_k[2 * t + s] * pbc_vec_d(P, p, xk);
+                }
+    }
+    if ((term_mask & (1u << ENE_RG)) && P.flg_bias_rg) {    // src/force_rg.F90:18-39
+        double rg = R.rg_val;
+        if (!(P.bias_rg_pott == 2 && rg <= R.bias_rg_0)) {
+            double factor = -P.bias_rg_k * (rg - R.bias_rg_0) / (rg * nmp);
+            F += factor * (xk - mk(R.rg_cm[0], R.rg_cm[1], R.rg_cm[2]));
+        }
+    }
+    if (term_mask & (1u << ENE_REST)) {                     // src/force_restraint.F90:19-41
+        for (int t = 0; t < P.nrest; t++) {
+            int ia = S.rest_id[3 * t], ib = S.rest_id[3 * t + 1], ty = S.rest_id[3 * t + 2];
+            if (ia != k && ib != k) continue;
+            Vec3 v = pbc_vec_d(P, v3(pos[ia]), v3(pos[ib]));
+            double r = sqrt(dot(v, v));
+            if (r >= S.rest_rcut[t]) continue;
+            double eps = S.rest_para[3 * t], d = S.rest_para[3 * t + 1], s = S.rest_para[3 * t + 2];
+            double th = tanh((r - d) / s);
+            double coef = 0.5 * eps / s * (1.0 - th * th) / r;
+            if (ia == k) F -= coef * v;
+            else if (ty == 1) F += coef * v;
+        }
+    }
+    return F;
+}
+
 // bonded terms (src/force_bond.F90, force_angl*.F90, force_dih_*.F90), one term instance per
 // lane: 2 bonds, 3 angles, 4 dihedrals; plus the per-bead biases on one lane
 // (src/force_stage.F90, force_tweezers.F90, force_rg.F90, force_restraint.F90)
@@ -220,50 +273,7 @@ SIS_HD Vec3 local_force(const DevSys &S, const FFParams &P, const RepParams &R, 
             F += f;
         }
     }
-    if (lane == (G > 9 ? 9 : 0)) {
-        if ((term_mask & (1u << ENE_STAGE)) && P.flg_stage) {   // src/force_stage.F90:17-37
-            double z = xk.z;
-            if (z < SIS_SMALL_VALUE) z = SIS_SMALL_VALUE;
-            z = P.stage_sigma / z;
-            F.z += (24.0 * P.stage_eps / P.stage_sigma) * (2 * powi(z, 13) - powi(z, 7));
-        }
-        if (term_mask & (1u << ENE_TWZ)) {                      // src/force_tweezers.F90:27-61
-            for (int t = 0; t < P.ntwz_DCF; t++) {
-                Vec3 f = R.twz_force * mk(S.twz_dir[3 * t], S.twz_dir[3 * t + 1], S.twz_dir[3 * t + 2]);
-                if (S.twz_pairs[2 * t] == k) F += f;
-                if (S.twz_pairs[2 * t + 1] == k) F -= f;
-            }
-            for (int t = 0; t < P.ntwz_FR; t++)
-                for (int s = 0; s < 2; s++)
-                    if (S.twzfr_pairs[2 * t + s] == k) {
-                        const double *ini = S.twzfr_init + 6 * t + 3 * s, *vel = S.twzfr_velo + 6 * t + 3 * s;
-                        double st = (double)istep;
-                        Vec3 p = mk(ini[0] + vel[0] * st, ini[1] + vel[1] * st, ini[2] + vel[2] * st);
-                        F += S.twzfr_k[2 * t + s] * pbc_vec_d(P, p, xk);
-                    }
-        }
-        if ((term_mask & (1u << ENE_RG)) && P.flg_bias_rg) {    // src/force_rg.F90:18-39
-            double rg = R.rg_val;
-            if (!(P.bias_rg_pott == 2 && rg <= R.bias_rg_0)) {
-                double factor = -P.bias_rg_k * (rg - R.bias_rg_0) / (rg * nmp);
-                F += factor * (xk - mk(R.rg_cm[0], R.rg_cm[1], R.rg_cm[2]));
-            }
-        }
-        if (term_mask & (1u << ENE_REST)) {                     // src/force_restraint.F90:19-41
-            for (int t = 0; t < P.nrest; t++) {
-                int ia = S.rest_id[3 * t], ib = S.rest_id[3 * t + 1], ty = S.rest_id[3 * t + 2];
-                if (ia != k && ib != k) continue;
-                Vec3 v = pbc_vec_d(P, v3(pos[ia]), v3(pos[ib]));
-                double r = sqrt(dot(v, v));
-                if (r >= S.rest_rcut[t]) continue;
-                double eps = S.rest_para[3 * t], d = S.rest_para[3 * t + 1], s = S.rest_para[3 * t + 2];
-                double th = tanh((r - d) / s);
-                double coef = 0.5 * eps / s * (1.0 - th * th) / r;
-                if (ia == k) F -= coef * v;
-                else if (ty == 1) F += coef * v;
-            }
-        }
-    }
+    if (lane == (G > 9 ? 9 : 0)) F += bias_force(S, P, R, pos, k, xk, term_mask, istep);
     return F;
 }
 
@@ -874,6 +884,7 @@ __global__ void __launch_bounds__(1024) k_nl_plan(DevSys S, NlPlanArgs A, int *r
     __shared__ double s_lo[3][32], s_hi[3][32];
     const int tid = threadIdx.x, R = S.nrep, nmp = S.nmp;
     const DevCtl ctl = S.ctl[0];
+    const long long stop = A.stop < 0 ? S.misc->stop_step : A.stop;   // < 0: the device-side stop step (k_md_big cycles)
     // lists already marked invalid (a row of an earlier chain of this batch did not fit): nothing is
     // rebuilt and the overflow marks are kept for the host, which grows the capacities
     const bool invalid = S.misc->lists_invalid != 0;
@@ -882,7 +893,7 @@ __global__ void __launch_bounds__(1024) k_nl_plan(DevSys S, NlPlanArgs A, int *r
     for (int r = tid; r < R; r += blockDim.x) {
         const unsigned long long *t = S.top2 + ((size_t)r * 2 + (ctl.step & 1ull)) * 2;
         const double m1 = __longlong_as_double((long long)t[0]), m2 = __longlong_as_double((long long)t[1]);
-        const int need = !invalid && (A.force_all || ((long long)ctl.step < A.stop && sqrt(m1) + sqrt(m2) > S.nl_margin));
+        const int need = !invalid && (A.force_all || ((long long)ctl.step < stop && sqrt(m1) + sqrt(m2) > S.nl_margin));
         rep_active[r] = need;
         if (need) {
             s_any = 1;

@@ -9,6 +9,7 @@
 #include "sis_kernels.cuh"
 #include "sis_fused.cuh"
 #include "sis_fast.cuh"
+#include "sis_big.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -108,6 +109,10 @@ struct sisgpu {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaGraphExec_t graph_chunk = nullptr;               // `chunk` MD steps as one graph launch
     int graph_chunk_steps = 0;
+    cudaGraphExec_t graph_big = nullptr;                 // `big_chunk` launches of k_md_big (large systems)
+    int graph_big_steps = 0, graph_big_bpc = 0;
+    int big_kernel = 1, big_chunk = 16;                  // options "big_kernel" (0: k_md_fused instead), "big_chunk" (even)
+    bool big_smem_set = false;
     bool finalized = false;
     // topology
     int nmp = 0, nchains = 0;
@@ -289,6 +294,7 @@ int sisgpu_destroy(sisgpu_t *h)
     h->d_lab_temp.release(); h->d_vscale.release(); h->d_lab_rp.release();
     h->d_rp.release(); h->d_rp_alt.release(); h->d_sync.release();
     if (h->graph_chunk) cudaGraphExecDestroy(h->graph_chunk);
+    if (h->graph_big) cudaGraphExecDestroy(h->graph_big);
     h->d_f_pair.release(); h->d_f_loc.release(); h->d_f_bp.release(); h->d_bp_half.release(); h->d_nbp_half.release();
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
@@ -305,6 +311,7 @@ int sisgpu_destroy(sisgpu_t *h)
 static void invalidate_graphs(sisgpu *h)
 {
     if (h->graph_chunk) { cudaGraphExecDestroy(h->graph_chunk); h->graph_chunk = nullptr; }
+    if (h->graph_big) { cudaGraphExecDestroy(h->graph_big); h->graph_big = nullptr; }
 }
 
 // ---- set-up -------------------------------------------------------------------------------
@@ -920,6 +927,47 @@ int sisgpu_get_step(sisgpu_t *h, int64_t *istep)
     return 0;
 }
 
+// State of the counter-based generators for the .rst file (the reference stores 643 int32 of
+// Mersenne-Twister state per stream under the PRNG / PRNGREP tags, src/write_rst.F90:69-131).  A
+// counter-based stream has no hidden state: what a restart needs is the seed, the step counter (the
+// Gaussian counter of every bead), the draw counter of the Monte-Carlo base-pair pruning of every local
+// replica and the draw counter of the exchange stream.  state[0] = seed, [1] = istep,
+// [2] = exchange counter (PRNGREP), [3] = nrep_proc, [4 .. 4 + nrep_proc) = Monte-Carlo counters (PRNG).
+int sisgpu_get_rng_state(sisgpu_t *h, int64_t *state, int cap, int *n)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    const int need = 4 + h->nrep;
+    if (n) *n = need;
+    if (!state) return 0;
+    if (cap < need) return set_err("rng state needs %d words, caller holds %d", need, cap);
+    CK(cudaSetDevice(h->device));
+    TRY(sync_ctl(h));
+    std::vector<unsigned long long> mc(h->nrep);
+    CK(cudaMemcpy(mc.data(), h->d_mc_counter.p, h->nrep * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    state[0] = (int64_t)h->seed; state[1] = (int64_t)h->h_ctl->step; state[2] = (int64_t)h->exchange_counter;
+    state[3] = h->nrep;
+    for (int r = 0; r < h->nrep; r++) state[4 + r] = (int64_t)mc[r];
+    return 0;
+}
+int sisgpu_set_rng_state(sisgpu_t *h, const int64_t *state, int n)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    if (n < 4 || state[3] != h->nrep || n < 4 + h->nrep)
+        return set_err("rng state of %lld replicas does not fit nrep_proc = %d", n >= 4 ? (long long)state[3] : -1ll, h->nrep);
+    CK(cudaSetDevice(h->device));
+    h->seed = (unsigned long long)state[0];
+    invalidate_graphs(h);     // the seed is a kernel argument of the replayed graphs
+    TRY(sisgpu_set_step(h, state[1]));
+    h->exchange_counter = (unsigned long long)state[2];
+    std::vector<unsigned long long> mc(h->nrep);
+    for (int r = 0; r < h->nrep; r++) mc[r] = (unsigned long long)state[4 + r];
+    CK(cudaMemcpy(h->d_mc_counter.p, mc.data(), h->nrep * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    return 0;
+}
+// REPLICA block of the .rst (src/write_rst.F90:41-60: nrep_all, (i, rep2lab(i))): put the label
+// permutation back and refresh the parameters of the local replicas (src/read_rst.F90:405-460)
+int sisgpu_remd_set_labels(sisgpu_t *h, const int *rep2lab, int idx_pair);
+
 // ---- neighbour lists ----------------------------------------------------------------------
 static void timer_begin(sisgpu *h) { if (h->timing) cudaEventRecord(h->ev0, h->stream); }
 static void timer_end(sisgpu *h, double &acc)
@@ -1196,7 +1244,7 @@ static int enqueue_nl_chain(sisgpu *h, int force_all, long long stop)
     if (h->flg_replica) rc = std::max(rc, h->remd_cut_max);   // labels met during an enqueued batch
     PA.rc = rc + h->nl_margin;
     PA.ele_cutoff_inp = h->ele_cutoff_inp; PA.ele_cutoff_type = h->ele_cutoff_type; PA.flg_ele = h->P.flg_ele;
-    PA.pbc = h->P.flg_pbc; PA.force_all = force_all; PA.stop = stop;
+    PA.pbc = h->P.flg_pbc; PA.force_all = force_all; PA.stop = stop;   // stop < 0: S.misc->stop_step
     if (h->P.flg_pbc) {
         double lo[3] = {0.0, 0.0, 0.0}, hi[3] = {h->P.box[0], h->P.box[1], h->P.box[2]};
         GridInfo Gd{};
@@ -1732,6 +1780,20 @@ int sisgpu_remd_state(sisgpu_t *h, int *rep2lab, int *lab2rep, double *lab2val)
     if (lab2val) std::copy(h->lab2val.begin(), h->lab2val.end(), lab2val);
     return 0;
 }
+int sisgpu_remd_set_labels(sisgpu_t *h, const int *rep2lab, int idx_pair)
+{
+    if (!h->flg_replica) return set_err("REMD not configured");
+    const int n = h->nrep_all;
+    std::vector<int> seen(n, 0);
+    for (int g = 0; g < n; g++) {
+        if (rep2lab[g] < 1 || rep2lab[g] > n || seen[rep2lab[g] - 1]++) return set_err("rep2lab is not a permutation of 1..%d", n);
+    }
+    for (int g = 0; g < n; g++) { h->rep2lab[g] = rep2lab[g]; h->lab2rep[rep2lab[g] - 1] = g + 1; }
+    if (idx_pair >= 1 && idx_pair <= 2 * h->ndim_replica) h->idx_pair = idx_pair;
+    for (int irep = 0; irep < h->nrep; irep++) apply_label(h, irep, h->rep2lab[h->rank * h->nrep + irep]);
+    return push_rp(h);
+}
+int sisgpu_remd_get_idx_pair(sisgpu_t *h, int *idx_pair) { *idx_pair = h->idx_pair; return 0; }
 int sisgpu_remd_stats(sisgpu_t *h, int64_t *n_attempt, int64_t *n_accept)
 {
     *n_attempt = h->n_attempt; *n_accept = h->n_accept;
@@ -2015,6 +2077,56 @@ static int launch_persistent(sisgpu *h, long long stop)
     return 0;
 }
 
+// ---- k_md_big: one launch per MD step, replayed as graph chunks (large systems) ----------------------
+// beads per CTA: rows of K entries must fit the quad map, and the grid should fill whole waves of
+// 3 CTAs per SM
+static int big_bpc_of(sisgpu *h)
+{
+    if (ensure_coop_blocks(h)) return 0;
+    const int per_quads = (h->K + 3) / 4;
+    int bpc = std::min(BIG_BPC, BIG_QMAP / std::max(1, per_quads));
+    if (bpc < 4) return 0;
+    const long long nitems = (long long)h->nrep * h->nmp;
+    const long long slots = (long long)BIG_MINB * h->coop_blocks;
+    const long long waves = (nitems + slots * bpc - 1) / (slots * bpc);
+    const int even = (int)((nitems + slots * waves - 1) / (slots * waves));
+    return std::max(4, std::min(bpc, even));
+}
+static bool big_ok(sisgpu *h)
+{
+    return h->big_kernel && h->nstep_bp_MC == 0 && !h->P.flg_bias_rg && !h->P.flg_bias_ss && big_bpc_of(h) > 0;
+}
+// `big_chunk` step kernels as one graph; launch idx reads S.ctl[idx & 1] and publishes S.ctl[(idx + 1) & 1],
+// so an even chunk leaves the current bookkeeping in S.ctl[0] where every other kernel reads it
+static int launch_big_chunk(sisgpu *h)
+{
+    const int bpc = big_bpc_of(h);
+    const int G = std::max(2, h->big_chunk & ~1);
+    const size_t smem = sizeof(BigShared);
+    if (!h->big_smem_set) {
+        CK(cudaFuncSetAttribute((void *)k_md_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->big_smem_set = true;
+    }
+    if (!h->graph_big || h->graph_big_steps != G || h->graph_big_bpc != bpc) {
+        if (h->graph_big) { cudaGraphExecDestroy(h->graph_big); h->graph_big = nullptr; }
+        const StepArgs A = step_args(h, 0x7FEu, 0, -1, 1);
+        const long long nitems = (long long)h->nrep * h->nmp;
+        const int ncta = (int)((nitems + bpc - 1) / bpc);
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < G; i++) k_md_big<<<ncta, BIG_THREADS, smem, h->stream>>>(h->S, h->P, A, i, bpc);
+        CK(cudaStreamEndCapture(h->stream, &graph));
+        CK(cudaGraphInstantiate(&h->graph_big, graph, 0));
+        CK(cudaGraphDestroy(graph));
+        h->graph_big_steps = G; h->graph_big_bpc = bpc;
+    }
+    CK(cudaGraphLaunch(h->graph_big, h->stream));
+    h->launches += G;
+    h->last_launch_local = false;
+    h->last_step_kernel = "k_md_big";
+    return 0;
+}
+
 // post-sync bookkeeping shared by the persistent paths
 static int after_persistent_sync(sisgpu *h)
 {
@@ -2027,6 +2139,8 @@ static int after_persistent_sync(sisgpu *h)
         CK(cudaMemcpy(&h->S.misc->max_force_flag, &h->h_misc->max_force_flag, sizeof(int), cudaMemcpyHostToDevice));
         h->fast_kernel = 0;
     }
+    if (h->h_misc->max_force_flag & 8)
+        return set_err("k_md_big: a warp's chain neighbours or base-pair survivors exceed its shared-memory tables (K = %d)", h->K);
     return 0;
 }
 
@@ -2046,6 +2160,17 @@ static int md_run_pipelined(sisgpu *h, long long stop)
         persistent_choice(h, &local, &fast_ok_, &want_);
         if (h->h_misc->max_force_flag & 4) local = false;
         if (local) ncyc = 1;      // the kernel rebuilds its own lists and always reaches `stop`
+        const bool big = !(fast_ok_ && !(h->h_misc->max_force_flag & 4)) && big_ok(h);
+        if (big) {
+            // [rebuild chain, graph of G step kernels] cycles; a step blocked by the rebuild test makes the
+            // rest of its chunk fall through, the next cycle's chain rebuilds
+            const int G = std::max(2, h->big_chunk & ~1);
+            const double per_cycle = G * h->est_cycle_steps / (h->est_cycle_steps + 0.5 * G);
+            ncyc = std::max(1, std::min((int)ceil((double)(stop - cur) / std::max(1.0, per_cycle)) + 1, 96));
+            h->h_misc->stop_step = stop;
+            CK(cudaMemcpyAsync(&h->S.misc->stop_step, &h->h_misc->stop_step, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemsetAsync(h->d_bar.p, 0, 64 * sizeof(unsigned), h->stream));
+        }
         for (int c = 0; c < ncyc; c++) {
             if (!local) {
                 const int sp = span_begin(h);
@@ -2053,7 +2178,8 @@ static int md_run_pipelined(sisgpu *h, long long stop)
                 span_end(h, sp, &h->t_nl);
             }
             const int sp = span_begin(h);
-            TRY(launch_persistent(h, stop));
+            if (big) TRY(launch_big_chunk(h));
+            else TRY(launch_persistent(h, stop));
             span_end(h, sp, &h->t_step);
         }
         TRY(sync_ctl(h));
@@ -2310,6 +2436,8 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
     else if (s == "chunk") { h->chunk = std::max(1, (int)value); invalidate_graphs(h); }
     else if (s == "timing") h->timing = (int)value;
     else if (s == "fast_kernel") h->fast_kernel = (int)value;
+    else if (s == "big_kernel") h->big_kernel = (int)value;
+    else if (s == "big_chunk") { h->big_chunk = std::max(2, (int)value); invalidate_graphs(h); }
     else if (s == "pipeline") h->pipeline = (int)value;
     else if (s == "remd_device") h->remd_device = (int)value;
     else if (s == "list_capacity") {    // row capacity K (tests: a tight K makes device-side rebuilds overflow)

@@ -346,6 +346,28 @@ module sisgpu_mod
          type(c_ptr), value :: h, rep2lab, lab2rep, lab2val
          integer(c_int) :: rc
       end function
+      function sisgpu_get_rng_state(h, state, cap, n) bind(C, name='sisgpu_get_rng_state') result(rc)
+         import :: c_ptr, c_int, c_int64_t
+         type(c_ptr), value :: h
+         integer(c_int64_t), intent(out) :: state(*)
+         integer(c_int), value :: cap
+         integer(c_int), intent(out) :: n
+         integer(c_int) :: rc
+      end function
+      function sisgpu_set_rng_state(h, state, n) bind(C, name='sisgpu_set_rng_state') result(rc)
+         import :: c_ptr, c_int, c_int64_t
+         type(c_ptr), value :: h
+         integer(c_int64_t), intent(in) :: state(*)
+         integer(c_int), value :: n
+         integer(c_int) :: rc
+      end function
+      function sisgpu_remd_set_labels(h, rep2lab, idx_pair) bind(C, name='sisgpu_remd_set_labels') result(rc)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: h
+         integer(c_int), intent(in) :: rep2lab(*)
+         integer(c_int), value :: idx_pair
+         integer(c_int) :: rc
+      end function
    end interface
 
 contains
@@ -479,6 +501,36 @@ contains
       integer, intent(in) :: irep
       call gpu_check(sisgpu_get_state(h, int(irep - 1, c_int), c_loc(xyz(1, 1, irep)), c_loc(velos(1, 1, irep)), &
                                       c_loc(accels(1, 1, irep))), 'get_state')
+   end subroutine
+
+   ! PRNG / PRNGREP blocks of the .rst file (src/write_rst.F90:69-131, src/read_rst.F90:405-600): the
+   ! counter-based device generators have no Mersenne-Twister state; their restart payload is
+   ! (seed, istep, exchange draw counter, nrep_proc, Monte-Carlo draw counter per local replica),
+   ! written under a new tag RSTBLK%PRNGCTR = 12 next to the existing ones (src/const_idx.F90:73-85)
+   subroutine gpu_write_rst_prng(lunout)
+      use var_replica, only : nrep_proc
+      integer, intent(in) :: lunout
+      integer(c_int64_t) :: st(4 + nrep_proc)
+      integer(c_int) :: n
+      call gpu_check(sisgpu_get_rng_state(h, st, int(size(st), c_int), n), 'get_rng_state')
+      write(lunout) 12                                   ! RSTBLK%PRNGCTR
+      write(lunout) int(8 * n, kind=4)                   ! nbytes
+      write(lunout) st(1:n)
+   end subroutine
+
+   subroutine gpu_read_rst_prng(lunin, nbytes)
+      integer, intent(in) :: lunin, nbytes
+      integer(c_int64_t) :: st(nbytes / 8)
+      read(lunin) st
+      call gpu_check(sisgpu_set_rng_state(h, st, int(size(st), c_int)), 'set_rng_state')
+   end subroutine
+
+   ! REPLICA block (src/read_rst.F90:405-460): labels read from the .rst go back to the device tables
+   subroutine gpu_remd_set_labels()
+      use var_replica, only : rep2lab, nrep_all
+      integer(c_int) :: r2l(nrep_all)
+      r2l(:) = int(rep2lab(1:nrep_all), c_int)
+      call gpu_check(sisgpu_remd_set_labels(h, r2l, int(0, c_int)), 'remd_set_labels')
    end subroutine
 
    subroutine gpu_neighbor_list(irep)

@@ -204,18 +204,24 @@ def test_persistent_kernels_match_stream_path(name):
     spec.nl_margin = 3.0
     _, r0, x0, v0, a0 = _run_mode(spec, 60, launch_mode=0)
     g1, r1, x1, v1, a1 = _run_mode(spec, 60, launch_mode=2, fast_kernel=1)
-    _, r2, x2, v2, a2 = _run_mode(spec, 60, launch_mode=2, fast_kernel=0)
-    assert r0 == r1 == r2
-    for x, v, a in ((x1, v1, a1), (x2, v2, a2)):
+    g2, r2, x2, v2, a2 = _run_mode(spec, 60, launch_mode=2, fast_kernel=0)                  # k_md_big
+    g3, r3, x3, v3, a3 = _run_mode(spec, 60, launch_mode=2, fast_kernel=0, big_kernel=0)    # k_md_fused
+    assert g1.last_step_kernel().startswith("k_md_fast") and g2.last_step_kernel() == "k_md_big"
+    assert g3.last_step_kernel() == "k_md_fused"
+    assert r0 == r1 == r2 == r3
+    for x, v, a in ((x1, v1, a1), (x2, v2, a2), (x3, v3, a3)):
         assert np.abs(x - x0).max() < 1e-7
         assert np.abs(v - v0).max() < 1e-7   # rounding differences grow along the trajectory
         assert np.abs(a - a0).max() < 1e-12
+    assert g2.get_step() == 60 and g3.get_step() == 60
+    s_big, e_big = g2.get_bp_state(0)
     assert g1.get_step() == 60
     # cached bp state of the last force evaluation (write_bp / flg_bp_energy semantics)
     s_ref, e_ref = _run_mode(spec, 60, launch_mode=0)[0].get_bp_state(0)
     s_fast, e_fast = g1.get_bp_state(0)
-    assert np.array_equal(s_ref, s_fast)
+    assert np.array_equal(s_ref, s_fast) and np.array_equal(s_ref, s_big)
     assert np.allclose(e_ref, e_fast, rtol=1e-7, atol=1e-10)
+    assert np.allclose(e_ref, e_big, rtol=1e-7, atol=1e-10)
 
 
 def test_persistent_kernel_multi_replica():
