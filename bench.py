@@ -203,7 +203,7 @@ class Ctx:
         return g
 
 
-def run_remd_c3(cx, nrep_all=64, nex=10, md_steps=2000, steps=5, warmup=2):
+def run_remd_c3(cx, nrep_all=64, nex=int(os.environ.get("SIS_NEX", "10")), md_steps=2000, steps=5, warmup=2):
     """BASELINE config 3: T2S2HP T-REMD (check/T2S2HP_REMD_T/input_REMD.toml with 64 temperatures
     293.15 .. 363.15 K), nrep_all replicas split over the ranks, exchange attempt every `nex` steps"""
     from sis_b200 import fixtures as fx
@@ -223,6 +223,8 @@ def run_remd_c3(cx, nrep_all=64, nex=10, md_steps=2000, steps=5, warmup=2):
         g.neighbor_list(r)
     for _ in range(warmup):
         g.md_steps(md_steps)
+    if cx.args.profile:
+        g.set_option("profile", 1)
     g.set_option("timing", 1)
     g.get_timers(reset=True)
     l0 = g.launch_count()

@@ -53,6 +53,7 @@ struct FastBpCand {
     size_t pb;      // index of the pair in bp_status / ene_bp
     double dG;
 };
+constexpr int REMD_LOCAL_MAX = 1024;          // replicas (labels) the in-kernel exchange of the replica-local mode handles
 constexpr int FAST_NEXTRA = 160;   // chain neighbours of the CTA's beads outside its range
 
 // state of one owned bead, resident in shared memory for the whole launch
@@ -62,6 +63,13 @@ struct FastBead {
     double ele_coef, inv_lambdaD, cut2;
     int4 meta;
     int rep, k, nn, valid;
+};
+
+// exchange-step bookkeeping of a launch (identical in every CTA: each replays every decision)
+struct FastRemdState {
+    int idx_pair, attempt;
+    unsigned long long counter;
+    long long natt, nacc;
 };
 
 struct FastShared {
@@ -83,6 +91,14 @@ struct FastShared {
     int tbead[FAST_NT];              // ... its flattened item, -1 = no such bead
     int blocked[2];             // rebuild verdict, indexed by iteration parity
     double top[2];
+    // exchange step inside the kernel (fast_remd_exchange): energy reduction scratch and this CTA's private
+    // copy of the label tables (every CTA replays every decision, so the copies stay identical)
+    double xred[16][2 * ENE_N];
+    double xE[4];
+    int x_newlab, x_natt, x_nacc;
+    double x_vscale;
+    FastRemdState xs;
+    int x_r2l[REMD_LOCAL_MAX], x_l2r[REMD_LOCAL_MAX];
 };
 
 SIS_D void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -157,7 +173,9 @@ struct FastCtx {
     bool after_rebuild;   // this segment follows an in-kernel list rebuild: its first step is a Monte-Carlo step
     unsigned long long seed;
     int max_bp_per_nt;
+    bool xch;             // exchange steps inside the kernel (replica-local mode, S.remd set)
 };
+SIS_D void fast_remd_hook(const DevSys &S, const FFParams &P, const FastCtx &C, FastShared &sh, unsigned long long step, int cur);
 SIS_D void cta_sync() { named_bar_sync(0, FAST_THREADS); }
 SIS_D void fast_bp_eval(const DevSys &S, const FFParams &P, FastShared &sh, const double4 *pos, int lo_item, int hi_item,
                         int q, int nact);
@@ -450,6 +468,7 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
         step++;
         cur ^= 1;
         cta_sync();
+        fast_remd_hook(S, P, C, sh, step, cur);
     }
     cta_sync();                                        // everybody is out of the loop
     if (B.valid && comp < 3 && rows_fit) {
@@ -614,7 +633,7 @@ SIS_D int fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fas
             if (P.bp_triplet) {
                 const double2 cf = S.bp_coef[pbase + ibp];
                 dG = cf.x - S.rp[rep].tempK * cf.y;             // src/force_bp_triplet.F90:77
-                if (dG >= 0.0) {                                // never active at this temperature
+                if (dG >= 0.0 && !C.xch) {                      // never active at this temperature (an exchange can change that)
                     if (own) { S.bp_status[pbase + ibp] = 0; S.ene_bp[pbase + ibp] = 0.0; }
                     continue;
                 }
@@ -657,11 +676,11 @@ SIS_D int fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fas
             const Vec3 v12 = pbc_vec_d(P, v3(pos[cd.b[0]]), v3(pos[cd.b[1]]));
             const double a12 = sqrt(dot(v12, v12));
             const int type = cd.type;
-            const bool masked_in = !use_mc || S.bp_status_MC[cd.pb] != 0;   // use_mask = 1 of the stream path
+            const bool masked_in = (!use_mc || S.bp_status_MC[cd.pb] != 0) && (!P.bp_triplet || cd.dG < 0.0);   // use_mask = 1 of the stream path; dG >= 0: cycle
             if (masked_in && fabs(a12 - P.bp[type].bond_r) <= P.bp[type].cutoff_ddist) {
                 sh.active[atomicAdd(&sh.nactive[n & 1], 1)] = i;
             } else {
-                if (P.bp_triplet && P.flg_bias_ss) {           // src/force_bp_triplet.F90:85-93
+                if (P.bp_triplet && P.flg_bias_ss && cd.dG < 0.0) {   // src/force_bp_triplet.F90:85-93
                     const double sc = P.bias_ss_force / a12;
                     if (in_range(cd.b[0])) {
                         double *fi = sh.fbp[cd.b[0] - lo_item];
@@ -701,6 +720,7 @@ SIS_D int fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fas
         cur ^= 1;
         cta_sync();
         if (sh.blocked[n & 1]) break;
+        fast_remd_hook(S, P, C, sh, C.step0 + (unsigned long long)n + 1ull, cur);
     }
     cta_sync();
     return n;
@@ -837,6 +857,7 @@ SIS_D int fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, c
         cur ^= 1;
         cta_sync();
         if (sh.blocked[n & 1]) break;
+        fast_remd_hook(S, P, C, sh, step, cur);
     }
     cta_sync();
     return n;
@@ -877,6 +898,227 @@ SIS_D void fast_local_rebuild(const DevSys &S, const FFParams &P, NlArgs NA, int
     named_bar_sync(2, FAST_MAIN);
 }
 
+
+// ---- exchange step inside the replica-local kernel (src/job_md.F90:474-481,514-570) -----------------------
+// energy_replica (src/energy_replica.F90:45-163) for the CTA's replica: total energy with its own
+// parameters (bp energies as cached by the last force evaluation: flg_bp_energy) and with the
+// partner label's parameters (bp term recomputed on the energy side, :72, :121) -- same thread
+// decomposition and summation order as k_energy<8> / k_bp_eval<1>, so both paths give the same
+// bits; nothing is written to bp_status / ene_bp (the reference restores them, :64-70,157-162).
+SIS_D void fast_remd_energies(const DevSys &S, const FFParams &P, FastShared &sh, int rep, int cur, const RepParams &Rown,
+                              const RepParams &Ralt, bool has_opp)
+{
+    const int tid = threadIdx.x, lane = tid & 7, k = tid >> 3, nmp = S.nmp, KB = S.KB;
+    const size_t rbase = (size_t)rep * nmp, pbase = rbase * KB;
+    const double4 *pos = S.pos[cur] + rbase;
+    double e[ENE_N], ea[ENE_N];
+#pragma unroll
+    for (int t = 0; t < ENE_N; t++) { e[t] = 0.0; ea[t] = 0.0; }
+    if (k < nmp) {
+        const int4 mk4 = S.meta[k];
+        const Vec3 xk = v3(pos[k]);
+        const uint32_t *row = S.nbr + (rbase + k) * S.K;
+        const int nn = S.nnbr[rbase + k];
+        for (int q = lane; q < nn; q += 8) {
+            const uint32_t ent = row[q];
+            const int j = ent & NB_IDX;
+            if (j < k) continue;
+            const Vec3 v = pbc_vec_d(P, xk, v3(pos[j]));
+            const double d2 = dot(v, v);
+            if (ent & NB_WCA) { const double w = wca_energy(P, d2); e[ENE_EXV] += w; ea[ENE_EXV] += w; }
+            if ((ent & NB_ELE) && P.flg_ele) { e[ENE_ELE] += dh_energy(P, Rown, d2); if (has_opp) ea[ENE_ELE] += dh_energy(P, Ralt, d2); }
+        }
+        if (lane < 3) {
+            const int span = lane + 1;
+            const bool exists = (mk4.w & MF_CIRC) ? (mk4.y > span) : (mk4.z + span < mk4.y);
+            if (exists) {
+                const Vec3 x1 = v3(pos[chain_nb(mk4, 1)]);
+                double t = 0.0;
+                if (lane == 0) { t = bond_energy(P, xk, x1); e[ENE_BOND] += t; ea[ENE_BOND] += t; }
+                else if (lane == 1) { t = angl_energy(P, xk, x1, v3(pos[chain_nb(mk4, 2)])); e[ENE_ANGL] += t; ea[ENE_ANGL] += t; }
+                else if (P.flg_dih_cos || P.flg_dih_exp) {
+                    t = dih_energy(P, xk, x1, v3(pos[chain_nb(mk4, 2)]), v3(pos[chain_nb(mk4, 3)]));
+                    e[ENE_DIHE] += t; ea[ENE_DIHE] += t;
+                }
+            }
+        }
+        const int nrow = S.nbp_row[rbase + k];
+        for (int q = lane; q < nrow; q += 8) {
+            const int2 ent = S.bprow[(rbase + k) * KB + q];
+            if (ent.x <= k) continue;                   // owner = lower bead
+            if (S.bp_status[pbase + ent.y]) e[ENE_BP] += S.ene_bp[pbase + ent.y];
+            if (has_opp) {                              // k_bp_eval<1> with the partner temperature
+                const int type = S.bp_type[pbase + ent.y];
+                double dG = 1.0;
+                bool active = true;
+                if (P.bp_triplet) {
+                    const double tK = P.temp_independent ? 0.0 : Ralt.tempK;   // src/energy_bp_triplet.F90:27-31
+                    const double2 cf = S.bp_coef[pbase + ent.y];
+                    dG = cf.x - tK * cf.y;
+                    if (dG >= 0.0) active = false;
+                }
+                if (active) {
+                    const int j = ent.x;
+                    const int4 mj = S.meta[j];
+                    Vec3 xs[6];
+                    xs[0] = xk; xs[1] = v3(pos[j]);
+                    xs[2] = v3(pos[chain_nb(mk4, -1)]); xs[3] = v3(pos[chain_nb(mj, -1)]);
+                    xs[4] = v3(pos[chain_nb(mk4, +1)]); xs[5] = v3(pos[chain_nb(mj, +1)]);
+                    double u;
+                    if (bp_energy_u(P, P.bp[type], xs, &u)) {
+                        const double ene = P.bp_triplet ? P.bp[type].U0 * dG * exp(-u) : P.bp[type].U0 * exp(-u);
+                        if (ene <= P.bp_cutoff_energy) ea[ENE_BP] += ene;
+                    }
+                }
+            }
+        }
+    }
+    // reduction in the order of k_energy<8>: warp tree, the 8 warps of a 32-bead block in order, the blocks in order
+    const int warp = tid >> 5;
+    if (warp < 16) {
+#pragma unroll
+        for (int t = 1; t <= ENE_ELE; t++) {
+            double v = e[t], va = ea[t];
+            for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); va += __shfl_xor_sync(0xffffffffu, va, o); }
+            if ((tid & 31) == 0) { sh.xred[warp][t] = v; sh.xred[warp][ENE_N + t] = va; }
+        }
+    }
+    cta_sync();
+    if (tid == 0) {
+        const int nblk = (nmp + 31) / 32;
+        double tot[2] = {0.0, 0.0};
+        for (int side = 0; side < 2; side++) {
+            double et[ENE_N];
+            for (int t = 1; t <= ENE_ELE; t++) {
+                double v = 0.0;
+                for (int b = 0; b < nblk; b++) {
+                    double vb = 0.0;
+                    for (int w = 0; w < 8; w++) vb += sh.xred[8 * b + w][side * ENE_N + t];
+                    v += vb;
+                }
+                et[t] = v;
+            }
+            double sum = 0.0;
+            for (int t = 1; t < ENE_N; t++) sum += (t <= ENE_ELE ? et[t] : 0.0);   // no bias terms in the replica-local mode
+            tot[side] = sum;
+        }
+        sh.xE[0] = tot[0];
+        sh.xE[1] = has_opp ? tot[1] : 0.0;
+    }
+    cta_sync();
+}
+
+// One exchange attempt after the step `step` (a multiple of nstep_rep_exchange): energies of the CTA's replica,
+// a flag barrier over the CTAs of the launch (they are co-resident: cooperative launch), then EVERY CTA replays
+// replica_exchange (src/replica_exchange.F90:44-154) on its private label tables from the energies of all
+// replicas and the shared counter-based uniform stream -- no second exchange of data -- refreshes the parameters
+// of its replica (src/job_md.F90:538-567) and rescales its velocities (scale_velo, :175-213).
+SIS_D void fast_remd_exchange(const DevSys &S, const FFParams &P, FastShared &sh, int rep, int cur)
+{
+    const FastRemdState X = sh.xs;
+    RemdDev &D = *S.remd;
+    const int tid = threadIdx.x, n = D.n, R = D.R, nmp = S.nmp;
+    const int grep = D.rank * R + rep;
+    const int label_own = sh.x_r2l[grep];
+    const int label_opp = D.pair_tb[(size_t)(X.idx_pair - 1) * n + label_own - 1];
+    const bool has_opp = label_opp != 0 && label_opp <= n;
+    const RepParams Rown = S.rp[rep];
+    RepParams Ralt = Rown;
+    if (has_opp) remd_apply_label(D, Ralt, D.lab_rp[label_opp - 1]);
+    fast_remd_energies(S, P, sh, rep, cur, Rown, Ralt, has_opp);
+    double *E = D.xch_E + (size_t)(X.attempt & 1) * 2 * n;
+    if (tid == 0) {
+        E[2 * grep] = sh.xE[0];
+        E[2 * grep + 1] = sh.xE[1];
+        __threadfence();
+        red_release_add(D.xch_bar, 1u);
+        const unsigned target = (unsigned)(X.attempt + 1) * gridDim.x;
+        const long long t0 = clock64();
+        while (ld_acquire_u32(D.xch_bar) < target)
+            if (clock64() - t0 > 4000000000ll) { S.misc->max_force_flag |= 16; break; }   // ~2 s: a CTA of the launch is missing
+        sh.x_newlab = label_own; sh.x_vscale = 1.0; sh.x_natt = 0; sh.x_nacc = 0;
+    }
+    cta_sync();
+    // ---- replay of the decisions: warp 0, one lane per label; pair k in label order uses uniform k ----
+    if (tid < 32) {
+        const int *tb = D.pair_tb + (size_t)(X.idx_pair - 1) * n;
+        int base = 0;
+        for (int l0 = 0; l0 < n; l0 += 32) {
+            const int l = l0 + tid;
+            const int l_j = l < n ? tb[l] : 0;
+            const bool is_pair = l < n && l_j >= l + 1;
+            const unsigned m = __ballot_sync(0xffffffffu, is_pair);
+            if (is_pair) {
+                const int nrand = base + __popc(m & ((1u << tid) - 1u));
+                const int l_i = l + 1;
+                const double rnd = uniform_counter(D.seed, 0x7fffffffu, X.counter + (unsigned long long)nrand);
+                const int rep_i = sh.x_l2r[l_i - 1], rep_j = sh.x_l2r[l_j - 1];
+                double temp_m, temp_n;
+                if (D.flg_temp) { temp_m = D.lab_temp[l_i - 1]; temp_n = D.lab_temp[l_j - 1]; }
+                else temp_m = temp_n = D.tempK_default;
+                const double pot_i_m = __ldcg(E + 2 * (rep_i - 1)), pot_i_n = __ldcg(E + 2 * (rep_i - 1) + 1);
+                const double pot_j_n = __ldcg(E + 2 * (rep_j - 1)), pot_j_m = __ldcg(E + 2 * (rep_j - 1) + 1);
+                const double delta = ((pot_j_m - pot_i_m) / temp_m - (pot_j_n - pot_i_n) / temp_n) / SIS_BOLTZ_KCAL_MOL;
+                atomicAdd(&sh.x_natt, 1);
+                if (delta < 0.0 || rnd <= exp(-delta)) {
+                    atomicAdd(&sh.x_nacc, 1);
+                    sh.x_r2l[rep_i - 1] = l_j; sh.x_r2l[rep_j - 1] = l_i;
+                    sh.x_l2r[l_i - 1] = rep_j; sh.x_l2r[l_j - 1] = rep_i;
+                    const double sf = D.flg_temp ? sqrt(temp_n / temp_m) : 1.0;   // scale_velo
+                    if (rep_i - 1 == grep) { sh.x_newlab = l_j; sh.x_vscale = sf; }
+                    if (rep_j - 1 == grep) { sh.x_newlab = l_i; sh.x_vscale = 1.0 / sf; }
+                }
+            }
+            base += __popc(m);
+        }
+    }
+    cta_sync();
+    // parameter refresh of the replica (src/job_md.F90:538-567); the caller rescales the velocities it holds
+    if (tid == 0) {
+        FastRemdState Y = X;
+        Y.natt += sh.x_natt; Y.nacc += sh.x_nacc;
+        Y.idx_pair = (X.idx_pair == D.ncol) ? 1 : X.idx_pair + 1;       // set_forward
+        Y.counter += (unsigned long long)((n + 1) / 2);                 // the reference draws ceil(n / 2) numbers up front
+        Y.attempt++;
+        sh.xs = Y;
+        RepParams rp = S.rp[rep];
+        remd_apply_label(D, rp, D.lab_rp[sh.x_newlab - 1]);
+        S.rp[rep] = rp;
+    }
+    __threadfence_block();
+    cta_sync();
+}
+
+// Called by every thread of the CTA at the end of a completed step: on a multiple of nstep_rep_exchange the
+// exchange attempt, then the state the roles keep on chip follows the new label -- velocities (scale_velo,
+// src/replica_exchange.F90:175-213), noise amplitude and Debye-Hueckel coefficients of the owned beads
+// (set_md_coef / set_ele, src/job_md.F90:538-567; ele_cutoff stays: only neighbor_list refreshes it), dG of
+// the cached base-pair candidates (src/force_bp_triplet.F90:77)
+SIS_D void fast_remd_hook(const DevSys &S, const FFParams &P, const FastCtx &C, FastShared &sh, unsigned long long step, int cur)
+{
+    if (!C.xch || step % (unsigned long long)S.remd->nex != 0ull) return;
+    const int tid = threadIdx.x, rep = C.item0 / C.nmp;
+    fast_remd_exchange(S, P, sh, rep, cur);
+    const RepParams &Rp = S.rp[rep];
+    if (tid < FAST_MAIN) {
+        const double vs = sh.x_vscale;
+        for (int s = tid; s < C.nb; s += FAST_MAIN) {
+            FastBead &B = sh.bead[s];
+            B.v[0] *= vs; B.v[1] *= vs; B.v[2] *= vs;
+            B.noise = S.coef[B.k].w * Rp.sqrt_tempK;
+            B.ele_coef = Rp.ele_coef; B.inv_lambdaD = Rp.inv_lambdaD;
+        }
+    } else if (tid < FAST_MAIN + FAST_BP) {
+        if (P.bp_triplet)
+            for (int i = tid - FAST_MAIN; i < min(sh.ncand, FAST_BPC); i += FAST_BP) {
+                const double2 cf = S.bp_coef[sh.cand[i].pb];
+                sh.cand[i].dG = cf.x - Rp.tempK * cf.y;
+            }
+    }
+    __threadfence_block();
+    cta_sync();
+}
+
 template <int U, bool LOCAL>
 __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams P, StepArgs A, long long target, NlArgs NA)
 {
@@ -898,7 +1140,22 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams 
     C.after_rebuild = false; C.seed = A.seed; C.max_bp_per_nt = A.max_bp_per_nt; C.no_loc_help = S.dbg_no_loc_help != 0;
     const int tid = threadIdx.x;
     // A launch is one segment (prologue, step loop) unless the CTA rebuilds its own lists (LOCAL):
-    // then a segment ends at the rebuild test and the next one starts on the new lists.
+    // then a segment ends at the rebuild test and the next one starts on the new lists.  With the
+    // exchange step inside the kernel (S.remd) a segment also ends at every multiple of
+    // nstep_rep_exchange: the exchange works on the state in global memory and the next segment's
+    // prologue picks up the new parameters and the rescaled velocities.
+    const bool xch = LOCAL && S.remd != nullptr;
+    C.xch = xch;
+    if (xch) {
+        const RemdDev &D = *S.remd;
+        if (tid == 0) {
+            FastRemdState X;
+            X.idx_pair = D.idx_pair; X.counter = D.exchange_counter; X.attempt = 0; X.natt = 0; X.nacc = 0;
+            sh.xs = X;
+        }
+        for (int i = tid; i < D.n; i += FAST_THREADS) { sh.x_r2l[i] = D.rep2lab[i]; sh.x_l2r[i] = D.lab2rep[i]; }
+        // (cta_sync before the first use: every role's prologue ends with one)
+    }
     int done = 0;
     for (;;) {
         C.nsteps = nsteps - done;
@@ -916,6 +1173,13 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams 
         if (tid < FAST_MAIN) fast_local_rebuild(S, P, NA, C.item0 / C.nmp, C.cur0 ^ (n & 1));
         C.after_rebuild = true;
         cta_sync();
+    }
+    if (xch && blockIdx.x == 0 && tid == 0) {              // tables and counters of the exchange back for the host / the next launch
+        RemdDev &D = *S.remd;
+        const FastRemdState X = sh.xs;
+        for (int i = 0; i < D.n; i++) { D.rep2lab[i] = sh.x_r2l[i]; D.lab2rep[i] = sh.x_l2r[i]; }
+        D.idx_pair = X.idx_pair; D.exchange_counter = X.counter;
+        D.n_attempt += X.natt; D.n_accept += X.nacc;
     }
     if (tid >= FAST_MAIN) return;
     if (S.prof != nullptr && blockIdx.x == 0 && tid == 0) {   // whole-launch clocks: prologue share = total - steps * per-step

@@ -84,6 +84,7 @@ struct DevSys {
     int ncell_cap;
     GridInfo *grid;               // the cell grid of the current build (host- or k_nl_plan-written)
     int dbg_no_loc_help;          // option "loc_help" = 0: the LOC warps of k_md_fast do not join the base-pair evaluation
+    struct RemdDev *remd;         // non-null: k_md_fast<U, true> runs the exchange step itself every remd->nex steps
     // parameters
     RepParams *rp;
     DevCtl *ctl;                  // [2]: A, B
@@ -855,6 +856,34 @@ __global__ void k_init_velocities(DevSys S, unsigned long long seed, int rep)
     S.acc[o] = (S.coef[k].w * R.sqrt_tempK) * gauss_component(seed, (uint32_t)R.stream, 0x8000000000000001ull, (uint32_t)k, c);
 }
 
+// displacement top-2 of every replica recomputed from xyz_move into the slot of `step` (the other slot
+// cleared): after sisgpu_set_step moved the step counter the pending rebuild trigger of
+// src/job_md.F90:376-388 must stay where the new parity looks for it.  One block per replica.
+__global__ void __launch_bounds__(256) k_top2_from_move(DevSys S, unsigned long long step)
+{
+    const int rep = blockIdx.x, nmp = S.nmp;
+    const double *mv = S.move + (size_t)rep * nmp * 3;
+    double t1 = 0.0, t2 = 0.0;
+    for (int i = threadIdx.x; i < nmp; i += blockDim.x)
+        top2_merge(t1, t2, mv[3 * i] * mv[3 * i] + mv[3 * i + 1] * mv[3 * i + 1] + mv[3 * i + 2] * mv[3 * i + 2], 0.0);
+    __shared__ double sh[8][2];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double b1 = __shfl_xor_sync(0xffffffffu, t1, o), b2 = __shfl_xor_sync(0xffffffffu, t2, o);
+        top2_merge(t1, t2, b1, b2);
+    }
+    if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5][0] = t1; sh[threadIdx.x >> 5][1] = t2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a1 = 0.0, a2 = 0.0;
+        for (int w = 0; w < 8; w++) top2_merge(a1, a2, sh[w][0], sh[w][1]);
+        unsigned long long *t = S.top2 + ((size_t)rep * 2 + (step & 1ull)) * 2;
+        t[0] = (unsigned long long)__double_as_longlong(a1); t[1] = (unsigned long long)__double_as_longlong(a2);
+        t = S.top2 + ((size_t)rep * 2 + ((step + 1ull) & 1ull)) * 2;
+        t[0] = 0ull; t[1] = 0ull;
+    }
+}
+
 // T-REMD velocity rescale (src/replica_exchange.F90:175-213)
 __global__ void k_scale_velocities(DevSys S, int rep, double factor)
 {
@@ -1382,6 +1411,10 @@ struct RemdDev {
     int *has_opp;             // [R]
     double *send, *recv;      // [2 R], [2 n]: replica_energies(2, :) of src/job_md.F90:475
     double *vscale;           // [R]
+    // exchange inside the replica-local persistent kernel (k_md_fast<U, true>, fast_remd_exchange)
+    int nex;                  // nstep_rep_exchange
+    double *xch_E;            // [2 parities][n][2]: (own, cross) total energies of every replica of an attempt
+    unsigned *xch_bar;        // arrivals of the local CTAs, monotonic over the attempts of one launch (zeroed by the host)
 };
 SIS_D void remd_apply_label(const RemdDev &D, RepParams &dst, const RepParams &lab)
 {

@@ -173,7 +173,8 @@ struct sisgpu {
         d_twzfr_pairs, d_rest_id;
     DBuf<double4> d_coef, d_pos0, d_pos1;
     DBuf<double> d_f_pair, d_f_loc, d_f_bp;
-    DBuf<int> d_bp_half, d_nbp_half;
+    DBuf<int> d_bp_half, d_nbp_half, d_bp_status_save;   // _save: bp_status / ene_bp around the cross-energy pass
+    DBuf<double> d_ene_bp_save;
     DBuf<double> d_mass, d_bp3_dH, d_bp3_dS, d_vel, d_acc, d_move, d_force, d_ene_bp,
         d_ene_partial, d_ene_out, d_kin, d_twz_dir, d_twzfr_k, d_twzfr_init, d_twzfr_velo, d_rest_rcut,
         d_rest_para, d_gather_send, d_gather_recv;
@@ -192,6 +193,9 @@ struct sisgpu {
     bool last_launch_local = false;
     const char *last_step_kernel = "k_force_local + k_force_bp + k_integrate";   // what md_steps launched last
     // device-resident REMD state (exchange steps inside md_steps without host round trips)
+    int remd_inkernel = 1;               // option "remd_inkernel": exchange steps inside the replica-local kernel (one launch per md_steps call)
+    DBuf<double> d_xch_E;
+    DBuf<unsigned> d_xch_bar;
     int remd_device = 1;                 // option "remd_device"
     bool remd_on_device = false;         // inside an md_steps call whose exchange steps run on the device: host tables are stale
     double remd_cut_max = 0.0;           // largest ele_cutoff any label can bring to a local replica (cutoff_type 2)
@@ -291,11 +295,12 @@ int sisgpu_destroy(sisgpu_t *h)
     for (auto e : h->ev_free) cudaEventDestroy(e);
     h->ev_free.clear();
     h->d_remd.release(); h->d_pair_tb.release(); h->d_rep2lab.release(); h->d_lab2rep.release(); h->d_has_opp.release();
-    h->d_lab_temp.release(); h->d_vscale.release(); h->d_lab_rp.release();
+    h->d_lab_temp.release(); h->d_vscale.release(); h->d_lab_rp.release(); h->d_xch_E.release(); h->d_xch_bar.release();
     h->d_rp.release(); h->d_rp_alt.release(); h->d_sync.release();
     if (h->graph_chunk) cudaGraphExecDestroy(h->graph_chunk);
     if (h->graph_big) cudaGraphExecDestroy(h->graph_big);
     h->d_f_pair.release(); h->d_f_loc.release(); h->d_f_bp.release(); h->d_bp_half.release(); h->d_nbp_half.release();
+    h->d_bp_status_save.release(); h->d_ene_bp_save.release();
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaEventDestroy(h->ev_fork);
@@ -674,6 +679,8 @@ static int alloc_lists(sisgpu *h, int K, int KB)
         TRY(h->d_bp_status_MC.alloc(R * N * KB));
         TRY(h->d_ene_bp.alloc(R * N * KB));
         TRY(h->d_bp_half.alloc(R * N * KB));
+        TRY(h->d_bp_status_save.alloc(R * N * KB));
+        TRY(h->d_ene_bp_save.alloc(R * N * KB));
     }
     invalidate_graphs(h);
     DevSys &S = h->S;
@@ -911,13 +918,18 @@ int sisgpu_get_state(sisgpu_t *h, int irep, double *xyz, double *velos, double *
 
 int sisgpu_set_step(sisgpu_t *h, int64_t istep)
 {
+    if (!h->finalized) return set_err("finalize_setup not called");
+    CK(cudaSetDevice(h->device));
     TRY(sync_ctl(h));
     h->h_ctl->step = (unsigned long long)istep;
-    // keep the displacement slot of the current step where the new parity expects it
     CK(cudaMemcpy(h->d_sync.p, h->h_sync, sizeof(DevCtl), cudaMemcpyHostToDevice));
-    // the displacement slots are indexed by step parity: restart them (recomputed every step)
-    CK(cudaMemset(h->S.top2, 0, (size_t)h->nrep * 4 * sizeof(unsigned long long)));
+    // the displacement slots are indexed by step parity: recompute the slot of the new step from xyz_move
+    // (a pending rebuild trigger, src/job_md.F90:376-388, must survive) and clear the other one
+    k_top2_from_move<<<h->nrep, 256, 0, h->stream>>>(h->S, (unsigned long long)istep);
+    h->launches++;
     h->istep_host = istep;
+    TRY(sync_ctl(h));
+    CK(cudaGetLastError());
     return 0;
 }
 int sisgpu_get_step(sisgpu_t *h, int64_t *istep)
@@ -1533,7 +1545,8 @@ int sisgpu_energy_sumup(sisgpu_t *h, int irep, double tempK, int recompute_bp, d
 int sisgpu_dcd_energies(sisgpu_t *h, int nframes, const float *xyz32, double tempK, double *energies)
 {
     if (!h->finalized) return set_err("finalize_setup not called");
-    if (!h->lists_built) return set_err("dcd_energies needs lists (sisgpu_full_lists, as job = DCD does: src/main.F90:148-154)");
+    if (!h->lists_built || !h->lists_full)
+        return set_err("dcd_energies needs the cutoff-free lists (sisgpu_full_lists, as job = DCD does: src/main.F90:148-154)");
     CK(cudaSetDevice(h->device));
     const int R = h->nrep, N = h->nmp;
     const size_t fbytes = (size_t)N * 3 * sizeof(float);
@@ -1800,6 +1813,22 @@ int sisgpu_remd_stats(sisgpu_t *h, int64_t *n_attempt, int64_t *n_accept)
     return 0;
 }
 
+// The cross-energy pass re-evaluates the base pairs with the partner's parameters into bp_status / ene_bp;
+// the reference saves and restores both around it (src/energy_replica.F90:64-70,157-162) so that write_bp /
+// write_out of a save step that is also an exchange step see the replica's own values
+static int bp_state_save(sisgpu *h, bool restore)
+{
+    const size_t n = (size_t)h->nrep * h->nmp * h->KB;
+    if (!restore) {
+        CK(cudaMemcpyAsync(h->d_bp_status_save.p, h->d_bp_status.p, n * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_ene_bp_save.p, h->d_ene_bp.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+        CK(cudaMemcpyAsync(h->d_bp_status.p, h->d_bp_status_save.p, n * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_ene_bp.p, h->d_ene_bp_save.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return 0;
+}
+
 // energy_replica on an exchange step (src/energy_replica.F90:45-163): own-parameter energies
 // (cached bp energies), then partner-parameter energies with the bp term recomputed, then the
 // allgather that replaces MPI_ALLREDUCE (src/job_md.F90:531-533)
@@ -1835,14 +1864,17 @@ int sisgpu_energy_replica(sisgpu_t *h, double *energies, double *replica_energie
         // swap in the alternative block for the bp evaluation (tempK per replica comes from rp)
         CK(cudaStreamSynchronize(h->stream));
         const bool limit = h->flg_bp_MC != 0;
+        TRY(bp_state_save(h, false));
         RepParams *saved = h->S.rp;
         h->S.rp = h->d_rp_alt.p;
         launch_bp_eval<1>(h, -1, limit, 0.0, 0, (!limit && h->nstep_bp_MC > 0) ? 1 : 0, 0, h->P.temp_independent);
         launch_rg(h, -1);
-        TRY(energy_launch(h, -1, nullptr));
-        h->S.rp = saved;
+        const int rc = energy_launch(h, -1, nullptr);
+        h->S.rp = saved;                 // restored on every path
+        if (rc) return rc;
     }
     CK(cudaMemcpyAsync(e_opp.data(), h->S.ene_out, e_opp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    TRY(bp_state_save(h, true));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
     std::vector<double> send(2 * (size_t)R);
@@ -1939,6 +1971,7 @@ static int remd_upload(sisgpu *h)
     }
     if (h->d_pair_tb.n != h->pair_tb.size()) TRY(h->d_pair_tb.alloc(h->pair_tb.size()));
     if (h->d_gather_recv.n < 2 * (size_t)n) TRY(h->d_gather_recv.alloc(2 * (size_t)n));
+    if (h->d_xch_E.n != 4 * (size_t)n) { TRY(h->d_xch_E.alloc(4 * (size_t)n)); TRY(h->d_xch_bar.alloc(32)); }
     // parameter block of every label: what apply_label + fill_rp give a replica that holds it
     std::vector<RepParams> lab(n);
     std::vector<double> ltemp(n);
@@ -1962,6 +1995,7 @@ static int remd_upload(sisgpu *h)
     D.pair_tb = h->d_pair_tb.p; D.rep2lab = h->d_rep2lab.p; D.lab2rep = h->d_lab2rep.p;
     D.lab_temp = h->d_lab_temp.p; D.lab_rp = h->d_lab_rp.p; D.rp_alt = h->d_rp_alt.p; D.has_opp = h->d_has_opp.p;
     D.send = h->d_gather_send.p; D.recv = h->nranks > 1 ? h->d_gather_recv.p : h->d_gather_send.p; D.vscale = h->d_vscale.p;
+    D.nex = h->nstep_exchange; D.xch_E = h->d_xch_E.p; D.xch_bar = h->d_xch_bar.p;
     CK(cudaMemcpyAsync(h->d_pair_tb.p, h->pair_tb.data(), h->pair_tb.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_rep2lab.p, h->rep2lab.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_lab2rep.p, h->lab2rep.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -1999,12 +2033,15 @@ static int enqueue_exchange(sisgpu *h)
     k_remd_prepare<<<(R + 63) / 64, 64, 0, h->stream>>>(h->S, h->d_remd.p);
     {
         // cross energies: bp term recomputed with the partner temperature (flg_bp_energy = .False., :72)
+        TRY(bp_state_save(h, false));
         RepParams *saved = h->S.rp;
         h->S.rp = h->d_rp_alt.p;
         launch_bp_eval<1>(h, -1, limit, 0.0, 0, (!limit && h->nstep_bp_MC > 0) ? 1 : 0, 0, h->P.temp_independent);
         launch_rg(h, -1);
-        TRY(energy_launch(h, -1, nullptr));
-        h->S.rp = saved;
+        const int rc = energy_launch(h, -1, nullptr);
+        h->S.rp = saved;                 // restored on every path
+        if (rc) return rc;
+        TRY(bp_state_save(h, true));     // k_energy has consumed the partner-parameter values
     }
     k_remd_pack<<<(R + 63) / 64, 64, 0, h->stream>>>(h->S, h->d_remd.p);
     if (h->nranks > 1) {
@@ -2252,7 +2289,25 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
             bool local_, fast_ok_;
             int want_;
             persistent_choice(h, &local_, &fast_ok_, &want_);
-            if (local_ && !(h->h_misc->max_force_flag & 4)) {
+            if (local_ && !(h->h_misc->max_force_flag & 4) && h->remd_inkernel && h->nranks == 1 && h->nstep_bp_MC == 0 &&
+                h->nrep_all <= REMD_LOCAL_MAX) {
+                // the exchange steps run inside the replica-local kernel: ONE launch up to the target
+                const long long stop = std::min<long long>(target, cur + (1ll << 20));
+                CK(cudaMemsetAsync(h->d_xch_bar.p, 0, 32 * sizeof(unsigned), h->stream));
+                h->S.remd = h->d_remd.p;
+                const int sp = span_begin(h);
+                const int rc = launch_persistent(h, stop);
+                h->S.remd = nullptr;
+                if (rc) return rc;
+                span_end(h, sp, &h->t_step);
+                if (!h->last_launch_local) return set_err("internal: replica-local kernel not selected");
+                TRY(sync_ctl(h));
+                CK(cudaGetLastError());
+                spans_resolve(h);
+                TRY(after_persistent_sync(h));
+                if (h->h_misc->max_force_flag & 16) return set_err("in-kernel exchange: a CTA did not reach the exchange barrier");
+                if ((long long)h->h_ctl->step != stop) return set_err("internal: replica-local kernel stopped at step %lld, expected %lld", (long long)h->h_ctl->step, stop);
+            } else if (local_ && !(h->h_misc->max_force_flag & 4)) {
                 long long s = cur;
                 for (int nint = 0; s < target && nint < 64; nint++) {
                     const long long stop = std::min<long long>(target, (s / nex + 1) * nex);
@@ -2440,6 +2495,7 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
     else if (s == "big_chunk") { h->big_chunk = std::max(2, (int)value); invalidate_graphs(h); }
     else if (s == "pipeline") h->pipeline = (int)value;
     else if (s == "remd_device") h->remd_device = (int)value;
+    else if (s == "remd_inkernel") h->remd_inkernel = (int)value;
     else if (s == "list_capacity") {    // row capacity K (tests: a tight K makes device-side rebuilds overflow)
         if (!h->finalized) return set_err("finalize_setup not called");
         TRY(alloc_lists(h, std::max(8, (int)value), h->KB));

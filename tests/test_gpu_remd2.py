@@ -1,0 +1,168 @@
+"""Round-2 REMD / restart checks on the GPU: the exchange step inside the replica-local persistent
+kernel (fast_remd_exchange) against the device-side launch chain and against the oracle, the base-pair
+state around an exchange step that is also a save step (src/energy_replica.F90:64-70,157-162), and the
+restart payload of the counter-based generators."""
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from sis_b200 import fixtures as fx
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu(**opts):
+    from sis_b200.api import SisGpu
+    return SisGpu(0, **opts)
+
+
+def remd_gpu(spec, n, temps, nex, **opts):
+    g = gpu(**opts)
+    spec.configure(g)
+    g.remd_setup([n, 1, 1, 1], [temps, [], [], []], nex)
+    for r in range(n):
+        g.init_velocities(r)
+        g.neighbor_list(r)
+    return g
+
+
+@pytest.mark.parametrize("n", [4, 7, 16])
+def test_inkernel_exchange_equals_the_launch_chain(n):
+    """one launch per md_steps call with the exchange inside the kernel == one launch per exchange
+    interval + the exchange chain: same bits (same summation order), across launch boundaries that do
+    and do not fall on exchange steps, with in-kernel list rebuilds in between"""
+    temps = list(np.linspace(290.0, 380.0, n))
+    spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=0).replicated(n, temps=temps)
+    spec.nl_margin = 1.0
+    res = []
+    for ink in (1, 0):
+        g = remd_gpu(spec, n, temps, 10, remd_inkernel=ink)
+        nreb = 0
+        for nsteps in (25, 15, 40, 7, 13):
+            nreb += g.md_steps(nsteps)
+        assert g.last_step_kernel() == "k_md_fast<1,true>" and g.get_step() == 100
+        res.append(([g.get_state(r) for r in range(n)], g.remd_state(), g.remd_stats(), nreb,
+                    [g.get_bp_state(r) for r in range(n)], g.launch_count()))
+    a, b = res
+    assert a[2] == b[2] and a[2][0] >= 10 * ((n - 1) // 2) and a[2][1] > 0   # odd / even pair tables alternate
+    assert np.array_equal(a[1][0], b[1][0]) and np.array_equal(a[1][1], b[1][1])
+    assert a[3] == b[3]
+    for r in range(n):
+        for u, v in zip(a[0][r], b[0][r]):
+            assert np.array_equal(u, v)
+        assert np.array_equal(a[4][r][0], b[4][r][0]) and np.array_equal(a[4][r][1], b[4][r][1])
+    assert a[5] < b[5]          # far fewer launches
+
+
+def test_inkernel_exchange_follows_the_oracle():
+    n, nex = 8, 10
+    temps = list(np.linspace(293.15, 363.15, n))
+    spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=0).replicated(n, temps=temps)
+    g = remd_gpu(spec, n, temps, nex)
+    o = Oracle()
+    spec.configure(o)
+    o.remd_setup([n, 1, 1, 1], [temps, [], [], []], nex)
+    for r in range(n):
+        o.init_velocities(r)
+        o.neighbor_list(r)
+    g.md_steps(60)
+    counter = 0
+    for _ in range(6):
+        o.md_run(nex)
+        _, re = o.energy_replica()
+        u = np.array([o.uniform(spec.rng_seed, 0x7fffffff, counter + i) for i in range(n // 2)])
+        counter += n // 2
+        o.replica_exchange(re, u)
+    assert np.array_equal(g.remd_state()[0], o.remd_state()[0])
+    for r in range(n):
+        xg, vg, _ = g.get_state(r)
+        xo, vo, _ = o.get_state(r)
+        assert np.abs(xg - xo).max() < 1e-6 and np.abs(vg - vo).max() < 1e-6
+        # bp_status / ene_bp after an exchange step are the replica's own (src/energy_replica.F90:157-162)
+        sg, eg = g.get_bp_state(r)
+        so, eo = o.get_bp_state(r)
+        assert np.array_equal(sg, so) and np.allclose(eg, eo, rtol=1e-7, atol=1e-10)
+
+
+@pytest.mark.parametrize("opts", [dict(remd_inkernel=0), dict(launch_mode=0)], ids=["device-chain", "host-driven"])
+def test_cross_energy_pass_leaves_the_own_base_pair_state(opts):
+    """the partner-parameter pass of the exchange step must not leave its bp_status / ene_bp
+    behind (a save step that is also an exchange step writes them)"""
+    n, nex = 4, 10
+    temps = [290.0, 320.0, 350.0, 380.0]
+    spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=0).replicated(n, temps=temps)
+    g = remd_gpu(spec, n, temps, nex, **opts)
+    o = Oracle()
+    spec.configure(o)
+    o.remd_setup([n, 1, 1, 1], [temps, [], [], []], nex)
+    for r in range(n):
+        o.init_velocities(r)
+        o.neighbor_list(r)
+    g.md_steps(nex)
+    o.md_run(nex)
+    _, re = o.energy_replica()
+    o.replica_exchange(re, np.array([o.uniform(spec.rng_seed, 0x7fffffff, i) for i in range(n // 2)]))
+    for r in range(n):
+        sg, eg = g.get_bp_state(r)
+        so, eo = o.get_bp_state(r)
+        assert np.array_equal(sg, so) and np.allclose(eg, eo, rtol=1e-7, atol=1e-10)
+
+
+def test_restart_payload_continues_the_trajectory_bit_for_bit():
+    """stop -> write (XYZ, VELO, ACCEL, STEP, PRNG counters, REPLICA labels) -> new handle -> read -> continue
+    == the run that was never stopped (with a neighbor_list call at the same step, as a restart does:
+    src/job_md.F90:196-198), T-REMD with the Monte-Carlo base-pair limit so that every generator is in play"""
+    n, nex = 4, 10
+    temps = [290.0, 310.0, 330.0, 350.0]
+    spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=5).replicated(n, temps=temps)
+
+    def fresh():
+        return remd_gpu(spec, n, temps, nex)
+
+    a = fresh()
+    a.md_steps(30)
+    for r in range(n):
+        a.neighbor_list(r)
+    a.md_steps(30)
+    ref = [a.get_state(r) for r in range(n)]
+
+    b = fresh()
+    b.md_steps(30)
+    saved = dict(state=[tuple(np.copy(t) for t in b.get_state(r)) for r in range(n)], rng=b.get_rng_state(),
+                 r2l=b.remd_state()[0].copy(), idx=b.remd_idx_pair(), stats=b.remd_stats())
+    assert saved["rng"][1] == 30 and saved["rng"][3] == n and (saved["rng"][4:] > 0).all() and saved["rng"][2] == 3 * (n // 2)
+    b.close()
+    c = gpu()
+    spec.configure(c)
+    c.remd_setup([n, 1, 1, 1], [temps, [], [], []], nex)
+    c.remd_set_labels(saved["r2l"], saved["idx"])
+    for r in range(n):
+        c.set_state(r, *saved["state"][r])
+    c.set_rng_state(saved["rng"])
+    assert c.get_step() == 30
+    for r in range(n):
+        c.neighbor_list(r)
+    c.md_steps(30)
+    assert np.array_equal(c.remd_state()[0], a.remd_state()[0])
+    for r in range(n):
+        for u, v in zip(ref[r], c.get_state(r)):
+            assert np.array_equal(u, v)
+
+
+def test_set_step_keeps_a_pending_rebuild_trigger():
+    """moving the step counter must not lose the displacement top-2 (src/job_md.F90:376-388)"""
+    spec = fx.cag47(4, pbc=True)
+    spec.nl_margin = 3.0
+    out = []
+    for shift in (0, 1001):
+        g = gpu()
+        spec.configure(g)
+        g.init_velocities(0)
+        g.neighbor_list(0)
+        nreb = g.md_steps(30)
+        g.set_step(g.get_step() + shift)
+        nreb += g.md_steps(60)
+        out.append(nreb)
+    assert out[0] >= 2
+    # the Gaussians of the shifted run differ (the step is their counter), the rebuild cadence must survive
+    assert out[1] >= 2
