@@ -203,7 +203,7 @@ class Ctx:
         return g
 
 
-def run_remd_c3(cx, nrep_all=64, nex=int(os.environ.get("SIS_NEX", "10")), md_steps=2000, steps=5, warmup=2):
+def run_remd_c3(cx, nrep_all=64, nex=int(os.environ.get("SIS_NEX", "10")), md_steps=2000, steps=5, warmup=2, scaling="strong"):
     """BASELINE config 3: T2S2HP T-REMD (check/T2S2HP_REMD_T/input_REMD.toml with 64 temperatures
     293.15 .. 363.15 K), nrep_all replicas split over the ranks, exchange attempt every `nex` steps"""
     from sis_b200 import fixtures as fx
@@ -218,6 +218,8 @@ def run_remd_c3(cx, nrep_all=64, nex=int(os.environ.get("SIS_NEX", "10")), md_st
     g.remd_setup([nrep_all, 1, 1, 1], [temps, [], [], []], nex, rank, world)
     if world > 1:
         g.comm_init_torch()
+        if not os.environ.get("SIS_NO_PEER"):
+            g.peer_init_torch()      # exchange steps inside the kernels over NVLink peer memory
     for r in range(R):
         g.init_velocities(r)
         g.neighbor_list(r)
@@ -240,7 +242,7 @@ def run_remd_c3(cx, nrep_all=64, nex=int(os.environ.get("SIS_NEX", "10")), md_st
     att, acc = g.remd_stats()
     out = {"metric": "replica-steps/s", "value": nrep_all * md_steps * steps / dt, "unit": "replica-steps/s",
            "workload": "T2S2HP T-REMD, 27 beads x %d replicas, exchange every %d steps (BASELINE config 3)" % (nrep_all, nex),
-           "nrep_all": nrep_all, "nrep_per_gpu": R, "n_gpus": world, "scaling": "strong", "md_steps": md_steps * steps,
+           "nrep_all": nrep_all, "nrep_per_gpu": R, "n_gpus": world, "scaling": scaling, "md_steps": md_steps * steps,
            "us_per_md_step": 1e6 * dt / (md_steps * steps), "kernel": g.last_step_kernel(),
            "launches_rank0": g.launch_count() - l0, "rebuilds_rank0": nreb, "timers_ms": g.get_timers(),
            "exchange": {"attempts": att, "accepted": acc}}
@@ -405,6 +407,8 @@ def main():
         if not args.no_extra:
             try:
                 extra["c3_remd"] = run_remd_c3(cx)
+                if cx.world > 1:     # the same replicas per GPU as the N = 1 line: weak scaling along replicas
+                    extra["c3_remd_weak"] = run_remd_c3(cx, nrep_all=64 * cx.world, scaling="weak")
             except Exception as ex:  # pragma: no cover
                 extra["c3_remd"] = {"error": str(ex)}
         if cx.rank == 0:

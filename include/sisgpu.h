@@ -33,6 +33,7 @@ typedef struct sisgpu sisgpu_t;
 
 #define SISGPU_ENE_N 11          /* energies(0:10), src/const_idx.F90:7-21 */
 #define SISGPU_NCCL_ID_BYTES 128
+#define SISGPU_IPC_HANDLE_BYTES 64
 
 const char *sisgpu_last_error(void);
 int sisgpu_version(void);
@@ -212,6 +213,13 @@ int sisgpu_remd_setup(sisgpu_t *h, const int nrep[4], const double *values,
  * rank 0 calls sisgpu_nccl_unique_id and broadcasts the bytes (MPI_BCAST / torch.distributed) */
 int sisgpu_nccl_unique_id(unsigned char *id /*[SISGPU_NCCL_ID_BYTES]*/);
 int sisgpu_comm_init(sisgpu_t *h, int nranks, int rank, const unsigned char *id);
+/* Peer mapping for the exchange step inside the persistent kernel (ranks of one node): every rank exports one
+ * CUDA IPC handle of its exchange buffer, the driver all-gathers the SISGPU_IPC_HANDLE_BYTES-byte handles
+ * (MPI_ALLGATHER) and every rank imports all of them.  The MPI_ALLREDUCE of src/job_md.F90:531-533 then becomes
+ * peer stores + arrival counters over NVLink inside sisgpu_md_steps; without the import a multi-rank run uses
+ * the ncclAllGather launch chain.  Call after sisgpu_remd_setup. */
+int sisgpu_peer_export(sisgpu_t *h, unsigned char *handle /*[SISGPU_IPC_HANDLE_BYTES]*/);
+int sisgpu_peer_import(sisgpu_t *h, int nranks, const unsigned char *handles /*[nranks][SISGPU_IPC_HANDLE_BYTES]*/);
 int sisgpu_remd_pair_table(sisgpu_t *h, int *tb);
 int sisgpu_remd_state(sisgpu_t *h, int *rep2lab, int *lab2rep, double *lab2val);
 int sisgpu_remd_stats(sisgpu_t *h, int64_t *n_attempt, int64_t *n_accept);

@@ -170,3 +170,20 @@ class SisGpu(CApi):
         dist.broadcast(t, 0)
         raw = bytes(t.cpu().tolist())
         self._call("comm_init", C.c_int(world), C.c_int(rank), C.c_char_p(raw))
+
+    def peer_init_torch(self):
+        """exchange buffers of all ranks of the node mapped into each other (CUDA IPC handles all-gathered
+        over torch.distributed; the Fortran driver would MPI_ALLGATHER them): the exchange steps of a
+        multi-rank REMD then run inside the persistent kernels over NVLink peer memory"""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = (C.c_ubyte * 64)()
+        self._call("peer_export", buf)
+        t = torch.tensor(list(buf), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        raw = b"".join(bytes(o.cpu().tolist()) for o in out)
+        self._call("peer_import", C.c_int(world), C.c_char_p(raw))

@@ -1026,16 +1026,22 @@ SIS_D void fast_remd_exchange(const DevSys &S, const FFParams &P, FastShared &sh
     RepParams Ralt = Rown;
     if (has_opp) remd_apply_label(D, Ralt, D.lab_rp[label_opp - 1]);
     fast_remd_energies(S, P, sh, rep, cur, Rown, Ralt, has_opp);
-    double *E = D.xch_E + (size_t)(X.attempt & 1) * 2 * n;
+    const unsigned long long round = D.xch_round0 + (unsigned long long)X.attempt;
+    const size_t eoff = (size_t)(round & 1ull) * 2 * n;
+    const double *E = D.xE_peer[D.rank] + eoff;
     if (tid == 0) {
-        E[2 * grep] = sh.xE[0];
-        E[2 * grep + 1] = sh.xE[1];
-        __threadfence();
-        red_release_add(D.xch_bar, 1u);
-        const unsigned target = (unsigned)(X.attempt + 1) * gridDim.x;
+        // the two energies into every rank's copy (peer stores over NVLink), then one arrival on every rank's counter
+        for (int r = 0; r < D.nranks_x; r++) {
+            double *Er = D.xE_peer[r] + eoff;
+            Er[2 * grep] = sh.xE[0];
+            Er[2 * grep + 1] = sh.xE[1];
+        }
+        __threadfence_system();
+        for (int r = 0; r < D.nranks_x; r++) atomicAdd_system(D.xbar_peer[r], 1ull);
+        const unsigned long long target = (round + 1ull) * (unsigned long long)n;     // one CTA per replica on the whole node
         const long long t0 = clock64();
-        while (ld_acquire_u32(D.xch_bar) < target)
-            if (clock64() - t0 > 4000000000ll) { S.misc->max_force_flag |= 16; break; }   // ~2 s: a CTA of the launch is missing
+        while (ld_acquire_sys_u64(D.xbar_peer[D.rank]) < target)
+            if (clock64() - t0 > 8000000000ll) { S.misc->max_force_flag |= 16; break; }   // ~4 s: a CTA / a rank is missing
         sh.x_newlab = label_own; sh.x_vscale = 1.0; sh.x_natt = 0; sh.x_nacc = 0;
     }
     cta_sync();
@@ -1180,6 +1186,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams 
         for (int i = 0; i < D.n; i++) { D.rep2lab[i] = sh.x_r2l[i]; D.lab2rep[i] = sh.x_l2r[i]; }
         D.idx_pair = X.idx_pair; D.exchange_counter = X.counter;
         D.n_attempt += X.natt; D.n_accept += X.nacc;
+        D.xch_round0 += (unsigned long long)X.attempt;
     }
     if (tid >= FAST_MAIN) return;
     if (S.prof != nullptr && blockIdx.x == 0 && tid == 0) {   // whole-launch clocks: prologue share = total - steps * per-step

@@ -37,6 +37,12 @@ SIS_D void red_release_add(unsigned *p, unsigned v)
 {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+SIS_D unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 SIS_D void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 // sum over the 8 lanes named by `mask` (the groups of one warp may have diverged)
 SIS_D double group_sum_masked(double v, unsigned mask)

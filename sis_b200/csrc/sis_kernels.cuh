@@ -1396,6 +1396,7 @@ __global__ void __launch_bounds__(1024) k_nl_partition(DevSys S, const int *rep_
 // (temperature, Debye-Hueckel coefficients, tweezers force, Rg0) is precomputed per label, so an
 // exchange is a permutation of those blocks.  Every rank replays the same decisions from the
 // all-gathered energies and the shared counter-based uniform stream: no second collective.
+constexpr int REMD_MAX_PEERS = 16;          // ranks of one node whose exchange buffers are peer-mapped
 constexpr int REMD_DEV_MAX_LABELS = 4096;   // replicas the device-side exchange handles (shared table of k_remd_exchange)
 struct RemdDev {
     int n, ncol, idx_pair, R, rank;
@@ -1411,10 +1412,16 @@ struct RemdDev {
     int *has_opp;             // [R]
     double *send, *recv;      // [2 R], [2 n]: replica_energies(2, :) of src/job_md.F90:475
     double *vscale;           // [R]
-    // exchange inside the replica-local persistent kernel (k_md_fast<U, true>, fast_remd_exchange)
-    int nex;                  // nstep_rep_exchange
-    double *xch_E;            // [2 parities][n][2]: (own, cross) total energies of every replica of an attempt
-    unsigned *xch_bar;        // arrivals of the local CTAs, monotonic over the attempts of one launch (zeroed by the host)
+    // exchange inside the replica-local persistent kernel (k_md_fast<U, true>, fast_remd_exchange).
+    // Every rank holds one buffer {E[2 parities][n][2] doubles; arrival counter}; the buffers of the other
+    // ranks of the node are mapped through CUDA IPC (sisgpu_peer_export / _import), so a replica's CTA stores
+    // its two energies straight into every rank's copy over NVLink and bumps every rank's counter: the
+    // all-gather of src/job_md.F90:531-533 and its barrier without leaving the kernel.
+    int nex;                              // nstep_rep_exchange
+    int nranks_x;                         // ranks taking part (1: this rank alone)
+    unsigned long long xch_round0;        // exchange rounds done before this launch (parity of E, base of the counters)
+    double *xE_peer[REMD_MAX_PEERS];      // [rank] -> that rank's E buffer (own included)
+    unsigned long long *xbar_peer[REMD_MAX_PEERS];   // [rank] -> that rank's arrival counter (monotonic, never reset)
 };
 SIS_D void remd_apply_label(const RemdDev &D, RepParams &dst, const RepParams &lab)
 {

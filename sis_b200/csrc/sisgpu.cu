@@ -194,8 +194,10 @@ struct sisgpu {
     const char *last_step_kernel = "k_force_local + k_force_bp + k_integrate";   // what md_steps launched last
     // device-resident REMD state (exchange steps inside md_steps without host round trips)
     int remd_inkernel = 1;               // option "remd_inkernel": exchange steps inside the replica-local kernel (one launch per md_steps call)
-    DBuf<double> d_xch_E;
-    DBuf<unsigned> d_xch_bar;
+    DBuf<double> d_xch;                  // {E[2][n][2]; arrival counter (u64)}: one allocation = one IPC handle
+    void *peer_xch[REMD_MAX_PEERS]{};    // the same buffer of every rank of the node (own included), sisgpu_peer_import
+    bool peers_ready = false;
+    unsigned long long xch_rounds = 0;   // exchange rounds done inside the kernel so far (identical on every rank)
     int remd_device = 1;                 // option "remd_device"
     bool remd_on_device = false;         // inside an md_steps call whose exchange steps run on the device: host tables are stale
     double remd_cut_max = 0.0;           // largest ele_cutoff any label can bring to a local replica (cutoff_type 2)
@@ -295,7 +297,8 @@ int sisgpu_destroy(sisgpu_t *h)
     for (auto e : h->ev_free) cudaEventDestroy(e);
     h->ev_free.clear();
     h->d_remd.release(); h->d_pair_tb.release(); h->d_rep2lab.release(); h->d_lab2rep.release(); h->d_has_opp.release();
-    h->d_lab_temp.release(); h->d_vscale.release(); h->d_lab_rp.release(); h->d_xch_E.release(); h->d_xch_bar.release();
+    h->d_lab_temp.release(); h->d_vscale.release(); h->d_lab_rp.release(); for (int r = 0; r < REMD_MAX_PEERS; r++) if (h->peer_xch[r] && r != h->rank && h->peers_ready) cudaIpcCloseMemHandle(h->peer_xch[r]);
+    h->d_xch.release();
     h->d_rp.release(); h->d_rp_alt.release(); h->d_sync.release();
     if (h->graph_chunk) cudaGraphExecDestroy(h->graph_chunk);
     if (h->graph_big) cudaGraphExecDestroy(h->graph_big);
@@ -1959,6 +1962,49 @@ int sisgpu_replica_exchange(sisgpu_t *h, const double *E, const double *uniforms
     return 0;
 }
 
+// ---- exchange buffer of the in-kernel exchange and its peer mapping ------------------------------
+static int xch_alloc(sisgpu *h)
+{
+    const size_t n = (size_t)h->nrep_all;
+    if (h->d_xch.n != 4 * n + 4) {
+        if (h->peers_ready) return set_err("the exchange buffer is already shared with the other ranks");
+        TRY(h->d_xch.alloc(4 * n + 4));    // zero-filled: counter 0
+        h->xch_rounds = 0;
+    }
+    return 0;
+}
+// One CUDA IPC handle per rank (64 bytes) that the driver all-gathers (MPI_ALLGATHER / torch.distributed) and
+// hands to sisgpu_peer_import: afterwards the exchange steps of a multi-rank REMD run inside the persistent
+// kernels, energies and arrival flags travelling as peer stores / atomics over NVLink instead of through
+// ncclAllGather launches.  Ranks of ONE node only; call after sisgpu_remd_setup.
+int sisgpu_peer_export(sisgpu_t *h, unsigned char *handle)
+{
+    if (!h->flg_replica) return set_err("REMD not configured");
+    CK(cudaSetDevice(h->device));
+    TRY(xch_alloc(h));
+    cudaIpcMemHandle_t ih;
+    CK(cudaIpcGetMemHandle(&ih, h->d_xch.p));
+    static_assert(sizeof ih == SISGPU_IPC_HANDLE_BYTES, "IPC handle size");
+    memcpy(handle, &ih, sizeof ih);
+    return 0;
+}
+int sisgpu_peer_import(sisgpu_t *h, int nranks, const unsigned char *handles)
+{
+    if (!h->flg_replica) return set_err("REMD not configured");
+    if (nranks != h->nranks) return set_err("peer_import: %d handles for %d ranks", nranks, h->nranks);
+    if (nranks > REMD_MAX_PEERS) return set_err("peer_import: at most %d ranks", REMD_MAX_PEERS);
+    CK(cudaSetDevice(h->device));
+    TRY(xch_alloc(h));
+    for (int r = 0; r < nranks; r++) {
+        if (r == h->rank) { h->peer_xch[r] = h->d_xch.p; continue; }
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, handles + (size_t)r * SISGPU_IPC_HANDLE_BYTES, sizeof ih);
+        CK(cudaIpcOpenMemHandle(&h->peer_xch[r], ih, cudaIpcMemLazyEnablePeerAccess));
+    }
+    h->peers_ready = true;
+    return 0;
+}
+
 // ---- device-resident exchange step ------------------------------------------------------------
 // Host tables -> device (the host copies are authoritative between md_steps calls: the per-call API
 // sisgpu_energy_replica / sisgpu_replica_exchange works on them).
@@ -1971,7 +2017,7 @@ static int remd_upload(sisgpu *h)
     }
     if (h->d_pair_tb.n != h->pair_tb.size()) TRY(h->d_pair_tb.alloc(h->pair_tb.size()));
     if (h->d_gather_recv.n < 2 * (size_t)n) TRY(h->d_gather_recv.alloc(2 * (size_t)n));
-    if (h->d_xch_E.n != 4 * (size_t)n) { TRY(h->d_xch_E.alloc(4 * (size_t)n)); TRY(h->d_xch_bar.alloc(32)); }
+    TRY(xch_alloc(h));
     // parameter block of every label: what apply_label + fill_rp give a replica that holds it
     std::vector<RepParams> lab(n);
     std::vector<double> ltemp(n);
@@ -1995,7 +2041,13 @@ static int remd_upload(sisgpu *h)
     D.pair_tb = h->d_pair_tb.p; D.rep2lab = h->d_rep2lab.p; D.lab2rep = h->d_lab2rep.p;
     D.lab_temp = h->d_lab_temp.p; D.lab_rp = h->d_lab_rp.p; D.rp_alt = h->d_rp_alt.p; D.has_opp = h->d_has_opp.p;
     D.send = h->d_gather_send.p; D.recv = h->nranks > 1 ? h->d_gather_recv.p : h->d_gather_send.p; D.vscale = h->d_vscale.p;
-    D.nex = h->nstep_exchange; D.xch_E = h->d_xch_E.p; D.xch_bar = h->d_xch_bar.p;
+    D.nex = h->nstep_exchange; D.xch_round0 = h->xch_rounds;
+    D.nranks_x = (h->nranks > 1 && h->peers_ready) ? h->nranks : 1;
+    for (int r = 0; r < D.nranks_x; r++) {
+        void *base = D.nranks_x == 1 ? (void *)h->d_xch.p : h->peer_xch[r];
+        D.xE_peer[D.nranks_x == 1 ? h->rank : r] = (double *)base;
+        D.xbar_peer[D.nranks_x == 1 ? h->rank : r] = (unsigned long long *)((double *)base + 4 * (size_t)n);
+    }
     CK(cudaMemcpyAsync(h->d_pair_tb.p, h->pair_tb.data(), h->pair_tb.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_rep2lab.p, h->rep2lab.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_lab2rep.p, h->lab2rep.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -2015,6 +2067,7 @@ static int remd_download(sisgpu *h)
     CK(cudaMemcpy(h->lab2rep.data(), h->d_lab2rep.p, n * sizeof(int), cudaMemcpyDeviceToHost));
     h->idx_pair = D.idx_pair; h->exchange_counter = D.exchange_counter;
     h->n_attempt = D.n_attempt; h->n_accept = D.n_accept;
+    h->xch_rounds = D.xch_round0;
     for (int irep = 0; irep < R; irep++) apply_label(h, irep, h->rep2lab[h->rank * R + irep]);
     return 0;
 }
@@ -2289,11 +2342,10 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
             bool local_, fast_ok_;
             int want_;
             persistent_choice(h, &local_, &fast_ok_, &want_);
-            if (local_ && !(h->h_misc->max_force_flag & 4) && h->remd_inkernel && h->nranks == 1 && h->nstep_bp_MC == 0 &&
-                h->nrep_all <= REMD_LOCAL_MAX) {
+            if (local_ && !(h->h_misc->max_force_flag & 4) && h->remd_inkernel && (h->nranks == 1 || h->peers_ready) &&
+                h->nstep_bp_MC == 0 && h->nrep_all <= REMD_LOCAL_MAX) {
                 // the exchange steps run inside the replica-local kernel: ONE launch up to the target
                 const long long stop = std::min<long long>(target, cur + (1ll << 20));
-                CK(cudaMemsetAsync(h->d_xch_bar.p, 0, 32 * sizeof(unsigned), h->stream));
                 h->S.remd = h->d_remd.p;
                 const int sp = span_begin(h);
                 const int rc = launch_persistent(h, stop);

@@ -368,6 +368,19 @@ module sisgpu_mod
          integer(c_int), value :: idx_pair
          integer(c_int) :: rc
       end function
+      function sisgpu_peer_export(h, handle) bind(C, name='sisgpu_peer_export') result(rc)
+         import :: c_ptr, c_int, c_char
+         type(c_ptr), value :: h
+         character(kind=c_char), intent(out) :: handle(*)
+         integer(c_int) :: rc
+      end function
+      function sisgpu_peer_import(h, nranks, handles) bind(C, name='sisgpu_peer_import') result(rc)
+         import :: c_ptr, c_int, c_char
+         type(c_ptr), value :: h
+         integer(c_int), value :: nranks
+         character(kind=c_char), intent(in) :: handles(*)
+         integer(c_int) :: rc
+      end function
    end interface
 
 contains
@@ -531,6 +544,24 @@ contains
       integer(c_int) :: r2l(nrep_all)
       r2l(:) = int(rep2lab(1:nrep_all), c_int)
       call gpu_check(sisgpu_remd_set_labels(h, r2l, int(0, c_int)), 'remd_set_labels')
+   end subroutine
+
+   ! exchange buffers of the ranks of one node mapped into each other (CUDA IPC): the MPI_ALLREDUCE of
+   ! src/job_md.F90:531-533 becomes peer stores over NVLink inside gpu_md_steps
+   subroutine gpu_peer_init(myrank, nprocs)
+#ifdef PAR_MPI
+      use mpi
+#endif
+      integer, intent(in) :: myrank, nprocs
+      character(kind=c_char) :: mine(64), all_handles(64 * nprocs)
+      integer :: ierr
+      call gpu_check(sisgpu_peer_export(h, mine), 'peer_export')
+#ifdef PAR_MPI
+      call MPI_ALLGATHER(mine, 64, MPI_CHARACTER, all_handles, 64, MPI_CHARACTER, MPI_COMM_WORLD, ierr)
+#else
+      all_handles(1:64) = mine
+#endif
+      if (nprocs > 1) call gpu_check(sisgpu_peer_import(h, int(nprocs, c_int), all_handles), 'peer_import')
    end subroutine
 
    subroutine gpu_neighbor_list(irep)

@@ -29,8 +29,10 @@ def remd_gpu(spec, n, temps, nex, **opts):
 @pytest.mark.parametrize("n", [4, 7, 16])
 def test_inkernel_exchange_equals_the_launch_chain(n):
     """one launch per md_steps call with the exchange inside the kernel == one launch per exchange
-    interval + the exchange chain: same bits (same summation order), across launch boundaries that do
-    and do not fall on exchange steps, with in-kernel list rebuilds in between"""
+    interval + the exchange chain, across launch boundaries that do and do not fall on exchange steps, with
+    in-kernel list rebuilds in between.  Same energies bit for bit (same summation order); the trajectories
+    agree to rounding only: every launch re-partitions the on-chip rows by distance, so the two paths add the
+    pair forces in different orders"""
     temps = list(np.linspace(290.0, 380.0, n))
     spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=0).replicated(n, temps=temps)
     spec.nl_margin = 1.0
@@ -49,8 +51,8 @@ def test_inkernel_exchange_equals_the_launch_chain(n):
     assert a[3] == b[3]
     for r in range(n):
         for u, v in zip(a[0][r], b[0][r]):
-            assert np.array_equal(u, v)
-        assert np.array_equal(a[4][r][0], b[4][r][0]) and np.array_equal(a[4][r][1], b[4][r][1])
+            assert np.abs(u - v).max() < 1e-9
+        assert np.array_equal(a[4][r][0], b[4][r][0]) and np.allclose(a[4][r][1], b[4][r][1], rtol=1e-9, atol=1e-12)
     assert a[5] < b[5]          # far fewer launches
 
 
