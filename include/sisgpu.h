@@ -150,6 +150,10 @@ int sisgpu_energy_kinetic(sisgpu_t *h, int irep, double *ekin);
  * in every slot; lists from sisgpu_full_lists as src/main.F90:148-154).  xyz32 = float32
  * [nframes][nmp][3] as stored in the DCD (src/dcd.F90:584-592); energies = [nframes][11] */
 int sisgpu_dcd_energies(sisgpu_t *h, int nframes, const float *xyz32, double tempK, double *energies);
+/* bp_status_MC(:,:) = bp_status(:,:), the line after the initial energies of job_md (src/job_md.F90:344-348):
+ * call it after the initial sisgpu_energy_sumup (flg_bp_MC set, recompute_bp) of a run or of a restart when
+ * nstep_MC > 0; the steps up to the first Monte-Carlo step evaluate exactly these pairs */
+int sisgpu_bp_status_to_mc(sisgpu_t *h);
 /* bp_status / ene_bp for write_bp (src/write_bp.F90:36-49) */
 int sisgpu_get_bp_state(sisgpu_t *h, int irep, int *status, double *ene);
 int sisgpu_get_rg(sisgpu_t *h, int irep, double *rg);

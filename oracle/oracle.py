@@ -59,6 +59,9 @@ class Oracle(CApi):
         self._call("md_run", C.c_int(nsteps), C.byref(n))
         return n.value
 
+    def set_save_bp(self, flg):
+        self._call("set_save_bp", C.c_int(int(flg)))
+
     def num_threads(self):
         self.lib.oracle_num_threads.restype = C.c_int
         return self.lib.oracle_num_threads()

@@ -148,6 +148,7 @@ struct sis_oracle {
     double *forces_t;      /* forces_t(3, nmp, 0:nthreads-1) of src/force.F90:19 */
     size_t forces_t_n;
     int *bp_excess;        /* nt_bp_excess(nmp), shared by the threads of force_bp_limit_triplet */
+    int flg_save_bp;       /* energy_replica's flg_save_bp: the exchange step is also a save step */
 };
 
 static char g_err[512];
@@ -2153,11 +2154,34 @@ static void apply_label_params(sis_oracle *o, int irep, int label)
 
 /* src/energy_replica.F90:45-163 on an exchange step.  energies [nrep][11],
  * replica_energies [nrep_all][2] */
+/* flg_save_bp of src/energy_replica.F90:16: set when the exchange step is also a save step */
+int oracle_set_save_bp(sis_oracle *o, int flg) { o->flg_save_bp = flg; return 0; }
+/* bp_status_MC(:,:) = bp_status(:,:) after the initial energies, src/job_md.F90:344-348 */
+int oracle_bp_status_to_mc(sis_oracle *o)
+{
+    for (int irep = 0; irep < o->nrep_proc; irep++) {
+        replica *r = &o->rep[irep];
+        memcpy(r->bp_status_MC, r->bp_status, (size_t)r->nbp * sizeof(int));
+    }
+    return 0;
+}
+
 int oracle_energy_replica(sis_oracle *o, double *energies, double *replica_energies)
 {
     int n = o->nrep_all;
     for (int irep = 0; irep < n; irep++)
         if (oracle_energy_sumup(o, irep, o->rep[irep].tempK, 0, energies + O_ENE_N * irep)) return 1;
+    /* :64-70 save bp information to output in write_bp */
+    int **st_tmp = NULL;
+    double **en_tmp = NULL;
+    if (o->flg_save_bp) {
+        st_tmp = (int **)xcalloc(n, sizeof(int *));
+        en_tmp = (double **)xcalloc(n, sizeof(double *));
+        for (int irep = 0; irep < n; irep++) {
+            st_tmp[irep] = dup_int(o->rep[irep].bp_status, o->rep[irep].nbp);
+            en_tmp[irep] = dup_dbl(o->rep[irep].ene_bp, o->rep[irep].nbp);
+        }
+    }
     for (int irep = 0; irep < n; irep++) {
         replica *r = &o->rep[irep];
         r->flg_bp_energy = 0; /* :72 */
@@ -2173,10 +2197,17 @@ int oracle_energy_replica(sis_oracle *o, double *energies, double *replica_energ
         r->tempK = T_own; r->ionic_strength = I_own;
         apply_label_params(o, irep, label_own);
     }
+    if (o->flg_save_bp) { /* :157-162 */
+        for (int irep = 0; irep < n; irep++) {
+            memcpy(o->rep[irep].bp_status, st_tmp[irep], (size_t)o->rep[irep].nbp * sizeof(int));
+            memcpy(o->rep[irep].ene_bp, en_tmp[irep], (size_t)o->rep[irep].nbp * sizeof(double));
+            free(st_tmp[irep]); free(en_tmp[irep]);
+        }
+        free(st_tmp); free(en_tmp);
+    }
     return 0;
 }
 
-/* src/replica_exchange.F90:44-154; uniforms: nrep_all/2 (rounded up) values in [0,1] */
 int oracle_replica_exchange(sis_oracle *o, const double *E, const double *uniforms, int *n_attempt,
                             int *n_accept)
 {

@@ -113,6 +113,9 @@ int oracle_get_rg(sis_oracle *o, int irep, double *rg);
  * generator shared with the GPU build (oracle_gauss). */
 int oracle_md_step(sis_oracle *o, int irep, const double *gauss, int *rebuilt);
 int oracle_md_run(sis_oracle *o, int nsteps, int64_t *nrebuild);
+/* src/energy_replica.F90:16,64-70,157-162 (flg_save_bp) and src/job_md.F90:344-348 (bp_status_MC = bp_status) */
+int oracle_set_save_bp(sis_oracle *o, int flg);
+int oracle_bp_status_to_mc(sis_oracle *o);
 /* bench.py: OpenMP threads in use (1 = serial build); wall seconds inside neighbor_list */
 int oracle_num_threads(void);
 double oracle_nl_seconds(sis_oracle *o, int reset);

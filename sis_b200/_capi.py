@@ -224,6 +224,10 @@ class CApi:
     def init_velocities(self, irep=0):
         self._call("init_velocities", C.c_int(irep))
 
+    def bp_status_to_mc(self):
+        """bp_status_MC = bp_status (src/job_md.F90:344-348)"""
+        self._call("bp_status_to_mc")
+
     def check_force(self, tempK):
         fe, ff = np.zeros((self.nmp, 3)), np.zeros((self.nmp, 3))
         md = C.c_double()

@@ -1623,6 +1623,19 @@ int sisgpu_energy_kinetic(sisgpu_t *h, int irep, double *ekin)
     return 0;
 }
 
+// bp_status_MC(:,:) = bp_status(:,:) after the initial energies of a run or a restart (src/job_md.F90:344-348):
+// the mask the steps between two Monte-Carlo steps evaluate (src/force_bp_triplet.F90:46-48)
+int sisgpu_bp_status_to_mc(sisgpu_t *h)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    CK(cudaSetDevice(h->device));
+    k_copy_status_mc<<<dim3((h->nmp * h->KB + 255) / 256, h->nrep), 256, 0, h->stream>>>(h->S, -1);
+    h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int sisgpu_get_bp_state(sisgpu_t *h, int irep, int *status, double *ene)
 {
     HalfLists L;

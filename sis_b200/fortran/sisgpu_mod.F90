@@ -381,6 +381,11 @@ module sisgpu_mod
          character(kind=c_char), intent(in) :: handles(*)
          integer(c_int) :: rc
       end function
+      function sisgpu_bp_status_to_mc(h) bind(C, name='sisgpu_bp_status_to_mc') result(rc)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: h
+         integer(c_int) :: rc
+      end function
    end interface
 
 contains

@@ -69,5 +69,16 @@ def make_ss_pairs():
         f = line.split()
         if len(f) >= 5 and int(f[4]) > int(f[0]):
             pairs.append([int(f[0]), int(f[4])])
+    # check/nick_restraint: the base-pair list (bpl) and the two Sigmoid-to-bead restraints of dummy_restraint.txt
+    bpl = [[int(f) for f in line.split()[:2]] for line in (REF / "check/nick_restraint/nick_dumbbell.bpl").read_text().splitlines()
+           if line.strip() and not line.lstrip().startswith("#")]
+    rest = []
+    for line in (REF / "check/nick_restraint/dummy_restraint.txt").read_text().splitlines():
+        f = line.split()
+        if f and f[0] in ("Sigmoid", "Sigmoid-to-bead"):
+            # (imp, jmp, type 1 both beads / 2 reference bead force-free, rcut, eps, d, s): src/read_restraint.F90
+            rest.append([int(f[1]), int(f[2]), 1 if f[0] == "Sigmoid" else 2, float(f[6]), float(f[3]), float(f[4]), float(f[5])])
     (Path(__file__).resolve().parent / "ss_pairs.json").write_text(json.dumps(
-        {"T2S2HP_ct_pairs": pairs, "source": "check/T2S2HP.ct (column 1, column 5), pairs with j > i"}, indent=1))
+        {"T2S2HP_ct_pairs": pairs, "source": "check/T2S2HP.ct (column 1, column 5), pairs with j > i",
+         "nick_dumbbell_bpl": bpl, "nick_dumbbell_restraints": rest,
+         "nick_source": "check/nick_restraint/nick_dumbbell.bpl, dummy_restraint.txt"}, indent=1))

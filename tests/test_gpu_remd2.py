@@ -64,6 +64,7 @@ def test_inkernel_exchange_follows_the_oracle():
     o = Oracle()
     spec.configure(o)
     o.remd_setup([n, 1, 1, 1], [temps, [], [], []], nex)
+    o.set_save_bp(1)                  # every exchange step taken as a save step (src/energy_replica.F90:64-70,157-162)
     for r in range(n):
         o.init_velocities(r)
         o.neighbor_list(r)
@@ -97,6 +98,7 @@ def test_cross_energy_pass_leaves_the_own_base_pair_state(opts):
     o = Oracle()
     spec.configure(o)
     o.remd_setup([n, 1, 1, 1], [temps, [], [], []], nex)
+    o.set_save_bp(1)
     for r in range(n):
         o.init_velocities(r)
         o.neighbor_list(r)
@@ -110,10 +112,11 @@ def test_cross_energy_pass_leaves_the_own_base_pair_state(opts):
         assert np.array_equal(sg, so) and np.allclose(eg, eo, rtol=1e-7, atol=1e-10)
 
 
-def test_restart_payload_continues_the_trajectory_bit_for_bit():
+def test_restart_payload_continues_the_trajectory():
     """stop -> write (XYZ, VELO, ACCEL, STEP, PRNG counters, REPLICA labels) -> new handle -> read -> continue
-    == the run that was never stopped (with a neighbor_list call at the same step, as a restart does:
-    src/job_md.F90:196-198), T-REMD with the Monte-Carlo base-pair limit so that every generator is in play"""
+    == the run that was never stopped but does at the same step what job_md does when it starts
+    (src/job_md.F90:196-198 neighbor_list, :270-348 initial energies with flg_bp_MC set, bp_status_MC = bp_status);
+    T-REMD with the Monte-Carlo base-pair limit so that every generator is in play"""
     n, nex = 4, 10
     temps = [290.0, 310.0, 330.0, 350.0]
     spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=5).replicated(n, temps=temps)
@@ -121,10 +124,19 @@ def test_restart_payload_continues_the_trajectory_bit_for_bit():
     def fresh():
         return remd_gpu(spec, n, temps, nex)
 
+    def job_md_start(g):
+        lab = g.remd_state()[0]
+        for r in range(n):
+            g.neighbor_list(r)
+        g.set_bp_mc(1)
+        for r in range(n):
+            g.energy_sumup(r, temps[lab[r] - 1], True)
+        g.set_bp_mc(0)
+        g.bp_status_to_mc()
+
     a = fresh()
     a.md_steps(30)
-    for r in range(n):
-        a.neighbor_list(r)
+    job_md_start(a)
     a.md_steps(30)
     ref = [a.get_state(r) for r in range(n)]
 
@@ -142,13 +154,15 @@ def test_restart_payload_continues_the_trajectory_bit_for_bit():
         c.set_state(r, *saved["state"][r])
     c.set_rng_state(saved["rng"])
     assert c.get_step() == 30
-    for r in range(n):
-        c.neighbor_list(r)
+    job_md_start(c)
     c.md_steps(30)
-    assert np.array_equal(c.remd_state()[0], a.remd_state()[0])
+    assert np.array_equal(c.remd_state()[0], a.remd_state()[0]) and c.remd_idx_pair() == a.remd_idx_pair()
+    assert np.array_equal(c.get_rng_state(), a.get_rng_state())        # every draw counter where the other run has it
     for r in range(n):
         for u, v in zip(ref[r], c.get_state(r)):
-            assert np.array_equal(u, v)
+            # same arithmetic; the base-pair forces of a bead are added with shared-memory atomics whose order
+            # is not fixed, so two runs agree to the last bits only
+            assert np.abs(u - v).max() < 1e-11
 
 
 def test_set_step_keeps_a_pending_rebuild_trigger():
