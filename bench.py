@@ -12,7 +12,7 @@ along replicas, the only axis the reference shards on.
           steps and downloads xyz/velos/accels + the 11 energies (what the Fortran driver does
           at each save step)
 Both loops start from the SAME saved state (positions, velocities, beta, step counter, fresh
-lists), so they time the same trajectory.
+lists), so they time the same trajectory; the end-to-end loop runs first.
 
 `extra.c3_remd` (every N): BASELINE config 3 -- T2S2HP T-REMD, 64 replicas in total split over
 the N ranks (strong scaling along replicas), exchange attempt every 10 steps, replica-steps/s.
@@ -281,6 +281,25 @@ def run_md(cx, workload):
     if not os.environ.get("SIS_NO_SAMPLER"):
         th.start()
 
+    # ---- end to end through the C ABI with host buffers (the headline) ------------------
+    # every chunk: upload xyz / velos / accels, run the steps, download them + the 11 energies;
+    # same start state as the loop above
+    restart()
+    host = tuple(torch.empty((nmp, 3), dtype=torch.float64, pin_memory=True).numpy() for _ in range(3))
+    x, v, a = g.get_state(0, out=host)
+    g.set_option("timing", 1)      # the per-kernel event pairs of the device-resident loop, so that both loops carry them
+    cx.barrier()
+    g.mark(0)
+    for _ in range(args.steps):
+        g.set_state(0, x, v, a)
+        g.md_steps(args.md_steps)
+        x, v, a = g.get_state(0, out=host)
+        g.energy_sumup(0, spec.tempK, False)
+    g.mark(1)
+    dte = 1e-3 * g.elapsed_ms()
+    cx.barrier()
+    dte = cx.max_over_ranks(dte)
+    e2e = world * nmp * args.md_steps * args.steps / dte
     # ---- device-resident throughput ---------------------------------------------------
     restart()
     st = list_stats(g)
@@ -305,24 +324,6 @@ def run_md(cx, workload):
     dt = cx.max_over_ranks(dt)
     value = world * nmp * args.md_steps * args.steps / dt
 
-    # ---- end to end through the C ABI with host buffers (the headline) ------------------
-    # every chunk: upload xyz / velos / accels, run the steps, download them + the 11 energies;
-    # same start state as the loop above
-    restart()
-    host = tuple(torch.empty((nmp, 3), dtype=torch.float64, pin_memory=True).numpy() for _ in range(3))
-    x, v, a = g.get_state(0, out=host)
-    cx.barrier()
-    g.mark(0)
-    for _ in range(args.steps):
-        g.set_state(0, x, v, a)
-        g.md_steps(args.md_steps)
-        x, v, a = g.get_state(0, out=host)
-        g.energy_sumup(0, spec.tempK, False)
-    g.mark(1)
-    dte = 1e-3 * g.elapsed_ms()
-    cx.barrier()
-    dte = cx.max_over_ranks(dte)
-    e2e = world * nmp * args.md_steps * args.steps / dte
     stop.set()
     if th.is_alive():
         th.join(timeout=2)

@@ -446,6 +446,8 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
                     __threadfence();
                     (void)ld_acquire_u32(C.bar_pos);
                 } else {
+                    // (a two-level arrival -- groups of 6 / 12 / 24 CTAs on their own line, the last of a group on the
+                    // root -- was measured: 10.86 / 10.95 / 10.91 us per C4 step against 10.81 flat, so the flat one stays)
                     red_release_add(C.bar_pos, 1u);
                     const unsigned target = (unsigned)(n + 1) * (unsigned)C.ncta;
                     while (ld_acquire_u32(C.bar_pos) < target) { }

@@ -103,6 +103,8 @@ struct DBuf {   // device buffer
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+constexpr int BAR_WORDS = 64;
+
 struct sisgpu {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: the bp task branch of the step
@@ -812,7 +814,7 @@ int sisgpu_finalize_setup(sisgpu_t *h)
     h->sync_bytes = sizeof(DevSyncHdr) + (size_t)R * 4 * sizeof(unsigned long long);
     TRY(h->d_sync.alloc(h->sync_bytes));
     TRY(h->d_kin.alloc(R));
-    TRY(h->d_bar.alloc(64));
+    TRY(h->d_bar.alloc(BAR_WORDS));   // [0] bp / last-CTA counter, [32] position barrier
     TRY(h->d_top2_slots.alloc(2 * FAST_MAX_CTA));
     TRY(h->d_cta_item0.alloc(FAST_MAX_CTA + 1));
     const int nblk = (N + 63) / 64;            // integrate kernel: 64 beads per block
@@ -2149,7 +2151,7 @@ static int launch_persistent(sisgpu *h, long long stop)
     TRY(ensure_coop_blocks(h));
     StepArgs A = step_args(h, 0x7FEu, 0, -1, 1);
     const long long nitems = (long long)R * h->nmp;
-    CK(cudaMemsetAsync(h->d_bar.p, 0, 64 * sizeof(unsigned), h->stream));
+    CK(cudaMemsetAsync(h->d_bar.p, 0, BAR_WORDS * sizeof(unsigned), h->stream));
     NlArgs NA = nl_args(h, false);
     void *args[] = {&h->S, &h->P, &A, &stop, &NA};
     // k_md_fast: rows / candidates / bonded tables on chip
@@ -2272,7 +2274,7 @@ static int md_run_pipelined(sisgpu *h, long long stop)
             ncyc = std::max(1, std::min((int)ceil((double)(stop - cur) / std::max(1.0, per_cycle)) + 1, 96));
             h->h_misc->stop_step = stop;
             CK(cudaMemcpyAsync(&h->S.misc->stop_step, &h->h_misc->stop_step, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
-            CK(cudaMemsetAsync(h->d_bar.p, 0, 64 * sizeof(unsigned), h->stream));
+            CK(cudaMemsetAsync(h->d_bar.p, 0, BAR_WORDS * sizeof(unsigned), h->stream));
         }
         for (int c = 0; c < ncyc; c++) {
             if (!local) {

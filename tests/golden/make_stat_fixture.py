@@ -12,7 +12,10 @@ The protocol (shared with tests/test_gpu_statistics.py through `protocol()` / `s
   REMD 8 temperatures 293.15 .. 363.15 K (check/T2S2HP_REMD_T/input_REMD.toml), exchange every 10
        steps, nstep_MC 0: acceptance ratio of every neighbouring label pair, mean E_pot and mean
        base-pair count per temperature label.
-Seeds differ between the oracle (123) and the CUDA run (777): only distributions are compared."""
+The hairpin has slow modes (an extra terminal base pair that lives for ~1e5 steps at the lowest
+temperatures), so a single run's block-averaged error underestimates the true one: the fixture holds
+the oracle's summaries for SEVERAL seeds, and the test compares the CUDA runs (other seeds) with the
+oracle's mean over seeds using the seed-to-seed spread.  Only distributions are compared."""
 import json
 import sys
 from pathlib import Path
@@ -25,6 +28,8 @@ from sis_b200 import fixtures as fx  # noqa: E402
 
 KB = 0.0019872042586408316
 NEQ, NPROD, NSAMP = 20000, 200000, 100
+NPROD_REMD = 100000
+ORACLE_SEEDS = [123, 777, 4242, 9001]
 REMD_T = [293.15 + 10.0 * k for k in range(8)]
 NEX = 10
 
@@ -79,7 +84,7 @@ def run_remd(be, seed, oracle):
     acc = np.zeros(n - 1)
     s = {f"E_pot_T{k}": [] for k in range(n)}
     s.update({f"n_bp_T{k}": [] for k in range(n)})
-    ntot = (NEQ + NPROD) // NEX
+    ntot = (NEQ + NPROD_REMD) // NEX
     for it in range(ntot):
         before = be.remd_state()[0].copy()
         if oracle:
@@ -104,7 +109,7 @@ def run_remd(be, seed, oracle):
             for r in range(n):
                 lab = int(after[r]) - 1
                 T = REMD_T[lab]
-                e = be.energy_sumup(r, T, False)
+                e = be.energy_sumup(r, T, True)       # bp term re-evaluated at the label's temperature on both sides
                 st, en = be.get_bp_state(r)
                 s[f"E_pot_T{lab}"].append(e[0])
                 s[f"n_bp_T{lab}"].append(int(((st != 0) & (en <= -T * KB)).sum()))
@@ -115,11 +120,14 @@ def run_remd(be, seed, oracle):
 
 def main():
     from oracle.oracle import Oracle
-    res = {"protocol": {"neq": NEQ, "nprod": NPROD, "nsamp": NSAMP, "remd_T": REMD_T, "nex": NEX, "seed": 123},
-           "c1": run_c1(Oracle(), 123), "remd": run_remd(Oracle(), 123, True)}
+    res = {"protocol": {"neq": NEQ, "nprod": NPROD, "nprod_remd": NPROD_REMD, "nsamp": NSAMP, "remd_T": REMD_T, "nex": NEX,
+                        "seeds": ORACLE_SEEDS},
+           "c1": {}, "remd": {}}
+    for seed in ORACLE_SEEDS:
+        res["c1"][str(seed)] = run_c1(Oracle(), seed)
+        res["remd"][str(seed)] = run_remd(Oracle(), seed, True)
+        print(seed, {k: round(v["mean"], 3) for k, v in res["c1"][str(seed)].items()}, res["remd"][str(seed)]["acceptance"], flush=True)
     (Path(__file__).resolve().parent / "stat_fixture.json").write_text(json.dumps(res, indent=1))
-    print(json.dumps(res["c1"], indent=1))
-    print(res["remd"]["acceptance"])
 
 
 if __name__ == "__main__":

@@ -1,9 +1,10 @@
-"""Long-run statistical parity (north_star check 3): the CUDA path with its own seed against the
+"""Long-run statistical parity (north_star check 3): the CUDA path with its own seeds against the
 committed statistics of the CPU oracle (tests/golden/stat_fixture.json, written by
 tests/golden/make_stat_fixture.py with the protocol imported below): potential-energy distribution
 and its terms, number of recorded base pairs, per-pair REMD acceptance ratios, mean energy and
-base-pair count per temperature.  Different RNG streams, 2.2e5 steps each: agreement within
-4 standard errors of the difference (block-averaged; binomial for the acceptance ratios)."""
+base-pair count per temperature.  Different RNG streams on the two sides.  The hairpin has slow
+modes, so the yardstick is the oracle's own seed-to-seed spread (4 seeds in the fixture) combined
+with the block-averaged errors: every CUDA run must sit within 4 sigma of the oracle's mean."""
 import importlib.util
 import json
 from pathlib import Path
@@ -14,6 +15,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 GOLDEN = Path(__file__).resolve().parent / "golden"
 NSIGMA = 4.0
+GPU_SEEDS = [555, 31337]
 
 
 def protocol():
@@ -28,41 +30,52 @@ def gpu():
     return SisGpu(0)
 
 
-def compare(got, ref, keys):
+def yardstick(runs, key):
+    """oracle mean over seeds, and the error of the difference to ONE more run: seed-to-seed spread (of a
+    single run and of the mean over the oracle's seeds) combined with the block-averaged errors"""
+    means = np.array([r[key]["mean"] for r in runs])
+    se_blk = np.array([r[key]["se"] for r in runs])
+    spread = means.std(ddof=1)
+    single = max(spread, float(np.sqrt((se_blk ** 2).mean())))
+    return means.mean(), single * np.sqrt(1.0 + 1.0 / len(means))
+
+
+def compare(got, runs, keys, floor_rel=2e-3):
     for k in keys:
-        g, r = got[k], ref[k]
-        se = np.hypot(g["se"], r["se"])
-        # a quantity that never fluctuated in either run (e.g. a base-pair count pinned at its maximum)
-        se = max(se, 1e-3 * max(1.0, abs(r["mean"])))
-        assert abs(g["mean"] - r["mean"]) <= NSIGMA * se, (k, g, r)
-        if r["std"] > 10 * se and g["n"] >= 1000:          # width of the distribution, where it is resolved
-            assert 0.8 < g["std"] / r["std"] < 1.25, (k, g["std"], r["std"])
+        mu, err = yardstick(runs, k)
+        err = max(err, floor_rel * max(1.0, abs(mu)))
+        assert abs(got[k]["mean"] - mu) <= NSIGMA * err, (k, got[k], mu, err)
+        widths = np.array([r[k]["std"] for r in runs])
+        if widths.min() > 0 and widths.std(ddof=1) < 0.15 * widths.mean():     # distribution width, where the seeds agree on it
+            assert 0.7 < got[k]["std"] / widths.mean() < 1.4, (k, got[k]["std"], widths)
 
 
-def test_c1_energy_distribution_and_base_pair_count():
+@pytest.mark.parametrize("seed", GPU_SEEDS)
+def test_c1_energy_distribution_and_base_pair_count(seed):
     m = protocol()
-    ref = json.loads((GOLDEN / "stat_fixture.json").read_text())
+    ref = json.loads((GOLDEN / "stat_fixture.json").read_text())["c1"]
     g = gpu()
-    got = m.run_c1(g, seed=777)
+    got = m.run_c1(g, seed=seed)
     assert g.last_step_kernel() == "k_md_fast<1,true>"
-    compare(got, ref["c1"], ["E_pot", "E_bp", "E_ele", "E_bond", "n_bp"])
+    compare(got, list(ref.values()), ["E_pot", "E_bp", "E_ele", "E_bond", "n_bp"])
 
 
-def test_remd_acceptance_ratios_and_per_temperature_means():
+@pytest.mark.parametrize("seed", GPU_SEEDS)
+def test_remd_acceptance_ratios_and_per_temperature_means(seed):
     m = protocol()
-    ref = json.loads((GOLDEN / "stat_fixture.json").read_text())["remd"]
+    ref = list(json.loads((GOLDEN / "stat_fixture.json").read_text())["remd"].values())
     g = gpu()
-    got = m.run_remd(g, seed=777, oracle=False)
+    got = m.run_remd(g, seed=seed, oracle=False)
     att_g, acc_g = np.array(got["acceptance"]["attempts"]), np.array(got["acceptance"]["accepted"])
-    att_r, acc_r = np.array(ref["acceptance"]["attempts"]), np.array(ref["acceptance"]["accepted"])
-    assert (att_g == att_r).all() and att_g.min() >= 5000
-    pg, pr = acc_g / att_g, acc_r / att_r
-    # successive attempts of a pair are correlated (the energies relax over ~100 steps): allow 3x the binomial error
-    se = 3.0 * np.sqrt(pg * (1 - pg) / att_g + pr * (1 - pr) / att_r)
-    assert (np.abs(pg - pr) <= NSIGMA * se).all(), (pg, pr, se)
-    assert 0.5 < pg.min() and pg.max() < 0.9
+    assert (att_g == np.array(ref[0]["acceptance"]["attempts"])).all() and att_g.min() >= 2500
+    pg = acc_g / att_g
+    pr = np.array([np.array(r["acceptance"]["accepted"]) / np.array(r["acceptance"]["attempts"]) for r in ref])
+    mu, spread = pr.mean(axis=0), pr.std(axis=0, ddof=1)
+    binom = np.sqrt(mu * (1 - mu) / att_g)
+    err = np.sqrt(np.maximum(spread, 3.0 * binom) ** 2 * (1.0 + 1.0 / len(ref)))     # attempts of a pair are correlated in time
+    assert (np.abs(pg - mu) <= NSIGMA * err).all(), (pg, mu, err)
+    assert 0.3 < pg.min() and pg.max() < 0.9
     n = len(m.REMD_T)
     compare(got, ref, [f"E_pot_T{k}" for k in range(n)] + [f"n_bp_T{k}" for k in range(n)])
-    # hotter labels have higher mean potential energy
     means = [got[f"E_pot_T{k}"]["mean"] for k in range(n)]
-    assert means[-1] > means[0]
+    assert all(b > a for a, b in zip(means, means[1:]))          # hotter labels have higher mean potential energy

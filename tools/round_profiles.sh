@@ -1,16 +1,22 @@
 #!/bin/bash
-# everything profiles/ holds for this round, in one GPU call (run under gpurun from the repo root)
+# everything profiles/ holds for round 2, in one 1-GPU call (run under gpurun from the repo root)
 set -x
 mkdir -p gpurun_out
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r01_bench_reference.json 2> gpurun_out/ref.err
-python bench.py > gpurun_out/r01_bench_c4.json 2> gpurun_out/bench.err
-python bench.py --steps 5 --warmup 3 --workload c5 --md-steps 200 --no-cpu > gpurun_out/r01_bench_c5.json 2>> gpurun_out/bench.err
-python tools/bench_remd.py > gpurun_out/r01_remd_c3.json 2>> gpurun_out/bench.err
-# launch list of the bench command (cold-cache, serialised: shares, not absolutes)
-tools/ncu_launches.sh gpurun_out/r01_launches_c4.csv python bench.py --steps 2 --warmup 1 --md-steps 300 --no-cpu > gpurun_out/r01_launches_c4_summary.txt 2>&1
-# full capture of the step kernel: first launch after fresh lists, 40 MD steps (no rebuild inside)
-ncu --set full --import-source on --clock-control none -k regex:k_md_fast -c 1 -o gpurun_out/r01_k_md_fast_c4 python bench.py --steps 1 --warmup 1 --md-steps 40 --no-cpu > /dev/null 2>&1
-ncu --set full --import-source on --clock-control none -k regex:k_nl_rows -c 1 -o gpurun_out/r01_k_nl_rows_c4 python bench.py --steps 1 --warmup 1 --md-steps 200 --no-cpu > /dev/null 2>&1
-ncu --set full --import-source on --clock-control none -k regex:k_md_fused -c 1 -o gpurun_out/r01_k_md_fused_c5 python bench.py --steps 1 --warmup 1 --md-steps 20 --workload c5 --no-cpu > /dev/null 2>&1
-ls -la gpurun_out/
+python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r02_bench_reference.json 2> gpurun_out/ref.err
+python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_c4.json 2> gpurun_out/bench.err
+python bench.py --steps 5 --warmup 3 --workload c5 --md-steps 200 --no-extra > gpurun_out/r02_bench_c5.json 2>> gpurun_out/bench.err
+python bench.py --steps 5 --warmup 2 --workload c3 --md-steps 2000 > gpurun_out/r02_bench_c3.json 2>> gpurun_out/bench.err
+python bench.py --steps 5 --warmup 2 --workload c3 --md-steps 2000 --opt remd_inkernel=0 > gpurun_out/r02_bench_c3_launch_chain.json 2>> gpurun_out/bench.err
+for n in 16 148; do python bench.py --steps 5 --warmup 2 --workload c3 --nrep $n --md-steps 2000 > gpurun_out/r02_bench_c3_nrep$n.json 2>> gpurun_out/bench.err; done
+python tools/c1_speed.py > gpurun_out/r02_c1_speed.txt 2>&1
+python tools/small_sys.py > gpurun_out/r02_small_sys.txt 2>&1
+# launch lists of the bench commands (cold-cache, serialised: shares, not absolutes)
+tools/ncu_launches.sh gpurun_out/r02_launches_c4.csv python bench.py --steps 2 --warmup 1 --md-steps 300 --no-cpu --no-extra > gpurun_out/r02_launches_c4_summary.txt 2>&1
+tools/ncu_launches.sh gpurun_out/r02_launches_c5.csv python bench.py --workload c5 --steps 1 --warmup 1 --md-steps 100 --no-cpu --no-extra > gpurun_out/r02_launches_c5_summary.txt 2>&1
+tools/ncu_launches.sh gpurun_out/r02_launches_c3.csv python bench.py --workload c3 --steps 1 --warmup 1 --md-steps 500 > gpurun_out/r02_launches_c3_summary.txt 2>&1
+# full captures of the step kernels: C4 first launch after fresh lists, 40 MD steps (no rebuild inside); C5 one MD step
+ncu --set full --import-source on --clock-control none -k regex:k_md_fast -c 1 -o gpurun_out/r02_k_md_fast_c4 python bench.py --steps 1 --warmup 1 --md-steps 40 --no-cpu --no-extra > /dev/null 2>&1
+ncu --set full --import-source on --clock-control none -k regex:k_md_big -s 60 -c 1 -o gpurun_out/r02_k_md_big_c5 python bench.py --workload c5 --steps 1 --warmup 1 --md-steps 100 --no-cpu --no-extra > /dev/null 2>&1
+ncu --set full --import-source on --clock-control none -k regex:k_nl_rows -c 1 -o gpurun_out/r02_k_nl_rows_c5 python bench.py --workload c5 --steps 1 --warmup 1 --md-steps 100 --no-cpu --no-extra > /dev/null 2>&1
+ls -la gpurun_out/ | tail -30
 tail -2 gpurun_out/bench.err gpurun_out/ref.err
