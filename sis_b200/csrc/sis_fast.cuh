@@ -193,7 +193,7 @@ SIS_D void fast_bp_eval(const DevSys &S, const FFParams &P, FastShared &sh, cons
 // iterations whatever the row lengths; each unit's force is written to a fixed slot and the bead's
 // owner adds its units in order (deterministic, no atomics).  Owner slot s < nb is held by the
 // 4-lane half (s / 64) of group s % 64.
-template <int U>
+template <int U, bool XCH>
 SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, const FastCtx &C, FastShared &sh,
                          uint32_t *s_rows)
 {
@@ -470,7 +470,7 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
         step++;
         cur ^= 1;
         cta_sync();
-        fast_remd_hook(S, P, C, sh, step, cur);
+        if (XCH) fast_remd_hook(S, P, C, sh, step, cur);
     }
     cta_sync();                                        // everybody is out of the loop
     if (B.valid && comp < 3 && rows_fit) {
@@ -573,7 +573,7 @@ SIS_D void fast_bp_mc_step(const DevSys &S, const FFParams &P, const FastCtx &C,
 // in shared memory: no cross-CTA dependency, no global atomics, no grid barrier for the base
 // pairs.  A pair is evaluated by the two or three CTAs that own its six beads; the CTA that owns
 // bead i also maintains bp_status / ene_bp (src/force_bp.F90:191-193).
-template <bool LOCAL>
+template <bool LOCAL, bool XCH>
 SIS_D int fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, FastShared &sh)
 {
     const int tid = threadIdx.x, bt = tid - FAST_MAIN;
@@ -722,12 +722,13 @@ SIS_D int fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fas
         cur ^= 1;
         cta_sync();
         if (sh.blocked[n & 1]) break;
-        fast_remd_hook(S, P, C, sh, C.step0 + (unsigned long long)n + 1ull, cur);
+        if (XCH) fast_remd_hook(S, P, C, sh, C.step0 + (unsigned long long)n + 1ull, cur);
     }
     cta_sync();
     return n;
 }
 
+template <bool XCH>
 SIS_D int fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, const FastCtx &C, FastShared &sh)
 {
     const int tid = threadIdx.x, lt = tid - FAST_MAIN - FAST_BP;
@@ -859,7 +860,7 @@ SIS_D int fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, c
         cur ^= 1;
         cta_sync();
         if (sh.blocked[n & 1]) break;
-        fast_remd_hook(S, P, C, sh, step, cur);
+        if (XCH) fast_remd_hook(S, P, C, sh, step, cur);
     }
     cta_sync();
     return n;
@@ -1127,8 +1128,11 @@ SIS_D void fast_remd_hook(const DevSys &S, const FFParams &P, const FastCtx &C, 
     cta_sync();
 }
 
-template <int U, bool LOCAL>
-__global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams P, StepArgs A, long long target, NlArgs NA)
+// XCH: the exchange step of REMD inside the kernel (replica-local mode only); a separate instantiation so that the
+// plain kernels do not carry its registers
+template <int U, bool LOCAL, bool XCH = false>
+__global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(const __grid_constant__ DevSys S, const __grid_constant__ FFParams P, StepArgs A,
+                                                              long long target, NlArgs NA)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastShared &sh = *reinterpret_cast<FastShared *>(smem_raw);
@@ -1152,7 +1156,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams 
     // exchange step inside the kernel (S.remd) a segment also ends at every multiple of
     // nstep_rep_exchange: the exchange works on the state in global memory and the next segment's
     // prologue picks up the new parameters and the rescaled velocities.
-    const bool xch = LOCAL && S.remd != nullptr;
+    const bool xch = XCH && LOCAL && S.remd != nullptr;
     C.xch = xch;
     if (xch) {
         const RemdDev &D = *S.remd;
@@ -1170,9 +1174,9 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(DevSys S, FFParams 
         C.step0 = ctl.step + (unsigned long long)done;
         C.cur0 = ctl.cur ^ (done & 1);
         int n;
-        if (tid >= FAST_MAIN + FAST_BP) n = fast_loc_role(S, P, A, C, sh);
-        else if (tid >= FAST_MAIN) n = fast_bp_role<LOCAL>(S, P, C, sh);
-        else n = fast_main_role<U>(S, P, A, C, sh, s_rows);
+        if (tid >= FAST_MAIN + FAST_BP) n = fast_loc_role<XCH>(S, P, A, C, sh);
+        else if (tid >= FAST_MAIN) n = fast_bp_role<LOCAL, XCH>(S, P, C, sh);
+        else n = fast_main_role<U, XCH>(S, P, A, C, sh, s_rows);
         done += n;
         if (!LOCAL || done >= nsteps) break;
         if (sh.ncand > FAST_BPC || sh.overflow) break;     // tables too small (the host checked: cannot happen)

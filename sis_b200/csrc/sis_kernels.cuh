@@ -1171,6 +1171,7 @@ SIS_D void nl_rows_bead_at(const DevSys &S, const FFParams &P, const NlArgs &A, 
     const Vec3 xi = v3(pos[i]);
     const double ele_cut = R.ele_cutoff + A.nl_margin;
     const double ele_nl_cut2 = ele_cut * ele_cut;
+    const double max_nl_cut2 = fmax(fmax(A.wca_nl_cut2, A.bp_nl_cut2), P.flg_ele ? ele_nl_cut2 : 0.0);
     uint32_t *row = S.nbr + (rbase + i) * S.K;
     int2 *brow = S.bprow + (rbase + i) * S.KB;
     int nn = 0, nb = 0;
@@ -1228,10 +1229,12 @@ SIS_D void nl_rows_bead_at(const DevSys &S, const FFParams &P, const NlArgs &A, 
                 }
                 j = cbeads[s_beg[lo] + (t - s_off[lo])];
             }
-            if (j != i) {
+            const Vec3 xj = j >= 0 ? v3(pos[j]) : xi;
+            const Vec3 v = pbc_vec_d(P, xi, xj);
+            // most candidates of the 27 cells lie outside every list radius (a sphere fills 15 % of the cube):
+            // they leave here, before their meta data is touched.  Same predicates for those that stay.
+            if (j != i && j >= 0 && (A.all_pairs == 1 || dot(v, v) <= max_nl_cut2)) {
                 const int4 mj = S.meta[j];
-                const Vec3 xj = v3(pos[j]);
-                Vec3 v = pbc_vec_d(P, xi, xj);
                 ent = nl_pair_flags(A, P, mi, mj, i, j, dot(v, v), ele_nl_cut2);
                 if (ent && nl_needs_image(P, A, xi, xj)) ent |= NB_IMG;
                 if (nl_bp_geometry(A, i, j, dot(v, v))) {

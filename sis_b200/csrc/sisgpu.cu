@@ -2164,7 +2164,7 @@ static int launch_persistent(sisgpu *h, long long stop)
     h->last_launch_local = local;
     h->last_step_kernel = fast_ok ? (local ? "k_md_fast<1,true>" : "k_md_fast<1,false>") : "k_md_fused";
     if (fast_ok) {
-        void *fn = local ? (void *)k_md_fast<1, true> : (void *)k_md_fast<1, false>;
+        void *fn = local ? (h->S.remd ? (void *)k_md_fast<1, true, true> : (void *)k_md_fast<1, true, false>) : (void *)k_md_fast<1, false, false>;
         if (smem_fast > h->fast_smem_set || fn != h->fast_fn_set) {
             CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
             h->fast_smem_set = smem_fast; h->fast_fn_set = fn;
