@@ -211,11 +211,19 @@ def run_remd_c3(cx, nrep_all=64, nex=int(os.environ.get("SIS_NEX", "10")), md_st
     if nrep_all % world:
         return {"error": f"{nrep_all} replicas do not split over {world} ranks"}
     R = nrep_all // world
-    temps = [293.15 + 70.0 / (nrep_all - 1) * k for k in range(nrep_all)]
-    spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=0).replicated(R, temps=temps[rank * R:(rank + 1) * R])
+    # up to 256 temperatures (MAX_REP_PER_DIM of the reference, src/const.F90:26-28); beyond that a second replica
+    # dimension: two ionic strengths per temperature (labels: the first variable varies slowest, src/init_replica.F90:70-92)
+    nion = 1 if nrep_all <= 256 else 2
+    ntemp = nrep_all // nion
+    tgrid = [293.15 + 70.0 / (ntemp - 1) * k for k in range(ntemp)]
+    igrid = [0.15, 0.16][:nion]
+    temps = [tgrid[l // nion] for l in range(nrep_all)]
+    ions = [igrid[l % nion] for l in range(nrep_all)]
+    spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=0).replicated(R, temps=temps[rank * R:(rank + 1) * R],
+                                                              ionic=ions[rank * R:(rank + 1) * R] if nion > 1 else None)
     g = cx.new_handle()
     spec.configure(g)
-    g.remd_setup([nrep_all, 1, 1, 1], [temps, [], [], []], nex, rank, world)
+    g.remd_setup([ntemp, 1, nion, 1], [tgrid, [], igrid if nion > 1 else [], []], nex, rank, world)
     if world > 1:
         g.comm_init_torch()
         if not os.environ.get("SIS_NO_PEER"):
@@ -408,10 +416,13 @@ def main():
         if not args.no_extra:
             try:
                 extra["c3_remd"] = run_remd_c3(cx)
-                if cx.world > 1:     # the same replicas per GPU as the N = 1 line: weak scaling along replicas
-                    extra["c3_remd_weak"] = run_remd_c3(cx, nrep_all=64 * cx.world, scaling="weak")
             except Exception as ex:  # pragma: no cover
                 extra["c3_remd"] = {"error": str(ex)}
+            if cx.world > 1:         # the same replicas per GPU as the N = 1 line: weak scaling along replicas
+                try:
+                    extra["c3_remd_weak"] = run_remd_c3(cx, nrep_all=64 * cx.world, scaling="weak")
+                except Exception as ex:  # pragma: no cover
+                    extra["c3_remd_weak"] = {"error": str(ex)}
         if cx.rank == 0:
             line["extra"] = extra
             # CPU baseline (oracle port with the reference's OpenMP threading, bounded sample) on this box's host cores

@@ -131,6 +131,11 @@ int sisgpu_get_lists(sisgpu_t *h, int irep, int *wca_mp, int *ele_mp, int *bp_mp
 int sisgpu_get_local_lists(sisgpu_t *h, int *nbond, int *nangl, int *ndih, int *bond_mp,
                            int *angl_mp, int *dih_mp);
 int sisgpu_bp3_table(sisgpu_t *h, int *n, int *hash4096, double *dH, double *dS);
+/* write_bpcoef (src/write_bpcoef.F90:30-83) without init_bp's N x N bp3_map: every sequence-allowed pair imp < jmp
+ * (1-based, the reference's loop order) with its dH and dS * 1e-3; the driver applies coef_dG * (dH - T dS) < 0 per
+ * replica and formats the line.  cap = 0 sizes the arrays (*n).  Bead ids are int32 here: the int16 of .bp
+ * (src/var_io.F90:25) is a property of the file format the driver writes */
+int sisgpu_bpcoef(sisgpu_t *h, int cap, int *n, int *imp, int *jmp, double *dH, double *dS);
 
 /* ---- hot path ----------------------------------------------------------------*/
 /* flg_bp_MC of src/job_md.F90:365-368 for the next force / energy call */

@@ -228,6 +228,15 @@ class CApi:
         """bp_status_MC = bp_status (src/job_md.F90:344-348)"""
         self._call("bp_status_to_mc")
 
+    def bpcoef(self):
+        """write_bpcoef's table: (imp, jmp, dH, dS * 1e-3) of every sequence-allowed pair, 1-based"""
+        n = C.c_int()
+        self._call("bpcoef", C.c_int(0), C.byref(n), None, None, None, None)
+        i, j = np.zeros(n.value, dtype=np.int32), np.zeros(n.value, dtype=np.int32)
+        dH, dS = np.zeros(n.value), np.zeros(n.value)
+        self._call("bpcoef", C.c_int(n.value), C.byref(n), _i(i), _i(j), _d(dH), _d(dS))
+        return i, j, dH, dS
+
     def check_force(self, tempK):
         fe, ff = np.zeros((self.nmp, 3)), np.zeros((self.nmp, 3))
         md = C.c_double()

@@ -384,6 +384,12 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
                 if (l >= 3) f += (&sh.dihf[s0 - 3][3].x)[comp];
             }
             if (circ && l < 3) f += fast_closure_terms(S, P, S.pos[cur] + (size_t)B.rep * nmp, meta, B.k, comp);
+            // dual constant-force tweezers (src/force_tweezers.F90:27-35): +f on the first bead of a pair, -f on the second
+            for (int t = 0; t < P.ntwz_DCF; t++) {
+                const double ft = S.rp[B.rep].twz_force * S.twz_dir[3 * t + comp];
+                if (S.twz_pairs[2 * t] == B.k) f += ft;
+                if (S.twz_pairs[2 * t + 1] == B.k) f -= ft;
+            }
         }
         if (prof) c2 = clock64();
         // ---- integrate (src/job_md.F90:415-456) ----------------------------------------------
@@ -1001,8 +1007,15 @@ SIS_D void fast_remd_energies(const DevSys &S, const FFParams &P, FastShared &sh
                 }
                 et[t] = v;
             }
+            // the only bias the replica-local mode admits: dual constant-force tweezers (src/energy_tweezers.F90:21-31)
+            double etwz = 0.0;
+            for (int t = 0; t < P.ntwz_DCF; t++) {
+                const Vec3 v = pbc_vec_d(P, v3(pos[S.twz_pairs[2 * t]]), v3(pos[S.twz_pairs[2 * t + 1]]));
+                etwz -= (side == 0 ? Rown.twz_force : Ralt.twz_force) *
+                        (v.x * S.twz_dir[3 * t] + v.y * S.twz_dir[3 * t + 1] + v.z * S.twz_dir[3 * t + 2]);
+            }
             double sum = 0.0;
-            for (int t = 1; t < ENE_N; t++) sum += (t <= ENE_ELE ? et[t] : 0.0);   // no bias terms in the replica-local mode
+            for (int t = 1; t < ENE_N; t++) sum += (t <= ENE_ELE ? et[t] : t == ENE_TWZ ? etwz : 0.0);
             tot[side] = sum;
         }
         sh.xE[0] = tot[0];

@@ -1091,7 +1091,8 @@ static bool fast_local_ok(sisgpu *h)
 {
     if (!h->fast_kernel || !h->local_kernel || ensure_coop_blocks(h)) return false;
     if (h->nmp > FAST_GROUPS || h->nrep > std::min(h->coop_blocks, FAST_MAX_CTA)) return false;
-    if (h->P.flg_stage || h->P.ntwz_DCF || h->P.ntwz_FR || h->P.nrest || h->P.flg_bias_ss || h->P.flg_bias_rg) return false;
+    // the replica-local kernel carries dual constant-force tweezers (F-REMD); the other biases go through k_md_big / per-phase kernels
+    if (h->P.flg_stage || h->P.ntwz_FR || h->P.nrest || h->P.flg_bias_ss || h->P.flg_bias_rg) return false;
     if (h->K < h->nmp || h->KB < h->nmp - 1) return false;
     return h->local_ncand >= 0 && h->local_ncand <= FAST_BPC;
 }
@@ -1414,6 +1415,46 @@ int sisgpu_get_local_lists(sisgpu_t *h, int *nbond, int *nangl, int *ndih, int *
     if (bond_mp) std::copy(bd.begin(), bd.end(), bond_mp);
     if (angl_mp) std::copy(an.begin(), an.end(), angl_mp);
     if (dih_mp) std::copy(di.begin(), di.end(), dih_mp);
+    return 0;
+}
+
+// write_bpcoef (src/write_bpcoef.F90:30-83) without the N x N bp3_map: every sequence-allowed pair imp < jmp in the
+// reference's loop order with its (dH, dS * 1e-3); the driver applies coef_dG * (dH - T dS) < 0 per replica and
+// formats the line.  imp / jmp 1-based; cap = capacity of the arrays; *n = pairs found (call with cap = 0 to size).
+// Host-side enumeration: meant for the system sizes whose .bpcoef file is usable (it has O(N^2) lines).
+int sisgpu_bpcoef(sisgpu_t *h, int cap, int *n, int *imp, int *jmp, double *dH, double *dS)
+{
+    if (!h->finalized) return set_err("finalize_setup not called");
+    if (h->bp_model != 5) { *n = 0; return 0; }       // the reference writes the table for model 5 only (:24)
+    std::vector<int4> meta;
+    std::vector<double4> coef;
+    // meta as finalize_setup built it
+    meta.resize(h->nmp);
+    for (int i = 0; i < h->nmp; i++) {
+        const int c = h->ichain[i];
+        int fl = h->seq[i] & MF_SEQ_MASK;
+        if (h->has_charge[i]) fl |= MF_CHARGE;
+        if (h->moltypes[c] == MOLT_CIRC) fl |= MF_CIRC;
+        if (h->is_frozen[i]) fl |= MF_FROZEN;
+        meta[i] = make_int4(h->chain_start[c], h->nmp_chain[c], h->lmp[i], fl);
+    }
+    const BpRestrict rs = host_restrict(h);
+    long long cnt = 0;
+    for (int i = 0; i < h->nmp - 1; i++)
+        for (int j = i + 1; j < h->nmp; j++) {
+            int t = 0;
+            const int b3 = bp_lookup_r(rs, h->bp_model, h->bp_min_loop, h->bp3_hash.data(), h->seq.data(), i, meta[i], j, meta[j], &t);
+            if (b3 <= 0) continue;
+            if (cnt < cap) {
+                if (imp) imp[cnt] = i + 1;
+                if (jmp) jmp[cnt] = j + 1;
+                if (dH) dH[cnt] = h->bp3_dH[b3];
+                if (dS) dS[cnt] = h->bp3_dS[b3];
+            }
+            cnt++;
+        }
+    if (cnt > 0x7fffffffll) return set_err("bpcoef: more than 2^31 pairs");
+    *n = (int)cnt;
     return 0;
 }
 
@@ -2138,7 +2179,7 @@ static void persistent_choice(sisgpu *h, bool *local, bool *fast_ok, int *want_f
     *want_fast = *local ? R : (h->fast_kernel ? fast_ncta_of(h) : 0);
     long long ncand_total = 0;
     for (int r = 0; r < R; r++) ncand_total += h->nbp_half_rep.empty() ? h->nbp_half_max : h->nbp_half_rep[r];
-    const bool biases = h->P.flg_stage || h->P.ntwz_DCF || h->P.ntwz_FR || h->P.nrest;
+    const bool biases = h->P.flg_stage || (h->P.ntwz_DCF && !*local) || h->P.ntwz_FR || h->P.nrest;
     *fast_ok = *want_fast > 0 && !biases && h->K >= 24 && h->K <= 512 && fast_smem_bytes() <= 200 * 1024 &&
                (*local || 3 * (ncand_total / *want_fast) + 16 <= FAST_BPC);
     if (!*fast_ok) *local = false;

@@ -386,6 +386,15 @@ module sisgpu_mod
          type(c_ptr), value :: h
          integer(c_int) :: rc
       end function
+      function sisgpu_bpcoef(h, cap, n, imp, jmp, dH, dS) bind(C, name='sisgpu_bpcoef') result(rc)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: h
+         integer(c_int), value :: cap
+         integer(c_int), intent(out) :: n
+         integer(c_int), intent(out) :: imp(*), jmp(*)
+         real(c_double), intent(out) :: dH(*), dS(*)
+         integer(c_int) :: rc
+      end function
    end interface
 
 contains

@@ -211,3 +211,25 @@ def test_unequal_chain_lengths():
     for t in (1, 2, 3, 4, 5, 6):
         assert rel(g.force_terms(0, 1 << t), o.force_terms(0, 1 << t)) < FORCE_TOL
     run_both(g, o, 30, xtol=1e-7, vtol=1e-7)
+
+
+def test_bpcoef_table_without_the_n_by_n_map():
+    """write_bpcoef's content (src/write_bpcoef.F90:30-83) from the sequence alone: the same pairs and (dH, dS) the
+    oracle's bp_lookup / bp3 table give, in (imp, jmp) order; 468-entry invariant of the table behind it"""
+    spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=0)
+    g, o = both(spec)
+    i, j, dH, dS = g.bpcoef()
+    n3, _, tH, tS = o.bp3_table()
+    assert n3 == 468
+    want = []
+    for a in range(1, spec.nmp):
+        for b in range(a + 1, spec.nmp + 1):
+            t, b3 = o.bp_lookup(a, b)          # 1-based, as bp_map(imp, jmp)
+            if b3 > 0:
+                want.append((a, b, tH[b3 - 1], tS[b3 - 1]))
+    assert len(want) == len(i) > 0
+    assert [(int(a), int(b)) for a, b in zip(i, j)] == [(w[0], w[1]) for w in want]
+    assert np.allclose(dH, [w[2] for w in want], rtol=0, atol=1e-14) and np.allclose(dS, [w[3] for w in want], rtol=0, atol=1e-17)
+    # what the driver prints for tempK = 300: pairs with dG < 0
+    dG = dH - 300.0 * dS
+    assert 0 < (dG < 0).sum() <= len(dG)

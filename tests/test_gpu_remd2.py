@@ -182,3 +182,50 @@ def test_set_step_keeps_a_pending_rebuild_trigger():
     assert out[0] >= 2
     # the Gaussians of the shifted run differ (the step is their counter), the rebuild cadence must survive
     assert out[1] >= 2
+
+
+@pytest.mark.parametrize("nstep_MC", [0, 10])
+def test_force_remd_in_the_replica_local_kernel(nstep_MC):
+    """F-REMD (check/T2S2HP_REMD_F: dual constant-force tweezers on beads (1, 27), the force magnitude is the
+    replica variable): the replica-local persistent kernel carries the tweezers force; without the Monte-Carlo
+    limit the exchange step runs inside the kernel (tweezers energy -F.(x_i - x_j) with own and partner force,
+    src/energy_tweezers.F90:21-31), with it (the input's nstep_MC = 10) through the launch chain"""
+    from sis_b200.system import PN2KCALMOLA
+    n, nex = 4, 10
+    forces = [f * PN2KCALMOLA for f in (0.0, 6.0, 12.0, 18.0)]
+    spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=nstep_MC).replicated(n)
+    spec.twz_dcf_pairs = [(1, 27)]
+    spec.twz_dcf_forces = [(1.0, 0.0, 0.0)]
+    res = []
+    for opts in (dict(launch_mode=0), dict()):
+        g = gpu(**opts)
+        spec.configure(g)
+        g.remd_setup([1, n, 1, 1], [[], forces, [], []], nex)
+        for r in range(n):
+            g.init_velocities(r)
+            g.neighbor_list(r)
+        g.md_steps(60)
+        res.append(([g.get_state(r) for r in range(n)], g.remd_state()[0].copy(), g.remd_stats(), g.last_step_kernel(), g.launch_count()))
+    assert res[1][3] == "k_md_fast<1,true>"
+    assert np.array_equal(res[0][1], res[1][1]) and res[0][2] == res[1][2] and res[0][2][0] > 0
+    for r in range(n):
+        for a, b in zip(res[0][0][r], res[1][0][r]):
+            assert np.abs(a - b).max() < 1e-7
+    if nstep_MC == 0:
+        assert res[1][4] < res[0][4] // 4      # one launch per md_steps call: the exchange ran inside the kernel
+        o = Oracle()
+        spec.configure(o)
+        o.remd_setup([1, n, 1, 1], [[], forces, [], []], nex)
+        for r in range(n):
+            o.init_velocities(r)
+            o.neighbor_list(r)
+        counter = 0
+        for _ in range(6):
+            o.md_run(nex)
+            _, re = o.energy_replica()
+            u = np.array([o.uniform(spec.rng_seed, 0x7fffffff, counter + i) for i in range(n // 2)])
+            counter += n // 2
+            o.replica_exchange(re, u)
+        assert np.array_equal(res[1][1], o.remd_state()[0])
+        for r in range(n):
+            assert np.abs(res[1][0][r][0] - o.get_state(r)[0]).max() < 1e-6
