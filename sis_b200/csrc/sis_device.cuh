@@ -275,10 +275,11 @@ SIS_HD double dh_scalar(double ele_coef, double inv_lambdaD, double d2)
 #ifdef __CUDACC__
 // Straight-line (branch-free) versions for the pair loop of k_md_big, where four pairs are
 // evaluated side by side and any branch would serialise them.
-// 1 / sqrt(x) for normal x: single-precision seed + two Newton steps (error below 1 ulp of the result)
+// 1 / sqrt(x) for normal x: MUFU seed + two Newton steps (error ~1 ulp of the result)
 SIS_D double rsqrt_sl(double x)
 {
-    double y = (double)rsqrtf((float)x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));      // MUFU.RSQ64H: relative error 2^-22
     const double h = 0.5 * x;
     double e = fma(-h * y, y, 0.5);
     y = fma(y, e, y);

@@ -130,7 +130,16 @@ SIS_D void fast_pair_one(const FFParams &P, uint32_t ent, Vec3 xk, Vec3 xj, doub
     const double d2 = dot(v, v);
     double s = 0.0;
     if ((ent & NB_WCA) && d2 < P.wca_sigma2) s += wca_scalar(P, d2);
+#ifdef FAST_PAIR_LIBM
     if ((ent & NB_ELE) && d2 <= cut2) s += dh_scalar(ele_coef, inv_lambdaD, d2);
+#else
+    if ((ent & NB_ELE) && d2 <= cut2) {
+        // the shorter dependency chain of the branch-free forms (Newton rsqrt on the MUFU seed, Taylor exp): the pair
+        // loop of this kernel is bound by the latency of one pair's chain, not by instruction count
+        const double ri = rsqrt_sl(d2);
+        s += ele_coef * ri * ri * (ri + inv_lambdaD) * exp_neg_sl((d2 * ri) * inv_lambdaD);
+    }
+#endif
     F += s * v;
 }
 // (rep, bead) of a flattened item
