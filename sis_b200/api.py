@@ -29,6 +29,9 @@ def library() -> C.CDLL:
 
 
 class SisGpu(CApi):
+    # options applied to every new handle before the caller's own (tests: run a suite on another kernel variant)
+    default_options: dict = {}
+
     def __init__(self, device: int = 0, **options):
         lib = library()
         h = C.c_void_p()
@@ -36,7 +39,7 @@ class SisGpu(CApi):
         if lib.sisgpu_create(C.byref(h), C.c_int(device)) != 0:
             raise SisError("sisgpu_create: " + lib.sisgpu_last_error().decode())
         super().__init__(lib, "sisgpu_", h)
-        for k, v in options.items():
+        for k, v in {**SisGpu.default_options, **options}.items():
             self.set_option(k, v)
 
     def close(self):

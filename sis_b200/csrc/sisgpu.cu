@@ -10,6 +10,7 @@
 #include "sis_fused.cuh"
 #include "sis_fast.cuh"
 #include "sis_big.cuh"
+#include "sis_rep.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -226,6 +227,9 @@ struct sisgpu {
     int mc_persistent = 1;               // option "mc_persistent": Monte-Carlo base-pair limit inside the replica-local k_md_fast
     int local_kernel = 1;                // option "local_kernel": replica-local mode of k_md_fast (one CTA per replica)
     int local_ncand = -1;                // sequence-allowed base pairs of one replica (bound of the per-CTA candidates)
+    int rep_kernel = 1;                  // option "rep_kernel": k_md_rep (right-sized CTA per replica, static pair tables) in the replica-local mode
+    int rep_threads = 0;                 // option "rep_threads": 128 / 256 threads per replica (0: by the number of replicas)
+    size_t rep_smem_set[4] = {0, 0, 0, 0};
     int pipeline = 1;                    // option "pipeline": device-driven list rebuilds inside md_steps
     double est_cycle_steps = 50.0;       // running estimate of MD steps between two list rebuilds
     DBuf<RepParams> d_rp, d_rp_alt;
@@ -1086,15 +1090,53 @@ static int fast_ncta_of(sisgpu *h)
     return std::max(1, std::max(ncta, ncta_min));
 }
 
+static int rep_threads_of(sisgpu *h, int nlab, bool xch);
 // replica-local mode of k_md_fast: one CTA owns one whole replica and rebuilds its lists itself
 static bool fast_local_ok(sisgpu *h)
 {
     if (!h->fast_kernel || !h->local_kernel || ensure_coop_blocks(h)) return false;
-    if (h->nmp > FAST_GROUPS || h->nrep > std::min(h->coop_blocks, FAST_MAX_CTA)) return false;
+    if (h->nmp > FAST_GROUPS || h->nrep > FAST_MAX_CTA) return false;
+    if (h->nrep > h->coop_blocks && !rep_threads_of(h, h->nrep_all, true)) return false;   // beyond one replica per SM: k_md_rep only
     // the replica-local kernel carries dual constant-force tweezers (F-REMD); the other biases go through k_md_big / per-phase kernels
     if (h->P.flg_stage || h->P.ntwz_FR || h->P.nrest || h->P.flg_bias_ss || h->P.flg_bias_rg) return false;
     if (h->K < h->nmp || h->KB < h->nmp - 1) return false;
     return h->local_ncand >= 0 && h->local_ncand <= FAST_BPC;
+}
+
+// k_md_rep: the replica-local mode with a CTA sized to the replica (sis_rep.cuh).  Returns the threads per
+// replica (128 / 256) or 0 when the kernel cannot take the run; *nlab_out = labels of the in-kernel exchange tables
+static size_t rep_smem_bytes(sisgpu *h, int nlab)
+{
+    return rep_carve(nullptr, h->nmp, std::max(1, h->local_ncand), nlab).bytes;
+}
+static int rep_capacity(sisgpu *h, int nt, int nlab, bool xch)
+{
+    const size_t smem = rep_smem_bytes(h, nlab);
+    void *fn = nt == 128 ? (xch ? (void *)k_md_rep<128, true> : (void *)k_md_rep<128, false>)
+                         : (xch ? (void *)k_md_rep<256, true> : (void *)k_md_rep<256, false>);
+    const int slot = (nt == 256 ? 2 : 0) + (xch ? 1 : 0);
+    if (smem > h->rep_smem_set[slot]) {
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+        h->rep_smem_set[slot] = smem;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, nt, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return per_sm * h->coop_blocks;
+}
+static int rep_threads_of(sisgpu *h, int nlab, bool xch)
+{
+    if (!h->rep_kernel || !h->fast_kernel || !h->local_kernel || ensure_coop_blocks(h)) return 0;
+    if (h->nmp > REP_MAXB || h->nmp < 2 || h->local_ncand < 0 || h->local_ncand > REP_MAXC) return 0;
+    if (h->P.flg_stage || h->P.ntwz_FR || h->P.nrest || h->P.flg_bias_ss || h->P.flg_bias_rg) return 0;
+    if (h->K < h->nmp || h->KB < h->nmp - 1) return 0;
+    if (rep_smem_bytes(h, nlab) > 200 * 1024) return 0;
+    // 256 threads per replica while the GPU has room for it (step latency), 128 beyond
+    const int want = h->rep_threads == 128 || h->rep_threads == 256 ? h->rep_threads : 0;
+    for (int nt = 256; nt >= 128; nt -= 128) {
+        if (want && nt != want) continue;
+        if (h->nrep <= rep_capacity(h, nt, nlab, xch)) return nt;
+    }
+    return 0;
 }
 
 // cell grid over [lo, hi] with cells of at least rc
@@ -2204,7 +2246,19 @@ static int launch_persistent(sisgpu *h, long long stop)
         return set_err("internal: the Monte-Carlo base-pair limit needs the replica-local kernel");
     h->last_launch_local = local;
     h->last_step_kernel = fast_ok ? (local ? "k_md_fast<1,true>" : "k_md_fast<1,false>") : "k_md_fused";
-    if (fast_ok) {
+    const bool xch = h->S.remd != nullptr;
+    const int nlab = xch ? h->nrep_all : 0;
+    const int rep_nt = (fast_ok && local) ? rep_threads_of(h, nlab, xch) : 0;
+    if (fast_ok && local && !rep_nt && R > h->coop_blocks) return set_err("internal: %d replicas need k_md_rep", R);
+    if (rep_nt) {
+        void *fn = rep_nt == 128 ? (xch ? (void *)k_md_rep<128, true> : (void *)k_md_rep<128, false>)
+                                 : (xch ? (void *)k_md_rep<256, true> : (void *)k_md_rep<256, false>);
+        int ccap = std::max(1, h->local_ncand), nl = nlab;
+        const size_t smem = rep_smem_bytes(h, nlab);
+        void *rargs[] = {&h->S, &h->P, &A, &stop, &NA, &ccap, &nl};
+        h->last_step_kernel = rep_nt == 128 ? "k_md_rep<128>" : "k_md_rep<256>";
+        CK(cudaLaunchCooperativeKernel(fn, dim3(R), dim3(rep_nt), rargs, smem, h->stream));
+    } else if (fast_ok) {
         void *fn = local ? (h->S.remd ? (void *)k_md_fast<1, true, true> : (void *)k_md_fast<1, true, false>) : (void *)k_md_fast<1, false, false>;
         if (smem_fast > h->fast_smem_set || fn != h->fast_fn_set) {
             CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
@@ -2617,6 +2671,8 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
     }
     else if (s == "fast_max_cta") { h->fast_max_cta = (int)value; h->lists_built = false; }
     else if (s == "mc_persistent") h->mc_persistent = (int)value;
+    else if (s == "rep_kernel") h->rep_kernel = (int)value;
+    else if (s == "rep_threads") h->rep_threads = (int)value;
     else if (s == "loc_help") h->S.dbg_no_loc_help = value == 0 ? 1 : 0;
     else if (s == "local_kernel") { h->local_kernel = (int)value; h->lists_built = false; }
     else if (s == "profile") {   // phase clocks of the persistent kernel (block 0): get_timers out[4..8]
