@@ -39,7 +39,8 @@
 
 constexpr int REP_MAXB = 64;       // beads per replica
 constexpr int REP_MAXC = 1024;     // base-pair candidates per replica
-constexpr int REP_ACT = 64;        // formed base pairs whose six bead forces get a slot (beyond: shared-memory atomics)
+constexpr int REP_ACT = 32;        // gate survivors evaluated role by role with slots for their results (beyond: one thread each, atomics)
+constexpr int REP_ROLE = 46;       // doubles one survivor's six roles leave: 4 angles x {u, fi, fk}, 2 dihedrals x {u, fi, fl, ra, rb}
 constexpr int REP_BPL = 8;         // base-pair force slots listed per bead (beyond: shared-memory atomics)
 constexpr int REP_BENT = 9;        // bonded terms a bead takes part in: 2 bonds, 3 angles, 4 dihedrals
 
@@ -48,10 +49,11 @@ struct RepSm {
     double *x, *v, *a, *m, *g, *fbp, *xreb;       // [3 n]
     double *ca, *cb, *cc, *nz0, *d2;              // [n]
     double *bf;                                   // [8 n][3]  bond k | angle n + 3 k + p | dihedral 4 n + 4 k + p
-    double *Fp;                                   // [npair][3], npair = n (n - 1) / 2: pair (i, j) at i (2 n - i - 1) / 2 + j - i - 1
+    double *Fp;                                   // [n][n][3]: force on bead k from bead j at (k n + j) 3 (both directions stored; 0 = no pair)
     double *bpF;                                  // [REP_ACT][6][3]
+    double *bpR;                                  // [REP_ACT][REP_ROLE]
     double *c_ene, *c_dG, *c_dH, *c_dS;           // [ccap]
-    double *red;                                  // [2 * 8]
+    double *red;                                  // [2 * 16]: two partial sums per warp
     int4 *meta;                                   // [n]
     uint32_t *pl;                                 // [npair]  i | j << 8 | flags (NB_WCA, NB_ELE); 0 = pair excluded
     unsigned short *bent;                         // [n][REP_BENT]  index into bf | 0x8000 (subtract)
@@ -67,7 +69,7 @@ struct RepSm {
     double *xE;                                   // [4]: own, cross, vscale
     size_t bytes;
 };
-enum { RC_NACT = 0, RC_WORK, RC_NCAND, RC_NEWLAB, RC_NATT, RC_NACC, RC_OVER, RC_FAR0, RC_FAR1 };
+enum { RC_NACT = 0, RC_WORK, RC_NCAND, RC_NEWLAB, RC_NATT, RC_NACC, RC_OVER, RC_FAR0, RC_FAR1, RC_ROLES };
 
 SIS_HD RepSm rep_carve(unsigned char *base, int n, int ccap, int nlab)
 {
@@ -84,11 +86,12 @@ SIS_HD RepSm rep_carve(unsigned char *base, int n, int ccap, int nlab)
     s.ca = (double *)take(8 * n, 8); s.cb = (double *)take(8 * n, 8); s.cc = (double *)take(8 * n, 8);
     s.nz0 = (double *)take(8 * n, 8); s.d2 = (double *)take(8 * REP_MAXB, 8);
     s.bf = (double *)take(8 * 3 * 8 * (size_t)n, 8);
-    s.Fp = (double *)take(8 * 3 * npair, 8);
+    s.Fp = (double *)take(8 * 3 * (size_t)n * n, 8);
     s.bpF = (double *)take(8 * 18 * REP_ACT, 8);
+    s.bpR = (double *)take(8 * REP_ROLE * REP_ACT, 8);
     s.c_ene = (double *)take(8 * ccap, 8); s.c_dG = (double *)take(8 * ccap, 8);
     s.c_dH = (double *)take(8 * ccap, 8); s.c_dS = (double *)take(8 * ccap, 8);
-    s.red = (double *)take(8 * 16, 8);
+    s.red = (double *)take(8 * 2 * 16, 8);
     s.xE = (double *)take(8 * 4, 8);
     s.pl = (uint32_t *)take(4 * npair, 4);
     s.c_pb = (int *)take(4 * ccap, 4);
@@ -127,9 +130,8 @@ SIS_D Vec3 rep_pair_force(const FFParams &P, uint32_t e, const double *x, double
     return s * v;
 }
 
-// full evaluation of one candidate by one thread (bp_force_all: the four angles and two dihedrals are independent
-// chains the scheduler interleaves): pair energy, status, the six bead forces into the slot of active entry `a`
-SIS_D void rep_bp_eval(const FFParams &P, const RepSm &sm, int a, int c, bool forces)
+// survivors beyond the REP_ACT role slots: full evaluation of one candidate by one thread (bp_force_all), forces by atomics
+SIS_D void rep_bp_eval(const FFParams &P, const RepSm &sm, int c, bool forces)
 {
     unsigned char *b = sm.c_b + 8 * c;
     const int type = (signed char)b[6];
@@ -152,13 +154,106 @@ SIS_D void rep_bp_eval(const FFParams &P, const RepSm &sm, int a, int c, bool fo
     for (int t = 0; t < 6; t++) {
         const Vec3 F = ene * fr[t];
         const int bead = b[t];
-        int slot = REP_BPL;
-        if (a < REP_ACT) slot = atomicAdd(&sm.bcnt[bead], 1);
+        atomicAdd(&sm.fbp[3 * bead], F.x); atomicAdd(&sm.fbp[3 * bead + 1], F.y); atomicAdd(&sm.fbp[3 * bead + 2], F.z);
+    }
+}
+
+// Role-major evaluation of the gate survivors (the first REP_ACT of them): one ITEM = one angle or one dihedral of one
+// survivor, so a warp runs one code path (the 8-lane groups of k_md_fast run bond / angle / dihedral lanes one after the
+// other).  Same expressions as bp_force_role (src/force_bp.F90:60-190); an item leaves {u, fi, fk} or {u, fi, fl, ra, rb}.
+SIS_D void rep_bp_role_item(const FFParams &P, const RepSm &sm, int a, int role)
+{
+    const unsigned char *b = sm.c_b + 8 * sm.act[a];
+    const BpPara &p = P.bp[(signed char)b[6]];
+    const Vec3 x0 = rep_x(sm.x, b[0]), x1 = rep_x(sm.x, b[1]);
+    const Vec3 v12 = pbc_vec_d(P, x0, x1);
+    const double d1212 = dot(v12, v12);
+    double *out = sm.bpR + REP_ROLE * a;
+    if (role <= 4) {
+        // angle between v12 and w; odd roles: w = x0 - xa (vertex i), even roles: w = xa - x1 (vertex j)
+        const double a12 = sqrt(d1212);
+        const bool at_i = role & 1;
+        const Vec3 xa = rep_x(sm.x, b[role + 1]);
+        const Vec3 w = at_i ? pbc_vec_d(P, x0, xa) : pbc_vec_d(P, xa, x1);
+        const double k = role == 1 ? p.angl_k2 : role == 2 ? p.angl_k1 : role == 3 ? p.angl_k4 : p.angl_k3;
+        const double th = role == 1 ? p.angl_theta2 : role == 2 ? p.angl_theta1 : role == 3 ? p.angl_theta4 : p.angl_theta3;
+        const double dww = dot(w, w), d12w = dot(v12, w);
+        const double cosine = d12w / (sqrt(dww) * a12);
+        const double d = acos(cosine) - th;
+        const double pre = 2.0 * k * d / sqrt(dww * d1212 - d12w * d12w);
+        const double r12w = d12w / d1212;
+        Vec3 fi, fk;
+        if (at_i) { fi = pre * (v12 - (d12w / dww) * w); fk = pre * (w - r12w * v12); }
+        else { fi = (-pre) * (w - r12w * v12); fk = (-pre) * (v12 - (d12w / dww) * w); }
+        out += 7 * (role - 1);
+        out[0] = k * d * d;
+        out[1] = fi.x; out[2] = fi.y; out[3] = fi.z; out[4] = fk.x; out[5] = fk.y; out[6] = fk.z;
+    } else {
+        // dihedral a-2=1-b: a on the j side (bead 3 or 5), b on the i side (bead 2 or 4)
+        const Vec3 xa = rep_x(sm.x, b[role == 5 ? 3 : 5]), xb = rep_x(sm.x, b[role == 5 ? 2 : 4]);
+        const Vec3 va2 = pbc_vec_d(P, xa, x1), v1b = pbc_vec_d(P, x0, xb);
+        const double ra = dot(v12, va2) / d1212, rb = dot(v12, v1b) / d1212;
+        const Vec3 m = cross(va2, v12), n = cross(v12, v1b);
+        // cos(phi + phi0), sin(phi + phi0) from (X, Y) / |(X, Y)|, phi = atan2(Y, X); |v12| X, |v12|^2 ... as bp_force_role
+        const double a12 = sqrt(d1212);
+        const double Y = dot(va2, n) * a12, X = dot(m, n);
+        const double kk = role == 5 ? p.dihd_k1 : p.dihd_k2;
+        const double c0 = role == 5 ? p.cos_phi1 : p.cos_phi2, s0 = role == 5 ? p.sin_phi1 : p.sin_phi2;
+        const double rinv = rsqrt(X * X + Y * Y);
+        const double cosd = (X * c0 - Y * s0) * rinv, sind = (Y * c0 + X * s0) * rinv;
+        const double pre = -kk * sind * a12;
+        const Vec3 fi = (pre / dot(m, m)) * m;
+        const Vec3 fl = (-pre / dot(n, n)) * n;
+        out += 28 + 9 * (role - 5);
+        out[0] = kk * (1.0 + cosd);
+        out[1] = fi.x; out[2] = fi.y; out[3] = fi.z; out[4] = fl.x; out[5] = fl.y; out[6] = fl.z;
+        out[7] = ra; out[8] = rb;
+    }
+}
+// the six roles of survivor `a` are in: pair energy and status (do_e), the six bead forces into the slot of `a` (do_f);
+// count_excess: the per-nucleotide count of the Monte-Carlo step
+SIS_D void rep_bp_combine(const FFParams &P, const RepSm &sm, int a, bool do_e, bool do_f, bool count_excess)
+{
+    const int c = sm.act[a];
+    unsigned char *b = sm.c_b + 8 * c;
+    const BpPara &p = P.bp[(signed char)b[6]];
+    const double *r = sm.bpR + REP_ROLE * a;
+    const Vec3 v12 = pbc_vec_d(P, rep_x(sm.x, b[0]), rep_x(sm.x, b[1]));
+    const double a12 = sqrt(dot(v12, v12)), d = a12 - p.bond_r;
+    double ene;
+    if (do_e) {
+        const double u = p.bond_k * d * d + ((r[0] + r[7]) + (r[14] + r[21])) + (r[28] + r[37]);
+        ene = P.bp_triplet ? p.U0 * sm.c_dG[c] * exp(-u) : p.U0 * exp(-u);
+        const bool on = ene <= P.bp_cutoff_energy;
+        if (on) { b[7] |= 1; sm.c_ene[c] = ene; } else { b[7] &= ~1; sm.c_ene[c] = 0.0; }
+        if (on && count_excess) { atomicAdd(&sm.excess[b[0]], 1); atomicAdd(&sm.excess[b[1]], 1); }
+    }
+    if (!do_f || !(b[7] & 1)) return;
+    ene = sm.c_ene[c];
+    auto V = [&](int o) { return mk(r[o], r[o + 1], r[o + 2]); };
+    const Vec3 f0 = (2.0 * p.bond_k * d / a12) * v12;
+    // angle roles 1, 3 (vertex i): c0 = -fi - fk, c1 = fk, ca = fi; roles 2, 4 (vertex j): c0 = fi, c1 = -fi - fk, ca = fk
+    // dihedral roles: ca = fi, cb = fl, c1 = (ra - 1) fi - rb fl, c0 = (rb - 1) fl - ra fi
+    const Vec3 fi1 = V(1), fk1 = V(4), fi2 = V(8), fk2 = V(11), fi3 = V(15), fk3 = V(18), fi4 = V(22), fk4 = V(25);
+    const Vec3 di5 = V(29), dl5 = V(32), di6 = V(38), dl6 = V(41);
+    const double ra5 = r[35], rb5 = r[36], ra6 = r[44], rb6 = r[45];
+    Vec3 F[6];
+    F[0] = f0 - (fi1 + fk1) + fi2 - (fi3 + fk3) + fi4 + ((rb5 - 1.0) * dl5 - ra5 * di5) + ((rb6 - 1.0) * dl6 - ra6 * di6);
+    F[1] = -f0 + fk1 - (fi2 + fk2) + fk3 - (fi4 + fk4) + ((ra5 - 1.0) * di5 - rb5 * dl5) + ((ra6 - 1.0) * di6 - rb6 * dl6);
+    F[2] = fi1 + dl5;
+    F[3] = fk2 + di5;
+    F[4] = fi3 + dl6;
+    F[5] = fk4 + di6;
+#pragma unroll
+    for (int t = 0; t < 6; t++) {
+        const int bead = b[t];
+        const int slot = atomicAdd(&sm.bcnt[bead], 1);
+        const Vec3 Ft = ene * F[t];
         if (slot < REP_BPL) {
-            rep_put(sm.bpF, a * 6 + t, F);
+            rep_put(sm.bpF, a * 6 + t, Ft);
             sm.blst[bead * REP_BPL + slot] = (unsigned short)(a * 6 + t);
         } else {
-            atomicAdd(&sm.fbp[3 * bead], F.x); atomicAdd(&sm.fbp[3 * bead + 1], F.y); atomicAdd(&sm.fbp[3 * bead + 2], F.z);
+            atomicAdd(&sm.fbp[3 * bead], Ft.x); atomicAdd(&sm.fbp[3 * bead + 1], Ft.y); atomicAdd(&sm.fbp[3 * bead + 2], Ft.z);
         }
     }
 }
@@ -193,28 +288,24 @@ SIS_D void rep_bp_gate(const FFParams &P, const RepSm &sm, int ncand, bool use_m
     }
 }
 
-// Monte-Carlo step (src/force_bp_limit_triplet.F90:85-328): pass 1 = every candidate evaluated, excess of
-// formed pairs per nucleotide; pass 2 = the reference's sequential delete loop on warp 0 (bp_prune_warp's
-// arithmetic and uniform stream, on the shared-memory tables: a nucleotide's formed pairs in ascending
-// partner order = table order; the uniforms of one deletion are drawn side by side, one per lane); then
-// bp_status_MC = bp_status (src/job_md.F90:399-401)
+// Monte-Carlo step (src/force_bp_limit_triplet.F90:85-328).  Pass 1 (every candidate evaluated, excess of formed pairs
+// per nucleotide) runs in the step's work queue; this is pass 2 = the reference's sequential delete loop on warp 0
+// (bp_prune_warp's arithmetic and uniform stream, on the shared-memory tables: a nucleotide's formed pairs in ascending
+// partner order = table order; the uniforms of one deletion are drawn side by side, one per lane); then the forces of
+// the pairs that stay, and bp_status_MC = bp_status (src/job_md.F90:399-401)
 template <int NT>
-SIS_D void rep_mc_step(const FFParams &P, const RepSm &sm, int n, int ncand, unsigned long long seed, int max_bp_per_nt,
-                       unsigned long long *mc_ctr)
+SIS_D void rep_mc_prune(const FFParams &P, const RepSm &sm, int n, int ncand, unsigned long long seed, unsigned long long *mc_ctr,
+                         unsigned long long *prof_slot)
 {
     const int tid = threadIdx.x, lane = tid & 31;
-    for (int i = tid; i < n; i += NT) sm.excess[i] = -max_bp_per_nt;
-    rep_bp_gate<NT>(P, sm, ncand, false);
-    rep_sync<NT>();
     const int nact = sm.ctl[RC_NACT];
-    for (int a = tid; a < nact; a += NT) rep_bp_eval(P, sm, a, sm.act[a], false);
-    rep_sync<NT>();
     if (tid < 32) {
         const RepParams &R = *sm.rp;
         const double beta = 1.0 / (SIS_BOLTZ_KCAL_MOL * R.tempK);
         unsigned long long ctr = *mc_ctr;
         const uint32_t stream = 0x40000000u + (uint32_t)R.stream;
-        int *seq = sm.act;          // free between the passes
+        int *seq = reinterpret_cast<int *>(sm.bpF);          // the slots are free until the force pass
+        int ndel = 0;
         for (;;) {
             const bool e0 = lane < n && sm.excess[lane] > 0, e1 = lane + 32 < n && sm.excess[lane + 32] > 0;
             const unsigned m0 = __ballot_sync(0xffffffffu, e0), m1 = __ballot_sync(0xffffffffu, e1);
@@ -269,16 +360,21 @@ SIS_D void rep_mc_step(const FFParams &P, const RepSm &sm, int n, int ncand, uns
                 sm.excess[b[1]] -= 1;
             }
             ctr += 1ull + (unsigned long long)used;
+            ndel++;
             __syncwarp();
         }
         if (lane == 0) *mc_ctr = ctr;
+        if (lane == 0 && prof_slot) *prof_slot += (unsigned long long)ndel;
     }
     rep_sync<NT>();
+    for (int a = tid; a < nact; a += NT) {
+        if (a < REP_ACT) rep_bp_combine(P, sm, a, false, true, false);
+        else if (sm.c_b[8 * sm.act[a] + 7] & 1) rep_bp_eval(P, sm, sm.act[a], true);
+    }
     for (int c = tid; c < ncand; c += NT) {
         unsigned char *b = sm.c_b + 8 * c;
         b[7] = (unsigned char)((b[7] & 1) * 3);
     }
-    if (tid == 0) sm.ctl[RC_NACT] = 0;
     rep_sync<NT>();
 }
 
@@ -451,7 +547,7 @@ SIS_D void rep_remd_exchange(const DevSys &S, const FFParams &P, const RepSm &sm
 }
 
 template <int NT, bool XCH>
-__global__ void __launch_bounds__(NT, 512 / NT) k_md_rep(const __grid_constant__ DevSys S, const __grid_constant__ FFParams P, StepArgs A,
+__global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const __grid_constant__ DevSys S, const __grid_constant__ FFParams P, StepArgs A,
                                                           long long target, NlArgs NA, int ccap, int nlab)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -484,7 +580,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_md_rep(const __grid_constant__
         sm.bcnt[k] = 0;
     }
     for (int k = tid; k < REP_MAXB; k += NT) sm.d2[k] = 0.0;
-    for (int t = tid; t < 3 * npair; t += NT) sm.Fp[t] = 0.0;
+    for (int t = tid; t < 3 * n * n; t += NT) sm.Fp[t] = 0.0;
     if (tid == 0) {
         *sm.rp = S.rp[rep];
         for (int i = 0; i < 16; i++) sm.ctl[i] = 0;
@@ -605,12 +701,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_md_rep(const __grid_constant__
             after_rebuild = true;
             rep_sync<NT>();
         }
-        if (use_mc) {
-            const bool mc = (istep % (unsigned long long)P.nstep_bp_MC == 0ull) || after_rebuild;
-            if (mc) rep_mc_step<NT>(P, sm, n, ncand, A.seed, A.max_bp_per_nt, &s_mc_ctr);
-        }
+        const bool mc = use_mc && ((istep % (unsigned long long)P.nstep_bp_MC == 0ull) || after_rebuild);
         after_rebuild = false;
-        rep_bp_gate<NT>(P, sm, ncand, use_mc);
+        if (mc) for (int i = tid; i < n; i += NT) sm.excess[i] = -A.max_bp_per_nt;
+        rep_bp_gate<NT>(P, sm, ncand, use_mc && !mc);
         const RepParams &Rp = *sm.rp;
         const double ele_coef = Rp.ele_coef, inv_lambdaD = Rp.inv_lambdaD;
         const double cut2 = P.flg_ele ? Rp.ele_cutoff * Rp.ele_cutoff : -1.0;
@@ -620,17 +714,33 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_md_rep(const __grid_constant__
         // ---- P1: every warp draws chunks from the shared counter ----------------------------------------------
         {
             const int nact = sm.ctl[RC_NACT];
-            const int cbp = (nact + 31) >> 5;
+            const int nar = min(nact, REP_ACT);
+            // chunks: angle roles, dihedral roles, survivors beyond the role slots, static work, pairs, combine (last: it needs the roles)
+            const int cang = (4 * nar + 31) >> 5, cdih = (2 * nar + 31) >> 5, cov = (nact - nar + 31) >> 5, ccomb = (nar + 31) >> 5;
+            const int cbp = cang + cdih + cov;
             bool first = true;
             for (;;) {
                 int ch = 0;
                 if (lane == 0) ch = atomicAdd(&sm.ctl[RC_WORK], 1);
                 ch = __shfl_sync(0xffffffffu, ch, 0);
                 if (prof && first) { c2 = clock64(); first = false; }
-                if (ch >= cbp + cstat + cpair) break;
-                if (ch < cbp) {                         // base-pair survivors, one thread each
-                    const int a = 32 * ch + lane;
-                    if (a < nact) rep_bp_eval(P, sm, a, sm.act[a], true);
+                if (ch >= cbp + cstat + cpair + ccomb) break;
+                if (ch < cang + cdih) {                 // base-pair roles, one code path per warp
+                    const bool ang = ch < cang;
+                    const int it = 32 * (ang ? ch : ch - cang) + lane;
+                    if (ang) { if (it < 4 * nar) rep_bp_role_item(P, sm, it >> 2, 1 + (it & 3)); }
+                    else if (it < 2 * nar) rep_bp_role_item(P, sm, it >> 1, 5 + (it & 1));
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(&sm.ctl[RC_ROLES], 1);
+                } else if (ch < cbp) {
+                    const int a = REP_ACT + 32 * (ch - cang - cdih) + lane;
+                    if (a < nact) rep_bp_eval(P, sm, sm.act[a], !mc);
+                } else if (ch >= cbp + cstat + cpair) {
+                    while (*(volatile int *)&sm.ctl[RC_ROLES] < cang + cdih) { }
+                    __threadfence_block();
+                    const int a = 32 * (ch - cbp - cstat - cpair) + lane;
+                    if (a < nar) rep_bp_combine(P, sm, a, true, !mc, mc);
                 } else if (ch < cbp + cstat) {
                     const int it = 32 * (ch - cbp) + lane;
                     if (it < nG) {                      // Gaussians of this step: draw 0 -> (x, y), draw 1 -> z
@@ -668,13 +778,14 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_md_rep(const __grid_constant__
                     Vec3 f0 = mk(0.0, 0.0, 0.0), f1 = f0;
                     if (e0) f0 = rep_pair_force(P, e0, sm.x, ele_coef, inv_lambdaD, cut2);
                     if (e1) f1 = rep_pair_force(P, e1, sm.x, ele_coef, inv_lambdaD, cut2);
-                    if (e0) rep_put(sm.Fp, q0, f0);
-                    if (e1) rep_put(sm.Fp, q1, f1);
+                    if (e0) { const int i = e0 & 0xFF, j = (e0 >> 8) & 0xFF; rep_put(sm.Fp, i * n + j, f0); rep_put(sm.Fp, j * n + i, -f0); }
+                    if (e1) { const int i = e1 & 0xFF, j = (e1 >> 8) & 0xFF; rep_put(sm.Fp, i * n + j, f1); rep_put(sm.Fp, j * n + i, -f1); }
                 }
             }
         }
         if (wprof) w0 = clock64();
         rep_sync<NT>();
+        if (mc) rep_mc_prune<NT>(P, sm, n, ncand, A.seed, &s_mc_ctr, S.prof ? pc + 6 : nullptr);
         if (prof) c3 = clock64();
         // ---- P2: assemble and integrate (src/job_md.F90:409-456) ------------------------------------------------
         bool far = false;
@@ -683,22 +794,15 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_md_rep(const __grid_constant__
             const int comp = tid & 3;
             double mv = 0.0;
             if (k < n && comp < 3) {
-                // pair slots: (i, k) for i < k with the sign flipped, then the row (k, j)
-                double fa0 = 0.0, fa1 = 0.0, fb0 = 0.0, fb1 = 0.0;
+                // the row of pair forces on bead k (zeros where there is no pair)
+                double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
                 {
-                    int i = 0;
-                    for (; i + 1 < k; i += 2) {
-                        fa0 -= sm.Fp[3 * (rep_rowbase(i, n) + k - i - 1) + comp];
-                        fa1 -= sm.Fp[3 * (rep_rowbase(i + 1, n) + k - i - 2) + comp];
-                    }
-                    if (i < k) fa0 -= sm.Fp[3 * (rep_rowbase(i, n) + k - i - 1) + comp];
-                    const double *row = sm.Fp + 3 * rep_rowbase(k, n) + comp;
-                    const int nr = n - 1 - k;
-                    int t = 0;
-                    for (; t + 1 < nr; t += 2) { fb0 += row[3 * t]; fb1 += row[3 * t + 3]; }
-                    if (t < nr) fb0 += row[3 * t];
+                    const double *row = sm.Fp + 3 * k * n + comp;
+                    int j = 0;
+                    for (; j + 3 < n; j += 4) { f0 += row[3 * j]; f1 += row[3 * j + 3]; f2 += row[3 * j + 6]; f3 += row[3 * j + 9]; }
+                    for (; j < n; j++) f0 += row[3 * j];
                 }
-                double f = (fa0 + fa1) + (fb0 + fb1);
+                double f = (f0 + f1) + (f2 + f3);
                 const unsigned short *be = sm.bent + REP_BENT * k;
                 const int ne = sm.bn[k];
                 for (int e = 0; e < ne; e++) {
@@ -738,7 +842,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_md_rep(const __grid_constant__
             __syncwarp();
             if (k < n && comp == 3) sm.bcnt[k] = 0;
         }
-        if (tid == 0) { sm.ctl[RC_NACT] = 0; sm.ctl[RC_WORK] = 0; sm.ctl[RC_FAR0 + ((done + 1) & 1)] = 0; }
+        if (tid == 0) { sm.ctl[RC_NACT] = 0; sm.ctl[RC_WORK] = 0; sm.ctl[RC_ROLES] = 0; sm.ctl[RC_FAR0 + ((done + 1) & 1)] = 0; }
         // "is any displacement beyond half the margin": only then the exact top-2 test (flag by step parity)
         if (__any_sync(0xffffffffu, far) && lane == 0) sm.ctl[RC_FAR0 + (done & 1)] = 1;
         if (wprof) { w0 = clock64(); aw[1] += w0 - w1; }

@@ -229,7 +229,7 @@ struct sisgpu {
     int local_ncand = -1;                // sequence-allowed base pairs of one replica (bound of the per-CTA candidates)
     int rep_kernel = 1;                  // option "rep_kernel": k_md_rep (right-sized CTA per replica, static pair tables) in the replica-local mode
     int rep_threads = 0;                 // option "rep_threads": 128 / 256 threads per replica (0: by the number of replicas)
-    size_t rep_smem_set[4] = {0, 0, 0, 0};
+    size_t rep_smem_set[6] = {0, 0, 0, 0, 0, 0};
     int pipeline = 1;                    // option "pipeline": device-driven list rebuilds inside md_steps
     double est_cycle_steps = 50.0;       // running estimate of MD steps between two list rebuilds
     DBuf<RepParams> d_rp, d_rp_alt;
@@ -1109,12 +1109,18 @@ static size_t rep_smem_bytes(sisgpu *h, int nlab)
 {
     return rep_carve(nullptr, h->nmp, std::max(1, h->local_ncand), nlab).bytes;
 }
+static void *rep_kernel_fn(int nt, bool xch)
+{
+    if (nt == 512) return xch ? (void *)k_md_rep<512, true> : (void *)k_md_rep<512, false>;
+    if (nt == 256) return xch ? (void *)k_md_rep<256, true> : (void *)k_md_rep<256, false>;
+    return xch ? (void *)k_md_rep<128, true> : (void *)k_md_rep<128, false>;
+}
+// replicas the GPU holds co-resident with `nt` threads each (the exchange barrier needs every replica's CTA resident)
 static int rep_capacity(sisgpu *h, int nt, int nlab, bool xch)
 {
     const size_t smem = rep_smem_bytes(h, nlab);
-    void *fn = nt == 128 ? (xch ? (void *)k_md_rep<128, true> : (void *)k_md_rep<128, false>)
-                         : (xch ? (void *)k_md_rep<256, true> : (void *)k_md_rep<256, false>);
-    const int slot = (nt == 256 ? 2 : 0) + (xch ? 1 : 0);
+    void *fn = rep_kernel_fn(nt, xch);
+    const int slot = (nt == 512 ? 4 : nt == 256 ? 2 : 0) + (xch ? 1 : 0);
     if (smem > h->rep_smem_set[slot]) {
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
         h->rep_smem_set[slot] = smem;
@@ -1130,9 +1136,9 @@ static int rep_threads_of(sisgpu *h, int nlab, bool xch)
     if (h->P.flg_stage || h->P.ntwz_FR || h->P.nrest || h->P.flg_bias_ss || h->P.flg_bias_rg) return 0;
     if (h->K < h->nmp || h->KB < h->nmp - 1) return 0;
     if (rep_smem_bytes(h, nlab) > 200 * 1024) return 0;
-    // 256 threads per replica while the GPU has room for it (step latency), 128 beyond
-    const int want = h->rep_threads == 128 || h->rep_threads == 256 ? h->rep_threads : 0;
-    for (int nt = 256; nt >= 128; nt -= 128) {
+    // the widest CTA the replica count leaves room for: a replica's step is a latency chain, more warps shorten it
+    const int want = h->rep_threads == 128 || h->rep_threads == 256 || h->rep_threads == 512 ? h->rep_threads : 0;
+    for (int nt = 512; nt >= 128; nt >>= 1) {
         if (want && nt != want) continue;
         if (h->nrep <= rep_capacity(h, nt, nlab, xch)) return nt;
     }
@@ -2251,12 +2257,11 @@ static int launch_persistent(sisgpu *h, long long stop)
     const int rep_nt = (fast_ok && local) ? rep_threads_of(h, nlab, xch) : 0;
     if (fast_ok && local && !rep_nt && R > h->coop_blocks) return set_err("internal: %d replicas need k_md_rep", R);
     if (rep_nt) {
-        void *fn = rep_nt == 128 ? (xch ? (void *)k_md_rep<128, true> : (void *)k_md_rep<128, false>)
-                                 : (xch ? (void *)k_md_rep<256, true> : (void *)k_md_rep<256, false>);
+        void *fn = rep_kernel_fn(rep_nt, xch);
         int ccap = std::max(1, h->local_ncand), nl = nlab;
         const size_t smem = rep_smem_bytes(h, nlab);
         void *rargs[] = {&h->S, &h->P, &A, &stop, &NA, &ccap, &nl};
-        h->last_step_kernel = rep_nt == 128 ? "k_md_rep<128>" : "k_md_rep<256>";
+        h->last_step_kernel = rep_nt == 128 ? "k_md_rep<128>" : rep_nt == 256 ? "k_md_rep<256>" : "k_md_rep<512>";
         CK(cudaLaunchCooperativeKernel(fn, dim3(R), dim3(rep_nt), rargs, smem, h->stream));
     } else if (fast_ok) {
         void *fn = local ? (h->S.remd ? (void *)k_md_fast<1, true, true> : (void *)k_md_fast<1, true, false>) : (void *)k_md_fast<1, false, false>;

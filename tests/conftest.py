@@ -37,5 +37,5 @@ def is_replica_local(name: str) -> bool:
     """`name` (sisgpu_last_step_kernel) is the replica-local kernel the current test variant selects."""
     from sis_b200.api import SisGpu
     if SisGpu.default_options.get("rep_kernel", 1):
-        return name in ("k_md_rep<128>", "k_md_rep<256>")
+        return name in ("k_md_rep<128>", "k_md_rep<256>", "k_md_rep<512>")
     return name == "k_md_fast<1,true>"

@@ -49,7 +49,9 @@ def compare(got, runs, keys, floor_rel=2e-3):
         assert abs(got[k]["mean"] - mu) <= NSIGMA * err, (k, got[k], mu, err)
         widths = np.array([r[k]["std"] for r in runs])
         rel = widths.std(ddof=1) / widths.mean() if widths.min() > 0 else 1.0
-        if rel < 0.15:     # distribution width, where the seeds agree on it; the band follows their spread
+        # distribution width, where the seeds agree on it; the band follows their spread.  Energies only: the base-pair
+        # counts sit on one integer and leave it in rare, long-lived excursions, so their width is a rare-event estimate
+        if rel < 0.15 and k.startswith("E_"):
             band = max(0.3, NSIGMA * rel * np.sqrt(1.0 + 1.0 / len(widths)))
             assert 1.0 - band < got[k]["std"] / widths.mean() < 1.0 + 1.35 * band, (k, got[k]["std"], widths)
 
