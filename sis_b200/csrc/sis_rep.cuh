@@ -46,7 +46,8 @@ constexpr int REP_BENT = 9;        // bonded terms a bead takes part in: 2 bonds
 
 // shared-memory carve-up: identical arithmetic on host (size) and device (pointers)
 struct RepSm {
-    double *x, *v, *a, *m, *g, *fbp, *xreb;       // [3 n]
+    double *x, *v, *a, *m, *fbp, *xreb, *fsum;    // [3 n]
+    double *g;                                    // [2][3 n] Gaussians by step parity
     double *ca, *cb, *cc, *nz0, *d2;              // [n]
     double *bf;                                   // [8 n][3]  bond k | angle n + 3 k + p | dihedral 4 n + 4 k + p
     double *Fp;                                   // [n][n][3]: force on bead k from bead j at (k n + j) 3 (both directions stored; 0 = no pair)
@@ -69,7 +70,7 @@ struct RepSm {
     double *xE;                                   // [4]: own, cross, vscale
     size_t bytes;
 };
-enum { RC_NACT = 0, RC_WORK, RC_NCAND, RC_NEWLAB, RC_NATT, RC_NACC, RC_OVER, RC_FAR0, RC_FAR1, RC_ROLES };
+enum { RC_NACT = 0, RC_WORK, RC_NCAND, RC_NEWLAB, RC_NATT, RC_NACC, RC_OVER, RC_FAR0, RC_FAR1, RC_ROLES, RC_STAT };
 
 SIS_HD RepSm rep_carve(unsigned char *base, int n, int ccap, int nlab)
 {
@@ -81,7 +82,8 @@ SIS_HD RepSm rep_carve(unsigned char *base, int n, int ccap, int nlab)
     s.xs = (FastRemdState *)take(sizeof(FastRemdState), 16);
     s.meta = (int4 *)take(sizeof(int4) * n, 16);
     s.x = (double *)take(8 * 3 * n, 8); s.v = (double *)take(8 * 3 * n, 8); s.a = (double *)take(8 * 3 * n, 8);
-    s.m = (double *)take(8 * 3 * n, 8); s.g = (double *)take(8 * 3 * n, 8); s.fbp = (double *)take(8 * 3 * n, 8);
+    s.m = (double *)take(8 * 3 * n, 8); s.g = (double *)take(8 * 6 * n, 8); s.fbp = (double *)take(8 * 3 * n, 8);
+    s.fsum = (double *)take(8 * 3 * n, 8);
     s.xreb = (double *)take(8 * 3 * n, 8);
     s.ca = (double *)take(8 * n, 8); s.cb = (double *)take(8 * n, 8); s.cc = (double *)take(8 * n, 8);
     s.nz0 = (double *)take(8 * n, 8); s.d2 = (double *)take(8 * REP_MAXB, 8);
@@ -657,6 +659,14 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
         }
         if (lane == 0) { sm.ctl[RC_NCAND] = min(nc, ccap); if (nc > ccap) { sm.ctl[RC_OVER] = 1; atomicOr(&S.misc->max_force_flag, 4); } }
     }
+    // Gaussians of the first step (every later step finds its own drawn one step ahead)
+    for (int it = tid; it < 2 * n; it += NT) {
+        const int k = it >> 1, draw = it & 1;
+        double g0, g1;
+        gauss_pair(A.seed, (uint32_t)S.rp[rep].stream, ctl.step + 1ull, (uint32_t)k, (uint32_t)draw, &g0, &g1);
+        double *gn = sm.g + 3 * n * (int)((ctl.step + 1ull) & 1ull);
+        if (draw == 0) { gn[3 * k] = g0; gn[3 * k + 1] = g1; } else gn[3 * k + 2] = g0;
+    }
     // rebuild verdict on the displacements the previous launch left (src/job_md.F90:376-388)
     bool blocked;
     double top1, top2v;
@@ -674,14 +684,16 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
     const bool overflow = sm.ctl[RC_OVER] != 0;
     const uint32_t stream = (uint32_t)sm.rp->stream;
     // work of P1 in chunks of one warp: base-pair survivors, Gaussians, dihedrals, bond + angle, then the pairs (64 per chunk)
-    const int nG = 2 * n, nD = dih_on ? n : 0, nB = n;
-    const int nstat = nG + nD + nB, cstat = (nstat + 31) >> 5, cpair = (npair + 63) >> 6;
+    // (each kind starts on a chunk boundary: a warp runs one code path)
+    const int cD = dih_on ? (n + 31) >> 5 : 0, cB = (n + 31) >> 5, cpair = (npair + 127) >> 7, cG = (2 * n + 31) >> 5, cA = (3 * n + 31) >> 5;
+    const int cstat = cD + cB + cpair;          // chunks the owners' sums wait for
     // optional phase clocks (option "profile"): per CTA {P0, P1 wait for the first chunk, P1 work, P2, verdict, exchange, exchange wait, steps}
     const bool prof = S.prof != nullptr && tid == 0;
     unsigned long long *pc = S.prof + 16 + 8 * (blockIdx.x % FAST_MAX_CTA);
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
     const bool wprof = S.prof != nullptr && blockIdx.x == 0 && lane == 0 && warp < 4;     // block 0, warps 0-3: {B2 wait, P2, B3 wait}
     long long w0 = 0, w1 = 0, aw[3] = {0, 0, 0};
+    const bool tprof = S.prof != nullptr && blockIdx.x == 0;      // block 0: cycles and count per chunk type of the P1 queue
 
     int done = 0;
     if (!overflow)
@@ -724,8 +736,11 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
                 if (lane == 0) ch = atomicAdd(&sm.ctl[RC_WORK], 1);
                 ch = __shfl_sync(0xffffffffu, ch, 0);
                 if (prof && first) { c2 = clock64(); first = false; }
-                if (ch >= cbp + cstat + cpair + ccomb) break;
+                if (ch >= cbp + cstat + cG + cA + ccomb) break;
+                const long long tq0 = tprof ? clock64() : 0;
+                int ttype = 0;
                 if (ch < cang + cdih) {                 // base-pair roles, one code path per warp
+                    ttype = ch < cang ? 0 : 1;
                     const bool ang = ch < cang;
                     const int it = 32 * (ang ? ch : ch - cang) + lane;
                     if (ang) { if (it < 4 * nar) rep_bp_role_item(P, sm, it >> 2, 1 + (it & 3)); }
@@ -734,52 +749,104 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
                     __syncwarp();
                     if (lane == 0) atomicAdd(&sm.ctl[RC_ROLES], 1);
                 } else if (ch < cbp) {
+                    ttype = 2;
                     const int a = REP_ACT + 32 * (ch - cang - cdih) + lane;
                     if (a < nact) rep_bp_eval(P, sm, sm.act[a], !mc);
-                } else if (ch >= cbp + cstat + cpair) {
-                    while (*(volatile int *)&sm.ctl[RC_ROLES] < cang + cdih) { }
-                    __threadfence_block();
-                    const int a = 32 * (ch - cbp - cstat - cpair) + lane;
-                    if (a < nar) rep_bp_combine(P, sm, a, true, !mc, mc);
                 } else if (ch < cbp + cstat) {
-                    const int it = 32 * (ch - cbp) + lane;
-                    if (it < nG) {                      // Gaussians of this step: draw 0 -> (x, y), draw 1 -> z
-                        const int k = it >> 1, draw = it & 1;
-                        double g0, g1;
-                        gauss_pair(A.seed, stream, istep, (uint32_t)k, (uint32_t)draw, &g0, &g1);
-                        if (draw == 0) { sm.g[3 * k] = g0; sm.g[3 * k + 1] = g1; } else sm.g[3 * k + 2] = g0;
-                    } else if (it < nG + nD) {          // dihedral starting at bead k
-                        const int k = it - nG;
-                        const int4 m = sm.meta[k];
-                        if (rep_term(m, 3)) {
-                            Vec3 f4[4];
-                            dih_force_vecs(P, rep_x(sm.x, k), rep_x(sm.x, chain_nb(m, 1)), rep_x(sm.x, chain_nb(m, 2)),
-                                           rep_x(sm.x, chain_nb(m, 3)), f4);
+                    const int cs = ch - cbp;
+                    if (cs < cD) {                      // dihedral starting at bead k
+                        ttype = 4;
+                        const int k = 32 * cs + lane;
+                        if (k < n) {
+                            const int4 m = sm.meta[k];
+                            if (rep_term(m, 3)) {
+                                Vec3 f4[4];
+                                dih_force_vecs(P, rep_x(sm.x, k), rep_x(sm.x, chain_nb(m, 1)), rep_x(sm.x, chain_nb(m, 2)),
+                                               rep_x(sm.x, chain_nb(m, 3)), f4);
 #pragma unroll
-                            for (int p = 0; p < 4; p++) rep_put(sm.bf, 4 * n + 4 * k + p, f4[p]);
-                        }
-                    } else if (it < nstat) {            // bond and angle starting at bead k
-                        const int k = it - nG - nD;
-                        const int4 m = sm.meta[k];
-                        if (rep_term(m, 1)) {
-                            const Vec3 x0 = rep_x(sm.x, k), x1 = rep_x(sm.x, chain_nb(m, 1));
-                            rep_put(sm.bf, k, bond_force_vec(P, x0, x1));
-                            if (rep_term(m, 2)) {
-                                Vec3 fa, fc;
-                                if (P.flg_angl_ReB) angl_ReB_force_vecs(P, x0, x1, rep_x(sm.x, chain_nb(m, 2)), &fa, &fc);
-                                else angl_force_vecs(P, x0, x1, rep_x(sm.x, chain_nb(m, 2)), &fa, &fc);
-                                rep_put(sm.bf, n + 3 * k, fa); rep_put(sm.bf, n + 3 * k + 1, -(fa + fc)); rep_put(sm.bf, n + 3 * k + 2, fc);
+                                for (int p = 0; p < 4; p++) rep_put(sm.bf, 4 * n + 4 * k + p, f4[p]);
                             }
                         }
+                    } else if (cs < cD + cB) {          // bond and angle starting at bead k
+                        ttype = 5;
+                        const int k = 32 * (cs - cD) + lane;
+                        if (k < n) {
+                            const int4 m = sm.meta[k];
+                            if (rep_term(m, 1)) {
+                                const Vec3 x0 = rep_x(sm.x, k), x1 = rep_x(sm.x, chain_nb(m, 1));
+                                rep_put(sm.bf, k, bond_force_vec(P, x0, x1));
+                                if (rep_term(m, 2)) {
+                                    Vec3 fa, fc;
+                                    if (P.flg_angl_ReB) angl_ReB_force_vecs(P, x0, x1, rep_x(sm.x, chain_nb(m, 2)), &fa, &fc);
+                                    else angl_force_vecs(P, x0, x1, rep_x(sm.x, chain_nb(m, 2)), &fa, &fc);
+                                    rep_put(sm.bf, n + 3 * k, fa); rep_put(sm.bf, n + 3 * k + 1, -(fa + fc)); rep_put(sm.bf, n + 3 * k + 2, fc);
+                                }
+                            }
+                        }
+                    } else {                            // 128 pairs: four per lane side by side
+                        ttype = 6;
+                        const int q0 = 128 * (cs - cD - cB) + lane;
+                        uint32_t e[4];
+                        Vec3 f[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) e[u] = q0 + 32 * u < npair ? sm.pl[q0 + 32 * u] : 0u;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) f[u] = e[u] ? rep_pair_force(P, e[u], sm.x, ele_coef, inv_lambdaD, cut2) : mk(0.0, 0.0, 0.0);
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (e[u]) { const int i = e[u] & 0xFF, j = (e[u] >> 8) & 0xFF; rep_put(sm.Fp, i * n + j, f[u]); rep_put(sm.Fp, j * n + i, -f[u]); }
                     }
-                } else {
-                    const int q0 = 64 * (ch - cbp - cstat) + lane, q1 = q0 + 32;
-                    const uint32_t e0 = q0 < npair ? sm.pl[q0] : 0u, e1 = q1 < npair ? sm.pl[q1] : 0u;
-                    Vec3 f0 = mk(0.0, 0.0, 0.0), f1 = f0;
-                    if (e0) f0 = rep_pair_force(P, e0, sm.x, ele_coef, inv_lambdaD, cut2);
-                    if (e1) f1 = rep_pair_force(P, e1, sm.x, ele_coef, inv_lambdaD, cut2);
-                    if (e0) { const int i = e0 & 0xFF, j = (e0 >> 8) & 0xFF; rep_put(sm.Fp, i * n + j, f0); rep_put(sm.Fp, j * n + i, -f0); }
-                    if (e1) { const int i = e1 & 0xFF, j = (e1 >> 8) & 0xFF; rep_put(sm.Fp, i * n + j, f1); rep_put(sm.Fp, j * n + i, -f1); }
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(&sm.ctl[RC_STAT], 1);
+                } else if (ch < cbp + cstat + cG) {     // Gaussians of the NEXT step (nothing waits for them in this one): draw 0 -> (x, y), draw 1 -> z
+                    ttype = 3;
+                    const int it = 32 * (ch - cbp - cstat) + lane;
+                    if (it < 2 * n) {
+                        const int k = it >> 1, draw = it & 1;
+                        double g0, g1;
+                        gauss_pair(A.seed, stream, istep + 1ull, (uint32_t)k, (uint32_t)draw, &g0, &g1);
+                        double *gn = sm.g + 3 * n * (int)((istep + 1ull) & 1ull);
+                        if (draw == 0) { gn[3 * k] = g0; gn[3 * k + 1] = g1; } else gn[3 * k + 2] = g0;
+                    }
+                } else if (ch < cbp + cstat + cG + cA) {   // owners' sums: pair row, bonded terms, tweezers
+                    ttype = 7;
+                    while (*(volatile int *)&sm.ctl[RC_STAT] < cstat) { }
+                    __threadfence_block();
+                    const int it = 32 * (ch - cbp - cstat - cG) + lane;
+                    if (it < 3 * n) {
+                        const int k = it / 3, comp = it - 3 * k;
+                        double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
+                        const double *row = sm.Fp + 3 * k * n + comp;
+                        int j = 0;
+                        for (; j + 3 < n; j += 4) { f0 += row[3 * j]; f1 += row[3 * j + 3]; f2 += row[3 * j + 6]; f3 += row[3 * j + 9]; }
+                        for (; j < n; j++) f0 += row[3 * j];
+                        double f = (f0 + f1) + (f2 + f3);
+                        const unsigned short *be = sm.bent + REP_BENT * k;
+                        const int ne = sm.bn[k];
+                        for (int e = 0; e < ne; e++) {
+                            const unsigned w = be[e];
+                            const double t = sm.bf[3 * (w & 0x7FFF) + comp];
+                            f += (w & 0x8000) ? -t : t;
+                        }
+                        // dual constant-force tweezers (src/force_tweezers.F90:27-35): +f on the first bead of a pair, -f on the second
+                        for (int t = 0; t < P.ntwz_DCF; t++) {
+                            const double ft = twz_force * S.twz_dir[3 * t + comp];
+                            if (S.twz_pairs[2 * t] == k) f += ft;
+                            if (S.twz_pairs[2 * t + 1] == k) f -= ft;
+                        }
+                        sm.fsum[it] = f;
+                    }
+                } else {                                // combine (last: it needs the roles)
+                    ttype = 2;
+                    while (*(volatile int *)&sm.ctl[RC_ROLES] < cang + cdih) { }
+                    __threadfence_block();
+                    const int a = 32 * (ch - cbp - cstat - cG - cA) + lane;
+                    if (a < nar) rep_bp_combine(P, sm, a, true, !mc, mc);
+                }
+                if (tprof) {
+                    __syncwarp();
+                    if (lane == 0) { atomicAdd(S.prof + 16 + 8 * 1000 + 2 * ttype, (unsigned long long)(clock64() - tq0)); atomicAdd(S.prof + 16 + 8 * 1000 + 2 * ttype + 1, 1ull); }
                 }
             }
         }
@@ -794,33 +861,12 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
             const int comp = tid & 3;
             double mv = 0.0;
             if (k < n && comp < 3) {
-                // the row of pair forces on bead k (zeros where there is no pair)
-                double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
-                {
-                    const double *row = sm.Fp + 3 * k * n + comp;
-                    int j = 0;
-                    for (; j + 3 < n; j += 4) { f0 += row[3 * j]; f1 += row[3 * j + 3]; f2 += row[3 * j + 6]; f3 += row[3 * j + 9]; }
-                    for (; j < n; j++) f0 += row[3 * j];
-                }
-                double f = (f0 + f1) + (f2 + f3);
-                const unsigned short *be = sm.bent + REP_BENT * k;
-                const int ne = sm.bn[k];
-                for (int e = 0; e < ne; e++) {
-                    const unsigned w = be[e];
-                    const double t = sm.bf[3 * (w & 0x7FFF) + comp];
-                    f += (w & 0x8000) ? -t : t;
-                }
-                // dual constant-force tweezers (src/force_tweezers.F90:27-35): +f on the first bead of a pair, -f on the second
-                for (int t = 0; t < P.ntwz_DCF; t++) {
-                    const double ft = twz_force * S.twz_dir[3 * t + comp];
-                    if (S.twz_pairs[2 * t] == k) f += ft;
-                    if (S.twz_pairs[2 * t + 1] == k) f -= ft;
-                }
+                double f = sm.fsum[3 * k + comp];
                 const int nb = min(sm.bcnt[k], REP_BPL);
                 for (int s = 0; s < nb; s++) f += sm.bpF[3 * sm.blst[REP_BPL * k + s] + comp];
                 const double fo = sm.fbp[3 * k + comp];      // base pairs beyond the slot tables
                 if (fo != 0.0) { f += fo; sm.fbp[3 * k + comp] = 0.0; }
-                const double gz = sm.g[3 * k + comp], noise = sm.nz0[k] * noise_T;
+                const double gz = sm.g[3 * n * (int)(istep & 1ull) + 3 * k + comp], noise = sm.nz0[k] * noise_T;
                 double dx;
                 if (P.integrator == 1) {
                     const double accels_pre = noise * gz;
@@ -842,7 +888,7 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
             __syncwarp();
             if (k < n && comp == 3) sm.bcnt[k] = 0;
         }
-        if (tid == 0) { sm.ctl[RC_NACT] = 0; sm.ctl[RC_WORK] = 0; sm.ctl[RC_ROLES] = 0; sm.ctl[RC_FAR0 + ((done + 1) & 1)] = 0; }
+        if (tid == 0) { sm.ctl[RC_NACT] = 0; sm.ctl[RC_WORK] = 0; sm.ctl[RC_ROLES] = 0; sm.ctl[RC_STAT] = 0; sm.ctl[RC_FAR0 + ((done + 1) & 1)] = 0; }
         // "is any displacement beyond half the margin": only then the exact top-2 test (flag by step parity)
         if (__any_sync(0xffffffffu, far) && lane == 0) sm.ctl[RC_FAR0 + (done & 1)] = 1;
         if (wprof) { w0 = clock64(); aw[1] += w0 - w1; }

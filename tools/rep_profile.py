@@ -39,7 +39,8 @@ dt = time.perf_counter() - t0
 import ctypes as C
 raw = np.zeros(16)
 g._call("get_timers", raw.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(0))
-p = g.cta_profile(min(n, 1024))
+pall = g.cta_profile(1024)
+p = pall[:min(n, 1000)]
 steps = p[:, 7].mean()
 names = ["P0 gate/mc", "P1 bp", "P1 static", "P2 integrate", "verdict", "exchange", "(xch wait)"]
 print(f"{g.last_step_kernel()} nrep {n} nex {a.nex} mc {a.mc}: {1e6 * dt / a.md_steps:.2f} us/step wall, "
@@ -48,3 +49,6 @@ for i, nm in enumerate(names):
     print(f"  {nm:14s} {p[:, i].mean() / steps:9.0f} cycles/step  (min {p[:, i].min() / steps:.0f}, max {p[:, i].max() / steps:.0f})")
 print(f"  total          {p[:, :6].sum(axis=1).mean() / steps:9.0f} cycles/step")
 print("  block 0:", [round(v / steps) for v in p[0, :6]], " warps 0-3 {B2 wait, P2, B3 wait}:", [round(v / steps) for v in raw[4:16]])
+tq = pall[1000:1002].reshape(-1)
+names = ["bp angle roles", "bp dihedral roles", "bp combine", "gauss", "dihedral", "bond+angle", "pairs (128)", "owner sums"]
+print("  block 0 chunks: " + ", ".join(f"{nm} {tq[2 * i] / max(1, tq[2 * i + 1]):.0f} cyc x {tq[2 * i + 1] / steps:.1f}/step" for i, nm in enumerate(names)))
