@@ -41,7 +41,7 @@ constexpr int REP_MAXB = 64;       // beads per replica
 constexpr int REP_MAXC = 1024;     // base-pair candidates per replica
 constexpr int REP_ACT = 32;        // gate survivors evaluated role by role with slots for their results (beyond: one thread each, atomics)
 constexpr int REP_ROLE = 46;       // doubles one survivor's six roles leave: 4 angles x {u, fi, fk}, 2 dihedrals x {u, fi, fl, ra, rb}
-constexpr int REP_BPL = 8;         // base-pair force slots listed per bead (beyond: shared-memory atomics)
+constexpr int REP_BPL = 16;        // base-pair force slots listed per bead (beyond: shared-memory atomics)
 constexpr int REP_BENT = 9;        // bonded terms a bead takes part in: 2 bonds, 3 angles, 4 dihedrals
 
 // shared-memory carve-up: identical arithmetic on host (size) and device (pointers)
@@ -53,6 +53,7 @@ struct RepSm {
     double *Fp;                                   // [n][n][3]: force on bead k from bead j at (k n + j) 3 (both directions stored; 0 = no pair)
     double *bpF;                                  // [REP_ACT][6][3]
     double *bpR;                                  // [REP_ACT][REP_ROLE]
+    double *eA;                                   // [REP_ACT] pair energy of a survivor, 0 = not formed: the owners' scale factor
     double *c_ene, *c_dG, *c_dH, *c_dS;           // [ccap]
     double *red;                                  // [2 * 16]: two partial sums per warp
     int4 *meta;                                   // [n]
@@ -70,7 +71,7 @@ struct RepSm {
     double *xE;                                   // [4]: own, cross, vscale
     size_t bytes;
 };
-enum { RC_NACT = 0, RC_WORK, RC_NCAND, RC_NEWLAB, RC_NATT, RC_NACC, RC_OVER, RC_FAR0, RC_FAR1, RC_ROLES, RC_STAT };
+enum { RC_NACT = 0, RC_WORK, RC_NCAND, RC_NEWLAB, RC_NATT, RC_NACC, RC_OVER, RC_FAR0, RC_FAR1, RC_ROLES, RC_STAT, RC_SPILL };
 
 SIS_HD RepSm rep_carve(unsigned char *base, int n, int ccap, int nlab)
 {
@@ -91,6 +92,7 @@ SIS_HD RepSm rep_carve(unsigned char *base, int n, int ccap, int nlab)
     s.Fp = (double *)take(8 * 3 * (size_t)n * n, 8);
     s.bpF = (double *)take(8 * 18 * REP_ACT, 8);
     s.bpR = (double *)take(8 * REP_ROLE * REP_ACT, 8);
+    s.eA = (double *)take(8 * REP_ACT, 8);
     s.c_ene = (double *)take(8 * ccap, 8); s.c_dG = (double *)take(8 * ccap, 8);
     s.c_dH = (double *)take(8 * ccap, 8); s.c_dS = (double *)take(8 * ccap, 8);
     s.red = (double *)take(8 * 2 * 16, 8);
@@ -109,6 +111,12 @@ SIS_HD RepSm rep_carve(unsigned char *base, int n, int ccap, int nlab)
 }
 
 #ifdef __CUDACC__
+// wait until a shared-memory counter reaches `target` (chunks of the work queue that need earlier chunks complete)
+SIS_D void rep_wait(const int *ctr, int target)
+{
+    while (*(volatile const int *)ctr < target) __nanosleep(32);
+    __threadfence_block();
+}
 // NT == blockDim.x: the plain CTA barrier (the compiler reconverges the warp in front of it)
 template <int NT> SIS_D void rep_sync() { __syncthreads(); }
 
@@ -212,52 +220,52 @@ SIS_D void rep_bp_role_item(const FFParams &P, const RepSm &sm, int a, int role)
         out[7] = ra; out[8] = rb;
     }
 }
-// the six roles of survivor `a` are in: pair energy and status (do_e), the six bead forces into the slot of `a` (do_f);
-// count_excess: the per-nucleotide count of the Monte-Carlo step
-SIS_D void rep_bp_combine(const FFParams &P, const RepSm &sm, int a, bool do_e, bool do_f, bool count_excess)
+// the six roles of survivor `a` are in -- two independent pieces of work:
+// (1) its energy: U0 dG exp(-sum u) (src/force_bp_triplet.F90:200), status, the per-nucleotide count of a Monte-Carlo step;
+//     eA[a] = the factor the owners scale the pair's forces with (0 = not formed)
+SIS_D void rep_bp_energy(const FFParams &P, const RepSm &sm, int a, bool count_excess)
 {
     const int c = sm.act[a];
     unsigned char *b = sm.c_b + 8 * c;
     const BpPara &p = P.bp[(signed char)b[6]];
     const double *r = sm.bpR + REP_ROLE * a;
     const Vec3 v12 = pbc_vec_d(P, rep_x(sm.x, b[0]), rep_x(sm.x, b[1]));
-    const double a12 = sqrt(dot(v12, v12)), d = a12 - p.bond_r;
-    double ene;
-    if (do_e) {
-        const double u = p.bond_k * d * d + ((r[0] + r[7]) + (r[14] + r[21])) + (r[28] + r[37]);
-        ene = P.bp_triplet ? p.U0 * sm.c_dG[c] * exp(-u) : p.U0 * exp(-u);
-        const bool on = ene <= P.bp_cutoff_energy;
-        if (on) { b[7] |= 1; sm.c_ene[c] = ene; } else { b[7] &= ~1; sm.c_ene[c] = 0.0; }
-        if (on && count_excess) { atomicAdd(&sm.excess[b[0]], 1); atomicAdd(&sm.excess[b[1]], 1); }
-    }
-    if (!do_f || !(b[7] & 1)) return;
-    ene = sm.c_ene[c];
+    const double d = sqrt(dot(v12, v12)) - p.bond_r;
+    const double u = p.bond_k * d * d + ((r[0] + r[7]) + (r[14] + r[21])) + (r[28] + r[37]);
+    const double ene = P.bp_triplet ? p.U0 * sm.c_dG[c] * exp(-u) : p.U0 * exp(-u);
+    const bool on = ene <= P.bp_cutoff_energy;
+    if (on) { b[7] |= 1; sm.c_ene[c] = ene; } else { b[7] &= ~1; sm.c_ene[c] = 0.0; }
+    sm.eA[a] = on ? ene : 0.0;
+    if (on && count_excess) { atomicAdd(&sm.excess[b[0]], 1); atomicAdd(&sm.excess[b[1]], 1); }
+}
+// (2) the unscaled force on bead t (0..5 = i, j, i-1, j-1, i+1, j+1) of survivor `a` into its slot, listed at the bead
+SIS_D void rep_bp_gather(const FFParams &P, const RepSm &sm, int a, int t)
+{
+    const unsigned char *b = sm.c_b + 8 * sm.act[a];
+    const double *r = sm.bpR + REP_ROLE * a;
     auto V = [&](int o) { return mk(r[o], r[o + 1], r[o + 2]); };
-    const Vec3 f0 = (2.0 * p.bond_k * d / a12) * v12;
     // angle roles 1, 3 (vertex i): c0 = -fi - fk, c1 = fk, ca = fi; roles 2, 4 (vertex j): c0 = fi, c1 = -fi - fk, ca = fk
-    // dihedral roles: ca = fi, cb = fl, c1 = (ra - 1) fi - rb fl, c0 = (rb - 1) fl - ra fi
-    const Vec3 fi1 = V(1), fk1 = V(4), fi2 = V(8), fk2 = V(11), fi3 = V(15), fk3 = V(18), fi4 = V(22), fk4 = V(25);
-    const Vec3 di5 = V(29), dl5 = V(32), di6 = V(38), dl6 = V(41);
-    const double ra5 = r[35], rb5 = r[36], ra6 = r[44], rb6 = r[45];
-    Vec3 F[6];
-    F[0] = f0 - (fi1 + fk1) + fi2 - (fi3 + fk3) + fi4 + ((rb5 - 1.0) * dl5 - ra5 * di5) + ((rb6 - 1.0) * dl6 - ra6 * di6);
-    F[1] = -f0 + fk1 - (fi2 + fk2) + fk3 - (fi4 + fk4) + ((ra5 - 1.0) * di5 - rb5 * dl5) + ((ra6 - 1.0) * di6 - rb6 * dl6);
-    F[2] = fi1 + dl5;
-    F[3] = fk2 + di5;
-    F[4] = fi3 + dl6;
-    F[5] = fk4 + di6;
-#pragma unroll
-    for (int t = 0; t < 6; t++) {
-        const int bead = b[t];
-        const int slot = atomicAdd(&sm.bcnt[bead], 1);
-        const Vec3 Ft = ene * F[t];
-        if (slot < REP_BPL) {
-            rep_put(sm.bpF, a * 6 + t, Ft);
-            sm.blst[bead * REP_BPL + slot] = (unsigned short)(a * 6 + t);
-        } else {
-            atomicAdd(&sm.fbp[3 * bead], Ft.x); atomicAdd(&sm.fbp[3 * bead + 1], Ft.y); atomicAdd(&sm.fbp[3 * bead + 2], Ft.z);
-        }
-    }
+    // dihedral roles 5, 6: ca = fi, cb = fl, c1 = (ra - 1) fi - rb fl, c0 = (rb - 1) fl - ra fi
+    // layout: angle role q at 7 (q - 1): {u, fi, fk}; dihedral role q at 28 + 9 (q - 5): {u, fi, fl, ra, rb}
+    Vec3 F;
+    if (t < 2) {
+        const BpPara &p = P.bp[(signed char)b[6]];
+        const Vec3 v12 = pbc_vec_d(P, rep_x(sm.x, b[0]), rep_x(sm.x, b[1]));
+        const double a12 = sqrt(dot(v12, v12));
+        const Vec3 f0 = (2.0 * p.bond_k * (a12 - p.bond_r) / a12) * v12;
+        const Vec3 di5 = V(29), dl5 = V(32), di6 = V(38), dl6 = V(41);
+        const double ra5 = r[35], rb5 = r[36], ra6 = r[44], rb6 = r[45];
+        if (t == 0) F = f0 - (V(1) + V(4)) + V(8) - (V(15) + V(18)) + V(22) + ((rb5 - 1.0) * dl5 - ra5 * di5) + ((rb6 - 1.0) * dl6 - ra6 * di6);
+        else F = -f0 + V(4) - (V(8) + V(11)) + V(18) - (V(22) + V(25)) + ((ra5 - 1.0) * di5 - rb5 * dl5) + ((ra6 - 1.0) * di6 - rb6 * dl6);
+    } else if (t == 2) F = V(1) + V(32);
+    else if (t == 3) F = V(11) + V(29);
+    else if (t == 4) F = V(15) + V(41);
+    else F = V(25) + V(38);
+    const int bead = b[t];
+    const int slot = atomicAdd(&sm.bcnt[bead], 1);
+    rep_put(sm.bpF, a * 6 + t, F);
+    if (slot < REP_BPL) sm.blst[bead * REP_BPL + slot] = (unsigned short)(a * 6 + t);
+    else atomicOr(&sm.ctl[RC_SPILL], 1);      // more pairs at one bead than list slots: the owners scan every survivor
 }
 
 // the distance gate of all candidates (one thread each): survivors -> act[], the others lose bp_status.
@@ -369,9 +377,10 @@ SIS_D void rep_mc_prune(const FFParams &P, const RepSm &sm, int n, int ncand, un
         if (lane == 0 && prof_slot) *prof_slot += (unsigned long long)ndel;
     }
     rep_sync<NT>();
-    for (int a = tid; a < nact; a += NT) {
-        if (a < REP_ACT) rep_bp_combine(P, sm, a, false, true, false);
-        else if (sm.c_b[8 * sm.act[a] + 7] & 1) rep_bp_eval(P, sm, sm.act[a], true);
+    for (int a = tid; a < nact; a += NT) {      // the pairs that stay keep their forces
+        const bool on = sm.c_b[8 * sm.act[a] + 7] & 1;
+        if (a < REP_ACT) { if (!on) sm.eA[a] = 0.0; }
+        else if (on) rep_bp_eval(P, sm, sm.act[a], true);
     }
     for (int c = tid; c < ncand; c += NT) {
         unsigned char *b = sm.c_b + 8 * c;
@@ -382,42 +391,76 @@ SIS_D void rep_mc_prune(const FFParams &P, const RepSm &sm, int n, int ncand, un
 
 // energy_replica (src/energy_replica.F90:45-163) for the CTA's replica on the shared-memory state: total energy
 // with its own parameters (bp energies as cached by the last force evaluation: flg_bp_energy) and with the partner
-// label's parameters (bp term recomputed on the energy side, :72, :121) -> sm.xE[0], sm.xE[1].  One item loop over
-// candidates, bonded terms and pairs, the expensive items first.
+// label's parameters (bp term recomputed on the energy side, :72, :121) -> sm.xE[0], sm.xE[1].
+// The cross base-pair energies follow the force path's shape: distance gate, survivors compacted, one angle or
+// dihedral of one survivor per item (mp_angle / mp_dihedral of src/energy_bp.F90:76-118), then the exponent per survivor.
 template <int NT>
 SIS_D void rep_remd_energies(const DevSys &S, const FFParams &P, const RepSm &sm, int n, int npair, int ncand,
                              const RepParams &Rown, const RepParams &Ralt, bool has_opp)
 {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const bool dih_on = P.flg_dih_cos || P.flg_dih_exp;
+    const double tK_alt = P.temp_independent ? 0.0 : Ralt.tempK;     // src/energy_bp_triplet.F90:27-31
     double eo = 0.0, ea = 0.0;
-    for (int it = tid; it < ncand + 3 * n + npair; it += NT) {
-        if (it < ncand) {
-            const int c = it;
+    // gate with the partner's dG (k_bp_eval<1>); own bp energy = the cached one
+    for (int c0 = 0; c0 < ncand; c0 += NT) {
+        const int c = c0 + tid;
+        bool pass = false;
+        if (c < ncand) {
             const unsigned char *b = sm.c_b + 8 * c;
             if (b[7] & 1) eo += sm.c_ene[c];
-            if (has_opp) {                              // k_bp_eval<1> with the partner temperature
-                const int type = (signed char)b[6];
-                double dG = 1.0;
-                bool active = true;
-                if (P.bp_triplet) {
-                    const double tK = P.temp_independent ? 0.0 : Ralt.tempK;   // src/energy_bp_triplet.F90:27-31
-                    dG = sm.c_dH[c] - tK * sm.c_dS[c];
-                    if (dG >= 0.0) active = false;
-                }
-                if (active) {
-                    Vec3 xs[6];
-#pragma unroll
-                    for (int t = 0; t < 6; t++) xs[t] = rep_x(sm.x, b[t]);
-                    double u;
-                    if (bp_energy_u(P, P.bp[type], xs, &u)) {
-                        const double ene = P.bp_triplet ? P.bp[type].U0 * dG * exp(-u) : P.bp[type].U0 * exp(-u);
-                        if (ene <= P.bp_cutoff_energy) ea += ene;
-                    }
-                }
+            if (has_opp && (!P.bp_triplet || sm.c_dH[c] - tK_alt * sm.c_dS[c] < 0.0)) {
+                const BpPara &p = P.bp[(signed char)b[6]];
+                const Vec3 v = pbc_vec_d(P, rep_x(sm.x, b[0]), rep_x(sm.x, b[1]));
+                pass = fabs(sqrt(dot(v, v)) - p.bond_r) <= p.cutoff_ddist;
             }
-        } else if (it < ncand + 3 * n) {
-            const int t = it - ncand, span = 3 - t / n, k = t % n;       // dihedrals first
+        }
+        const unsigned mb = __ballot_sync(0xffffffffu, pass);
+        if (mb) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&sm.ctl[RC_NACT], __popc(mb));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) sm.act[base + __popc(mb & ((1u << lane) - 1u))] = c;
+        }
+    }
+    rep_sync<NT>();
+    const int nact = sm.ctl[RC_NACT], nar = min(nact, REP_ACT);
+    double *uR = sm.bpR;        // [nar][6]: free between two force evaluations
+    for (int it = tid; it < 6 * nar + (nact - nar) + 3 * n + npair; it += NT) {
+        if (it < 6 * nar) {
+            const int a = it / 6, r = it - 6 * a;
+            const unsigned char *b = sm.c_b + 8 * sm.act[a];
+            const BpPara &p = P.bp[(signed char)b[6]];
+            const Vec3 x0 = rep_x(sm.x, b[0]), x1 = rep_x(sm.x, b[1]);
+            double u;
+            if (r < 4) {
+                // angles 1=2-4, 3-1=2, 1=2-6, 5-1=2 in the order of bp_energy_u
+                const double t = r == 0 ? mp_angle(P, x0, x1, rep_x(sm.x, b[3])) : r == 1 ? mp_angle(P, rep_x(sm.x, b[2]), x0, x1)
+                               : r == 2 ? mp_angle(P, x0, x1, rep_x(sm.x, b[5])) : mp_angle(P, rep_x(sm.x, b[4]), x0, x1);
+                const double k = r == 0 ? p.angl_k1 : r == 1 ? p.angl_k2 : r == 2 ? p.angl_k3 : p.angl_k4;
+                const double th = r == 0 ? p.angl_theta1 : r == 1 ? p.angl_theta2 : r == 2 ? p.angl_theta3 : p.angl_theta4;
+                u = k * (t - th) * (t - th);
+            } else {
+                const double t = r == 4 ? mp_dihedral(P, rep_x(sm.x, b[2]), x0, x1, rep_x(sm.x, b[3]))
+                                        : mp_dihedral(P, rep_x(sm.x, b[4]), x0, x1, rep_x(sm.x, b[5]));
+                u = r == 4 ? p.dihd_k1 * (1.0 + cos(t + p.dihd_phi1)) : p.dihd_k2 * (1.0 + cos(t + p.dihd_phi2));
+            }
+            uR[it] = u;
+        } else if (it < 6 * nar + (nact - nar)) {       // survivors beyond the slots: one thread each
+            const int c = sm.act[REP_ACT + it - 6 * nar];
+            const unsigned char *b = sm.c_b + 8 * c;
+            const int type = (signed char)b[6];
+            Vec3 xs[6];
+#pragma unroll
+            for (int t = 0; t < 6; t++) xs[t] = rep_x(sm.x, b[t]);
+            double u;
+            if (bp_energy_u(P, P.bp[type], xs, &u)) {
+                const double dG = P.bp_triplet ? sm.c_dH[c] - tK_alt * sm.c_dS[c] : 1.0;
+                const double ene = P.bp_triplet ? P.bp[type].U0 * dG * exp(-u) : P.bp[type].U0 * exp(-u);
+                if (ene <= P.bp_cutoff_energy) ea += ene;
+            }
+        } else if (it < 6 * nar + (nact - nar) + 3 * n) {
+            const int t = it - 6 * nar - (nact - nar), span = 3 - t / n, k = t % n;       // dihedrals first
             const int4 m = sm.meta[k];
             if (!rep_term(m, span) || (span == 3 && !dih_on)) continue;
             const Vec3 x0 = rep_x(sm.x, k), x1 = rep_x(sm.x, chain_nb(m, 1));
@@ -427,7 +470,7 @@ SIS_D void rep_remd_energies(const DevSys &S, const FFParams &P, const RepSm &sm
             else w = dih_energy(P, x0, x1, rep_x(sm.x, chain_nb(m, 2)), rep_x(sm.x, chain_nb(m, 3)));
             eo += w; ea += w;
         } else {
-            const uint32_t e = sm.pl[it - ncand - 3 * n];
+            const uint32_t e = sm.pl[it - 6 * nar - (nact - nar) - 3 * n];
             if (!e) continue;
             const Vec3 v = pbc_vec_d(P, rep_x(sm.x, e & 0xFF), rep_x(sm.x, (e >> 8) & 0xFF));
             const double d2 = dot(v, v);
@@ -441,15 +484,29 @@ SIS_D void rep_remd_energies(const DevSys &S, const FFParams &P, const RepSm &sm
             const double proj = v.x * S.twz_dir[3 * t] + v.y * S.twz_dir[3 * t + 1] + v.z * S.twz_dir[3 * t + 2];
             eo -= Rown.twz_force * proj; ea -= Ralt.twz_force * proj;
         }
+    rep_sync<NT>();
+    for (int a = tid; a < nar; a += NT) {               // exponent and energy of a survivor
+        const int c = sm.act[a];
+        const unsigned char *b = sm.c_b + 8 * c;
+        const BpPara &p = P.bp[(signed char)b[6]];
+        const Vec3 v = pbc_vec_d(P, rep_x(sm.x, b[0]), rep_x(sm.x, b[1]));
+        const double d = sqrt(dot(v, v)) - p.bond_r;
+        const double *ur = uR + 6 * a;
+        const double u = p.bond_k * d * d + ur[0] + ur[1] + ur[2] + ur[3] + ur[4] + ur[5];     // the order of bp_energy_u
+        const double dG = P.bp_triplet ? sm.c_dH[c] - tK_alt * sm.c_dS[c] : 1.0;
+        const double ene = P.bp_triplet ? p.U0 * dG * exp(-u) : p.U0 * exp(-u);
+        if (ene <= P.bp_cutoff_energy) ea += ene;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { eo += __shfl_xor_sync(0xffffffffu, eo, o); ea += __shfl_xor_sync(0xffffffffu, ea, o); }
-    if ((tid & 31) == 0) { sm.red[2 * (tid >> 5)] = eo; sm.red[2 * (tid >> 5) + 1] = ea; }
+    if (lane == 0) { sm.red[2 * (tid >> 5)] = eo; sm.red[2 * (tid >> 5) + 1] = ea; }
     rep_sync<NT>();
     if (tid == 0) {
         double so = 0.0, sa = 0.0;
         for (int w = 0; w < NT / 32; w++) { so += sm.red[2 * w]; sa += sm.red[2 * w + 1]; }
         sm.xE[0] = so;
         sm.xE[1] = has_opp ? sa : 0.0;
+        sm.ctl[RC_NACT] = 0;
     }
     rep_sync<NT>();
 }
@@ -496,16 +553,19 @@ SIS_D void rep_remd_exchange(const DevSys &S, const FFParams &P, const RepSm &sm
         sm.ctl[RC_NEWLAB] = label_own; sm.xE[2] = 1.0; sm.ctl[RC_NATT] = 0; sm.ctl[RC_NACC] = 0;
     }
     rep_sync<NT>();
-    if (tid < 32) {     // replay of the decisions: one lane per label; pair k in label order uses uniform k
+    {   // replay of the decisions: one lane per label, the blocks of 32 labels on the warps side by side (the pairs are
+        // disjoint); pair k in label order uses uniform k
         const int *tb = D.pair_tb + (size_t)(X.idx_pair - 1) * nl;
-        int base = 0;
-        for (int l0 = 0; l0 < nl; l0 += 32) {
-            const int l = l0 + tid;
+        const int lane = tid & 31;
+        for (int l0 = 32 * (tid >> 5); l0 < nl; l0 += NT) {
+            int base = 0;
+            for (int b0 = 0; b0 < l0; b0 += 32) base += __popc(__ballot_sync(0xffffffffu, tb[b0 + lane] >= b0 + lane + 1));
+            const int l = l0 + lane;
             const int l_j = l < nl ? tb[l] : 0;
             const bool is_pair = l < nl && l_j >= l + 1;
             const unsigned m = __ballot_sync(0xffffffffu, is_pair);
             if (is_pair) {
-                const int nrand = base + __popc(m & ((1u << tid) - 1u));
+                const int nrand = base + __popc(m & ((1u << lane) - 1u));
                 const int l_i = l + 1;
                 const double rnd = uniform_counter(D.seed, 0x7fffffffu, X.counter + (unsigned long long)nrand);
                 const int rep_i = sm.l2r[l_i - 1], rep_j = sm.l2r[l_j - 1];
@@ -525,7 +585,6 @@ SIS_D void rep_remd_exchange(const DevSys &S, const FFParams &P, const RepSm &sm
                     if (rep_j - 1 == grep) { sm.ctl[RC_NEWLAB] = l_i; sm.xE[2] = 1.0 / sf; }
                 }
             }
-            base += __popc(m);
         }
     }
     rep_sync<NT>();
@@ -716,6 +775,7 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
         const bool mc = use_mc && ((istep % (unsigned long long)P.nstep_bp_MC == 0ull) || after_rebuild);
         after_rebuild = false;
         if (mc) for (int i = tid; i < n; i += NT) sm.excess[i] = -A.max_bp_per_nt;
+        if (tid == 0) sm.ctl[RC_SPILL] = 0;
         rep_bp_gate<NT>(P, sm, ncand, use_mc && !mc);
         const RepParams &Rp = *sm.rp;
         const double ele_coef = Rp.ele_coef, inv_lambdaD = Rp.inv_lambdaD;
@@ -724,11 +784,12 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
         rep_sync<NT>();
         if (prof) c1 = clock64();
         // ---- P1: every warp draws chunks from the shared counter ----------------------------------------------
+        const int nact = sm.ctl[RC_NACT];
+        const int nar = min(nact, REP_ACT);
         {
-            const int nact = sm.ctl[RC_NACT];
-            const int nar = min(nact, REP_ACT);
             // chunks: angle roles, dihedral roles, survivors beyond the role slots, static work, pairs, combine (last: it needs the roles)
-            const int cang = (4 * nar + 31) >> 5, cdih = (2 * nar + 31) >> 5, cov = (nact - nar + 31) >> 5, ccomb = (nar + 31) >> 5;
+            const int cang = (4 * nar + 31) >> 5, cdih = (2 * nar + 31) >> 5, cov = (nact - nar + 31) >> 5;
+            const int cene = (nar + 31) >> 5, cgat = ((NT >= 512 ? 6 : 1) * nar + 31) >> 5, ccomb = cene + cgat;
             const int cbp = cang + cdih + cov;
             bool first = true;
             for (;;) {
@@ -809,11 +870,21 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
                         double *gn = sm.g + 3 * n * (int)((istep + 1ull) & 1ull);
                         if (draw == 0) { gn[3 * k] = g0; gn[3 * k + 1] = g1; } else gn[3 * k + 2] = g0;
                     }
-                } else if (ch < cbp + cstat + cG + cA) {   // owners' sums: pair row, bonded terms, tweezers
+                } else if (ch < cbp + cstat + cG + ccomb) {   // energies, per-bead forces of the survivors (they need the roles)
+                    ttype = 2;
+                    rep_wait(&sm.ctl[RC_ROLES], cang + cdih);
+                    const int cc = ch - cbp - cstat - cG;
+                    if (cc < cene) { const int a = 32 * cc + lane; if (a < nar) rep_bp_energy(P, sm, a, mc); }
+                    else if (NT >= 512) { const int it = 32 * (cc - cene) + lane; if (it < 6 * nar) rep_bp_gather(P, sm, it / 6, it % 6); }
+                    else {
+                        const int a = 32 * (cc - cene) + lane;
+                        if (a < nar)
+                            for (int t = 0; t < 6; t++) rep_bp_gather(P, sm, a, t);
+                    }
+                } else {                                // owners' sums: pair row, bonded terms, tweezers (last: they need the pairs)
                     ttype = 7;
-                    while (*(volatile int *)&sm.ctl[RC_STAT] < cstat) { }
-                    __threadfence_block();
-                    const int it = 32 * (ch - cbp - cstat - cG) + lane;
+                    rep_wait(&sm.ctl[RC_STAT], cstat);
+                    const int it = 32 * (ch - cbp - cstat - cG - ccomb) + lane;
                     if (it < 3 * n) {
                         const int k = it / 3, comp = it - 3 * k;
                         double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
@@ -837,12 +908,6 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
                         }
                         sm.fsum[it] = f;
                     }
-                } else {                                // combine (last: it needs the roles)
-                    ttype = 2;
-                    while (*(volatile int *)&sm.ctl[RC_ROLES] < cang + cdih) { }
-                    __threadfence_block();
-                    const int a = 32 * (ch - cbp - cstat - cG - cA) + lane;
-                    if (a < nar) rep_bp_combine(P, sm, a, true, !mc, mc);
                 }
                 if (tprof) {
                     __syncwarp();
@@ -856,14 +921,24 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
         if (prof) c3 = clock64();
         // ---- P2: assemble and integrate (src/job_md.F90:409-456) ------------------------------------------------
         bool far = false;
+        const bool spill = sm.ctl[RC_SPILL] != 0;
         if (wprof) { w1 = clock64(); aw[0] += w1 - w0; }
         for (int k = tid >> 2; k < ((n + NT / 4 - 1) / (NT / 4)) * (NT / 4); k += NT / 4) {
             const int comp = tid & 3;
             double mv = 0.0;
             if (k < n && comp < 3) {
                 double f = sm.fsum[3 * k + comp];
-                const int nb = min(sm.bcnt[k], REP_BPL);
-                for (int s = 0; s < nb; s++) f += sm.bpF[3 * sm.blst[REP_BPL * k + s] + comp];
+                const int nb = sm.bcnt[k];
+                if (!spill) {
+                    for (int s = 0; s < nb; s++) { const int w = sm.blst[REP_BPL * k + s]; f += sm.eA[w / 6] * sm.bpF[3 * w + comp]; }
+                } else if (nb) {
+                    for (int a = 0; a < nar; a++) {
+                        const unsigned char *b = sm.c_b + 8 * sm.act[a];
+#pragma unroll
+                        for (int t = 0; t < 6; t++)
+                            if (b[t] == k) f += sm.eA[a] * sm.bpF[3 * (6 * a + t) + comp];
+                    }
+                }
                 const double fo = sm.fbp[3 * k + comp];      // base pairs beyond the slot tables
                 if (fo != 0.0) { f += fo; sm.fbp[3 * k + comp] = 0.0; }
                 const double gz = sm.g[3 * n * (int)(istep & 1ull) + 3 * k + comp], noise = sm.nz0[k] * noise_T;
