@@ -40,7 +40,7 @@
 constexpr int REP_MAXB = 64;       // beads per replica
 constexpr int REP_MAXC = 1024;     // base-pair candidates per replica
 constexpr int REP_ACT = 32;        // gate survivors evaluated role by role with slots for their results (beyond: one thread each, atomics)
-constexpr int REP_ROLE = 46;       // doubles one survivor's six roles leave: 4 angles x {u, fi, fk}, 2 dihedrals x {u, fi, fl, ra, rb}
+constexpr int REP_ROLE = 50;       // doubles one survivor's seven roles leave: 4 angles x {u, fi, fk}, 2 dihedrals x {u, fi, fl, ra, rb}, bond {u, fi}
 constexpr int REP_BPL = 16;        // base-pair force slots listed per bead (beyond: shared-memory atomics)
 constexpr int REP_BENT = 9;        // bonded terms a bead takes part in: 2 bonds, 3 angles, 4 dihedrals
 
@@ -50,7 +50,7 @@ struct RepSm {
     double *g;                                    // [2][3 n] Gaussians by step parity
     double *ca, *cb, *cc, *nz0, *d2;              // [n]
     double *bf;                                   // [8 n][3]  bond k | angle n + 3 k + p | dihedral 4 n + 4 k + p
-    double *Fp;                                   // [n][n][3]: force on bead k from bead j at (k n + j) 3 (both directions stored; 0 = no pair)
+    double *Fp;                                   // [n][3][npad]: component c of the force on bead k from bead j at (3 k + c) npad + j (both directions stored; 0 = no pair)
     double *bpF;                                  // [REP_ACT][6][3]
     double *bpR;                                  // [REP_ACT][REP_ROLE]
     double *eA;                                   // [REP_ACT] pair energy of a survivor, 0 = not formed: the owners' scale factor
@@ -71,7 +71,7 @@ struct RepSm {
     double *xE;                                   // [4]: own, cross, vscale
     size_t bytes;
 };
-enum { RC_NACT = 0, RC_WORK, RC_NCAND, RC_NEWLAB, RC_NATT, RC_NACC, RC_OVER, RC_FAR0, RC_FAR1, RC_ROLES, RC_STAT, RC_SPILL };
+enum { RC_NACT = 0, RC_WORK, RC_NCAND, RC_NEWLAB, RC_NATT, RC_NACC, RC_OVER, RC_FAR0, RC_FAR1, RC_ROLES, RC_STAT, RC_SPILL0, RC_SPILL1, RC_GATE };
 
 SIS_HD RepSm rep_carve(unsigned char *base, int n, int ccap, int nlab)
 {
@@ -89,7 +89,7 @@ SIS_HD RepSm rep_carve(unsigned char *base, int n, int ccap, int nlab)
     s.ca = (double *)take(8 * n, 8); s.cb = (double *)take(8 * n, 8); s.cc = (double *)take(8 * n, 8);
     s.nz0 = (double *)take(8 * n, 8); s.d2 = (double *)take(8 * REP_MAXB, 8);
     s.bf = (double *)take(8 * 3 * 8 * (size_t)n, 8);
-    s.Fp = (double *)take(8 * 3 * (size_t)n * n, 8);
+    s.Fp = (double *)take(8 * 3 * (size_t)n * ((n + 1) & ~1), 16);
     s.bpF = (double *)take(8 * 18 * REP_ACT, 8);
     s.bpR = (double *)take(8 * REP_ROLE * REP_ACT, 8);
     s.eA = (double *)take(8 * REP_ACT, 8);
@@ -179,22 +179,28 @@ SIS_D void rep_bp_role_item(const FFParams &P, const RepSm &sm, int a, int role)
     const Vec3 v12 = pbc_vec_d(P, x0, x1);
     const double d1212 = dot(v12, v12);
     double *out = sm.bpR + REP_ROLE * a;
-    if (role <= 4) {
-        // angle between v12 and w; odd roles: w = x0 - xa (vertex i), even roles: w = xa - x1 (vertex j)
-        const double a12 = sqrt(d1212);
+    if (role == 0) {
+        // bond 1=2: u and the force vector fi (+fi on bead i, -fi on bead j)
+        const double a12 = sqrt(d1212), d = a12 - p.bond_r;
+        const Vec3 fi = (2.0 * p.bond_k * d / a12) * v12;
+        out[46] = p.bond_k * d * d;
+        out[47] = fi.x; out[48] = fi.y; out[49] = fi.z;
+    } else if (role <= 4) {
+        // angle between v12 and w; odd roles: w = x0 - xa (vertex i), even roles: w = xa - x1 (vertex j).
+        // cos = (v12 . w) / (|v12| |w|) and the 1 / sin factor through one reciprocal square root each
         const bool at_i = role & 1;
         const Vec3 xa = rep_x(sm.x, b[role + 1]);
         const Vec3 w = at_i ? pbc_vec_d(P, x0, xa) : pbc_vec_d(P, xa, x1);
         const double k = role == 1 ? p.angl_k2 : role == 2 ? p.angl_k1 : role == 3 ? p.angl_k4 : p.angl_k3;
         const double th = role == 1 ? p.angl_theta2 : role == 2 ? p.angl_theta1 : role == 3 ? p.angl_theta4 : p.angl_theta3;
-        const double dww = dot(w, w), d12w = dot(v12, w);
-        const double cosine = d12w / (sqrt(dww) * a12);
+        const double dww = dot(w, w), d12w = dot(v12, w), dd = dww * d1212;
+        const double cosine = d12w * rsqrt(dd);
         const double d = acos(cosine) - th;
-        const double pre = 2.0 * k * d / sqrt(dww * d1212 - d12w * d12w);
-        const double r12w = d12w / d1212;
+        const double pre = 2.0 * k * d * rsqrt(dd - d12w * d12w);
+        const double r12w = d12w / d1212, rww = d12w / dww;
         Vec3 fi, fk;
-        if (at_i) { fi = pre * (v12 - (d12w / dww) * w); fk = pre * (w - r12w * v12); }
-        else { fi = (-pre) * (w - r12w * v12); fk = (-pre) * (v12 - (d12w / dww) * w); }
+        if (at_i) { fi = pre * (v12 - rww * w); fk = pre * (w - r12w * v12); }
+        else { fi = (-pre) * (w - r12w * v12); fk = (-pre) * (v12 - rww * w); }
         out += 7 * (role - 1);
         out[0] = k * d * d;
         out[1] = fi.x; out[2] = fi.y; out[3] = fi.z; out[4] = fk.x; out[5] = fk.y; out[6] = fk.z;
@@ -204,7 +210,7 @@ SIS_D void rep_bp_role_item(const FFParams &P, const RepSm &sm, int a, int role)
         const Vec3 va2 = pbc_vec_d(P, xa, x1), v1b = pbc_vec_d(P, x0, xb);
         const double ra = dot(v12, va2) / d1212, rb = dot(v12, v1b) / d1212;
         const Vec3 m = cross(va2, v12), n = cross(v12, v1b);
-        // cos(phi + phi0), sin(phi + phi0) from (X, Y) / |(X, Y)|, phi = atan2(Y, X); |v12| X, |v12|^2 ... as bp_force_role
+        // cos(phi + phi0), sin(phi + phi0) from (X, Y) / |(X, Y)|, phi = atan2(Y, X), as bp_force_role
         const double a12 = sqrt(d1212);
         const double Y = dot(va2, n) * a12, X = dot(m, n);
         const double kk = role == 5 ? p.dihd_k1 : p.dihd_k2;
@@ -229,9 +235,7 @@ SIS_D void rep_bp_energy(const FFParams &P, const RepSm &sm, int a, bool count_e
     unsigned char *b = sm.c_b + 8 * c;
     const BpPara &p = P.bp[(signed char)b[6]];
     const double *r = sm.bpR + REP_ROLE * a;
-    const Vec3 v12 = pbc_vec_d(P, rep_x(sm.x, b[0]), rep_x(sm.x, b[1]));
-    const double d = sqrt(dot(v12, v12)) - p.bond_r;
-    const double u = p.bond_k * d * d + ((r[0] + r[7]) + (r[14] + r[21])) + (r[28] + r[37]);
+    const double u = r[46] + ((r[0] + r[7]) + (r[14] + r[21])) + (r[28] + r[37]);
     const double ene = P.bp_triplet ? p.U0 * sm.c_dG[c] * exp(-u) : p.U0 * exp(-u);
     const bool on = ene <= P.bp_cutoff_energy;
     if (on) { b[7] |= 1; sm.c_ene[c] = ene; } else { b[7] &= ~1; sm.c_ene[c] = 0.0; }
@@ -239,7 +243,7 @@ SIS_D void rep_bp_energy(const FFParams &P, const RepSm &sm, int a, bool count_e
     if (on && count_excess) { atomicAdd(&sm.excess[b[0]], 1); atomicAdd(&sm.excess[b[1]], 1); }
 }
 // (2) the unscaled force on bead t (0..5 = i, j, i-1, j-1, i+1, j+1) of survivor `a` into its slot, listed at the bead
-SIS_D void rep_bp_gather(const FFParams &P, const RepSm &sm, int a, int t)
+SIS_D void rep_bp_gather(const FFParams &P, const RepSm &sm, int a, int t, int spill_slot)
 {
     const unsigned char *b = sm.c_b + 8 * sm.act[a];
     const double *r = sm.bpR + REP_ROLE * a;
@@ -249,10 +253,7 @@ SIS_D void rep_bp_gather(const FFParams &P, const RepSm &sm, int a, int t)
     // layout: angle role q at 7 (q - 1): {u, fi, fk}; dihedral role q at 28 + 9 (q - 5): {u, fi, fl, ra, rb}
     Vec3 F;
     if (t < 2) {
-        const BpPara &p = P.bp[(signed char)b[6]];
-        const Vec3 v12 = pbc_vec_d(P, rep_x(sm.x, b[0]), rep_x(sm.x, b[1]));
-        const double a12 = sqrt(dot(v12, v12));
-        const Vec3 f0 = (2.0 * p.bond_k * (a12 - p.bond_r) / a12) * v12;
+        const Vec3 f0 = V(47);
         const Vec3 di5 = V(29), dl5 = V(32), di6 = V(38), dl6 = V(41);
         const double ra5 = r[35], rb5 = r[36], ra6 = r[44], rb6 = r[45];
         if (t == 0) F = f0 - (V(1) + V(4)) + V(8) - (V(15) + V(18)) + V(22) + ((rb5 - 1.0) * dl5 - ra5 * di5) + ((rb6 - 1.0) * dl6 - ra6 * di6);
@@ -265,36 +266,32 @@ SIS_D void rep_bp_gather(const FFParams &P, const RepSm &sm, int a, int t)
     const int slot = atomicAdd(&sm.bcnt[bead], 1);
     rep_put(sm.bpF, a * 6 + t, F);
     if (slot < REP_BPL) sm.blst[bead * REP_BPL + slot] = (unsigned short)(a * 6 + t);
-    else atomicOr(&sm.ctl[RC_SPILL], 1);      // more pairs at one bead than list slots: the owners scan every survivor
+    else atomicOr(&sm.ctl[spill_slot], 1);      // more pairs at one bead than list slots: the owners scan every survivor
 }
 
-// the distance gate of all candidates (one thread each): survivors -> act[], the others lose bp_status.
+// the distance gate of 32 candidates (one lane each): survivors -> act[], the others lose bp_status.
 // |r - r0| <= cutoff_ddist (src/force_bp.F90:64) tested on r^2.  use_mask: only pairs with bp_status_MC
-template <int NT>
-SIS_D void rep_bp_gate(const FFParams &P, const RepSm &sm, int ncand, bool use_mask)
+SIS_D void rep_bp_gate_warp(const FFParams &P, const RepSm &sm, int c, int ncand, bool use_mask)
 {
     const int lane = threadIdx.x & 31;
-    for (int c0 = 0; c0 < ncand; c0 += NT) {
-        const int c = c0 + threadIdx.x;
-        bool pass = false;
-        if (c < ncand) {
-            unsigned char *b = sm.c_b + 8 * c;
-            const int type = (signed char)b[6];
-            if ((!use_mask || (b[7] & 2)) && (!P.bp_triplet || sm.c_dG[c] < 0.0)) {
-                const Vec3 v12 = pbc_vec_d(P, rep_x(sm.x, b[0]), rep_x(sm.x, b[1]));
-                const double d2 = dot(v12, v12), r0 = P.bp[type].bond_r, dc = P.bp[type].cutoff_ddist;
-                const double lo = fmax(r0 - dc, 0.0), hi = r0 + dc;
-                pass = d2 >= lo * lo && d2 <= hi * hi;
-            }
-            if (!pass) { b[7] &= ~1; sm.c_ene[c] = 0.0; }
+    bool pass = false;
+    if (c < ncand) {
+        unsigned char *b = sm.c_b + 8 * c;
+        const int type = (signed char)b[6];
+        if ((!use_mask || (b[7] & 2)) && (!P.bp_triplet || sm.c_dG[c] < 0.0)) {
+            const Vec3 v12 = pbc_vec_d(P, rep_x(sm.x, b[0]), rep_x(sm.x, b[1]));
+            const double d2 = dot(v12, v12), r0 = P.bp[type].bond_r, dc = P.bp[type].cutoff_ddist;
+            const double lo = fmax(r0 - dc, 0.0), hi = r0 + dc;
+            pass = d2 >= lo * lo && d2 <= hi * hi;
         }
-        const unsigned mb = __ballot_sync(0xffffffffu, pass);
-        if (mb) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&sm.ctl[RC_NACT], __popc(mb));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (pass) sm.act[base + __popc(mb & ((1u << lane) - 1u))] = c;
-        }
+        if (!pass) { b[7] &= ~1; sm.c_ene[c] = 0.0; }
+    }
+    const unsigned mb = __ballot_sync(0xffffffffu, pass);
+    if (mb) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&sm.ctl[RC_NACT], __popc(mb));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pass) sm.act[base + __popc(mb & ((1u << lane) - 1u))] = c;
     }
 }
 
@@ -304,7 +301,7 @@ SIS_D void rep_bp_gate(const FFParams &P, const RepSm &sm, int ncand, bool use_m
 // partner order = table order; the uniforms of one deletion are drawn side by side, one per lane); then the forces of
 // the pairs that stay, and bp_status_MC = bp_status (src/job_md.F90:399-401)
 template <int NT>
-SIS_D void rep_mc_prune(const FFParams &P, const RepSm &sm, int n, int ncand, unsigned long long seed, unsigned long long *mc_ctr,
+SIS_D void rep_mc_prune(const FFParams &P, const RepSm &sm, int n, int ncand, unsigned long long seed, int max_bp_per_nt, unsigned long long *mc_ctr,
                          unsigned long long *prof_slot)
 {
     const int tid = threadIdx.x, lane = tid & 31;
@@ -386,6 +383,7 @@ SIS_D void rep_mc_prune(const FFParams &P, const RepSm &sm, int n, int ncand, un
         unsigned char *b = sm.c_b + 8 * c;
         b[7] = (unsigned char)((b[7] & 1) * 3);
     }
+    for (int i = tid; i < n; i += NT) sm.excess[i] = -max_bp_per_nt;     // for the next Monte-Carlo step
     rep_sync<NT>();
 }
 
@@ -528,7 +526,11 @@ SIS_D void rep_remd_exchange(const DevSys &S, const FFParams &P, const RepSm &sm
     const RepParams Rown = *sm.rp;
     RepParams Ralt = Rown;
     if (has_opp) remd_apply_label(D, Ralt, D.lab_rp[label_opp - 1]);
+    const bool xprof = S.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    unsigned long long *xp = S.prof + 16 + 8 * 1003;
+    long long x0 = xprof ? clock64() : 0, x1;
     rep_remd_energies<NT>(S, P, sm, n, npair, ncand, Rown, Ralt, has_opp);
+    if (xprof) { x1 = clock64(); xp[0] += (unsigned long long)(x1 - x0); x0 = x1; }
     const unsigned long long round = D.xch_round0 + (unsigned long long)X.attempt;
     const size_t eoff = (size_t)(round & 1ull) * 2 * nl;
     const double *E = D.xE_peer[D.rank] + eoff;
@@ -547,10 +549,12 @@ SIS_D void rep_remd_exchange(const DevSys &S, const FFParams &P, const RepSm &sm
         }
         const unsigned long long target = (round + 1ull) * (unsigned long long)nl;     // one CTA per replica on the whole node
         const long long t0 = clock64();
+        if (xprof) { xp[1] += (unsigned long long)(t0 - x0); }
         while (ld_acquire_sys_u64(D.xbar_peer[D.rank]) < target)
             if (clock64() - t0 > 8000000000ll) { atomicOr(&S.misc->max_force_flag, 16); break; }   // ~4 s: a CTA / a rank is missing
         if (S.prof) S.prof[16 + 8 * (blockIdx.x % FAST_MAX_CTA) + 6] += (unsigned long long)(clock64() - t0);
         sm.ctl[RC_NEWLAB] = label_own; sm.xE[2] = 1.0; sm.ctl[RC_NATT] = 0; sm.ctl[RC_NACC] = 0;
+        if (xprof) { x0 = clock64(); xp[2] += (unsigned long long)(x0 - t0); }
     }
     rep_sync<NT>();
     {   // replay of the decisions: one lane per label, the blocks of 32 labels on the warps side by side (the pairs are
@@ -588,6 +592,7 @@ SIS_D void rep_remd_exchange(const DevSys &S, const FFParams &P, const RepSm &sm
         }
     }
     rep_sync<NT>();
+    if (xprof) { x1 = clock64(); xp[3] += (unsigned long long)(x1 - x0); x0 = x1; }
     if (tid == 0) {     // parameter refresh of the replica (src/job_md.F90:538-567)
         FastRemdState Y = X;
         Y.natt += sm.ctl[RC_NATT]; Y.nacc += sm.ctl[RC_NACC];
@@ -605,6 +610,7 @@ SIS_D void rep_remd_exchange(const DevSys &S, const FFParams &P, const RepSm &sm
     if (P.bp_triplet)
         for (int c = tid; c < ncand; c += NT) sm.c_dG[c] = sm.c_dH[c] - tK * sm.c_dS[c];
     rep_sync<NT>();
+    if (xprof) { xp[4] += (unsigned long long)(clock64() - x0); xp[5] += 1ull; }
 }
 
 template <int NT, bool XCH>
@@ -639,9 +645,10 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
         sm.ca[k] = cf.x; sm.cb[k] = cf.y; sm.cc[k] = cf.z; sm.nz0[k] = cf.w;
         sm.meta[k] = S.meta[k];
         sm.bcnt[k] = 0;
+        sm.excess[k] = -A.max_bp_per_nt;
     }
     for (int k = tid; k < REP_MAXB; k += NT) sm.d2[k] = 0.0;
-    for (int t = tid; t < 3 * n * n; t += NT) sm.Fp[t] = 0.0;
+    for (int t = tid; t < 3 * n * ((n + 1) & ~1); t += NT) sm.Fp[t] = 0.0;
     if (tid == 0) {
         *sm.rp = S.rp[rep];
         for (int i = 0; i < 16; i++) sm.ctl[i] = 0;
@@ -744,7 +751,10 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
     const uint32_t stream = (uint32_t)sm.rp->stream;
     // work of P1 in chunks of one warp: base-pair survivors, Gaussians, dihedrals, bond + angle, then the pairs (64 per chunk)
     // (each kind starts on a chunk boundary: a warp runs one code path)
-    const int cD = dih_on ? (n + 31) >> 5 : 0, cB = (n + 31) >> 5, cpair = (npair + 127) >> 7, cG = (2 * n + 31) >> 5, cA = (3 * n + 31) >> 5;
+    constexpr int PPL = NT >= 512 ? 2 : 4;       // pairs per lane of a pair chunk
+    const int cD = dih_on ? (n + 31) >> 5 : 0, cB = (n + 31) >> 5, cpair = (npair + 32 * PPL - 1) / (32 * PPL), cG = (2 * n + 31) >> 5, cA = (3 * n + 31) >> 5;
+    const int cgate = (ncand + 31) >> 5;
+    const int npad = (n + 1) & ~1;               // row length of the pair slots (16-byte rows)
     const int cstat = cD + cB + cpair;          // chunks the owners' sums wait for
     // optional phase clocks (option "profile"): per CTA {P0, P1 wait for the first chunk, P1 work, P2, verdict, exchange, exchange wait, steps}
     const bool prof = S.prof != nullptr && tid == 0;
@@ -774,47 +784,32 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
         }
         const bool mc = use_mc && ((istep % (unsigned long long)P.nstep_bp_MC == 0ull) || after_rebuild);
         after_rebuild = false;
-        if (mc) for (int i = tid; i < n; i += NT) sm.excess[i] = -A.max_bp_per_nt;
-        if (tid == 0) sm.ctl[RC_SPILL] = 0;
-        rep_bp_gate<NT>(P, sm, ncand, use_mc && !mc);
+        const bool gate_mask = use_mc && !mc;
         const RepParams &Rp = *sm.rp;
         const double ele_coef = Rp.ele_coef, inv_lambdaD = Rp.inv_lambdaD;
         const double cut2 = P.flg_ele ? Rp.ele_cutoff * Rp.ele_cutoff : -1.0;
         const double noise_T = Rp.sqrt_tempK, twz_force = Rp.twz_force;
-        rep_sync<NT>();
         if (prof) c1 = clock64();
         // ---- P1: every warp draws chunks from the shared counter ----------------------------------------------
-        const int nact = sm.ctl[RC_NACT];
-        const int nar = min(nact, REP_ACT);
+        int nact = -1, nar = 0, cang = 0, cdih = 0, cov = 0, cene = 0, ccomb = 0, cbp = 0;
+        const int cfix = cgate + cstat + cG;        // chunks whose meaning does not depend on the gate
         {
-            // chunks: angle roles, dihedral roles, survivors beyond the role slots, static work, pairs, combine (last: it needs the roles)
-            const int cang = (4 * nar + 31) >> 5, cdih = (2 * nar + 31) >> 5, cov = (nact - nar + 31) >> 5;
-            const int cene = (nar + 31) >> 5, cgat = ((NT >= 512 ? 6 : 1) * nar + 31) >> 5, ccomb = cene + cgat;
-            const int cbp = cang + cdih + cov;
             bool first = true;
             for (;;) {
                 int ch = 0;
                 if (lane == 0) ch = atomicAdd(&sm.ctl[RC_WORK], 1);
                 ch = __shfl_sync(0xffffffffu, ch, 0);
                 if (prof && first) { c2 = clock64(); first = false; }
-                if (ch >= cbp + cstat + cG + cA + ccomb) break;
                 const long long tq0 = tprof ? clock64() : 0;
                 int ttype = 0;
-                if (ch < cang + cdih) {                 // base-pair roles, one code path per warp
-                    ttype = ch < cang ? 0 : 1;
-                    const bool ang = ch < cang;
-                    const int it = 32 * (ang ? ch : ch - cang) + lane;
-                    if (ang) { if (it < 4 * nar) rep_bp_role_item(P, sm, it >> 2, 1 + (it & 3)); }
-                    else if (it < 2 * nar) rep_bp_role_item(P, sm, it >> 1, 5 + (it & 1));
+                if (ch < cgate) {                       // distance gate of 32 candidates
+                    ttype = 8;
+                    rep_bp_gate_warp(P, sm, 32 * ch + lane, ncand, gate_mask);
                     __threadfence_block();
                     __syncwarp();
-                    if (lane == 0) atomicAdd(&sm.ctl[RC_ROLES], 1);
-                } else if (ch < cbp) {
-                    ttype = 2;
-                    const int a = REP_ACT + 32 * (ch - cang - cdih) + lane;
-                    if (a < nact) rep_bp_eval(P, sm, sm.act[a], !mc);
-                } else if (ch < cbp + cstat) {
-                    const int cs = ch - cbp;
+                    if (lane == 0) atomicAdd(&sm.ctl[RC_GATE], 1);
+                } else if (ch < cgate + cstat) {
+                    const int cs = ch - cgate;
                     if (cs < cD) {                      // dihedral starting at bead k
                         ttype = 4;
                         const int k = 32 * cs + lane;
@@ -844,25 +839,30 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
                                 }
                             }
                         }
-                    } else {                            // 128 pairs: four per lane side by side
+                    } else {                            // 32 * PPL pairs: PPL per lane side by side
                         ttype = 6;
-                        const int q0 = 128 * (cs - cD - cB) + lane;
-                        uint32_t e[4];
-                        Vec3 f[4];
+                        const int q0 = 32 * PPL * (cs - cD - cB) + lane;
+                        uint32_t e[PPL];
+                        Vec3 f[PPL];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) e[u] = q0 + 32 * u < npair ? sm.pl[q0 + 32 * u] : 0u;
+                        for (int u = 0; u < PPL; u++) e[u] = q0 + 32 * u < npair ? sm.pl[q0 + 32 * u] : 0u;
 #pragma unroll
-                        for (int u = 0; u < 4; u++) f[u] = e[u] ? rep_pair_force(P, e[u], sm.x, ele_coef, inv_lambdaD, cut2) : mk(0.0, 0.0, 0.0);
+                        for (int u = 0; u < PPL; u++) f[u] = e[u] ? rep_pair_force(P, e[u], sm.x, ele_coef, inv_lambdaD, cut2) : mk(0.0, 0.0, 0.0);
 #pragma unroll
-                        for (int u = 0; u < 4; u++)
-                            if (e[u]) { const int i = e[u] & 0xFF, j = (e[u] >> 8) & 0xFF; rep_put(sm.Fp, i * n + j, f[u]); rep_put(sm.Fp, j * n + i, -f[u]); }
+                        for (int u = 0; u < PPL; u++)
+                            if (e[u]) {
+                                const int i = e[u] & 0xFF, j = (e[u] >> 8) & 0xFF;
+                                double *ri = sm.Fp + 3 * i * npad + j, *rj = sm.Fp + 3 * j * npad + i;
+                                ri[0] = f[u].x; ri[npad] = f[u].y; ri[2 * npad] = f[u].z;
+                                rj[0] = -f[u].x; rj[npad] = -f[u].y; rj[2 * npad] = -f[u].z;
+                            }
                     }
                     __threadfence_block();
                     __syncwarp();
                     if (lane == 0) atomicAdd(&sm.ctl[RC_STAT], 1);
-                } else if (ch < cbp + cstat + cG) {     // Gaussians of the NEXT step (nothing waits for them in this one): draw 0 -> (x, y), draw 1 -> z
+                } else if (ch < cfix) {                 // Gaussians of the NEXT step (nothing waits for them in this one): draw 0 -> (x, y), draw 1 -> z
                     ttype = 3;
-                    const int it = 32 * (ch - cbp - cstat) + lane;
+                    const int it = 32 * (ch - cgate - cstat) + lane;
                     if (it < 2 * n) {
                         const int k = it >> 1, draw = it & 1;
                         double g0, g1;
@@ -870,43 +870,69 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
                         double *gn = sm.g + 3 * n * (int)((istep + 1ull) & 1ull);
                         if (draw == 0) { gn[3 * k] = g0; gn[3 * k + 1] = g1; } else gn[3 * k + 2] = g0;
                     }
-                } else if (ch < cbp + cstat + cG + ccomb) {   // energies, per-bead forces of the survivors (they need the roles)
-                    ttype = 2;
-                    rep_wait(&sm.ctl[RC_ROLES], cang + cdih);
-                    const int cc = ch - cbp - cstat - cG;
-                    if (cc < cene) { const int a = 32 * cc + lane; if (a < nar) rep_bp_energy(P, sm, a, mc); }
-                    else if (NT >= 512) { const int it = 32 * (cc - cene) + lane; if (it < 6 * nar) rep_bp_gather(P, sm, it / 6, it % 6); }
-                    else {
-                        const int a = 32 * (cc - cene) + lane;
-                        if (a < nar)
-                            for (int t = 0; t < 6; t++) rep_bp_gather(P, sm, a, t);
+                } else {
+                    if (nact < 0) {                     // the chunks behind depend on the survivors: the gate must be complete
+                        rep_wait(&sm.ctl[RC_GATE], cgate);
+                        nact = sm.ctl[RC_NACT];
+                        nar = min(nact, REP_ACT);
+                        // angle roles, dihedral roles, survivors beyond the role slots, energies + per-bead forces, owners' sums
+                        cang = (4 * nar + 31) >> 5; cdih = (3 * nar + 31) >> 5; cov = (nact - nar + 31) >> 5;
+                        cene = (nar + 31) >> 5; ccomb = cene + (((NT >= 512 ? 6 : 1) * nar + 31) >> 5);
+                        cbp = cang + cdih + cov;
                     }
-                } else {                                // owners' sums: pair row, bonded terms, tweezers (last: they need the pairs)
-                    ttype = 7;
-                    rep_wait(&sm.ctl[RC_STAT], cstat);
-                    const int it = 32 * (ch - cbp - cstat - cG - ccomb) + lane;
-                    if (it < 3 * n) {
-                        const int k = it / 3, comp = it - 3 * k;
-                        double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
-                        const double *row = sm.Fp + 3 * k * n + comp;
-                        int j = 0;
-                        for (; j + 3 < n; j += 4) { f0 += row[3 * j]; f1 += row[3 * j + 3]; f2 += row[3 * j + 6]; f3 += row[3 * j + 9]; }
-                        for (; j < n; j++) f0 += row[3 * j];
-                        double f = (f0 + f1) + (f2 + f3);
-                        const unsigned short *be = sm.bent + REP_BENT * k;
-                        const int ne = sm.bn[k];
-                        for (int e = 0; e < ne; e++) {
-                            const unsigned w = be[e];
-                            const double t = sm.bf[3 * (w & 0x7FFF) + comp];
-                            f += (w & 0x8000) ? -t : t;
+                    ch -= cfix;
+                    if (ch >= cbp + ccomb + cA) break;
+                    if (ch < cang + cdih) {             // base-pair roles, one code path per warp
+                        ttype = ch < cang ? 0 : 1;
+                        const bool ang = ch < cang;
+                        const int it = 32 * (ang ? ch : ch - cang) + lane;
+                        if (ang) { if (it < 4 * nar) rep_bp_role_item(P, sm, it >> 2, 1 + (it & 3)); }
+                        else if (it < 3 * nar) { const int a = it / 3, q = it - 3 * a; rep_bp_role_item(P, sm, a, q == 2 ? 0 : 5 + q); }
+                        __threadfence_block();
+                        __syncwarp();
+                        if (lane == 0) atomicAdd(&sm.ctl[RC_ROLES], 1);
+                    } else if (ch < cbp) {
+                        ttype = 2;
+                        const int a = REP_ACT + 32 * (ch - cang - cdih) + lane;
+                        if (a < nact) rep_bp_eval(P, sm, sm.act[a], !mc);
+                    } else if (ch < cbp + ccomb) {      // energies, per-bead forces of the survivors (they need the roles)
+                        ttype = 2;
+                        rep_wait(&sm.ctl[RC_ROLES], cang + cdih);
+                        const int cc = ch - cbp;
+                        if (cc < cene) { const int a = 32 * cc + lane; if (a < nar) rep_bp_energy(P, sm, a, mc); }
+                        else if (NT >= 512) { const int it = 32 * (cc - cene) + lane; if (it < 6 * nar) rep_bp_gather(P, sm, it / 6, it % 6, RC_SPILL0 + (done & 1)); }
+                        else {
+                            const int a = 32 * (cc - cene) + lane;
+                            if (a < nar)
+                                for (int t = 0; t < 6; t++) rep_bp_gather(P, sm, a, t, RC_SPILL0 + (done & 1));
                         }
-                        // dual constant-force tweezers (src/force_tweezers.F90:27-35): +f on the first bead of a pair, -f on the second
-                        for (int t = 0; t < P.ntwz_DCF; t++) {
-                            const double ft = twz_force * S.twz_dir[3 * t + comp];
-                            if (S.twz_pairs[2 * t] == k) f += ft;
-                            if (S.twz_pairs[2 * t + 1] == k) f -= ft;
+                    } else {                            // owners' sums: pair row, bonded terms, tweezers (last: they need the pairs)
+                        ttype = 7;
+                        rep_wait(&sm.ctl[RC_STAT], cstat);
+                        const int it = 32 * (ch - cbp - ccomb) + lane;
+                        if (it < 3 * n) {
+                            const int k = it / 3, comp = it - 3 * k;
+                            double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
+                            const double2 *row = reinterpret_cast<const double2 *>(sm.Fp + (size_t)it * npad);
+                            int j = 0;
+                            for (; j + 1 < npad / 2; j += 2) { const double2 p0 = row[j], p1 = row[j + 1]; f0 += p0.x; f1 += p0.y; f2 += p1.x; f3 += p1.y; }
+                            if (j < npad / 2) { const double2 p0 = row[j]; f0 += p0.x; f1 += p0.y; }
+                            double f = (f0 + f1) + (f2 + f3);
+                            const unsigned short *be = sm.bent + REP_BENT * k;
+                            const int ne = sm.bn[k];
+                            for (int e = 0; e < ne; e++) {
+                                const unsigned w = be[e];
+                                const double t = sm.bf[3 * (w & 0x7FFF) + comp];
+                                f += (w & 0x8000) ? -t : t;
+                            }
+                            // dual constant-force tweezers (src/force_tweezers.F90:27-35): +f on the first bead of a pair, -f on the second
+                            for (int t = 0; t < P.ntwz_DCF; t++) {
+                                const double ft = twz_force * S.twz_dir[3 * t + comp];
+                                if (S.twz_pairs[2 * t] == k) f += ft;
+                                if (S.twz_pairs[2 * t + 1] == k) f -= ft;
+                            }
+                            sm.fsum[it] = f;
                         }
-                        sm.fsum[it] = f;
                     }
                 }
                 if (tprof) {
@@ -917,11 +943,11 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
         }
         if (wprof) w0 = clock64();
         rep_sync<NT>();
-        if (mc) rep_mc_prune<NT>(P, sm, n, ncand, A.seed, &s_mc_ctr, S.prof ? pc + 6 : nullptr);
+        if (mc) rep_mc_prune<NT>(P, sm, n, ncand, A.seed, A.max_bp_per_nt, &s_mc_ctr, S.prof ? pc + 6 : nullptr);
         if (prof) c3 = clock64();
         // ---- P2: assemble and integrate (src/job_md.F90:409-456) ------------------------------------------------
         bool far = false;
-        const bool spill = sm.ctl[RC_SPILL] != 0;
+        const bool spill = sm.ctl[RC_SPILL0 + (done & 1)] != 0;
         if (wprof) { w1 = clock64(); aw[0] += w1 - w0; }
         for (int k = tid >> 2; k < ((n + NT / 4 - 1) / (NT / 4)) * (NT / 4); k += NT / 4) {
             const int comp = tid & 3;
@@ -963,7 +989,7 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
             __syncwarp();
             if (k < n && comp == 3) sm.bcnt[k] = 0;
         }
-        if (tid == 0) { sm.ctl[RC_NACT] = 0; sm.ctl[RC_WORK] = 0; sm.ctl[RC_ROLES] = 0; sm.ctl[RC_STAT] = 0; sm.ctl[RC_FAR0 + ((done + 1) & 1)] = 0; }
+        if (tid == 0) { sm.ctl[RC_NACT] = 0; sm.ctl[RC_WORK] = 0; sm.ctl[RC_ROLES] = 0; sm.ctl[RC_STAT] = 0; sm.ctl[RC_GATE] = 0; sm.ctl[RC_SPILL0 + ((done + 1) & 1)] = 0; sm.ctl[RC_FAR0 + ((done + 1) & 1)] = 0; }
         // "is any displacement beyond half the margin": only then the exact top-2 test (flag by step parity)
         if (__any_sync(0xffffffffu, far) && lane == 0) sm.ctl[RC_FAR0 + (done & 1)] = 1;
         if (wprof) { w0 = clock64(); aw[1] += w0 - w1; }

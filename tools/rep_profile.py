@@ -52,3 +52,6 @@ print("  block 0:", [round(v / steps) for v in p[0, :6]], " warps 0-3 {B2 wait, 
 tq = pall[1000:1002].reshape(-1)
 names = ["bp angle roles", "bp dihedral roles", "bp combine", "gauss", "dihedral", "bond+angle", "pairs (128)", "owner sums"]
 print("  block 0 chunks: " + ", ".join(f"{nm} {tq[2 * i] / max(1, tq[2 * i + 1]):.0f} cyc x {tq[2 * i + 1] / steps:.1f}/step" for i, nm in enumerate(names)))
+xq = pall[1003]
+if xq[5] > 0:
+    print("  block 0 exchange (cycles per attempt): energies %.0f, publish %.0f, wait %.0f, replay %.0f, refresh %.0f" % tuple(xq[:5] / xq[5]))
