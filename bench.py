@@ -212,11 +212,11 @@ def run_remd_c3(cx, nrep_all=64, nex=int(os.environ.get("SIS_NEX", "10")), md_st
         return {"error": f"{nrep_all} replicas do not split over {world} ranks"}
     R = nrep_all // world
     # up to 256 temperatures (MAX_REP_PER_DIM of the reference, src/const.F90:26-28); beyond that a second replica
-    # dimension: two ionic strengths per temperature (labels: the first variable varies slowest, src/init_replica.F90:70-92)
-    nion = 1 if nrep_all <= 256 else 2
+    # dimension: a few ionic strengths per temperature (labels: the first variable varies slowest, src/init_replica.F90:70-92)
+    nion = next(d for d in range(1, nrep_all + 1) if nrep_all % d == 0 and nrep_all // d <= 256)
     ntemp = nrep_all // nion
     tgrid = [293.15 + 70.0 / (ntemp - 1) * k for k in range(ntemp)]
-    igrid = [0.15, 0.16][:nion]
+    igrid = [0.15 + 0.01 * k for k in range(nion)]
     temps = [tgrid[l // nion] for l in range(nrep_all)]
     ions = [igrid[l % nion] for l in range(nrep_all)]
     spec = fx.t2s2hp("T2S2HP_folded", nstep_MC=0).replicated(R, temps=temps[rank * R:(rank + 1) * R],
@@ -254,6 +254,32 @@ def run_remd_c3(cx, nrep_all=64, nex=int(os.environ.get("SIS_NEX", "10")), md_st
            "us_per_md_step": 1e6 * dt / (md_steps * steps), "kernel": g.last_step_kernel(),
            "launches_rank0": g.launch_count() - l0, "rebuilds_rank0": nreb, "timers_ms": g.get_timers(),
            "exchange": {"attempts": att, "accepted": acc}}
+    g.close()
+    return out
+
+
+def run_mixed(cx, workload, md_steps, steps, warmup):
+    """the same system in the mixed-precision mode (option precision = 1: fp32 pair scalars, everything else fp64;
+    stated force tolerance 2e-5, tests/test_gpu_mixed.py), device-resident loop only.  Reported beside the fp64
+    headline, never instead of it."""
+    spec, wl = build_system(workload)
+    g = cx.new_handle()
+    g.set_option("precision", 1)
+    spec.configure(g)
+    g.init_velocities(0)
+    g.neighbor_list(0)
+    for _ in range(warmup):
+        g.md_steps(md_steps)
+    cx.barrier()
+    g.mark(0)
+    nreb = 0
+    for _ in range(steps):
+        nreb += g.md_steps(md_steps)
+    g.mark(1)
+    dt = 1e-3 * g.elapsed_ms()
+    out = {"metric": "particle-steps/sec", "value": spec.nmp * md_steps * steps / dt, "unit": "particle-steps/s", "dtype": "f64 + f32 pair scalars",
+           "force_tolerance": 2e-5, "workload": wl, "us_per_md_step": 1e6 * dt / (md_steps * steps), "kernel": g.last_step_kernel(),
+           "rebuilds": nreb}
     g.close()
     return out
 
@@ -418,6 +444,16 @@ def main():
                 extra["c3_remd"] = run_remd_c3(cx)
             except Exception as ex:  # pragma: no cover
                 extra["c3_remd"] = {"error": str(ex)}
+            if cx.world == 1:
+                try:
+                    extra["mixed_precision"] = run_mixed(cx, args.workload, args.md_steps, max(2, args.steps // 2), args.warmup)
+                except Exception as ex:  # pragma: no cover
+                    extra["mixed_precision"] = {"error": str(ex)}
+            if cx.world == 1:        # the GPU filled with replicas (k_md_rep: 4 CTAs of 128 threads per SM): 296 temperatures x 2 ionic strengths
+                try:
+                    extra["c3_remd_filled"] = run_remd_c3(cx, nrep_all=592, md_steps=1000, steps=3, warmup=1)
+                except Exception as ex:  # pragma: no cover
+                    extra["c3_remd_filled"] = {"error": str(ex)}
             if cx.world > 1:         # the same replicas per GPU as the N = 1 line: weak scaling along replicas
                 try:
                     extra["c3_remd_weak"] = run_remd_c3(cx, nrep_all=64 * cx.world, scaling="weak")

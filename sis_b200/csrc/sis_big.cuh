@@ -145,6 +145,22 @@ template <int W>
 SIS_D void big_pairs_force(const FFParams &P, const uint32_t *ent, const double4 *pj, Vec3 xk, Vec3 inv_box,
                            double ec, double il, double c2, Vec3 &F)
 {
+    if (P.mixed) {        // fp32 pair scalars (pair_scalar_f32), W pairs side by side
+#pragma unroll
+        for (int u = 0; u < W; u++) {
+            double vx = xk.x - pj[u].x, vy = xk.y - pj[u].y, vz = xk.z - pj[u].z;
+            if (P.flg_pbc) {
+                vx = fma(-P.box[0], rint(vx * inv_box.x), vx);
+                vy = fma(-P.box[1], rint(vy * inv_box.y), vy);
+                vz = fma(-P.box[2], rint(vz * inv_box.z), vz);
+            }
+            const double d2 = vx * vx + vy * vy + vz * vz;
+            const bool e_on = (ent[u] & NB_ELE) && d2 <= c2, w_on = (ent[u] & NB_WCA) && d2 < P.wca_sigma2;
+            const double sc = pair_scalar_f32(P, w_on, e_on, (e_on || w_on) ? d2 : 1.0, ec, il);
+            F.x = fma(sc, vx, F.x); F.y = fma(sc, vy, F.y); F.z = fma(sc, vz, F.z);
+        }
+        return;
+    }
     double dd[W], y[W], h[W], e[W];
     bool ie[W], iw[W];
 #pragma unroll

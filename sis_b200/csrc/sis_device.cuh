@@ -54,6 +54,7 @@ struct FFParams {
     int flg_angl_ReB, flg_dih_cos, flg_dih_exp, flg_ele, flg_pbc, flg_stage, flg_bias_ss;
     int bp_triplet, nstep_bp_MC, temp_independent, integrator, flg_bias_rg, bias_rg_pott;
     int ntwz_DCF, ntwz_FR, nrest;
+    int mixed;            // option "precision" = 1: WCA / Debye-Hueckel pair scalars in fp32 (vectors, sums, everything else fp64)
     BpPara bp[7];
 };
 
@@ -314,6 +315,30 @@ SIS_D double exp_neg_sl(double x)
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 #endif
+// Mixed-precision mode (option "precision" = 1; tolerance 2e-5 of the largest force component, tests/test_gpu_mixed.py):
+// the scalar of one listed pair, coef ((s2/d2)^7 - (s2/d2)^4) + C/r^2 (1/r + 1/lambda) exp(-r/lambda), in fp32 from the
+// fp64 squared distance -- one MUFU.RSQ and one MUFU.EX2 instead of the fp64 Newton / Horner chains; the pair vector, the
+// product and every accumulation stay fp64
+SIS_HD double pair_scalar_f32(const FFParams &P, bool wca, bool ele, double d2, double ele_coef, double inv_lambdaD)
+{
+    const float d2f = (float)d2;
+#ifdef __CUDA_ARCH__
+    const float ri = rsqrtf(d2f);
+#else
+    const float ri = 1.0f / sqrtf(d2f);
+#endif
+    const float ri2 = ri * ri;
+    float s = 0.0f;
+    if (ele) {
+        const float il = (float)inv_lambdaD;
+        s = (float)ele_coef * ri2 * (ri + il) * expf(-(d2f * ri) * il);
+    }
+    if (wca) {
+        const float x = (float)P.wca_sigma2 * ri2, x2 = x * x, x4 = x2 * x2;
+        s += (float)P.wca_coef * (x4 * x2 * x - x4);
+    }
+    return (double)s;
+}
 // src/energy_wca.F90:19-35, src/energy_ele_DH.F90:20-40
 SIS_HD double wca_energy(const FFParams &P, double d2)
 {

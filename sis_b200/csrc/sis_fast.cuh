@@ -129,6 +129,12 @@ SIS_D void fast_pair_one(const FFParams &P, uint32_t ent, Vec3 xk, Vec3 xj, doub
     }
     const double d2 = dot(v, v);
     double s = 0.0;
+    if (P.mixed) {
+        const bool w_on = (ent & NB_WCA) && d2 < P.wca_sigma2, e_on = (ent & NB_ELE) && d2 <= cut2;
+        if (w_on || e_on) s = pair_scalar_f32(P, w_on, e_on, d2, ele_coef, inv_lambdaD);
+        F += s * v;
+        return;
+    }
     if ((ent & NB_WCA) && d2 < P.wca_sigma2) s += wca_scalar(P, d2);
 #ifdef FAST_PAIR_LIBM
     if ((ent & NB_ELE) && d2 <= cut2) s += dh_scalar(ele_coef, inv_lambdaD, d2);

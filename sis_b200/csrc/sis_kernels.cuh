@@ -176,8 +176,12 @@ SIS_HD Vec3 pair_force(const DevSys &S, const FFParams &P, const RepParams &R, c
             }
             const double d2 = dot(v, v);
             double s = 0.0;
-            if (do_wca && (ent[u] & NB_WCA) && d2 < P.wca_sigma2) s += wca_scalar(P, d2);
-            if (do_ele && (ent[u] & NB_ELE) && d2 <= cut2) s += dh_scalar(R.ele_coef, R.inv_lambdaD, d2);
+            const bool w_on = do_wca && (ent[u] & NB_WCA) && d2 < P.wca_sigma2, e_on = do_ele && (ent[u] & NB_ELE) && d2 <= cut2;
+            if (P.mixed) { if (w_on || e_on) s = pair_scalar_f32(P, w_on, e_on, d2, R.ele_coef, R.inv_lambdaD); }
+            else {
+                if (w_on) s += wca_scalar(P, d2);
+                if (e_on) s += dh_scalar(R.ele_coef, R.inv_lambdaD, d2);
+            }
             F += s * v;
         }
     }

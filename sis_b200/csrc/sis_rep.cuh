@@ -132,6 +132,11 @@ SIS_D Vec3 rep_pair_force(const FFParams &P, uint32_t e, const double *x, double
     const Vec3 v = pbc_vec_d(P, rep_x(x, e & 0xFF), rep_x(x, (e >> 8) & 0xFF));
     const double d2 = dot(v, v);
     double s = 0.0;
+    if (P.mixed) {
+        const bool w_on = (e & NB_WCA) && d2 < P.wca_sigma2, e_on = (e & NB_ELE) && d2 <= cut2;
+        if (w_on || e_on) s = pair_scalar_f32(P, w_on, e_on, d2, ele_coef, inv_lambdaD);
+        return s * v;
+    }
     if ((e & NB_WCA) && d2 < P.wca_sigma2) s += wca_scalar(P, d2);
     if ((e & NB_ELE) && d2 <= cut2) {
         const double ri = rsqrt_sl(d2);
@@ -379,6 +384,7 @@ SIS_D void rep_mc_prune(const FFParams &P, const RepSm &sm, int n, int ncand, un
         if (a < REP_ACT) { if (!on) sm.eA[a] = 0.0; }
         else if (on) rep_bp_eval(P, sm, sm.act[a], true);
     }
+    rep_sync<NT>();
     for (int c = tid; c < ncand; c += NT) {
         unsigned char *b = sm.c_b + 8 * c;
         b[7] = (unsigned char)((b[7] & 1) * 3);

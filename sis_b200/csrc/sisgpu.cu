@@ -2676,6 +2676,7 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
     }
     else if (s == "fast_max_cta") { h->fast_max_cta = (int)value; h->lists_built = false; }
     else if (s == "mc_persistent") h->mc_persistent = (int)value;
+    else if (s == "precision") { h->P.mixed = value != 0 ? 1 : 0; invalidate_graphs(h); }   // 0: fp64 (default); 1: mixed (fp32 pair scalars)
     else if (s == "rep_kernel") h->rep_kernel = (int)value;
     else if (s == "rep_threads") h->rep_threads = (int)value;
     else if (s == "loc_help") h->S.dbg_no_loc_help = value == 0 ? 1 : 0;
