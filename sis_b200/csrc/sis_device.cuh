@@ -521,6 +521,79 @@ SIS_HD BpSub bp_force_role(const FFParams &P, const BpPara &p, int role, Vec3 x0
     return o;
 }
 
+#ifdef __CUDACC__
+// Role-major form of the same arithmetic (k_md_rep, k_md_fast): ONE role of one base pair per thread, so that a warp
+// runs one code path; the results of the seven roles go to BP_ROLE doubles per pair:
+//   angle role q = 1..4 at 7 (q - 1): {u, fi, fk};  dihedral role q = 5, 6 at 28 + 9 (q - 5): {u, fi, fl, ra, rb};
+//   bond role 0 at 46: {u, fi}.
+// xa / xb as in bp_force_role.  The angles go through one reciprocal square root each (cos = v12.w rsqrt(|v12|^2 |w|^2)).
+constexpr int BP_ROLE = 50;
+SIS_D void bp_role_eval(const FFParams &P, const BpPara &p, int role, Vec3 x0, Vec3 x1, Vec3 xa, Vec3 xb, double *out)
+{
+    const Vec3 v12 = pbc_vec_d(P, x0, x1);
+    const double d1212 = dot(v12, v12);
+    if (role == 0) {
+        const double a12 = sqrt(d1212), d = a12 - p.bond_r;
+        const Vec3 fi = (2.0 * p.bond_k * d / a12) * v12;
+        out[46] = p.bond_k * d * d;
+        out[47] = fi.x; out[48] = fi.y; out[49] = fi.z;
+    } else if (role <= 4) {
+        const bool at_i = role & 1;
+        const Vec3 w = at_i ? pbc_vec_d(P, x0, xa) : pbc_vec_d(P, xa, x1);
+        const double k = role == 1 ? p.angl_k2 : role == 2 ? p.angl_k1 : role == 3 ? p.angl_k4 : p.angl_k3;
+        const double th = role == 1 ? p.angl_theta2 : role == 2 ? p.angl_theta1 : role == 3 ? p.angl_theta4 : p.angl_theta3;
+        const double dww = dot(w, w), d12w = dot(v12, w), dd = dww * d1212;
+        const double cosine = d12w * rsqrt(dd);
+        const double d = acos(cosine) - th;
+        const double pre = 2.0 * k * d * rsqrt(dd - d12w * d12w);
+        const double r12w = d12w / d1212, rww = d12w / dww;
+        Vec3 fi, fk;
+        if (at_i) { fi = pre * (v12 - rww * w); fk = pre * (w - r12w * v12); }
+        else { fi = (-pre) * (w - r12w * v12); fk = (-pre) * (v12 - rww * w); }
+        out += 7 * (role - 1);
+        out[0] = k * d * d;
+        out[1] = fi.x; out[2] = fi.y; out[3] = fi.z; out[4] = fk.x; out[5] = fk.y; out[6] = fk.z;
+    } else {
+        const Vec3 va2 = pbc_vec_d(P, xa, x1), v1b = pbc_vec_d(P, x0, xb);
+        const double ra = dot(v12, va2) / d1212, rb = dot(v12, v1b) / d1212;
+        const Vec3 m = cross(va2, v12), n = cross(v12, v1b);
+        const double a12 = sqrt(d1212);
+        const double Y = dot(va2, n) * a12, X = dot(m, n);
+        const double kk = role == 5 ? p.dihd_k1 : p.dihd_k2;
+        const double c0 = role == 5 ? p.cos_phi1 : p.cos_phi2, s0 = role == 5 ? p.sin_phi1 : p.sin_phi2;
+        const double rinv = rsqrt(X * X + Y * Y);
+        const double cosd = (X * c0 - Y * s0) * rinv, sind = (Y * c0 + X * s0) * rinv;
+        const double pre = -kk * sind * a12;
+        const Vec3 fi = (pre / dot(m, m)) * m;
+        const Vec3 fl = (-pre / dot(n, n)) * n;
+        out += 28 + 9 * (role - 5);
+        out[0] = kk * (1.0 + cosd);
+        out[1] = fi.x; out[2] = fi.y; out[3] = fi.z; out[4] = fl.x; out[5] = fl.y; out[6] = fl.z;
+        out[7] = ra; out[8] = rb;
+    }
+}
+// exponent of the pair from its roles
+SIS_D double bp_roles_u(const double *r) { return r[46] + ((r[0] + r[7]) + (r[14] + r[21])) + (r[28] + r[37]); }
+// unscaled force on bead t (0..5 = i, j, i-1, j-1, i+1, j+1) from the roles:
+// angle roles 1, 3 (vertex i): c0 = -fi - fk, c1 = fk, ca = fi; roles 2, 4 (vertex j): c0 = fi, c1 = -fi - fk, ca = fk;
+// dihedral roles 5, 6: ca = fi, cb = fl, c1 = (ra - 1) fi - rb fl, c0 = (rb - 1) fl - ra fi; bond: +fi on i, -fi on j
+SIS_D Vec3 bp_roles_bead_force(const double *r, int t)
+{
+    auto V = [&](int o) { return mk(r[o], r[o + 1], r[o + 2]); };
+    if (t < 2) {
+        const Vec3 f0 = V(47);
+        const Vec3 di5 = V(29), dl5 = V(32), di6 = V(38), dl6 = V(41);
+        const double ra5 = r[35], rb5 = r[36], ra6 = r[44], rb6 = r[45];
+        if (t == 0) return f0 - (V(1) + V(4)) + V(8) - (V(15) + V(18)) + V(22) + ((rb5 - 1.0) * dl5 - ra5 * di5) + ((rb6 - 1.0) * dl6 - ra6 * di6);
+        return -f0 + V(4) - (V(8) + V(11)) + V(18) - (V(22) + V(25)) + ((ra5 - 1.0) * di5 - rb5 * dl5) + ((ra6 - 1.0) * di6 - rb6 * dl6);
+    }
+    if (t == 2) return V(1) + V(32);
+    if (t == 3) return V(11) + V(29);
+    if (t == 4) return V(15) + V(41);
+    return V(25) + V(38);
+}
+#endif
+
 // Energy side: src/energy_bp.F90:40-62,76-118 (clamped acos, mp_dihedral)
 SIS_HD double mp_angle(const FFParams &P, Vec3 x1, Vec3 x2, Vec3 x3)
 {

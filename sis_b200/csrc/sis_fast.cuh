@@ -83,6 +83,7 @@ struct FastShared {
     FastBpCand cand[FAST_BPC];
     int active[FAST_BPC];
     int nactive[2], bp_next[2];      // survivors of the distance gate / next one to evaluate, by step parity
+    int roles_done[2];               // role chunks of the step's survivors that are complete (fast_bp_eval_roles), by step parity
     int ncand, nextra, overflow, overflow_rows;
     int gate_done[2];                // step index + 1 of the last completed distance-gate pass, by step parity
     int extra[FAST_NEXTRA];
@@ -505,8 +506,8 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
 // lane, bp_force_role) draw survivors from a shared counter.  The BP groups start right after the
 // gate; the MAIN groups join when their pair units are done, so a CTA with many formed base pairs
 // is not held up by its four BP warps.
-SIS_D void fast_bp_eval(const DevSys &S, const FFParams &P, FastShared &sh, const double4 *pos, int lo_item, int hi_item,
-                        int q, int nact)
+SIS_D void fast_bp_eval_groups(const DevSys &S, const FFParams &P, FastShared &sh, const double4 *pos, int lo_item, int hi_item,
+                               int q, int nact)
 {
     const int bl = threadIdx.x & 7;
     const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
@@ -551,6 +552,78 @@ SIS_D void fast_bp_eval(const DevSys &S, const FFParams &P, FastShared &sh, cons
             cd.last = on ? 1 : 0;
         }
     }
+}
+
+// Role-major evaluation of the survivors (as k_md_rep): whole warps draw chunks of 32 items from the shared counter.
+// First the role items -- one angle (4 per survivor) or one dihedral / the bond (3 per survivor) per lane, so a warp runs
+// ONE code path instead of the bond / angle / dihedral lanes of an 8-lane group one after the other; then, once every
+// role chunk is complete, one lane per (survivor, bead): pair energy from the seven exponent parts, the bead's force,
+// added to the CTA's shared force array if the bead is one of its own.  The role results (BP_ROLE doubles per survivor)
+// live in the shared-memory scratch behind the unit tables, free once the prologue is over.
+constexpr int FAST_ACT = 48;          // survivors of one CTA the role slots hold (more: the 8-lane groups)
+SIS_D double *fast_bp_role_slots(FastShared &sh)
+{
+    return reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(&sh) + ((sizeof(FastShared) + 15) & ~size_t(15)) +
+                                      2 * FAST_EMAX * sizeof(uint32_t) + 4096);
+}
+SIS_D void fast_bp_eval_roles(const DevSys &S, const FFParams &P, FastShared &sh, const double4 *pos, int lo_item, int hi_item,
+                              int q, int nact)
+{
+    const int lane = threadIdx.x & 31;
+    double *slots = fast_bp_role_slots(sh);
+    const int cang = (4 * nact + 31) >> 5, cdih = (3 * nact + 31) >> 5, nrole = cang + cdih, cbead = (6 * nact + 31) >> 5;
+    for (;;) {
+        int ch = 0;
+        if (lane == 0) ch = atomicAdd(&sh.bp_next[q], 1);
+        ch = __shfl_sync(0xffffffffu, ch, 0);
+        if (ch >= nrole + cbead) break;
+        if (ch < nrole) {
+            const bool ang = ch < cang;
+            const int it = 32 * (ang ? ch : ch - cang) + lane;
+            int a = -1, role = 0;
+            if (ang) { if (it < 4 * nact) { a = it >> 2; role = 1 + (it & 3); } }
+            else if (it < 3 * nact) { a = it / 3; const int r3 = it - 3 * a; role = r3 == 2 ? 0 : 5 + r3; }
+            if (a >= 0) {
+                const FastBpCand &cd = sh.cand[sh.active[a]];
+                const Vec3 x0 = v3(pos[cd.b[0]]), x1 = v3(pos[cd.b[1]]);
+                const int tA = bp_role_A(role), tB = bp_role_B(role);
+                const Vec3 xa = tA >= 0 ? v3(pos[cd.b[tA]]) : x0, xb = tB >= 0 ? v3(pos[cd.b[tB]]) : x0;
+                bp_role_eval(P, P.bp[cd.type], role, x0, x1, xa, xb, slots + BP_ROLE * a);
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) atomicAdd(&sh.roles_done[q], 1);
+        } else {
+            while (*(volatile int *)&sh.roles_done[q] < nrole) __nanosleep(32);
+            __threadfence_block();
+            const int it = 32 * (ch - nrole) + lane;
+            if (it < 6 * nact) {
+                const int a = it / 6, t = it - 6 * a;
+                FastBpCand &cd = sh.cand[sh.active[a]];
+                const double *r = slots + BP_ROLE * a;
+                const double u = bp_roles_u(r);
+                const double ene = P.bp_triplet ? P.bp[cd.type].U0 * cd.dG * exp(-u) : P.bp[cd.type].U0 * exp(-u);
+                const bool on = ene <= P.bp_cutoff_energy;
+                const int it_bead = cd.b[t];
+                if (on && it_bead >= lo_item && it_bead < hi_item) {
+                    const Vec3 Ft = bp_roles_bead_force(r, t);
+                    double *fb = sh.fbp[it_bead - lo_item];
+                    atomicAdd(fb, ene * Ft.x); atomicAdd(fb + 1, ene * Ft.y); atomicAdd(fb + 2, ene * Ft.z);
+                }
+                if (t == 0 && cd.own) {
+                    S.bp_status[cd.pb] = on ? 1 : 0;
+                    S.ene_bp[cd.pb] = on ? ene : 0.0;
+                    cd.last = on ? 1 : 0;
+                }
+            }
+        }
+    }
+}
+SIS_D void fast_bp_eval(const DevSys &S, const FFParams &P, FastShared &sh, const double4 *pos, int lo_item, int hi_item,
+                        int q, int nact)
+{
+    if (nact <= FAST_ACT && !S.dbg_bp_groups) fast_bp_eval_roles(S, P, sh, pos, lo_item, hi_item, q, nact);
+    else fast_bp_eval_groups(S, P, sh, pos, lo_item, hi_item, q, nact);
 }
 
 // Monte-Carlo step of the BP role (replica-local mode): passes 1-2 of src/force_bp_limit_triplet.F90.
@@ -603,7 +676,7 @@ SIS_D int fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fas
     int cur = C.cur0;
     auto in_range = [&](int it) { return it >= lo_item && it < hi_item; };
     // ---- E = the CTA's beads + their chain neighbours outside the range ---------------------------
-    if (bt == 0) { sh.ncand = 0; sh.nactive[0] = sh.nactive[1] = 0; sh.bp_next[0] = sh.bp_next[1] = 0; sh.nextra = 0; sh.overflow = 0; sh.gate_done[0] = sh.gate_done[1] = 0; }
+    if (bt == 0) { sh.ncand = 0; sh.nactive[0] = sh.nactive[1] = 0; sh.bp_next[0] = sh.bp_next[1] = 0; sh.roles_done[0] = sh.roles_done[1] = 0; sh.nextra = 0; sh.overflow = 0; sh.gate_done[0] = sh.gate_done[1] = 0; }
     for (int i = bt; i < FAST_OWN * 3; i += FAST_BP) (&sh.fbp[0][0])[i] = 0.0;
     named_bar_sync(1, FAST_BP);
     for (int q = bt; q < C.nb; q += FAST_BP) {
@@ -725,7 +798,7 @@ SIS_D int fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fas
         const int nact = sh.nactive[n & 1];
         if (bt == 0) { __threadfence_block(); *(volatile int *)&sh.gate_done[n & 1] = n + 1; }   // the LOC groups may join
         bar_arrive(4, FAST_MAIN + FAST_BP);                    // gate complete: the MAIN groups may join the evaluation
-        if (bt == 0) { sh.nactive[(n + 1) & 1] = 0; sh.bp_next[(n + 1) & 1] = 0; }
+        if (bt == 0) { sh.nactive[(n + 1) & 1] = 0; sh.bp_next[(n + 1) & 1] = 0; sh.roles_done[(n + 1) & 1] = 0; }
         fast_bp_eval(S, P, sh, pos, lo_item, hi_item, n & 1, nact);
         if (prof) b2 = clock64();
         __threadfence_block();

@@ -83,6 +83,7 @@ struct DevSys {
     int *cell_sorted;             // cell_beads with every cell in ascending bead order (k_nl_rank)
     int ncell_cap;
     GridInfo *grid;               // the cell grid of the current build (host- or k_nl_plan-written)
+    int dbg_bp_groups;            // option "bp_groups" = 1: k_md_fast evaluates the base-pair survivors with 8-lane role groups (round-1 form)
     int dbg_no_loc_help;          // option "loc_help" = 0: the LOC warps of k_md_fast do not join the base-pair evaluation
     struct RemdDev *remd;         // non-null: k_md_fast<U, true> runs the exchange step itself every remd->nex steps
     // parameters

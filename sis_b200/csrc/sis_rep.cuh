@@ -40,7 +40,7 @@
 constexpr int REP_MAXB = 64;       // beads per replica
 constexpr int REP_MAXC = 1024;     // base-pair candidates per replica
 constexpr int REP_ACT = 32;        // gate survivors evaluated role by role with slots for their results (beyond: one thread each, atomics)
-constexpr int REP_ROLE = 50;       // doubles one survivor's seven roles leave: 4 angles x {u, fi, fk}, 2 dihedrals x {u, fi, fl, ra, rb}, bond {u, fi}
+constexpr int REP_ROLE = BP_ROLE;       // doubles one survivor's seven roles leave: 4 angles x {u, fi, fk}, 2 dihedrals x {u, fi, fl, ra, rb}, bond {u, fi}
 constexpr int REP_BPL = 16;        // base-pair force slots listed per bead (beyond: shared-memory atomics)
 constexpr int REP_BENT = 9;        // bonded terms a bead takes part in: 2 bonds, 3 angles, 4 dihedrals
 
@@ -179,57 +179,10 @@ SIS_D void rep_bp_eval(const FFParams &P, const RepSm &sm, int c, bool forces)
 SIS_D void rep_bp_role_item(const FFParams &P, const RepSm &sm, int a, int role)
 {
     const unsigned char *b = sm.c_b + 8 * sm.act[a];
-    const BpPara &p = P.bp[(signed char)b[6]];
     const Vec3 x0 = rep_x(sm.x, b[0]), x1 = rep_x(sm.x, b[1]);
-    const Vec3 v12 = pbc_vec_d(P, x0, x1);
-    const double d1212 = dot(v12, v12);
-    double *out = sm.bpR + REP_ROLE * a;
-    if (role == 0) {
-        // bond 1=2: u and the force vector fi (+fi on bead i, -fi on bead j)
-        const double a12 = sqrt(d1212), d = a12 - p.bond_r;
-        const Vec3 fi = (2.0 * p.bond_k * d / a12) * v12;
-        out[46] = p.bond_k * d * d;
-        out[47] = fi.x; out[48] = fi.y; out[49] = fi.z;
-    } else if (role <= 4) {
-        // angle between v12 and w; odd roles: w = x0 - xa (vertex i), even roles: w = xa - x1 (vertex j).
-        // cos = (v12 . w) / (|v12| |w|) and the 1 / sin factor through one reciprocal square root each
-        const bool at_i = role & 1;
-        const Vec3 xa = rep_x(sm.x, b[role + 1]);
-        const Vec3 w = at_i ? pbc_vec_d(P, x0, xa) : pbc_vec_d(P, xa, x1);
-        const double k = role == 1 ? p.angl_k2 : role == 2 ? p.angl_k1 : role == 3 ? p.angl_k4 : p.angl_k3;
-        const double th = role == 1 ? p.angl_theta2 : role == 2 ? p.angl_theta1 : role == 3 ? p.angl_theta4 : p.angl_theta3;
-        const double dww = dot(w, w), d12w = dot(v12, w), dd = dww * d1212;
-        const double cosine = d12w * rsqrt(dd);
-        const double d = acos(cosine) - th;
-        const double pre = 2.0 * k * d * rsqrt(dd - d12w * d12w);
-        const double r12w = d12w / d1212, rww = d12w / dww;
-        Vec3 fi, fk;
-        if (at_i) { fi = pre * (v12 - rww * w); fk = pre * (w - r12w * v12); }
-        else { fi = (-pre) * (w - r12w * v12); fk = (-pre) * (v12 - rww * w); }
-        out += 7 * (role - 1);
-        out[0] = k * d * d;
-        out[1] = fi.x; out[2] = fi.y; out[3] = fi.z; out[4] = fk.x; out[5] = fk.y; out[6] = fk.z;
-    } else {
-        // dihedral a-2=1-b: a on the j side (bead 3 or 5), b on the i side (bead 2 or 4)
-        const Vec3 xa = rep_x(sm.x, b[role == 5 ? 3 : 5]), xb = rep_x(sm.x, b[role == 5 ? 2 : 4]);
-        const Vec3 va2 = pbc_vec_d(P, xa, x1), v1b = pbc_vec_d(P, x0, xb);
-        const double ra = dot(v12, va2) / d1212, rb = dot(v12, v1b) / d1212;
-        const Vec3 m = cross(va2, v12), n = cross(v12, v1b);
-        // cos(phi + phi0), sin(phi + phi0) from (X, Y) / |(X, Y)|, phi = atan2(Y, X), as bp_force_role
-        const double a12 = sqrt(d1212);
-        const double Y = dot(va2, n) * a12, X = dot(m, n);
-        const double kk = role == 5 ? p.dihd_k1 : p.dihd_k2;
-        const double c0 = role == 5 ? p.cos_phi1 : p.cos_phi2, s0 = role == 5 ? p.sin_phi1 : p.sin_phi2;
-        const double rinv = rsqrt(X * X + Y * Y);
-        const double cosd = (X * c0 - Y * s0) * rinv, sind = (Y * c0 + X * s0) * rinv;
-        const double pre = -kk * sind * a12;
-        const Vec3 fi = (pre / dot(m, m)) * m;
-        const Vec3 fl = (-pre / dot(n, n)) * n;
-        out += 28 + 9 * (role - 5);
-        out[0] = kk * (1.0 + cosd);
-        out[1] = fi.x; out[2] = fi.y; out[3] = fi.z; out[4] = fl.x; out[5] = fl.y; out[6] = fl.z;
-        out[7] = ra; out[8] = rb;
-    }
+    const int tA = bp_role_A(role), tB = bp_role_B(role);
+    const Vec3 xa = tA >= 0 ? rep_x(sm.x, b[tA]) : x0, xb = tB >= 0 ? rep_x(sm.x, b[tB]) : x0;
+    bp_role_eval(P, P.bp[(signed char)b[6]], role, x0, x1, xa, xb, sm.bpR + REP_ROLE * a);
 }
 // the six roles of survivor `a` are in -- two independent pieces of work:
 // (1) its energy: U0 dG exp(-sum u) (src/force_bp_triplet.F90:200), status, the per-nucleotide count of a Monte-Carlo step;
@@ -240,7 +193,7 @@ SIS_D void rep_bp_energy(const FFParams &P, const RepSm &sm, int a, bool count_e
     unsigned char *b = sm.c_b + 8 * c;
     const BpPara &p = P.bp[(signed char)b[6]];
     const double *r = sm.bpR + REP_ROLE * a;
-    const double u = r[46] + ((r[0] + r[7]) + (r[14] + r[21])) + (r[28] + r[37]);
+    const double u = bp_roles_u(r);
     const double ene = P.bp_triplet ? p.U0 * sm.c_dG[c] * exp(-u) : p.U0 * exp(-u);
     const bool on = ene <= P.bp_cutoff_energy;
     if (on) { b[7] |= 1; sm.c_ene[c] = ene; } else { b[7] &= ~1; sm.c_ene[c] = 0.0; }
@@ -252,21 +205,7 @@ SIS_D void rep_bp_gather(const FFParams &P, const RepSm &sm, int a, int t, int s
 {
     const unsigned char *b = sm.c_b + 8 * sm.act[a];
     const double *r = sm.bpR + REP_ROLE * a;
-    auto V = [&](int o) { return mk(r[o], r[o + 1], r[o + 2]); };
-    // angle roles 1, 3 (vertex i): c0 = -fi - fk, c1 = fk, ca = fi; roles 2, 4 (vertex j): c0 = fi, c1 = -fi - fk, ca = fk
-    // dihedral roles 5, 6: ca = fi, cb = fl, c1 = (ra - 1) fi - rb fl, c0 = (rb - 1) fl - ra fi
-    // layout: angle role q at 7 (q - 1): {u, fi, fk}; dihedral role q at 28 + 9 (q - 5): {u, fi, fl, ra, rb}
-    Vec3 F;
-    if (t < 2) {
-        const Vec3 f0 = V(47);
-        const Vec3 di5 = V(29), dl5 = V(32), di6 = V(38), dl6 = V(41);
-        const double ra5 = r[35], rb5 = r[36], ra6 = r[44], rb6 = r[45];
-        if (t == 0) F = f0 - (V(1) + V(4)) + V(8) - (V(15) + V(18)) + V(22) + ((rb5 - 1.0) * dl5 - ra5 * di5) + ((rb6 - 1.0) * dl6 - ra6 * di6);
-        else F = -f0 + V(4) - (V(8) + V(11)) + V(18) - (V(22) + V(25)) + ((ra5 - 1.0) * di5 - rb5 * dl5) + ((ra6 - 1.0) * di6 - rb6 * dl6);
-    } else if (t == 2) F = V(1) + V(32);
-    else if (t == 3) F = V(11) + V(29);
-    else if (t == 4) F = V(15) + V(41);
-    else F = V(25) + V(38);
+    const Vec3 F = bp_roles_bead_force(r, t);
     const int bead = b[t];
     const int slot = atomicAdd(&sm.bcnt[bead], 1);
     rep_put(sm.bpF, a * 6 + t, F);
@@ -318,16 +257,20 @@ SIS_D void rep_mc_prune(const FFParams &P, const RepSm &sm, int n, int ncand, un
         const uint32_t stream = 0x40000000u + (uint32_t)R.stream;
         int *seq = reinterpret_cast<int *>(sm.bpF);          // the slots are free until the force pass
         int ndel = 0;
+        unsigned long long wbase = ctr - 64ull;     // no window yet: the first deletion draws it
+        double umine = 0.0;
         for (;;) {
             const bool e0 = lane < n && sm.excess[lane] > 0, e1 = lane + 32 < n && sm.excess[lane + 32] > 0;
             const unsigned m0 = __ballot_sync(0xffffffffu, e0), m1 = __ballot_sync(0xffffffffu, e1);
             const int nnt = __popc(m0) + __popc(m1);
             if (nnt == 0) break;
-            // uniforms ctr, ctr + 1, ...: [0] picks the nucleotide, [1 .. nseq] shuffle, [nseq + 1 .. 2 nseq - 1] Metropolis sweep
-            const double umine = uniform_counter(seed, stream, ctr + (unsigned long long)lane);
+            // uniforms ctr, ctr + 1, ...: [0] picks the nucleotide, [1 .. nseq] shuffle, [nseq + 1 .. 2 nseq - 1] Metropolis sweep.
+            // A window of 32 of the stream is drawn side by side (one per lane) and serves several deletions
+            if (ctr - wbase >= 24ull) { wbase = ctr; umine = uniform_counter(seed, stream, wbase + (unsigned long long)lane); }
             auto uni = [&](int idx) {
-                double u = __shfl_sync(0xffffffffu, umine, idx & 31);
-                if (idx >= 32) u = uniform_counter(seed, stream, ctr + (unsigned long long)idx);
+                const unsigned long long off = ctr + (unsigned long long)idx - wbase;
+                double u = __shfl_sync(0xffffffffu, umine, (int)(off & 31ull));
+                if (off >= 32ull) u = uniform_counter(seed, stream, ctr + (unsigned long long)idx);
                 return u;
             };
             double rnd = uni(0);

@@ -2680,6 +2680,7 @@ int sisgpu_set_option(sisgpu_t *h, const char *name, double value)
     else if (s == "rep_kernel") h->rep_kernel = (int)value;
     else if (s == "rep_threads") h->rep_threads = (int)value;
     else if (s == "loc_help") h->S.dbg_no_loc_help = value == 0 ? 1 : 0;
+    else if (s == "bp_groups") h->S.dbg_bp_groups = value != 0 ? 1 : 0;
     else if (s == "local_kernel") { h->local_kernel = (int)value; h->lists_built = false; }
     else if (s == "profile") {   // phase clocks of the persistent kernel (block 0): get_timers out[4..8]
         if (value != 0) { TRY(h->d_prof.alloc(16 + 8 * FAST_MAX_CTA)); h->S.prof = h->d_prof.p; }
