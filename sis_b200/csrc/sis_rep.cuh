@@ -39,7 +39,7 @@
 
 constexpr int REP_MAXB = 64;       // beads per replica
 constexpr int REP_MAXC = 1024;     // base-pair candidates per replica
-constexpr int REP_ACT = 32;        // gate survivors evaluated role by role with slots for their results (beyond: one thread each, atomics)
+constexpr int REP_ACT = 24;        // gate survivors evaluated role by role with slots for their results (beyond: one thread each, atomics)
 constexpr int REP_ROLE = BP_ROLE;       // doubles one survivor's seven roles leave: 4 angles x {u, fi, fk}, 2 dihedrals x {u, fi, fl, ra, rb}, bond {u, fi}
 constexpr int REP_BPL = 16;        // base-pair force slots listed per bead (beyond: shared-memory atomics)
 constexpr int REP_BENT = 9;        // bonded terms a bead takes part in: 2 bonds, 3 angles, 4 dihedrals
@@ -64,7 +64,7 @@ struct RepSm {
     int *c_pb;                                    // [ccap]  slot in bp_status / ene_bp of the global lists (-1: not listed)
     int *act;                                     // [ccap]
     int *bn, *bcnt, *excess;                      // [n]
-    int *r2l, *l2r;                               // [nlab]
+    unsigned short *r2l, *l2r;                    // [nlab] label tables of the in-kernel exchange (1-based values, nlab <= REMD_LOCAL_MAX)
     int *ctl;                                     // [16] counters and flags (RC_*)
     RepParams *rp;
     FastRemdState *xs;
@@ -101,10 +101,10 @@ SIS_HD RepSm rep_carve(unsigned char *base, int n, int ccap, int nlab)
     s.c_pb = (int *)take(4 * ccap, 4);
     s.act = (int *)take(4 * ccap, 4);
     s.bn = (int *)take(4 * n, 4); s.bcnt = (int *)take(4 * n, 4); s.excess = (int *)take(4 * n, 4);
-    s.r2l = (int *)take(4 * nlab, 4); s.l2r = (int *)take(4 * nlab, 4);
     s.ctl = (int *)take(4 * 16, 4);
     s.bent = (unsigned short *)take(2 * REP_BENT * (size_t)n, 2);
     s.blst = (unsigned short *)take(2 * REP_BPL * (size_t)n, 2);
+    s.r2l = (unsigned short *)take(2 * (size_t)nlab, 2); s.l2r = (unsigned short *)take(2 * (size_t)nlab, 2);
     s.c_b = (unsigned char *)take(8 * (size_t)ccap, 8);
     s.bytes = (o + 15) & ~size_t(15);
     return s;
@@ -531,8 +531,8 @@ SIS_D void rep_remd_exchange(const DevSys &S, const FFParams &P, const RepSm &sm
                 atomicAdd(&sm.ctl[RC_NATT], 1);
                 if (delta < 0.0 || rnd <= exp(-delta)) {
                     atomicAdd(&sm.ctl[RC_NACC], 1);
-                    sm.r2l[rep_i - 1] = l_j; sm.r2l[rep_j - 1] = l_i;
-                    sm.l2r[l_i - 1] = rep_j; sm.l2r[l_j - 1] = rep_i;
+                    sm.r2l[rep_i - 1] = (unsigned short)l_j; sm.r2l[rep_j - 1] = (unsigned short)l_i;
+                    sm.l2r[l_i - 1] = (unsigned short)rep_j; sm.l2r[l_j - 1] = (unsigned short)rep_i;
                     const double sf = D.flg_temp ? sqrt(temp_n / temp_m) : 1.0;   // scale_velo
                     if (rep_i - 1 == grep) { sm.ctl[RC_NEWLAB] = l_j; sm.xE[2] = sf; }
                     if (rep_j - 1 == grep) { sm.ctl[RC_NEWLAB] = l_i; sm.xE[2] = 1.0 / sf; }
@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
             *sm.xs = X;
         }
     }
-    if (xch) for (int i = tid; i < S.remd->n; i += NT) { sm.r2l[i] = S.remd->rep2lab[i]; sm.l2r[i] = S.remd->lab2rep[i]; }
+    if (xch) for (int i = tid; i < S.remd->n; i += NT) { sm.r2l[i] = (unsigned short)S.remd->rep2lab[i]; sm.l2r[i] = (unsigned short)S.remd->lab2rep[i]; }
     rep_sync<NT>();
     // pair table: every pair the exclusion rules of src/neighbor_list.F90:122-180 admit (flags), 0 for the others
     for (int i = warp; i + 1 < n; i += NT / 32) {

@@ -1096,7 +1096,7 @@ static bool fast_local_ok(sisgpu *h)
 {
     if (!h->fast_kernel || !h->local_kernel || ensure_coop_blocks(h)) return false;
     if (h->nmp > FAST_GROUPS || h->nrep > FAST_MAX_CTA) return false;
-    if (h->nrep > h->coop_blocks && !rep_threads_of(h, h->nrep_all, true)) return false;   // beyond one replica per SM: k_md_rep only
+    if (h->nrep > h->coop_blocks && !rep_threads_of(h, 0, false)) return false;   // beyond one replica per SM: k_md_rep only
     // the replica-local kernel carries dual constant-force tweezers (F-REMD); the other biases go through k_md_big / per-phase kernels
     if (h->P.flg_stage || h->P.ntwz_FR || h->P.nrest || h->P.flg_bias_ss || h->P.flg_bias_rg) return false;
     if (h->K < h->nmp || h->KB < h->nmp - 1) return false;
@@ -1142,6 +1142,8 @@ static int rep_threads_of(sisgpu *h, int nlab, bool xch)
         if (want && nt != want) continue;
         if (h->nrep <= rep_capacity(h, nt, nlab, xch)) return nt;
     }
+    // more replicas than the GPU holds at once: fine in waves as long as no exchange barrier runs inside the kernel
+    if (!xch && rep_capacity(h, 128, nlab, false) > 0) return want ? want : 128;
     return 0;
 }
 
@@ -2262,7 +2264,8 @@ static int launch_persistent(sisgpu *h, long long stop)
         const size_t smem = rep_smem_bytes(h, nlab);
         void *rargs[] = {&h->S, &h->P, &A, &stop, &NA, &ccap, &nl};
         h->last_step_kernel = rep_nt == 128 ? "k_md_rep<128>" : rep_nt == 256 ? "k_md_rep<256>" : "k_md_rep<512>";
-        CK(cudaLaunchCooperativeKernel(fn, dim3(R), dim3(rep_nt), rargs, smem, h->stream));
+        if (xch || R <= rep_capacity(h, rep_nt, nlab, xch)) CK(cudaLaunchCooperativeKernel(fn, dim3(R), dim3(rep_nt), rargs, smem, h->stream));
+        else CK(cudaLaunchKernel(fn, dim3(R), dim3(rep_nt), rargs, smem, h->stream));      // in waves (no barrier between the CTAs)
     } else if (fast_ok) {
         void *fn = local ? (h->S.remd ? (void *)k_md_fast<1, true, true> : (void *)k_md_fast<1, true, false>) : (void *)k_md_fast<1, false, false>;
         if (smem_fast > h->fast_smem_set || fn != h->fast_fn_set) {
@@ -2458,7 +2461,8 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
             int want_;
             persistent_choice(h, &local_, &fast_ok_, &want_);
             if (local_ && !(h->h_misc->max_force_flag & 4) && h->remd_inkernel && (h->nranks == 1 || h->peers_ready) &&
-                h->nstep_bp_MC == 0 && h->nrep_all <= REMD_LOCAL_MAX) {
+                h->nstep_bp_MC == 0 && h->nrep_all <= REMD_LOCAL_MAX &&
+                (R <= h->coop_blocks || rep_threads_of(h, h->nrep_all, true) > 0)) {     // every replica's CTA co-resident
                 // the exchange steps run inside the replica-local kernel: ONE launch up to the target
                 const long long stop = std::min<long long>(target, cur + (1ll << 20));
                 h->S.remd = h->d_remd.p;

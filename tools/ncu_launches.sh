@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu launch list (gpu__time_duration) of a command; usage: tools/ncu_launches.sh out.csv <command...>
 out=$1; shift
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file "$out" "$@" > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c ${NCU_COUNT:-600} --csv --log-file "$out" "$@" > /dev/null 2>&1
 python - "$out" <<'PY'
 import csv, collections, sys
 rows = list(csv.reader(open(sys.argv[1], errors='ignore')))
