@@ -39,7 +39,7 @@
 
 constexpr int REP_MAXB = 64;       // beads per replica
 constexpr int REP_MAXC = 1024;     // base-pair candidates per replica
-constexpr int REP_ACT = 24;        // gate survivors evaluated role by role with slots for their results (beyond: one thread each, atomics)
+constexpr int REP_ACT = 32;        // gate survivors evaluated role by role with slots for their results (beyond: one thread each, atomics)
 constexpr int REP_ROLE = BP_ROLE;       // doubles one survivor's seven roles leave: 4 angles x {u, fi, fk}, 2 dihedrals x {u, fi, fl, ra, rb}, bond {u, fi}
 constexpr int REP_BPL = 16;        // base-pair force slots listed per bead (beyond: shared-memory atomics)
 constexpr int REP_BENT = 9;        // bonded terms a bead takes part in: 2 bonds, 3 angles, 4 dihedrals
@@ -54,7 +54,7 @@ struct RepSm {
     double *bpF;                                  // [REP_ACT][6][3]
     double *bpR;                                  // [REP_ACT][REP_ROLE]
     double *eA;                                   // [REP_ACT] pair energy of a survivor, 0 = not formed: the owners' scale factor
-    double *c_ene, *c_dG, *c_dH, *c_dS;           // [ccap]
+    double *c_ene, *c_dH, *c_dS;                  // [ccap]  (dG = dH - T dS, src/force_bp_triplet.F90:77, on the fly: rep_dG)
     double *red;                                  // [2 * 16]: two partial sums per warp
     int4 *meta;                                   // [n]
     uint32_t *pl;                                 // [npair]  i | j << 8 | flags (NB_WCA, NB_ELE); 0 = pair excluded
@@ -93,7 +93,7 @@ SIS_HD RepSm rep_carve(unsigned char *base, int n, int ccap, int nlab)
     s.bpF = (double *)take(8 * 18 * REP_ACT, 8);
     s.bpR = (double *)take(8 * REP_ROLE * REP_ACT, 8);
     s.eA = (double *)take(8 * REP_ACT, 8);
-    s.c_ene = (double *)take(8 * ccap, 8); s.c_dG = (double *)take(8 * ccap, 8);
+    s.c_ene = (double *)take(8 * ccap, 8);
     s.c_dH = (double *)take(8 * ccap, 8); s.c_dS = (double *)take(8 * ccap, 8);
     s.red = (double *)take(8 * 2 * 16, 8);
     s.xE = (double *)take(8 * 4, 8);
@@ -125,6 +125,7 @@ SIS_D void rep_put(double *t, int i, Vec3 f) { t[3 * i] = f.x; t[3 * i + 1] = f.
 // does the bonded term of `span` bonds that STARTS at the bead with meta m exist (src/list_local.F90:16-119)
 SIS_D bool rep_term(int4 m, int span) { return (m.w & MF_CIRC) ? m.y > span : m.z + span < m.y; }
 SIS_D int rep_rowbase(int i, int n) { return i * (2 * n - i - 1) / 2; }
+SIS_D double rep_dG(const FFParams &P, const RepSm &sm, int c) { return P.bp_triplet ? sm.c_dH[c] - sm.rp->tempK * sm.c_dS[c] : 1.0; }
 
 // one pair of the table: force on its first bead (the second one takes the negative)
 SIS_D Vec3 rep_pair_force(const FFParams &P, uint32_t e, const double *x, double ele_coef, double inv_lambdaD, double cut2)
@@ -156,7 +157,7 @@ SIS_D void rep_bp_eval(const FFParams &P, const RepSm &sm, int c, bool forces)
     double u, a12, ene = 0.0;
     bool on = false;
     if (bp_force_all(P, P.bp[type], xs, &u, fr, &a12, &v12)) {
-        ene = P.bp_triplet ? P.bp[type].U0 * sm.c_dG[c] * exp(-u) : P.bp[type].U0 * exp(-u);
+        ene = P.bp_triplet ? P.bp[type].U0 * rep_dG(P, sm, c) * exp(-u) : P.bp[type].U0 * exp(-u);
         on = ene <= P.bp_cutoff_energy;
     }
     if (on) { b[7] |= 1; sm.c_ene[c] = ene; } else { b[7] &= ~1; sm.c_ene[c] = 0.0; }
@@ -194,7 +195,7 @@ SIS_D void rep_bp_energy(const FFParams &P, const RepSm &sm, int a, bool count_e
     const BpPara &p = P.bp[(signed char)b[6]];
     const double *r = sm.bpR + REP_ROLE * a;
     const double u = bp_roles_u(r);
-    const double ene = P.bp_triplet ? p.U0 * sm.c_dG[c] * exp(-u) : p.U0 * exp(-u);
+    const double ene = P.bp_triplet ? p.U0 * rep_dG(P, sm, c) * exp(-u) : p.U0 * exp(-u);
     const bool on = ene <= P.bp_cutoff_energy;
     if (on) { b[7] |= 1; sm.c_ene[c] = ene; } else { b[7] &= ~1; sm.c_ene[c] = 0.0; }
     sm.eA[a] = on ? ene : 0.0;
@@ -222,7 +223,7 @@ SIS_D void rep_bp_gate_warp(const FFParams &P, const RepSm &sm, int c, int ncand
     if (c < ncand) {
         unsigned char *b = sm.c_b + 8 * c;
         const int type = (signed char)b[6];
-        if ((!use_mask || (b[7] & 2)) && (!P.bp_triplet || sm.c_dG[c] < 0.0)) {
+        if ((!use_mask || (b[7] & 2)) && (!P.bp_triplet || rep_dG(P, sm, c) < 0.0)) {
             const Vec3 v12 = pbc_vec_d(P, rep_x(sm.x, b[0]), rep_x(sm.x, b[1]));
             const double d2 = dot(v12, v12), r0 = P.bp[type].bond_r, dc = P.bp[type].cutoff_ddist;
             const double lo = fmax(r0 - dc, 0.0), hi = r0 + dc;
@@ -499,8 +500,10 @@ SIS_D void rep_remd_exchange(const DevSys &S, const FFParams &P, const RepSm &sm
         const unsigned long long target = (round + 1ull) * (unsigned long long)nl;     // one CTA per replica on the whole node
         const long long t0 = clock64();
         if (xprof) { xp[1] += (unsigned long long)(t0 - x0); }
-        while (ld_acquire_sys_u64(D.xbar_peer[D.rank]) < target)
+        while (ld_acquire_sys_u64(D.xbar_peer[D.rank]) < target) {     // (sleeping: the SM's other replicas keep their issue slots)
+            __nanosleep(64);
             if (clock64() - t0 > 8000000000ll) { atomicOr(&S.misc->max_force_flag, 16); break; }   // ~4 s: a CTA / a rank is missing
+        }
         if (S.prof) S.prof[16 + 8 * (blockIdx.x % FAST_MAX_CTA) + 6] += (unsigned long long)(clock64() - t0);
         sm.ctl[RC_NEWLAB] = label_own; sm.xE[2] = 1.0; sm.ctl[RC_NATT] = 0; sm.ctl[RC_NACC] = 0;
         if (xprof) { x0 = clock64(); xp[2] += (unsigned long long)(x0 - t0); }
@@ -554,10 +557,8 @@ SIS_D void rep_remd_exchange(const DevSys &S, const FFParams &P, const RepSm &sm
         *sm.rp = rp;
     }
     rep_sync<NT>();
-    const double vs = sm.xE[2], tK = sm.rp->tempK;
+    const double vs = sm.xE[2];
     for (int i = tid; i < 3 * n; i += NT) sm.v[i] *= vs;
-    if (P.bp_triplet)
-        for (int c = tid; c < ncand; c += NT) sm.c_dG[c] = sm.c_dH[c] - tK * sm.c_dS[c];
     rep_sync<NT>();
     if (xprof) { xp[4] += (unsigned long long)(clock64() - x0); xp[5] += 1ull; }
 }
@@ -666,7 +667,6 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
                         const bool m5 = NA.bp_model == 5;
                         sm.c_dH[c] = m5 ? S.bp3_dH[bp3] : 0.0;
                         sm.c_dS[c] = m5 ? S.bp3_dS[bp3] : 0.0;
-                        sm.c_dG[c] = P.bp_triplet ? sm.c_dH[c] - sm.rp->tempK * sm.c_dS[c] : 1.0;
                     }
                 }
                 nc += __popc(mb);
