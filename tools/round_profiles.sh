@@ -23,5 +23,17 @@ ncu --set full --import-source on --clock-control none -k regex:k_md_big -s 60 -
 ncu --set full --import-source on --clock-control none -k regex:k_md_rep -s 1 -c 1 -o gpurun_out/r02_k_md_rep_c3 python bench.py --workload c3 --steps 1 --warmup 1 --md-steps 200 > /dev/null 2>&1
 ncu --set full --import-source on --clock-control none -k regex:k_md_rep -s 1 -c 1 -o gpurun_out/r02_k_md_rep_c3_592 python bench.py --workload c3 --nrep 592 --steps 1 --warmup 1 --md-steps 100 > /dev/null 2>&1
 ncu --set full --import-source on --clock-control none -k regex:k_nl_rows -c 1 -o gpurun_out/r02_k_nl_rows_c5 python bench.py --workload c5 --steps 1 --warmup 1 --md-steps 100 --no-cpu --no-extra > /dev/null 2>&1
-ls -la gpurun_out/ | tail -30
-tail -2 gpurun_out/bench.err gpurun_out/ref.err
+# summaries here (ncu reads its own reports without a GPU too); the reports themselves are too large to bring back together
+for k in k_md_rep_c3 k_md_rep_c3_592 k_md_fast_c4 k_md_big_c5 k_nl_rows_c5; do
+    python tools/ncu_summary.py gpurun_out/r02_$k.ncu-rep --top 14 > gpurun_out/r02_${k}_ncu.txt 2>/dev/null
+    python tools/ncu_lines.py gpurun_out/r02_$k.ncu-rep >> gpurun_out/r02_${k}_ncu.txt 2>/dev/null
+done
+cp profiles/r02_kernel_metrics.json gpurun_out/ 2>/dev/null
+python tools/ncu_traffic.py gpurun_out/r02_k_md_fast_c4.ncu-rep c4 40
+python tools/ncu_traffic.py gpurun_out/r02_k_md_big_c5.ncu-rep c5 1
+python tools/ncu_traffic.py gpurun_out/r02_k_md_rep_c3.ncu-rep c3 200
+python tools/ncu_traffic.py gpurun_out/r02_k_md_rep_c3_592.ncu-rep c3_592 100
+cp profiles/r02_kernel_metrics.json gpurun_out/r02_kernel_metrics.json
+rm -f gpurun_out/*.ncu-rep
+ls -la gpurun_out/ | tail -40
+tail -n 2 gpurun_out/bench.err gpurun_out/ref.err
