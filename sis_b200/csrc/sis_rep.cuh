@@ -37,6 +37,13 @@
 
 #include "sis_fast.cuh"
 
+// -DSIS_REP_PROF: per-warp barrier waits, per-chunk-kind cycles of the work queue and the sections of the exchange
+// (block 0; tools/rep_profile.py prints them).  The per-CTA phase clocks behind option "profile" are always there.
+#ifdef SIS_REP_PROF
+constexpr bool REP_PROF = true;
+#else
+constexpr bool REP_PROF = false;
+#endif
 constexpr int REP_MAXB = 64;       // beads per replica
 constexpr int REP_MAXC = 1024;     // base-pair candidates per replica
 constexpr int REP_ACT = 32;        // gate survivors evaluated role by role with slots for their results (beyond: one thread each, atomics)
@@ -476,7 +483,7 @@ SIS_D void rep_remd_exchange(const DevSys &S, const FFParams &P, const RepSm &sm
     const RepParams Rown = *sm.rp;
     RepParams Ralt = Rown;
     if (has_opp) remd_apply_label(D, Ralt, D.lab_rp[label_opp - 1]);
-    const bool xprof = S.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    const bool xprof = REP_PROF && S.prof != nullptr && blockIdx.x == 0 && tid == 0;
     unsigned long long *xp = S.prof + 16 + 8 * 1003;
     long long x0 = xprof ? clock64() : 0, x1;
     rep_remd_energies<NT>(S, P, sm, n, npair, ncand, Rown, Ralt, has_opp);
@@ -504,7 +511,7 @@ SIS_D void rep_remd_exchange(const DevSys &S, const FFParams &P, const RepSm &sm
             __nanosleep(64);
             if (clock64() - t0 > 8000000000ll) { atomicOr(&S.misc->max_force_flag, 16); break; }   // ~4 s: a CTA / a rank is missing
         }
-        if (S.prof) S.prof[16 + 8 * (blockIdx.x % FAST_MAX_CTA) + 6] += (unsigned long long)(clock64() - t0);
+        if (REP_PROF && S.prof) S.prof[16 + 8 * (blockIdx.x % FAST_MAX_CTA) + 6] += (unsigned long long)(clock64() - t0);
         sm.ctl[RC_NEWLAB] = label_own; sm.xE[2] = 1.0; sm.ctl[RC_NATT] = 0; sm.ctl[RC_NACC] = 0;
         if (xprof) { x0 = clock64(); xp[2] += (unsigned long long)(x0 - t0); }
     }
@@ -709,9 +716,9 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
     const bool prof = S.prof != nullptr && tid == 0;
     unsigned long long *pc = S.prof + 16 + 8 * (blockIdx.x % FAST_MAX_CTA);
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
-    const bool wprof = S.prof != nullptr && blockIdx.x == 0 && lane == 0 && warp < 4;     // block 0, warps 0-3: {B2 wait, P2, B3 wait}
+    const bool wprof = REP_PROF && S.prof != nullptr && blockIdx.x == 0 && lane == 0 && warp < 4;     // block 0, warps 0-3: {B2 wait, P2, B3 wait}
     long long w0 = 0, w1 = 0, aw[3] = {0, 0, 0};
-    const bool tprof = S.prof != nullptr && blockIdx.x == 0;      // block 0: cycles and count per chunk type of the P1 queue
+    const bool tprof = REP_PROF && S.prof != nullptr && blockIdx.x == 0;      // block 0: cycles and count per chunk type of the P1 queue
 
     int done = 0;
     if (!overflow)

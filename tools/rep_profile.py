@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """phase clocks of k_md_rep (option "profile") on BASELINE config 3: cycles per MD step and per phase, averaged
-over the replicas' CTAs.  usage: rep_profile.py [--nrep N] [--nex N] [--mc N] [--opt k=v]"""
+over the replicas' CTAs.  usage: rep_profile.py [--nrep N] [--nex N] [--mc N] [--opt k=v]
+The per-warp / per-chunk-kind / exchange-section lines need the instrumented build:
+    python __graft_entry__.py --prof ;  SISGPU_LIB=sis_b200/libsisgpu_prof.so python tools/rep_profile.py ..."""
 import argparse, sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
