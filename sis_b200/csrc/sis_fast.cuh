@@ -32,6 +32,13 @@
 
 #include "sis_fused.cuh"
 
+// -DSIS_FAST_PROF: the phase clocks of option "profile" (bench.py --profile) compiled in; without it the step loops
+// carry no clock reads (the kernel is large enough for its instruction footprint to matter)
+#ifdef SIS_FAST_PROF
+constexpr bool FAST_PROF = true;
+#else
+constexpr bool FAST_PROF = false;
+#endif
 constexpr int FAST_MAIN_WARPS = 16, FAST_BP_WARPS = 4, FAST_LOC_WARPS = 4;
 constexpr int FAST_MAIN = 32 * FAST_MAIN_WARPS, FAST_BP = 32 * FAST_BP_WARPS, FAST_LOC = 32 * FAST_LOC_WARPS;
 constexpr int FAST_THREADS = FAST_MAIN + FAST_BP + FAST_LOC;
@@ -218,7 +225,7 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
     const int nmp = C.nmp, R = C.R;
     unsigned long long step = C.step0;
     int cur = C.cur0;
-    const bool prof = S.prof != nullptr && tid == 0;   // every CTA's thread 0: per-CTA phase clocks
+    const bool prof = FAST_PROF && S.prof != nullptr && tid == 0;   // every CTA's thread 0: per-CTA phase clocks
     long long c0 = 0, c1 = 0, c1b = 0, c2 = 0, c3 = 0, c4 = 0;
     // shared-memory regions behind the rows: prologue scratch, later the unit tables
     uint32_t *tmp_all = s_rows + FAST_EMAX;
@@ -506,7 +513,8 @@ SIS_D int fast_main_role(const DevSys &S, const FFParams &P, const StepArgs &A, 
 // lane, bp_force_role) draw survivors from a shared counter.  The BP groups start right after the
 // gate; the MAIN groups join when their pair units are done, so a CTA with many formed base pairs
 // is not held up by its four BP warps.
-SIS_D void fast_bp_eval_groups(const DevSys &S, const FFParams &P, FastShared &sh, const double4 *pos, int lo_item, int hi_item,
+// (kept out of line: it runs only with more survivors than role slots, or behind option "bp_groups")
+__device__ __noinline__ void fast_bp_eval_groups(const DevSys &S, const FFParams &P, FastShared &sh, const double4 *pos, int lo_item, int hi_item,
                                int q, int nact)
 {
     const int bl = threadIdx.x & 7;
@@ -749,7 +757,7 @@ SIS_D int fast_bp_role(const DevSys &S, const FFParams &P, const FastCtx &C, Fas
     cta_sync();
     const int ncand = min(sh.ncand, FAST_BPC);
     if (sh.ncand > FAST_BPC && bt == 0) S.misc->max_force_flag |= 4;   // the host checks the flag after the launch
-    const bool prof = S.prof != nullptr && bt == 0;
+    const bool prof = FAST_PROF && S.prof != nullptr && bt == 0;
     long long b0 = 0, b1 = 0, b2 = 0;
     int n = 0;
     if (!sh.blocked[0] && sh.ncand <= FAST_BPC && !sh.overflow)
@@ -871,7 +879,7 @@ SIS_D int fast_loc_role(const DevSys &S, const FFParams &P, const StepArgs &A, c
         sh.tbead[slot] = tb;
     }
     cta_sync();
-    const bool prof = S.prof != nullptr && blockIdx.x == 0 && lt == 0;
+    const bool prof = FAST_PROF && S.prof != nullptr && blockIdx.x == 0 && lt == 0;
     long long l0 = 0, l1 = 0;
     int n = 0;
     if (!sh.blocked[0] && sh.ncand <= FAST_BPC && !sh.overflow)
@@ -1296,7 +1304,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_md_fast(const __grid_consta
         D.xch_round0 += (unsigned long long)X.attempt;
     }
     if (tid >= FAST_MAIN) return;
-    if (S.prof != nullptr && blockIdx.x == 0 && tid == 0) {   // whole-launch clocks: prologue share = total - steps * per-step
+    if (FAST_PROF && S.prof != nullptr && blockIdx.x == 0 && tid == 0) {   // whole-launch clocks: prologue share = total - steps * per-step
         S.prof[10] += (unsigned long long)(clock64() - k_entry);
         S.prof[11] += 1ull;
     }
