@@ -498,8 +498,15 @@ SIS_D void rep_remd_exchange(const DevSys &S, const FFParams &P, const RepSm &sm
             Er[2 * grep + 1] = sm.xE[1];
         }
         if (D.nranks_x > 1) {
+            // two-level arrival: the replicas of this rank count themselves on a local word (the slot behind the
+            // arrival counter); the last one of the round adds R to every rank's counter -- nranks remote atomics per
+            // rank and round on a peer's counter instead of one per replica (512 on one address at 8 x 64 replicas)
             __threadfence_system();
-            for (int r = 0; r < D.nranks_x; r++) atomicAdd_system(D.xbar_peer[r], 1ull);
+            const unsigned long long mine = atomicAdd(D.xbar_peer[D.rank] + 1, 1ull) + 1ull;
+            if (mine == (round + 1ull) * (unsigned long long)R) {
+                __threadfence_system();
+                for (int r = 0; r < D.nranks_x; r++) atomicAdd_system(D.xbar_peer[r], (unsigned long long)R);
+            }
         } else {
             __threadfence();
             atomicAdd(D.xbar_peer[0], 1ull);
