@@ -2511,6 +2511,9 @@ int sisgpu_md_steps(sisgpu_t *h, int64_t nsteps, int64_t *nrebuild_out)
             for (int r = 0; r < R; r++) h->rep[r].ele_cutoff = rp[r].ele_cutoff;
         }
         TRY(refresh_half_counts(h));
+        TRY(sync_ctl(h));
+        // the energy evaluations of the device-side exchange steps carry the hard abort of src/energy_stage.F90:22-26
+        if (h->h_misc->max_force_flag & 2) return set_err("Error: Z-coordinate < 0.85 * stage_sigma in energy_stage. Abort!");
         if (h->h_misc->max_force_flag & 1) {
             fprintf(stderr, "Warning: maxval(forces) > 100.0 during the last md_steps call (step %lld)\n", (long long)h->h_ctl->step);
             h->h_misc->max_force_flag = 0;
