@@ -119,9 +119,15 @@ SIS_HD RepSm rep_carve(unsigned char *base, int n, int ccap, int nlab)
 
 #ifdef __CUDACC__
 // wait until a shared-memory counter reaches `target` (chunks of the work queue that need earlier chunks complete)
-SIS_D void rep_wait(const int *ctr, int target)
+SIS_D void rep_wait(const int *ctr, int target, int *flag)
 {
-    while (*(volatile const int *)ctr < target) __nanosleep(32);
+    if (*(volatile const int *)ctr < target) {
+        const long long t0 = clock64();
+        while (*(volatile const int *)ctr < target) {
+            __nanosleep(32);
+            if (clock64() - t0 > 4000000000ll) { atomicOr(flag, 16); break; }     // ~2 s: never hang the device on a lost chunk
+        }
+    }
     __threadfence_block();
 }
 // NT == blockDim.x: the plain CTA barrier (the compiler reconverges the warp in front of it)
@@ -835,7 +841,7 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
                     }
                 } else {
                     if (nact < 0) {                     // the chunks behind depend on the survivors: the gate must be complete
-                        rep_wait(&sm.ctl[RC_GATE], cgate);
+                        rep_wait(&sm.ctl[RC_GATE], cgate, &S.misc->max_force_flag);
                         nact = sm.ctl[RC_NACT];
                         nar = min(nact, REP_ACT);
                         // angle roles, dihedral roles, survivors beyond the role slots, energies + per-bead forces, owners' sums
@@ -860,7 +866,7 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
                         if (a < nact) rep_bp_eval(P, sm, sm.act[a], !mc);
                     } else if (ch < cbp + ccomb) {      // energies, per-bead forces of the survivors (they need the roles)
                         ttype = 2;
-                        rep_wait(&sm.ctl[RC_ROLES], cang + cdih);
+                        rep_wait(&sm.ctl[RC_ROLES], cang + cdih, &S.misc->max_force_flag);
                         const int cc = ch - cbp;
                         if (cc < cene) { const int a = 32 * cc + lane; if (a < nar) rep_bp_energy(P, sm, a, mc); }
                         else if (NT >= 512) { const int it = 32 * (cc - cene) + lane; if (it < 6 * nar) rep_bp_gather(P, sm, it / 6, it % 6, RC_SPILL0 + (done & 1)); }
@@ -871,7 +877,7 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 512 / NT) k_md_rep(const _
                         }
                     } else {                            // owners' sums: pair row, bonded terms, tweezers (last: they need the pairs)
                         ttype = 7;
-                        rep_wait(&sm.ctl[RC_STAT], cstat);
+                        rep_wait(&sm.ctl[RC_STAT], cstat, &S.misc->max_force_flag);
                         const int it = 32 * (ch - cbp - ccomb) + lane;
                         if (it < 3 * n) {
                             const int k = it / 3, comp = it - 3 * k;

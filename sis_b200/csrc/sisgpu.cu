@@ -2349,6 +2349,8 @@ static int after_persistent_sync(sisgpu *h)
     }
     if (h->h_misc->max_force_flag & 8)
         return set_err("k_md_big: a warp's chain neighbours or base-pair survivors exceed its shared-memory tables (K = %d)", h->K);
+    if (h->h_misc->max_force_flag & 16)
+        return set_err("persistent kernel: a wait inside the kernel timed out (exchange barrier or work queue)");
     return 0;
 }
 
