@@ -521,14 +521,21 @@ SIS_HD BpSub bp_force_role(const FFParams &P, const BpPara &p, int role, Vec3 x0
     return o;
 }
 
-#ifdef __CUDACC__
 // Role-major form of the same arithmetic (k_md_rep, k_md_fast): ONE role of one base pair per thread, so that a warp
 // runs one code path; the results of the seven roles go to BP_ROLE doubles per pair:
 //   angle role q = 1..4 at 7 (q - 1): {u, fi, fk};  dihedral role q = 5, 6 at 28 + 9 (q - 5): {u, fi, fl, ra, rb};
 //   bond role 0 at 46: {u, fi}.
 // xa / xb as in bp_force_role.  The angles go through one reciprocal square root each (cos = v12.w rsqrt(|v12|^2 |w|^2)).
 constexpr int BP_ROLE = 50;
-SIS_D void bp_role_eval(const FFParams &P, const BpPara &p, int role, Vec3 x0, Vec3 x1, Vec3 xa, Vec3 xb, double *out)
+SIS_HD double bp_rsqrt(double x)
+{
+#ifdef __CUDA_ARCH__
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+SIS_HD void bp_role_eval(const FFParams &P, const BpPara &p, int role, Vec3 x0, Vec3 x1, Vec3 xa, Vec3 xb, double *out)
 {
     const Vec3 v12 = pbc_vec_d(P, x0, x1);
     const double d1212 = dot(v12, v12);
@@ -543,9 +550,9 @@ SIS_D void bp_role_eval(const FFParams &P, const BpPara &p, int role, Vec3 x0, V
         const double k = role == 1 ? p.angl_k2 : role == 2 ? p.angl_k1 : role == 3 ? p.angl_k4 : p.angl_k3;
         const double th = role == 1 ? p.angl_theta2 : role == 2 ? p.angl_theta1 : role == 3 ? p.angl_theta4 : p.angl_theta3;
         const double dww = dot(w, w), d12w = dot(v12, w), dd = dww * d1212;
-        const double cosine = d12w * rsqrt(dd);
+        const double cosine = d12w * bp_rsqrt(dd);
         const double d = acos(cosine) - th;
-        const double pre = 2.0 * k * d * rsqrt(dd - d12w * d12w);
+        const double pre = 2.0 * k * d * bp_rsqrt(dd - d12w * d12w);
         const double r12w = d12w / d1212, rww = d12w / dww;
         Vec3 fi, fk;
         if (at_i) { fi = pre * (v12 - rww * w); fk = pre * (w - r12w * v12); }
@@ -561,7 +568,7 @@ SIS_D void bp_role_eval(const FFParams &P, const BpPara &p, int role, Vec3 x0, V
         const double Y = dot(va2, n) * a12, X = dot(m, n);
         const double kk = role == 5 ? p.dihd_k1 : p.dihd_k2;
         const double c0 = role == 5 ? p.cos_phi1 : p.cos_phi2, s0 = role == 5 ? p.sin_phi1 : p.sin_phi2;
-        const double rinv = rsqrt(X * X + Y * Y);
+        const double rinv = bp_rsqrt(X * X + Y * Y);
         const double cosd = (X * c0 - Y * s0) * rinv, sind = (Y * c0 + X * s0) * rinv;
         const double pre = -kk * sind * a12;
         const Vec3 fi = (pre / dot(m, m)) * m;
@@ -573,11 +580,11 @@ SIS_D void bp_role_eval(const FFParams &P, const BpPara &p, int role, Vec3 x0, V
     }
 }
 // exponent of the pair from its roles
-SIS_D double bp_roles_u(const double *r) { return r[46] + ((r[0] + r[7]) + (r[14] + r[21])) + (r[28] + r[37]); }
+SIS_HD double bp_roles_u(const double *r) { return r[46] + ((r[0] + r[7]) + (r[14] + r[21])) + (r[28] + r[37]); }
 // unscaled force on bead t (0..5 = i, j, i-1, j-1, i+1, j+1) from the roles:
 // angle roles 1, 3 (vertex i): c0 = -fi - fk, c1 = fk, ca = fi; roles 2, 4 (vertex j): c0 = fi, c1 = -fi - fk, ca = fk;
 // dihedral roles 5, 6: ca = fi, cb = fl, c1 = (ra - 1) fi - rb fl, c0 = (rb - 1) fl - ra fi; bond: +fi on i, -fi on j
-SIS_D Vec3 bp_roles_bead_force(const double *r, int t)
+SIS_HD Vec3 bp_roles_bead_force(const double *r, int t)
 {
     auto V = [&](int o) { return mk(r[o], r[o + 1], r[o + 2]); };
     if (t < 2) {
@@ -592,7 +599,6 @@ SIS_D Vec3 bp_roles_bead_force(const double *r, int t)
     if (t == 4) return V(15) + V(41);
     return V(25) + V(38);
 }
-#endif
 
 // Energy side: src/energy_bp.F90:40-62,76-118 (clamped acos, mp_dihedral)
 SIS_HD double mp_angle(const FFParams &P, Vec3 x1, Vec3 x2, Vec3 x3)

@@ -233,6 +233,59 @@ int hc_force_bp_roles(HostCheck *c, const double *xyz, double *forces)
     return 0;
 }
 
+// the role-major base-pair evaluation of k_md_rep / k_md_fast (bp_role_eval, bp_roles_u, bp_roles_bead_force):
+// seven role items per pair into BP_ROLE doubles, then energy and the six bead forces from them
+int hc_force_bp_role_major(HostCheck *c, const double *xyz, double *forces)
+{
+    const int N = c->h->nmp;
+    const FFParams &P = c->h->P;
+    c->pos.resize(N);
+    for (int i = 0; i < N; i++) c->pos[i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0);
+    for (int i = 0; i < 3 * N; i++) forces[i] = 0.0;
+    for (int k = 0; k < N; k++)
+        for (int e = 0; e < c->nbp_row[k]; e++) {
+            const int2 ent = c->bprow[(size_t)k * c->KB + e];
+            const int j = ent.x, ibp = ent.y;
+            if (j < k) continue;
+            const int type = c->bp_type[ibp];
+            double dG = 1.0;
+            if (P.bp_triplet) {
+                dG = c->bp_coef[ibp].x - c->rp.tempK * c->bp_coef[ibp].y;
+                if (dG >= 0.0) continue;
+            }
+            const BpPara &p = P.bp[type];
+            const int4 mi = c->meta[k], mj = c->meta[j];
+            const int beads[6] = {k, j, chain_nb(mi, -1), chain_nb(mj, -1), chain_nb(mi, +1), chain_nb(mj, +1)};
+            const Vec3 x0 = v3(c->pos[k]), x1 = v3(c->pos[j]);
+            const Vec3 v12 = pbc_vec_d(P, x0, x1);
+            if (fabs(sqrt(dot(v12, v12)) - p.bond_r) > p.cutoff_ddist) continue;
+            double r[BP_ROLE];
+            for (int role = 0; role < 7; role++) {
+                const int tA = bp_role_A(role), tB = bp_role_B(role);
+                const Vec3 xa = tA >= 0 ? v3(c->pos[beads[tA]]) : x0, xb = tB >= 0 ? v3(c->pos[beads[tB]]) : x0;
+                bp_role_eval(P, p, role, x0, x1, xa, xb, r);
+            }
+            const double u = bp_roles_u(r);
+            const double ene = P.bp_triplet ? p.U0 * dG * exp(-u) : p.U0 * exp(-u);
+            if (ene > P.bp_cutoff_energy) continue;
+            for (int t = 0; t < 6; t++) {
+                const Vec3 F = bp_roles_bead_force(r, t);
+                forces[3 * beads[t]] += ene * F.x; forces[3 * beads[t] + 1] += ene * F.y; forces[3 * beads[t] + 2] += ene * F.z;
+            }
+        }
+    return 0;
+}
+// the fp32 pair scalar of the mixed-precision mode against the fp64 scalars, for one squared distance
+double hc_pair_scalar(HostCheck *c, double d2, int wca, int ele, int mixed)
+{
+    const FFParams &P = c->h->P;
+    if (mixed) return pair_scalar_f32(P, wca != 0, ele != 0, d2, c->rp.ele_coef, c->rp.inv_lambdaD);
+    double s = 0.0;
+    if (wca) s += wca_scalar(P, d2);
+    if (ele) s += dh_scalar(c->rp.ele_coef, c->rp.inv_lambdaD, d2);
+    return s;
+}
+
 double hc_gauss(unsigned long long seed, unsigned stream, unsigned long long step, unsigned bead, int comp)
 {
     return gauss_component(seed, stream, step, bead, comp);

@@ -59,6 +59,15 @@ class HostCheck(CApi):
         self.lib.hc_force(self.hc, _d(self.xyz)[0], C.c_uint(mask), _d(f)[0])
         return f
 
+    def force_bp_role_major(self):
+        f = np.zeros((self.nmp, 3))
+        self.lib.hc_force_bp_role_major(self.hc, _d(self.xyz)[0], _d(f)[0])
+        return f
+
+    def pair_scalar(self, d2, wca, ele, mixed):
+        self.lib.hc_pair_scalar.restype = C.c_double
+        return self.lib.hc_pair_scalar(self.hc, C.c_double(d2), C.c_int(int(wca)), C.c_int(int(ele)), C.c_int(int(mixed)))
+
     def force_bp_roles(self):
         f = np.zeros((self.nmp, 3))
         self.lib.hc_force_bp_roles(self.hc, _d(self.xyz)[0], _d(f)[0])

@@ -132,6 +132,34 @@ def test_bp_role_split_matches_oracle(name):
     assert np.abs(fo - fh).max() / np.abs(fo).max() < 1e-10
 
 
+@pytest.mark.parametrize("name", list(SPECS))
+def test_bp_role_major_matches_oracle(name):
+    """k_md_rep / k_md_fast evaluate the survivors of the distance gate role-major: seven role items per pair
+    (bp_role_eval: the angles through one reciprocal square root each), then the pair energy and the six bead
+    forces from the role results (bp_roles_u, bp_roles_bead_force) -- must reproduce force_bp* of the oracle."""
+    spec = SPECS[name]()
+    o, hcx = both(spec)
+    o.neighbor_list(0)
+    hcx.build_lists(False)
+    fo = o.force_terms(0, 1 << TERMS["bp"])
+    fh = hcx.force_bp_role_major()
+    assert np.abs(fo).max() > 0
+    assert np.abs(fo - fh).max() / np.abs(fo).max() < 1e-10
+
+
+def test_mixed_mode_pair_scalar_within_the_stated_bound():
+    """pair_scalar_f32 (option precision = 1) against the fp64 WCA / Debye-Hueckel scalars over the distances a
+    listed pair can have: relative error of the scalar below the bound the GPU tests state for the forces"""
+    spec = fx.cag47(4, pbc=True)
+    o, hcx = both(spec)
+    for wca, ele, lo, hi in ((True, False, 4.0, 9.99), (False, True, 3.0, 50.0), (True, True, 4.0, 9.99)):
+        d = np.linspace(lo, hi, 400)
+        ref = np.array([hcx.pair_scalar(x * x, wca, ele, False) for x in d])
+        got = np.array([hcx.pair_scalar(x * x, wca, ele, True) for x in d])
+        assert np.abs(ref).max() > 0
+        assert np.abs(got - ref).max() / np.abs(ref).max() < 2e-6, (wca, ele)
+
+
 def test_bp3_table_matches_oracle():
     spec = fx.t2s2hp()
     o, hcx = both(spec)
