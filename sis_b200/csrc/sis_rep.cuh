@@ -1,10 +1,11 @@
 // sis_rep.cuh -- k_md_rep: the MD loop body (src/job_md.F90:374-460) for SMALL replicas (at most 64 beads:
 // BASELINE configs C1 and C3, the REMD inputs of check/), sized to the replica instead of to the SM.
 //
-// One CTA of 128 (or 256) threads owns one whole replica for the whole launch; four (two) CTAs share
-// an SM, so a GPU holds 592 (296) replicas.  Everything a step touches lives in the CTA's shared
-// memory: positions, velocities, beta, xyz_move, the STATIC pair table and the STATIC base-pair
-// candidate table.
+// One CTA of 128, 256 or 512 threads owns one whole replica for the whole launch; four, two or one CTAs share
+// an SM, so a GPU holds 592 / 296 / 148 replicas (the host picks the widest CTA the replica count leaves room
+// for: a replica's step is a latency chain that more warps shorten; without an exchange barrier inside the
+// kernel more replicas than that run in waves).  Everything a step touches lives in the CTA's shared memory:
+// positions, velocities, beta, xyz_move, the STATIC pair table and the STATIC base-pair candidate table.
 //
 // No neighbour list on the hot path.  With <= 64 beads the list of src/neighbor_list.F90 is a
 // superset filter and nothing else: a pair is listed when it is inside cutoff + margin at the last
@@ -21,18 +22,25 @@
 // the positions saved at the last rebuild event (nl_rows_bead_at, the same code as every other list
 // build), and bp_status / bp_status_MC / ene_bp are written back into their slots.
 //
-// A step (all warps take part in every phase; three block barriers):
-//   P0  rebuild verdict (every warp reduces the top-2 displacements itself), Monte-Carlo pass on the
-//       steps that have one, distance gate of the base-pair candidates (one thread each)
-//   P1  8-lane groups evaluate the survivors (one role per lane, bp_force_role), then every warp
-//       draws chunks of the static work from a shared counter: Gaussians of this step (Philox +
-//       Box-Muller), dihedrals, bonds + angles (each term ONCE), the pairs (each pair ONCE, two
-//       per lane, branch-free Debye-Hueckel), pair forces into fixed slots
-//   P2  owners (4 lanes per bead) add their pair slots in list order, the bonded tables, the
-//       base-pair part, tweezers; integrate (src/job_md.F90:409-456); displacement for the verdict
-// The exchange step of REMD (src/job_md.F90:474-570) runs inside the kernel as in k_md_fast
-// (fast_remd_exchange): own and cross energies, energies + arrival counters into every rank's
-// exchange buffer (NVLink peer stores), every CTA replays every Metropolis decision.
+// A step = one WORK QUEUE drained by all warps + one assemble / integrate phase, two block barriers.
+// The queue: chunks of 32 items drawn from a shared counter, every kind of work on chunk boundaries (a warp runs one
+// code path); a chunk that needs earlier chunks waits on a shared-memory counter (stores, fence, counter add on the
+// producer side; sleeping spin, fence on the consumer side):
+//   gate        distance gate of 32 base-pair candidates -> survivor list
+//   dihedrals, bonds + angles (each term ONCE, into one table of force vectors)
+//   pairs       64 / 128 pairs per chunk, each pair ONCE, 2 / 4 per lane side by side, branch-free Debye-Hueckel; both
+//               directions into [bead][component][partner] slots
+//   Gaussians   of the NEXT step (Philox + Box-Muller): nothing in this step waits for them
+//   roles       (after the gate) one angle, or one dihedral / the bond, of one survivor per lane: bp_role_eval
+//   energies    (after the roles) per survivor: exponent, U0 dG exp(-u), status, Monte-Carlo count;
+//   per-bead forces  per (survivor, bead): the unscaled force into a slot listed at the bead
+//   owners' sums     (after pairs + bonded) per (bead, component): 128-bit loads of the pair row, bonded entries, tweezers
+// then [Monte-Carlo steps: the reference's sequential delete loop on one warp, rep_mc_prune], owners add the
+// survivors' forces scaled by the pair energy, integrate (src/job_md.F90:409-456), and the rebuild verdict for the
+// next step costs a flag unless a displacement passes half the margin (then every warp reduces the top-2 itself).
+// The exchange step of REMD (src/job_md.F90:474-570) runs inside the kernel (rep_remd_exchange): own and cross
+// energies item by item, the two numbers into every rank's exchange buffer (NVLink peer stores), two-level arrival
+// (local word, then R on every rank's counter), every CTA replays every Metropolis decision on its own label tables.
 #pragma once
 
 #include "sis_fast.cuh"
